@@ -1,0 +1,142 @@
+"""Static world: 10 m occupancy grids, bounds and quadrant target pools.
+
+The reference derives its grid from a Singapore shapefile that is not in the repository
+(ATT/parameters:39, ATT/grid_env_generation:108-185; ATT = MADDPG_ownENV_randomOD_radar_one_model_att),
+so maps here are synthetic but follow the reference's grid conventions exactly:
+
+* cell centres sit on multiples of `grid_length` inside the closed bound
+  (ATT/grid_env_generation:169-174), each cell is the axis-aligned square centre +/- grid_length/2;
+* occupancy is indexed [ix, iy], ix-major -- the order in which the reference appends cells to
+  `world_map_2D_polyList[0][0]` / `[0][1]` (ATT/grid_env_generation:169-179);
+* free cells whose centre lies on a boundary line are not OD candidates, the rest fall into four
+  quadrant pools split at the bound's mid lines (ATT/env_simulator:143-197).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# bound table of the multipleMap variant (MM/parameters_randomOD_radar_multipleMap.py:52-55)
+MULTIMAP_BOUNDS = [
+    [0, 250, 550, 700], [230, 530, 1000, 1200], [815, 1015, 270, 385], [455, 680, 255, 385],
+    [250, 450, 260, 385], [585, 695, 165, 300], [1395, 1535, 615, 715], [815, 1000, 950, 1055],
+    [1005, 1155, 535, 620], [1535, 1675, 225, 345], [905, 1085, 105, 205], [1105, 1195, 385, 515],
+    [715, 845, 255, 355], [685, 825, 595, 705],
+]
+DEFAULT_BOUND = [455, 680, 255, 385]  # ATT/parameters:32-36
+
+
+@dataclass
+class GridMap:
+    bound: list            # [xmin, xmax, ymin, ymax]
+    grid_length: int       # 10
+    occ: np.ndarray        # uint8 [GX, GY], 1 = occupied
+    x0c: float = field(init=False)   # centre of cell column 0
+    y0c: float = field(init=False)
+
+    def __post_init__(self):
+        g = self.grid_length
+        self.x0c = float(math.ceil(self.bound[0] / g) * g)
+        self.y0c = float(math.ceil(self.bound[2] / g) * g)
+        gx, gy = grid_shape(self.bound, g)
+        assert self.occ.shape == (gx, gy), (self.occ.shape, gx, gy)
+
+    @property
+    def gx(self):
+        return self.occ.shape[0]
+
+    @property
+    def gy(self):
+        return self.occ.shape[1]
+
+    @property
+    def origin(self):
+        """Local-coordinate origin used by the kernels (bound centre)."""
+        return (0.5 * (self.bound[0] + self.bound[1]), 0.5 * (self.bound[2] + self.bound[3]))
+
+    def cell_centre(self, ix, iy):
+        return (self.x0c + ix * self.grid_length, self.y0c + iy * self.grid_length)
+
+    def target_pools(self):
+        """Four lists of free-cell centres (int tuples), reference order (ATT/env_simulator:154-197)."""
+        xmin, xmax, ymin, ymax = self.bound
+        xs = (xmax - xmin) / 2 + xmin
+        ys = (ymax - ymin) / 2 + ymin
+        pools = [[], [], [], []]
+        for ix in range(self.gx):
+            for iy in range(self.gy):
+                if self.occ[ix, iy]:
+                    continue
+                cx, cy = self.cell_centre(ix, iy)
+                if cx == xmin or cx == xmax or cy == ymin or cy == ymax:
+                    continue
+                c = (int(cx), int(cy))
+                if cx < xs and cy < ys:
+                    pools[0].append(c)
+                elif cx > xs and cy < ys:
+                    pools[1].append(c)
+                elif cx > xs and cy > ys:
+                    pools[2].append(c)
+                else:
+                    pools[3].append(c)
+        return pools
+
+    def cell_of(self, cx, cy):
+        g = self.grid_length
+        return (int(round((cx - self.x0c) / g)), int(round((cy - self.y0c) / g)))
+
+
+def grid_shape(bound, grid_length=10):
+    g = grid_length
+    ix0, ix1 = math.ceil(bound[0] / g), math.floor(bound[1] / g)
+    iy0, iy1 = math.ceil(bound[2] / g), math.floor(bound[3] / g)
+    return ix1 - ix0 + 1, iy1 - iy0 + 1
+
+
+def _fill_holes(occ):
+    """scipy.ndimage.binary_fill_holes without scipy: free cells not 4-connected to the border fill."""
+    gx, gy = occ.shape
+    reach = np.zeros_like(occ, dtype=bool)
+    stack = [(i, j) for i in range(gx) for j in (0, gy - 1)] + [(i, j) for j in range(gy) for i in (0, gx - 1)]
+    while stack:
+        i, j = stack.pop()
+        if i < 0 or j < 0 or i >= gx or j >= gy or reach[i, j] or occ[i, j]:
+            continue
+        reach[i, j] = True
+        stack += [(i + 1, j), (i - 1, j), (i, j + 1), (i, j - 1)]
+    return np.where(reach, 0, 1).astype(np.uint8)
+
+
+def synthetic_map(bound=None, seed=0, grid_length=10, fill=0.25):
+    """Random-rectangle buildings, ~`fill` occupied, border ring free, holes filled.
+
+    The border ring stays free so every free cell is 4-connected (the reference's A*,
+    ATT/jps_straight.py:17-70, returns None on an unreachable goal) and all four quadrant
+    pools are non-empty."""
+    bound = list(DEFAULT_BOUND if bound is None else bound)
+    gx, gy = grid_shape(bound, grid_length)
+    rng = np.random.default_rng(seed)
+    occ = np.zeros((gx, gy), dtype=np.uint8)
+    target = fill * gx * gy
+    guard = 0
+    while occ.sum() < target and guard < 1000:
+        guard += 1
+        w, h = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        if gx - 2 - w < 1 or gy - 2 - h < 1:
+            w = h = 1
+        i = int(rng.integers(1, gx - 1 - w + 1))
+        j = int(rng.integers(1, gy - 1 - h + 1))
+        occ[i:i + w, j:j + h] = 1
+    occ[0, :] = occ[-1, :] = 0
+    occ[:, 0] = occ[:, -1] = 0
+    occ = _fill_holes(occ)
+    m = GridMap(bound, grid_length, occ)
+    assert all(len(p) > 0 for p in m.target_pools())
+    return m
+
+
+def multimap_set(seed=0, grid_length=10):
+    """14 synthetic maps on the multipleMap variant's bound table (MM/parameters:52-55)."""
+    return [synthetic_map(b, seed=seed * 100 + k, grid_length=grid_length) for k, b in enumerate(MULTIMAP_BOUNDS)]

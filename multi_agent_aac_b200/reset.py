@@ -1,0 +1,181 @@
+"""Episode reset on the host: random origin/destination, grid path, reference line.
+
+Mirrors `env_simulator.reset_world` (ATT:251-405; ATT = MADDPG_ownENV_randomOD_radar_one_model_att/
+env_simulator_randomOD_radar_sur_drones_oneModel_att.py, identical in the forV2 variant V2:257-383):
+
+* per drone draw a start quadrant, a different target quadrant, a start cell and -- after the first
+  drone -- redraw until the start is more than 2*protectiveBound from every earlier start
+  (ATT:254-270); the draw order is kept so `random.seed(k)` reproduces the reference's episodes;
+* 4-connected grid search start->goal (`jps_find_path`, ATT/jps_straight.py:17-70), then drop
+  collinear interior points (ATT:321-331); the polyline through the surviving cell centres is the
+  drone's `ref_line`, its vertices after the first are `goal` / `waypoints` (ATT:334-347);
+* heading points at the first waypoint, velocity starts at zero (ATT:359-372).
+
+Two samplers share the planner: `sample_episode_reference_order` draws from a `random.Random` in the
+reference's exact call order (used by RefCompatEnv and the parity tests); `ScenarioBank` draws whole
+banks with a NumPy generator for the batched env.
+"""
+from __future__ import annotations
+
+import math
+import random as _random
+
+import numpy as np
+
+from .maps import GridMap
+
+_NEIGHBOURS = ((0, -1), (0, 1), (-1, 0), (1, 0))  # expansion order of ATT/jps_straight.py:46
+
+
+def plan_path(occ: np.ndarray, start, goal):
+    """Best-first grid search with the reference's tie-breaking (ATT/jps_straight.py:17-70).
+
+    The open set is kept in discovery order and the first entry with the smallest f = g + Manhattan
+    is expanded; a cell already discovered is never re-queued or re-costed.  Returns the list of
+    (ix, iy) cells from start to goal, or None when the goal is unreachable."""
+    gx, gy = occ.shape
+    n = gx * gy
+    UNSEEN, OPEN, CLOSED = 0, 1, 2
+    status = [UNSEEN] * n
+    g = [0] * n
+    f = [0] * n
+    parent = [-1] * n
+    s = start[0] * gy + start[1]
+    t = goal[0] * gy + goal[1]
+    frontier = [s]
+    status[s] = OPEN
+    while frontier:
+        k_best = 0
+        f_best = f[frontier[0]]
+        for k in range(1, len(frontier)):
+            if f[frontier[k]] < f_best:
+                f_best = f[frontier[k]]
+                k_best = k
+        cur = frontier.pop(k_best)
+        status[cur] = CLOSED
+        if cur == t:
+            out = []
+            while cur != -1:
+                out.append((cur // gy, cur % gy))
+                cur = parent[cur]
+            return out[::-1]
+        cx, cy = cur // gy, cur % gy
+        for dx, dy in _NEIGHBOURS:
+            nx, ny = cx + dx, cy + dy
+            if nx < 0 or ny < 0 or nx >= gx or ny >= gy or occ[nx, ny] != 0:
+                continue
+            c = nx * gy + ny
+            if status[c] != UNSEEN:
+                continue
+            g[c] = g[cur] + 1
+            f[c] = g[c] + abs(nx - goal[0]) + abs(ny - goal[1])
+            parent[c] = cur
+            status[c] = OPEN
+            frontier.append(c)
+    return None
+
+
+def prune_collinear(path):
+    """Keep the first cell, every turn cell and the last cell (ATT:321-331)."""
+    out = [path[0]]
+    cur = (path[1][0] - path[0][0], path[1][1] - path[0][1])
+    for k in range(2, len(path)):
+        nxt = (path[k][0] - path[k - 1][0], path[k][1] - path[k - 1][1])
+        if nxt != cur:
+            out.append(path[k - 1])
+            cur = nxt
+    out.append(path[-1])
+    return out
+
+
+def ref_line_cells(gmap: GridMap, start_xy, goal_xy):
+    s = gmap.cell_of(*start_xy)
+    t = gmap.cell_of(*goal_xy)
+    path = plan_path(gmap.occ, s, t)
+    if path is None:
+        raise ValueError("goal %s unreachable from %s" % (goal_xy, start_xy))
+    return prune_collinear(path)
+
+
+def sample_od_reference_order(rng: _random.Random, pools, n_agents, prot=2.5):
+    """Start/goal cell centres for one episode, drawing from `rng` exactly as ATT:254-276 does."""
+    starts, goals = [], []
+    for _ in range(n_agents):
+        si = rng.randint(0, len(pools) - 1)
+        left = list(range(0, si)) + list(range(si + 1, len(pools)))
+        ti = rng.choice(left)
+        start = rng.choice(pools[si])
+        if starts:
+            while len(starts) < n_agents:
+                si = rng.randint(0, len(pools) - 1)
+                left = list(range(0, si)) + list(range(si + 1, len(pools)))
+                ti = rng.choice(left)
+                start = rng.choice(pools[si])
+                if all(math.hypot(start[0] - p[0], start[1] - p[1]) > prot * 2 for p in starts):
+                    break
+        goal = rng.choice(pools[ti])
+        starts.append(start)
+        goals.append(goal)
+    return starts, goals
+
+
+class Episode:
+    """Reset data for one env: start positions, headings and reference lines (cell lists)."""
+
+    def __init__(self, gmap: GridMap, starts, goals):
+        self.gmap = gmap
+        self.starts = [tuple(float(v) for v in s) for s in starts]
+        self.cells = [ref_line_cells(gmap, s, t) for s, t in zip(starts, goals)]
+        self.lines = [np.array([gmap.cell_centre(ix, iy) for ix, iy in c], dtype=np.float64) for c in self.cells]
+        self.headings = [math.atan2(l[1][1] - l[0][1], l[1][0] - l[0][0]) for l in self.lines]
+
+    @property
+    def n_agents(self):
+        return len(self.starts)
+
+
+def sample_episode_reference_order(rng: _random.Random, gmap: GridMap, n_agents, prot=2.5) -> Episode:
+    starts, goals = sample_od_reference_order(rng, gmap.target_pools(), n_agents, prot)
+    return Episode(gmap, starts, goals)
+
+
+class ScenarioBank:
+    """S pre-planned episodes for one map, packed for upload (see include/aac_env.h AacBank).
+
+    `cells[s, i, k]` = ix * 256 + iy of vertex k of drone i's reference line, `w[s, i]` = vertex
+    count.  Envs pick scenario hash(global_env_id, episode_index) mod S on the device, so the
+    episodes an env sees do not depend on how envs are sharded over GPUs."""
+
+    def __init__(self, gmap: GridMap, n_agents, n_scenarios, w_max=32, seed=0, prot=2.5):
+        self.gmap, self.n_agents, self.w_max = gmap, n_agents, w_max
+        rng = np.random.default_rng(seed)
+        pools = gmap.target_pools()
+        pool_arr = [np.array(p, dtype=np.int64) for p in pools]
+        cells = np.zeros((n_scenarios, n_agents, w_max), dtype=np.uint16)
+        w = np.zeros((n_scenarios, n_agents), dtype=np.uint8)
+        cache = {}
+        for s in range(n_scenarios):
+            starts = []
+            for i in range(n_agents):
+                while True:
+                    si = int(rng.integers(0, 4))
+                    ti = int(rng.choice([q for q in range(4) if q != si]))
+                    st = tuple(int(v) for v in pool_arr[si][rng.integers(0, len(pool_arr[si]))])
+                    if all(math.hypot(st[0] - p[0], st[1] - p[1]) > prot * 2 for p in starts):
+                        break
+                gl = tuple(int(v) for v in pool_arr[ti][rng.integers(0, len(pool_arr[ti]))])
+                starts.append(st)
+                key = (st, gl)
+                if key not in cache:
+                    cache[key] = ref_line_cells(gmap, st, gl)
+                c = cache[key]
+                if len(c) > w_max:
+                    raise ValueError("reference line with %d vertices exceeds w_max=%d" % (len(c), w_max))
+                w[s, i] = len(c)
+                for k, (ix, iy) in enumerate(c):
+                    cells[s, i, k] = ix * 256 + iy
+        self.cells, self.w = cells, w
+
+    @property
+    def n_scenarios(self):
+        return self.cells.shape[0]

@@ -1,0 +1,134 @@
+"""ctypes front-end of the float64 CPU oracle (oracle/aac_oracle.c) -- TEST INFRASTRUCTURE ONLY.
+
+Allowed importers: tests/, __graft_entry__.smoke(), bench.py (cpu_baseline / --impl reference).
+The product package multi_agent_aac_b200 must never import this module.
+
+Parity status: control flow / layouts pinned against the unmodified reference run through
+oracle/geos_lite.py (tests/golden/); GEOS geometry primitives "parity unpinned" (see aac_oracle.c).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+VAR_ATT, VAR_V2, VAR_MM = 0, 1, 2
+RADAR_MIN, RADAR_LAST_HIT = 0, 1
+VARIANT_IDS = {"att": VAR_ATT, "v2": VAR_V2, "mm": VAR_MM}
+
+
+class OracleCfg(C.Structure):
+    _fields_ = [("variant", C.c_int32), ("n_agents", C.c_int32), ("n_rays", C.c_int32), ("w_max", C.c_int32),
+                ("radar_mode", C.c_int32), ("sum_reward", C.c_int32), ("gx", C.c_int32), ("gy", C.c_int32),
+                ("dt", C.c_double), ("vmax", C.c_double), ("acc_max", C.c_double), ("prot", C.c_double),
+                ("ray_len", C.c_double), ("goal_r", C.c_double), ("bound", C.c_double * 4),
+                ("x0c", C.c_double), ("y0c", C.c_double), ("cell", C.c_double)]
+
+
+_STATE_FIELDS = ["pos", "vel", "heading", "reach", "wp_cur", "wall_cnt", "prev_nn", "vflags", "ref_line", "ref_w"]
+_OUT_FIELDS = ["raw_own", "norm_own", "raw_nbr", "norm_nbr", "radar", "radar_min", "radar_hit", "raw_nbr6",
+               "norm_nbr6", "nbr_order", "tcpa", "conflict", "reward", "done", "check_goal", "bbc", "parts",
+               "margin", "branch"]
+
+
+class _State(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _STATE_FIELDS]
+
+
+class _Out(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _OUT_FIELDS]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "aac_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        assert _LIB.oracle_sizeof_cfg() == C.sizeof(OracleCfg)
+    return _LIB
+
+
+def own_dim(variant, n):
+    return {"att": 6 + 4 * (n - 1), "v2": 7, "mm": 6}[variant]
+
+
+class OracleEnv:
+    """E independent envs on one map, float64, stepping through oracle_step()."""
+
+    def __init__(self, variant, gmap, n_envs, n_agents, n_rays=18, w_max=32, radar_mode=None, sum_reward=None,
+                 vmax=5.0, acc_max=8.0):
+        self.variant, self.gmap, self.E, self.N, self.R, self.w_max = variant, gmap, n_envs, n_agents, n_rays, w_max
+        if radar_mode is None:
+            radar_mode = RADAR_LAST_HIT if variant == "v2" else RADAR_MIN
+        if sum_reward is None:
+            sum_reward = 1 if variant == "att" else 0   # ATT/ma_main:77 vs V2/ma_main:81
+        cfg = OracleCfg()
+        cfg.variant, cfg.n_agents, cfg.n_rays, cfg.w_max = VARIANT_IDS[variant], n_agents, n_rays, w_max
+        cfg.radar_mode, cfg.sum_reward, cfg.gx, cfg.gy = radar_mode, sum_reward, gmap.gx, gmap.gy
+        cfg.dt, cfg.vmax, cfg.acc_max, cfg.prot, cfg.ray_len, cfg.goal_r = 0.5, vmax, acc_max, 2.5, 15.0, 1.0
+        for k in range(4):
+            cfg.bound[k] = float(gmap.bound[k])
+        cfg.x0c, cfg.y0c, cfg.cell = gmap.x0c, gmap.y0c, float(gmap.grid_length)
+        self.cfg = cfg
+        self.occ = np.ascontiguousarray(gmap.occ, dtype=np.uint8)
+        E, N, R, M = n_envs, n_agents, n_rays, n_agents - 1
+        f, i = np.float64, np.int32
+        self.state = {
+            "pos": np.zeros((E, N, 2), f), "vel": np.zeros((E, N, 2), f), "heading": np.zeros((E, N), f),
+            "reach": np.zeros((E, N), i), "wp_cur": np.zeros((E, N), i), "wall_cnt": np.zeros((E, N), i),
+            "prev_nn": np.full((E, N, 2), -1, i), "vflags": np.zeros((E, N), i),
+            "ref_line": np.zeros((E, N, w_max, 2), f), "ref_w": np.full((E, N), 2, i),
+        }
+        d = own_dim(variant, N)
+        self.out = {
+            "raw_own": np.zeros((E, N, d), f), "norm_own": np.zeros((E, N, d), f),
+            "raw_nbr": np.zeros((E, N, 5 * M), f), "norm_nbr": np.zeros((E, N, 5 * M), f),
+            "radar": np.zeros((E, N, R), f), "radar_min": np.zeros((E, N, R), f), "radar_hit": np.zeros((E, N, R), i),
+            "raw_nbr6": np.zeros((E, N, M, 6), f), "norm_nbr6": np.zeros((E, N, M, 6), f),
+            "nbr_order": np.zeros((E, N, M), i), "tcpa": np.zeros((E, N, M, 4), f), "conflict": np.zeros((E, N, 2), i),
+            "reward": np.zeros((E, N), f), "done": np.zeros((E, N), i), "check_goal": np.zeros((E, N), i),
+            "bbc": np.zeros((E, 4), i), "parts": np.zeros((E, N, 8), f), "margin": np.zeros((E, N), f),
+            "branch": np.zeros((E, N), i),
+        }
+        self._s = _State(*[self.state[n].ctypes.data for n in _STATE_FIELDS])
+        self._o = _Out(*[self.out[n].ctypes.data for n in _OUT_FIELDS])
+
+    # ---- reset ---------------------------------------------------------------------------------
+    def set_episode(self, e, starts, lines, headings):
+        """Install reset data for env `e` (what reset_world leaves behind, ATT:301-372)."""
+        s = self.state
+        for i in range(self.N):
+            w = len(lines[i])
+            assert w <= self.w_max
+            s["pos"][e, i] = starts[i]
+            s["vel"][e, i] = 0.0
+            s["heading"][e, i] = headings[i]
+            s["ref_line"][e, i, :w] = lines[i]
+            s["ref_w"][e, i] = w
+        s["reach"][e] = 0
+        s["wp_cur"][e] = 0
+        s["wall_cnt"][e] = 0
+        s["vflags"][e] = 0
+        s["prev_nn"][e] = -1
+
+    def observe(self):
+        lib().oracle_observe(C.byref(self.cfg), self.occ.ctypes.data_as(C.c_void_p), C.c_int(self.E),
+                             C.byref(self._s), C.byref(self._o))
+        return self.out
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.float64)
+        assert a.shape == (self.E, self.N, 2)
+        lib().oracle_step(C.byref(self.cfg), self.occ.ctypes.data_as(C.c_void_p), C.c_int(self.E),
+                          C.byref(self._s), a.ctypes.data_as(C.c_void_p), C.byref(self._o))
+        return self.out

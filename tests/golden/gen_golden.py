@@ -1,0 +1,73 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference env classes.
+
+Build-container only:  python tests/golden/gen_golden.py
+Reads /root/reference (never copied), writes tests/golden/<case>.npz.  Geometry underneath the
+reference code is oracle/geos_lite.py (shapely is not installable here).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from multi_agent_aac_b200.maps import synthetic_map  # noqa: E402
+from tests.golden import ref_harness as H  # noqa: E402
+
+CASES = {
+    # name: (variant, N, seed, steps, episode_length, cluster_radius, min_sep, n_rays, map_seed, policy)
+    "att_n3_plain": ("att", 3, 0, 110, 50, None, 0.0, 18, 0, "random"),
+    "att_n3_seek": ("att", 3, 10, 150, 50, None, 0.0, 18, 0, "seek"),
+    "att_n3_cluster": ("att", 3, 1, 100, 50, 9.0, 0.0, 18, 0, "random"),
+    "att_n4_near": ("att", 4, 11, 120, 50, 12.0, 5.5, 18, 0, "random"),
+    "att_n5_near_r36": ("att", 5, 2, 80, 50, 14.0, 5.5, 36, 0, "seek"),
+    "v2_n3_plain": ("v2", 3, 3, 120, 100, None, 0.0, 18, 0, "random"),
+    "v2_n3_seek": ("v2", 3, 12, 200, 100, None, 0.0, 18, 0, "seek"),
+    "v2_n4_cluster": ("v2", 4, 4, 80, 100, 10.0, 0.0, 18, 0, "random"),
+    "v2_n4_near": ("v2", 4, 13, 120, 100, 12.0, 5.5, 18, 0, "seek"),
+    "v2_n6_near_r36": ("v2", 6, 5, 70, 100, 16.0, 5.5, 36, 1, "random"),
+}
+
+
+def pack(r):
+    out = {k: v for k, v in r.items() if k != "episodes"}
+    eps = r["episodes"]
+    n = eps[0]["start"].shape[0]
+    wmax = max(len(l) for e in eps for l in e["ref_lines"])
+    lines = np.zeros((len(eps), n, wmax, 2))
+    w = np.zeros((len(eps), n), dtype=np.int32)
+    for ei, e in enumerate(eps):
+        for i, l in enumerate(e["ref_lines"]):
+            lines[ei, i, :len(l)] = l
+            w[ei, i] = len(l)
+    out["ep_start"] = np.stack([e["start"] for e in eps])
+    out["ep_heading"] = np.stack([e["heading"] for e in eps])
+    out["ep_ref_line"] = lines
+    out["ep_ref_w"] = w
+    for part in range(len(eps[0]["raw"])):
+        out["ep_raw_%d" % part] = np.stack([e["raw"][part] for e in eps])
+        out["ep_norm_%d" % part] = np.stack([e["norm"][part] for e in eps])
+    return out
+
+
+def main(names=None):
+    for name, (variant, n, seed, steps, ep_len, cl, sep, rays, mseed, policy) in CASES.items():
+        if names and name not in names:
+            continue
+        t = time.time()
+        gmap = synthetic_map(seed=mseed)
+        r = H.rollout(variant, gmap, n, seed, steps, ep_len, cluster_radius=cl, n_rays=rays, cluster_min_sep=sep, policy=policy)
+        d = pack(r)
+        d["meta_variant"] = np.array(variant)
+        d["meta"] = np.array([n, seed, steps, ep_len, rays, mseed])
+        d["occ"] = gmap.occ
+        d["bound"] = np.array(gmap.bound, dtype=np.float64)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+        print("%s: %d steps, %d episodes, done=%d goal=%d  (%.1fs)" % (
+            name, steps, len(r["episodes"]), int(r["done"].any(1).sum()), int(r["check_goal"].sum()), time.time() - t))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

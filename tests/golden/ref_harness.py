@@ -1,0 +1,232 @@
+"""Run the UNMODIFIED reference env_simulator classes from /root/reference (build container only).
+
+Test infrastructure: used by gen_golden.py to produce the committed fixtures under tests/golden/.
+Nothing here runs on the GPU box (no /root/reference there).  shapely is replaced by
+oracle/geos_lite.py; matplotlib / rtree / openpyxl / geopandas are inert stubs (the hot path never
+calls them; SURVEY.md section 8c "upgrade path").
+"""
+import importlib
+import os
+import random
+import sys
+import types
+from types import SimpleNamespace
+from unittest import mock
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REFERENCE = "/root/reference"
+sys.path.insert(0, REPO)
+
+from oracle import geos_lite  # noqa: E402
+
+VARIANTS = {
+    "att": ("MADDPG_ownENV_randomOD_radar_one_model_att",
+            "env_simulator_randomOD_radar_sur_drones_oneModel_att"),
+    "v2": ("MADDPG_ownENV_randomOD_radar_N_model_use_tdCPA_forV2",
+           "env_simulator_randomOD_radar_sur_drones_N_Model_use_tdCPA_forV2"),
+    "mm": ("MADDPG_ownENV_randomOD_radar_multipleMap",
+           "env_simulator_randomOD_radar_multipleMap"),
+}
+
+
+def _install_stubs():
+    geos_lite.install_as_shapely()
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.markers", "matplotlib.transforms",
+                 "matplotlib.patches", "matplotlib.colors", "matplotlib.animation", "rtree", "openpyxl",
+                 "geopandas", "jps"):
+        if name not in sys.modules:
+            m = mock.MagicMock(name=name)
+            m.__path__ = []
+            sys.modules[name] = m
+
+
+def load_reference_module(variant):
+    """Import the reference env module for `variant` with stubs in place; returns the module."""
+    _install_stubs()
+    d, modname = VARIANTS[variant]
+    path = os.path.join(REFERENCE, d)
+    # each variant directory has same-named helper modules (jps_straight, ...): isolate them
+    for k in [k for k in sys.modules if k.startswith(("Utilities_own", "agent_", "jps_straight", "env_simulator"))]:
+        del sys.modules[k]
+    sys.path.insert(0, path)
+    try:
+        mod = importlib.import_module(modname)
+    finally:
+        sys.path.remove(path)
+    return mod
+
+
+def grid_polys(gmap):
+    """[[occupied squares, free squares]] exactly as ATT/grid_env_generation:169-180 builds them."""
+    ones, zeros = [], []
+    h = gmap.grid_length / 2
+    for ix in range(gmap.gx):
+        for iy in range(gmap.gy):
+            cx, cy = gmap.cell_centre(ix, iy)
+            sq = geos_lite.Point(cx, cy).buffer(h, cap_style=3)
+            (ones if gmap.occ[ix, iy] else zeros).append(sq)
+    return [[ones, zeros]]
+
+
+def make_reference_env(variant, gmap, n_agents, max_spd=5, acc_max=8):
+    mod = load_reference_module(variant)
+    if variant == "mm":
+        raise NotImplementedError
+    env = mod.env_simulator(gmap.occ.astype(float), [], gmap.grid_length, list(gmap.bound), grid_polys(gmap), None)
+    # current_observable_space (ATT:1607) only fills agent.observableSpace at reset, which
+    # cur_state_norm_state_v3 overwrites (ATT:1170) before anything reads it.
+    env.current_observable_space = lambda agent: []
+    env.create_world(n_agents, 2, 0.95, 0.01, 1, 0.15, 0.05, 0.15, (1800, 1300), max_spd, [-acc_max, acc_max])
+    return env, mod
+
+
+def flat(x):
+    return np.asarray(x, dtype=np.float64)
+
+
+def snapshot_agents(env, variant):
+    n = len(env.all_agents)
+    out = {
+        "pos": np.array([env.all_agents[i].pos for i in range(n)], dtype=np.float64),
+        "vel": np.array([env.all_agents[i].vel for i in range(n)], dtype=np.float64),
+        "reach": np.array([bool(env.all_agents[i].reach_target) for i in range(n)]),
+        "n_wp": np.array([len(env.all_agents[i].waypoints) for i in range(n)]),
+        "wall": np.array([env.all_agents[i].collide_wall_count for i in range(n)]),
+        "heading": np.array([env.all_agents[i].heading for i in range(n)], dtype=np.float64),
+    }
+    return out
+
+
+def ref_lines(env):
+    n = len(env.all_agents)
+    return [np.array(list(env.all_agents[i].ref_line.coords), dtype=np.float64) for i in range(n)]
+
+
+def pack_state_att(state, n):
+    """ATT state list -> (own[N, 6+4(N-1)], radar[N,R], nbr6[N,N-1,6])."""
+    own = np.stack([flat(a) for a in state[0]])
+    radar = np.stack([flat(a) for a in state[1]])
+    nbr6 = np.stack([np.concatenate([flat(b) for b in a], axis=0) for a in state[2]]) if n > 1 else np.zeros((n, 0, 6))
+    return own, radar, nbr6
+
+
+def pack_state_v2(state, n):
+    """V2 state list -> (own[N,7], nbr[N,5(N-1)], radar[N,R], nbr6[N,N-1,6])."""
+    own = np.stack([flat(a) for a in state[0]])
+    nbr = np.stack([flat(a) for a in state[1]])
+    radar = np.stack([flat(a) for a in state[2]])
+    nbr6 = np.stack([np.concatenate([flat(b) for b in a], axis=0) for a in state[3]])
+    return own, nbr, radar, nbr6
+
+
+def rollout(variant, gmap, n_agents, seed, n_steps, episode_length, action_scale=1.0, max_spd=5, acc_max=8,
+            quiet=True, cluster_radius=None, n_rays=18, cluster_min_sep=0.0, policy="random"):
+    """Seeded rollout of the reference env with auto-reset on (any done | all goal | step cap).
+
+    Returns a dict of stacked per-step arrays plus the per-episode reset data."""
+    env, mod = make_reference_env(variant, gmap, n_agents, max_spd, acc_max)
+    if n_rays != 18:
+        # the reference hard-codes `range(0, 360, 20)` (ATT:1058-1062); shadow the builtin inside the
+        # reference module only, so the same source casts 360/n_rays-degree fans
+        import builtins
+        step = 360 // n_rays
+        mod.range = lambda *a: builtins.range(0, 360, step) if a == (0, 360, 20) else builtins.range(*a)
+    rng = np.random.default_rng(seed)
+    crng = np.random.default_rng(seed + 7919)
+    random.seed(seed)
+    args = SimpleNamespace(mode="train")
+    rec = {k: [] for k in ("actions", "reward", "done", "check_goal", "bbc", "pos", "vel", "reach", "n_wp",
+                           "heading", "episode_id", "step_in_ep", "srr")}
+    obs_keys = ("own", "radar", "nbr6") if variant == "att" else ("own", "nbr", "radar", "nbr6")
+    for k in obs_keys:
+        rec["raw_" + k] = []
+        rec["norm_" + k] = []
+    episodes = []
+    devnull = open(os.devnull, "w")
+
+    def do_reset():
+        if variant == "att":
+            st, nst = env.reset_world(n_agents, None, 0)
+        else:
+            st, nst = env.reset_world(n_agents, False, 0)
+        if cluster_radius is not None:
+            # move drones 1.. next to drone 0 so radar / near-drone / collision branches fire;
+            # the state is then rebuilt by the reference's own cur_state_norm_state_v3
+            c = env.all_agents[0].pos.astype(float)
+            placed = [c]
+            for i in range(1, n_agents):
+                for _try in range(200):
+                    off = crng.uniform(-cluster_radius, cluster_radius, size=2)
+                    p = c + off
+                    ix, iy = gmap.cell_of(p[0], p[1])
+                    free = 0 <= ix < gmap.gx and 0 <= iy < gmap.gy and not gmap.occ[ix, iy]
+                    if cluster_min_sep <= 0.0 or (free and all(np.hypot(*(p - q)) >= cluster_min_sep for q in placed)):
+                        break
+                placed.append(p)
+                env.all_agents[i].pos = p.copy()
+                env.all_agents[i].pre_pos = p.copy()
+            for i in range(n_agents):
+                env.all_agents[i].surroundingNeighbor = {}
+                env.all_agents[i].pre_surroundingNeighbor = {}
+            out = env.cur_state_norm_state_v3({}, None if variant == "att" else False)
+            st, nst = out[0], out[1]
+        snap = snapshot_agents(env, variant)
+        lines = ref_lines(env)
+        pk = pack_state_att if variant == "att" else pack_state_v2
+        episodes.append({"start": snap["pos"].copy(), "heading": snap["heading"].copy(), "ref_lines": lines,
+                         "raw": pk(st, n_agents), "norm": pk(nst, n_agents)})
+
+    old_stdout = sys.stdout
+    if quiet:
+        sys.stdout = devnull
+    try:
+        do_reset()
+        ep_step = 0
+        for t in range(n_steps):
+            act = rng.uniform(-1.0, 1.0, size=(n_agents, 2)) * action_scale
+            if policy == "seek":  # steer at the next waypoint, plus noise: reaches goals, pops waypoints
+                for i in range(n_agents):
+                    ag = env.all_agents[i]
+                    to = np.array(ag.waypoints[0], dtype=float) - ag.pos
+                    want = to / max(np.linalg.norm(to), 1e-9) * max_spd * 0.9
+                    act[i] = np.clip((want - ag.vel) / (acc_max * 0.5) + 0.25 * act[i], -1.0, 1.0)
+            ep_step += 1
+            srr = [None] * n_agents
+            scr = [[] for _ in range(n_agents)]
+            if variant == "att":
+                out = env.step(act, ep_step, acc_max, None)
+                esh = [None] * n_agents
+                rw = env.ss_reward(ep_step, srr, esh, scr, (None, None), True, args)
+            else:
+                out = env.step(act, ep_step, acc_max, args, True, False)
+                rw = env.ss_reward_Mar(ep_step, srr, scr, (None, None), False, args, True)
+            st, nst = out[0], out[1]
+            reward, done, check_goal, srr_out, _, _, bbc = rw
+            pk = pack_state_att if variant == "att" else pack_state_v2
+            for k, a in zip(obs_keys, pk(st, n_agents)):
+                rec["raw_" + k].append(a)
+            for k, a in zip(obs_keys, pk(nst, n_agents)):
+                rec["norm_" + k].append(a)
+            snap = snapshot_agents(env, variant)
+            rec["actions"].append(act)
+            rec["reward"].append(np.array([float(r) for r in reward]))
+            rec["done"].append(np.array(done, dtype=bool))
+            rec["check_goal"].append(np.array(check_goal, dtype=bool))
+            rec["bbc"].append(np.array(bbc, dtype=bool))
+            rec["srr"].append(np.array([[float(v) for v in s] for s in srr_out]))
+            for k in ("pos", "vel", "reach", "n_wp", "heading"):
+                rec[k].append(snap[k])
+            rec["episode_id"].append(len(episodes) - 1)
+            rec["step_in_ep"].append(ep_step)
+            all_reach = all(env.all_agents[i].reach_target for i in range(n_agents))
+            if ep_step > episode_length or (True in done) or all(check_goal) or all_reach:
+                do_reset()
+                ep_step = 0
+    finally:
+        sys.stdout = old_stdout
+        devnull.close()
+    out = {k: np.stack(v) for k, v in rec.items() if len(v)}
+    out["episodes"] = episodes
+    return out
