@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""Benchmark of the batched drone-env step (BASELINE.json: agent-steps/s at 1/2/4/8 B200 vs the CPU env).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl reference]
+
+One "step" = env.step + ss_reward for every env of the shard followed by the auto-reset of finished
+episodes: two kernel launches through the C ABI (aac_step, aac_autoreset).  Prints ONE JSON line.
+Workloads: c2 = one_model_att 4096 envs x 3 drones x 36 rays; c3 (default, the
+configuration the 1/2/4/8-GPU metric and the north-star target are quoted on) = tdCPA_forV2 65536 envs x
+10 drones x 36 rays per GPU; c5 = 131072 envs x 20 drones x 72 rays per GPU (the 8-GPU 1M-env sweep).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (preset, envs per GPU, drones, rays, description)
+    "c2": ("att", 4096, 3, 36, "one_model_att 4096 envs x 3 drones, 36-ray radar, single grid map"),
+    "c2r18": ("att", 4096, 3, 18, "one_model_att 4096 envs x 3 drones, 18-ray radar, single grid map"),
+    "c3": ("tdcpa_v2", 65536, 10, 36, "tdCPA_forV2 65536 envs x 10 drones per GPU, 36-ray radar, single grid map"),
+    "c5": ("tdcpa_v2", 131072, 20, 72, "tdCPA_forV2 131072 envs x 20 drones per GPU, 72-ray radar (1M envs on 8 GPUs)"),
+}
+W_REF = 4  # reference-line vertices assumed by SURVEY.md section 8d's byte count
+
+
+def algorithmic_bytes(variant, n, r):
+    """4 * (26 + 2W + obs words) per agent-step, W = 4."""
+    obs = 7 + 5 * (n - 1) + r if variant != "att" else 6 + 4 * (n - 1) + r + 6 * (n - 1)
+    return 4 * (26 + 2 * W_REF + obs)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows for k in range(4) if len(r) > 2 + k and r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def build_world(wl, n_scen, seed):
+    from multi_agent_aac_b200.maps import synthetic_map
+    from multi_agent_aac_b200.reset import ScenarioBank
+    preset_name, envs, n, r, _ = WORKLOADS[wl]
+    gmap = synthetic_map(seed=0)
+    bank = ScenarioBank(gmap, n, n_scen, w_max=32, seed=seed)
+    return gmap, bank
+
+
+def cpu_reference_run(wl, steps, warmup, sample_envs, threads=None):
+    """The float64 oracle port (oracle/aac_oracle.c, OpenMP over envs) on the host cores."""
+    from oracle.oracle import OracleEnv, RADAR_LAST_HIT, RADAR_MIN
+    from multi_agent_aac_b200.reset import Episode
+    preset_name, _, n, r, desc = WORKLOADS[wl]
+    variant = "att" if preset_name == "att" else "v2"
+    cores = threads or os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    gmap, bank = build_world(wl, 64, seed=123)
+    E = sample_envs
+    orc = OracleEnv(variant, gmap, E, n, r, w_max=32, radar_mode=RADAR_LAST_HIT if variant == "v2" else RADAR_MIN)
+    g = gmap.grid_length
+    for e in range(E):
+        s = e % bank.n_scenarios
+        lines = []
+        for i in range(n):
+            w = int(bank.w[s, i])
+            c = bank.cells[s, i, :w].astype(np.int64)
+            lines.append(np.stack([gmap.x0c + (c >> 8) * g, gmap.y0c + (c & 255) * g], -1).astype(np.float64))
+        heads = [float(np.arctan2(l[1][1] - l[0][1], l[1][0] - l[0][0])) for l in lines]
+        orc.set_episode(e, [l[0] for l in lines], lines, heads)
+    orc.observe()
+    rng = np.random.default_rng(0)
+    acts = rng.uniform(-1, 1, size=(4, E, n, 2))
+    for k in range(warmup):
+        orc.step(acts[k % 4])
+    t0 = time.perf_counter()
+    for k in range(steps):
+        orc.step(acts[k % 4])
+    dt = time.perf_counter() - t0
+    return {"value": E * n * steps / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d envs x %d drones x %d rays, %d steps of the float64 C oracle (OpenMP over envs), no auto-reset" % (E, n, r, steps),
+            "seconds": dt}, dt / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scenarios", type=int, default=512)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cpu-envs", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--tile-envs", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    preset_name, envs, n, r, desc = WORKLOADS[args.workload]
+    if args.envs:
+        envs = args.envs
+    variant = "att" if preset_name == "att" else "v2"
+    bytes_per = algorithmic_bytes(variant, n, r)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = args.cpu_envs or max(64, min(4096, 20000 // n))
+        steps = max(1, min(args.steps, 20))
+        base, sec_per_step = cpu_reference_run(args.workload, steps, max(1, min(args.warmup, 2)), sample)
+        line = {"impl": "reference", "metric": "agent_steps_per_sec", "value": base["value"], "unit": "agent-steps/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": sec_per_step * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "sample_envs": sample, "drones": n, "rays": r},
+                "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": base["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from multi_agent_aac_b200 import _capi as K
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K.lib()
+    gmap, bank = build_world(args.workload, args.scenarios, seed=1000)
+    cfg = preset(preset_name, n_envs=envs, n_agents=n, n_rays=r, w_max=32, seed=1000, env_id_base=rank * envs,
+                 tile_envs=args.tile_envs, block_threads=args.threads)
+    env = BatchedDroneEnv(cfg, gmap, device=dev)
+    env.set_bank(bank)
+    env.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1 + rank)
+    n_act = 8
+    acts = [(torch.rand((envs, n, 2), device=dev, generator=gen) * 2 - 1).contiguous() for _ in range(n_act)]
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for k in range(max(args.warmup, 3)):
+        env.step(acts[k % n_act], autoreset=True)
+    barrier()
+    launches0 = env.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    K_ = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K_)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for k in range(K_):
+        ev[k][0].record(stream)
+        env.step(acts[k % n_act], autoreset=False)
+        ev[k][1].record(stream)
+        env.autoreset()
+        ev[k][2].record(stream)
+    t_end.record(stream)
+    barrier()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    step_kernel_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    reset_kernel_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    launches = env.launch_count - launches0
+    clocks = sampler.summary() if sampler else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    stats = torch.tensor(env.read_stats(), device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)  # episode statistics: the only collective of the path
+    stats = stats.cpu().numpy()
+
+    # end to end through the host-buffer entry point: pinned actions in, observations / reward / done out
+    host = env.host_buffers()
+    h_act = [a.cpu().pin_memory() for a in acts[:2]]
+    for k in range(2):
+        env.step_host(h_act[k % 2], autoreset=True)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.e2e_steps):
+        env.step_host(h_act[k % 2], autoreset=True)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = int(h_act[0].numel() * 4)
+    d2h = int(sum(v.numel() * v.element_size() for v in host.values()))
+
+    if rank == 0:
+        agents_total = envs * n * world
+        value = agents_total * K_ / (elapsed_ms * 1e-3)
+        peak, peak_kind = measured_peak()
+        achieved = envs * n * bytes_per / (step_kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K_,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / K_, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "envs_per_gpu": envs, "drones": n, "rays": r, "variant": preset_name,
+                       "radar_mode": "last_hit" if cfg.radar_mode else "min", "scenario_bank": args.scenarios,
+                       "l2": "state+actions+outputs per step = %.0f MB > 126 MB L2, 8 rotating action buffers; no flush needed" % (envs * n * bytes_per / 1e6),
+                       "tile_envs": args.tile_envs, "sharding": "envs by instance, no data-path collective"},
+            "e2e": {"value": agents_total * args.e2e_steps / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
+            "gpu_launches": int(launches),
+            "kernels": {"env_kernel(step)_ms": step_kernel_ms, "env_kernel(autoreset)_ms": reset_kernel_ms},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_kind": peak_kind, "bytes_per_agent_step": bytes_per,
+                         "kernel": "env_kernel<V2> step" if variant == "v2" else "env_kernel<ATT> step"},
+            "clocks": clocks,
+            "episode_stats": {k: float(v) for k, v in zip(K.STAT_NAMES, stats)},
+        }
+        if not args.no_cpu and world == 1:
+            sample = args.cpu_envs or max(64, min(4096, 20000 // n))
+            base, _ = cpu_reference_run(args.workload, 10, 1, sample)
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,121 @@
+"""ctypes binding of the C ABI declared in include/aac_env.h (libaac_env.so, built in-tree).
+
+There is no fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaac_env.so")
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("aac_kernels.cu", "aac_capi.cu")]
+HEADERS = [os.path.join(_HERE, "csrc", "aac_kernels.cuh"), os.path.join(os.path.dirname(_HERE), "include", "aac_env.h")]
+
+ABI_VERSION = 1
+VARIANT_ATT, VARIANT_V2, VARIANT_MM = 0, 1, 2
+RADAR_MIN, RADAR_LAST_HIT = 0, 1
+OUT_RAW, OUT_NBR6, OUT_TCPA_PAIR, OUT_RADAR_AUX, OUT_PARTS = 0x01, 0x02, 0x04, 0x08, 0x10
+MAP_STRIDE = 1024
+N_STATS = 16
+STAT_NAMES = ["episodes", "steps", "return_sum", "bound_crash", "building_crash", "drone_crash", "drone_crash_nearest",
+              "all_reached", "drones_reached", "step_cap"]
+
+EXPORTS = ["aac_create", "aac_destroy", "aac_set_maps", "aac_set_bank", "aac_bind_state", "aac_reset", "aac_observe",
+           "aac_step", "aac_autoreset", "aac_step_host", "aac_read_stats", "aac_launch_count", "aac_own_dim",
+           "aac_last_error"]
+
+
+class AacConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("variant", C.c_int32), ("n_envs", C.c_int32), ("n_agents", C.c_int32),
+                ("n_rays", C.c_int32), ("w_max", C.c_int32), ("radar_mode", C.c_int32), ("sum_reward", C.c_int32),
+                ("episode_length", C.c_int32), ("out_flags", C.c_int32), ("tile_envs", C.c_int32),
+                ("block_threads", C.c_int32), ("env_id_base", C.c_int64), ("seed", C.c_uint64),
+                ("dt", C.c_float), ("vmax", C.c_float), ("acc_max", C.c_float), ("prot", C.c_float),
+                ("ray_len", C.c_float), ("goal_r", C.c_float)]
+
+
+class AacMapDesc(C.Structure):
+    _fields_ = [("gx", C.c_int32), ("gy", C.c_int32), ("bound", C.c_float * 4), ("x0c", C.c_float), ("y0c", C.c_float),
+                ("cell", C.c_float), ("origin_x", C.c_float), ("origin_y", C.c_float)]
+
+
+STATE_FIELDS = ["px", "py", "vx", "vy", "heading", "meta", "ref_cells", "ref_w", "wall_count", "ep_step", "ep_index",
+                "ep_return", "map_id"]
+OUT_FIELDS = ["norm_own", "norm_nbr", "radar", "norm_nbr6", "raw_own", "raw_nbr", "raw_nbr6", "reward", "done",
+              "check_goal", "bbc", "terminated", "tcpa_min", "tcpa_pair", "nbr_order", "radar_min", "radar_hit", "parts",
+              "branch"]
+
+
+class AacState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in STATE_FIELDS]
+
+
+class AacOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in OUT_FIELDS]
+
+
+class AacBank(C.Structure):
+    _fields_ = [("n_scenarios", C.c_int32), ("cells", C.c_void_p), ("w", C.c_void_p), ("map_id", C.c_void_p)]
+
+
+class AacError(RuntimeError):
+    pass
+
+
+def nvcc_command(out=LIB_PATH):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+            "-Xcompiler", "-fPIC", "-shared", "-o", out] + SOURCES
+
+
+def build(force=False):
+    """Compile libaac_env.so for sm_100a (cross-compiles without a GPU)."""
+    newest = max(os.path.getmtime(p) for p in SOURCES + HEADERS)
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    subprocess.check_call(nvcc_command())
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AacError("libaac_env.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    P = C.c_void_p
+    L.aac_create.argtypes = [C.POINTER(AacConfig), C.POINTER(P)]
+    L.aac_destroy.argtypes = [P]
+    L.aac_destroy.restype = None
+    L.aac_set_maps.argtypes = [P, C.POINTER(AacMapDesc), P, C.c_int32]
+    L.aac_set_bank.argtypes = [P, C.POINTER(AacBank)]
+    L.aac_bind_state.argtypes = [P, C.POINTER(AacState)]
+    L.aac_reset.argtypes = [P, P, C.POINTER(AacOut), P]
+    L.aac_observe.argtypes = [P, C.POINTER(AacOut), P]
+    L.aac_step.argtypes = [P, P, C.POINTER(AacOut), P]
+    L.aac_autoreset.argtypes = [P, C.POINTER(AacOut), P]
+    L.aac_step_host.argtypes = [P, P, C.POINTER(AacOut), C.POINTER(AacOut), C.c_int32, P]
+    L.aac_read_stats.argtypes = [P, P, C.c_int32, P]
+    L.aac_launch_count.argtypes = [P]
+    L.aac_launch_count.restype = C.c_int64
+    L.aac_own_dim.argtypes = [C.c_int32, C.c_int32]
+    L.aac_last_error.restype = C.c_char_p
+    for name in EXPORTS:
+        if name not in ("aac_destroy", "aac_launch_count", "aac_last_error"):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise AacError("%s failed (%d): %s" % (what, rc, lib().aac_last_error().decode()))

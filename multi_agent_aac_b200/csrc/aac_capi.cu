@@ -1,0 +1,270 @@
+// C ABI of the batched drone environment (include/aac_env.h): handle management, map / scenario
+// upload and kernel launches.  No torch types, no exceptions across the boundary, no synchronisation
+// except where the header says so.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "aac_kernels.cuh"
+
+using namespace aac;
+
+struct AacEnv {
+    AacConfig cfg;
+    int device = 0;
+    int te = 0, threads = 0;
+    SmemLayout layout{};
+    MapDev *d_maps = nullptr;
+    int n_maps = 0;
+    float2 *d_ray = nullptr;
+    uint16_t *d_bank_cells = nullptr;
+    uint8_t *d_bank_w = nullptr;
+    int32_t *d_bank_map = nullptr;
+    int n_scen = 0;
+    float *d_actions = nullptr;  // staging for aac_step_host
+    double *d_stats = nullptr;
+    AacState st{};
+    bool bound = false;
+    int64_t launches = 0;
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return AAC_ERR_CUDA;
+}
+#define CU(call)                                             \
+    do {                                                     \
+        cudaError_t e_ = (call);                             \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
+    } while (0)
+
+extern "C" const char *aac_last_error(void) { return g_err; }
+
+extern "C" int aac_own_dim(int32_t variant, int32_t n_agents) { return own_dim(variant, n_agents); }
+
+extern "C" int64_t aac_launch_count(const AacEnv *env) { return env ? env->launches : 0; }
+
+extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
+    if (!cfg || !out) return fail(AAC_ERR_ARG, "aac_create: null argument");
+    if (cfg->abi_version != AAC_ABI_VERSION) return fail(AAC_ERR_ARG, "aac_create: abi_version mismatch");
+    if (cfg->variant != AAC_VARIANT_ATT && cfg->variant != AAC_VARIANT_V2)
+        return fail(AAC_ERR_ARG, "aac_create: variant must be AAC_VARIANT_ATT or AAC_VARIANT_V2");
+    if (cfg->n_envs < 1) return fail(AAC_ERR_ARG, "aac_create: n_envs < 1");
+    if (cfg->n_agents < 1 || cfg->n_agents > AAC_MAX_AGENTS) return fail(AAC_ERR_ARG, "aac_create: n_agents out of range");
+    if (cfg->n_rays < 1 || cfg->n_rays > AAC_MAX_RAYS || 360 % cfg->n_rays) return fail(AAC_ERR_ARG, "aac_create: n_rays must divide 360");
+    if (cfg->w_max < 2 || cfg->w_max > AAC_MAX_W || cfg->w_max % 8) return fail(AAC_ERR_ARG, "aac_create: w_max must be a multiple of 8 in [8, 64]");
+    if (!(cfg->dt > 0) || !(cfg->vmax > 0) || !(cfg->prot > 0) || !(cfg->ray_len > 0)) return fail(AAC_ERR_ARG, "aac_create: non-positive physical constant");
+    AacEnv *env = new (std::nothrow) AacEnv();
+    if (!env) return fail(AAC_ERR_STATE, "aac_create: out of host memory");
+    env->cfg = *cfg;
+    CU(cudaGetDevice(&env->device));
+    // tile: whole envs per CTA, about a hundred drones, a multiple of 4 envs so every output row block
+    // of a tile starts 16-byte aligned
+    int te = cfg->tile_envs > 0 ? cfg->tile_envs : ((96 + cfg->n_agents - 1) / cfg->n_agents + 3) / 4 * 4;
+    if (te < 1) te = 1;
+    const int optin = max_smem_optin();
+    SmemLayout L = make_layout(cfg->variant, te, cfg->n_agents, cfg->n_rays, cfg->w_max, cfg->out_flags);
+    while (te > 1 && (int)L.total > (optin > 0 ? optin / 2 : 100 * 1024)) {
+        te = te > 4 ? te - 4 : te - 1;
+        L = make_layout(cfg->variant, te, cfg->n_agents, cfg->n_rays, cfg->w_max, cfg->out_flags);
+    }
+    if (optin > 0 && (int)L.total > optin) { delete env; return fail(AAC_ERR_ARG, "aac_create: one env does not fit in shared memory"); }
+    env->te = te;
+    env->layout = L;
+    env->threads = cfg->block_threads > 0 ? cfg->block_threads : MAX_THREADS;
+    if (env->threads > MAX_THREADS || env->threads % 32) { delete env; return fail(AAC_ERR_ARG, "aac_create: block_threads must be a multiple of 32, <= 256"); }
+    cudaError_t e = upload_constants();
+    if (e != cudaSuccess) { delete env; return cuda_fail(e, "upload_constants"); }
+    // ray table: direction k*(360/R) degrees (ATT:1058-1066).  The reference adds 15*cos to a
+    // coordinate of a few hundred metres, so components below ~1e-14 vanish: axis rays are exact.
+    std::vector<float2> rays(cfg->n_rays);
+    const int step_deg = 360 / cfg->n_rays;
+    for (int k = 0; k < cfg->n_rays; ++k) {
+        const double rad = (double)(k * step_deg) * (M_PI / 180.0);
+        double c = cos(rad), s = sin(rad);
+        if (fabs(c) < 1e-12) c = 0.0;
+        if (fabs(s) < 1e-12) s = 0.0;
+        rays[k] = make_float2((float)c, (float)s);
+    }
+    CU(cudaMalloc(&env->d_ray, sizeof(float2) * cfg->n_rays));
+    CU(cudaMemcpy(env->d_ray, rays.data(), sizeof(float2) * cfg->n_rays, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&env->d_stats, sizeof(double) * AAC_N_STATS));
+    CU(cudaMemset(env->d_stats, 0, sizeof(double) * AAC_N_STATS));
+    *out = env;
+    return 0;
+}
+
+extern "C" void aac_destroy(AacEnv *env) {
+    if (!env) return;
+    cudaFree(env->d_maps);
+    cudaFree(env->d_ray);
+    cudaFree(env->d_bank_cells);
+    cudaFree(env->d_bank_w);
+    cudaFree(env->d_bank_map);
+    cudaFree(env->d_actions);
+    cudaFree(env->d_stats);
+    delete env;
+}
+
+extern "C" int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *occ, int32_t n_maps) {
+    if (!env || !maps || !occ || n_maps < 1) return fail(AAC_ERR_ARG, "aac_set_maps: bad argument");
+    if (env->cfg.variant != AAC_VARIANT_MM && n_maps != 1) return fail(AAC_ERR_ARG, "aac_set_maps: this variant uses exactly one map");
+    std::vector<MapDev> host(n_maps);
+    for (int m = 0; m < n_maps; ++m) {
+        const AacMapDesc &d = maps[m];
+        MapDev &o = host[m];
+        memset(&o, 0, sizeof(o));
+        if (d.gx < 1 || d.gy < 1 || d.gx > 255 || d.gy > 255 || d.gx * d.gy > AAC_MAP_STRIDE ||
+            (d.gx + 2 * MAP_PAD) * (d.gy + 2 * MAP_PAD) + 32 > MAP_WORDS * 32)
+            return fail(AAC_ERR_ARG, "aac_set_maps: grid too large");
+        if (!(d.cell > 0) || env->cfg.ray_len > 1.5f * d.cell || 2.0f * env->cfg.prot > d.cell)
+            return fail(AAC_ERR_ARG, "aac_set_maps: need ray_len <= 1.5*cell and 2*prot <= cell");
+        o.gx = d.gx; o.gy = d.gy; o.pgx = d.gx + 2 * MAP_PAD; o.pgy = d.gy + 2 * MAP_PAD;
+        o.hx = 0.5f * (d.bound[1] - d.bound[0]); o.hy = 0.5f * (d.bound[3] - d.bound[2]);
+        o.ox = d.origin_x; o.oy = d.origin_y;
+        o.ex0 = (d.x0c - 0.5f * d.cell) - d.origin_x; o.ey0 = (d.y0c - 0.5f * d.cell) - d.origin_y;
+        o.xmin_g = d.bound[0]; o.ymin_g = d.bound[2];
+        o.cell = d.cell; o.inv_cell = 1.0f / d.cell;
+        for (int ix = 0; ix < d.gx; ++ix)
+            for (int iy = 0; iy < d.gy; ++iy)
+                if (occ[(size_t)m * AAC_MAP_STRIDE + ix * d.gy + iy]) {
+                    const int b = (ix + MAP_PAD) * o.pgy + iy + MAP_PAD;
+                    o.bits[b >> 5] |= 1u << (b & 31);
+                }
+    }
+    if (env->d_maps) { CU(cudaFree(env->d_maps)); env->d_maps = nullptr; }
+    CU(cudaMalloc(&env->d_maps, sizeof(MapDev) * n_maps));
+    CU(cudaMemcpy(env->d_maps, host.data(), sizeof(MapDev) * n_maps, cudaMemcpyHostToDevice));
+    env->n_maps = n_maps;
+    return 0;
+}
+
+extern "C" int aac_set_bank(AacEnv *env, const AacBank *bank) {
+    if (!env || !bank || bank->n_scenarios < 1 || !bank->cells || !bank->w) return fail(AAC_ERR_ARG, "aac_set_bank: bad argument");
+    const size_t S = bank->n_scenarios, N = env->cfg.n_agents, W = env->cfg.w_max;
+    for (size_t k = 0; k < S * N; ++k)
+        if (bank->w[k] < 2 || bank->w[k] > W) return fail(AAC_ERR_ARG, "aac_set_bank: reference line needs 2..w_max vertices");
+    if (bank->map_id)
+        for (size_t k = 0; k < S; ++k)
+            if (bank->map_id[k] < 0 || bank->map_id[k] >= (env->n_maps ? env->n_maps : 1)) return fail(AAC_ERR_ARG, "aac_set_bank: map_id out of range");
+    cudaFree(env->d_bank_cells); cudaFree(env->d_bank_w); cudaFree(env->d_bank_map);
+    env->d_bank_cells = nullptr; env->d_bank_w = nullptr; env->d_bank_map = nullptr;
+    CU(cudaMalloc(&env->d_bank_cells, S * N * W * sizeof(uint16_t)));
+    CU(cudaMemcpy(env->d_bank_cells, bank->cells, S * N * W * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&env->d_bank_w, S * N));
+    CU(cudaMemcpy(env->d_bank_w, bank->w, S * N, cudaMemcpyHostToDevice));
+    if (bank->map_id) {
+        CU(cudaMalloc(&env->d_bank_map, S * sizeof(int32_t)));
+        CU(cudaMemcpy(env->d_bank_map, bank->map_id, S * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    env->n_scen = (int)S;
+    return 0;
+}
+
+extern "C" int aac_bind_state(AacEnv *env, const AacState *s) {
+    if (!env || !s) return fail(AAC_ERR_ARG, "aac_bind_state: null argument");
+    if (!s->px || !s->py || !s->vx || !s->vy || !s->heading || !s->meta || !s->ref_cells || !s->ref_w || !s->ep_step || !s->ep_index || !s->ep_return)
+        return fail(AAC_ERR_ARG, "aac_bind_state: a required state array is NULL");
+    env->st = *s;
+    env->bound = true;
+    return 0;
+}
+
+static int check_out(const AacEnv *env, const AacOut *o, int mode) {
+    const int f = env->cfg.out_flags;
+    const bool v2 = env->cfg.variant == AAC_VARIANT_V2;
+    if (!o) return fail(AAC_ERR_ARG, "output block is NULL");
+    if (!o->norm_own || !o->radar || (v2 && env->cfg.n_agents > 1 && !o->norm_nbr)) return fail(AAC_ERR_ARG, "norm_own / norm_nbr / radar must be provided");
+    if (mode == MODE_STEP && (!o->reward || !o->done || !o->check_goal || !o->bbc || !o->terminated || !o->tcpa_min))
+        return fail(AAC_ERR_ARG, "reward / done / check_goal / bbc / terminated / tcpa_min must be provided");
+    if ((f & AAC_OUT_NBR6) && !o->norm_nbr6) return fail(AAC_ERR_ARG, "AAC_OUT_NBR6 set but norm_nbr6 is NULL");
+    if ((f & AAC_OUT_RAW) && (!o->raw_own || (v2 && !o->raw_nbr) || ((f & AAC_OUT_NBR6) && !o->raw_nbr6))) return fail(AAC_ERR_ARG, "AAC_OUT_RAW set but a raw_* pointer is NULL");
+    if ((f & AAC_OUT_TCPA_PAIR) && (!o->tcpa_pair || !o->nbr_order)) return fail(AAC_ERR_ARG, "AAC_OUT_TCPA_PAIR set but tcpa_pair / nbr_order is NULL");
+    if ((f & AAC_OUT_RADAR_AUX) && (!o->radar_min || !o->radar_hit)) return fail(AAC_ERR_ARG, "AAC_OUT_RADAR_AUX set but radar_min / radar_hit is NULL");
+    if ((f & AAC_OUT_PARTS) && mode == MODE_STEP && (!o->parts || !o->branch)) return fail(AAC_ERR_ARG, "AAC_OUT_PARTS set but parts / branch is NULL");
+    return 0;
+}
+
+static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actions, const AacOut *out, void *stream) {
+    if (!env) return fail(AAC_ERR_ARG, "null handle");
+    if (!env->bound) return fail(AAC_ERR_STATE, "aac_bind_state has not been called");
+    if (!env->d_maps) return fail(AAC_ERR_STATE, "aac_set_maps has not been called");
+    if (mode == MODE_RESET && !env->d_bank_cells) return fail(AAC_ERR_STATE, "aac_set_bank has not been called");
+    if (mode == MODE_STEP && !actions) return fail(AAC_ERR_ARG, "actions is NULL");
+    const int rc = check_out(env, out, mode);
+    if (rc) return rc;
+    KParams p;
+    memset(&p, 0, sizeof(p));
+    const AacConfig &c = env->cfg;
+    p.E = c.n_envs; p.N = c.n_agents; p.R = c.n_rays; p.W = c.w_max; p.TE = env->te;
+    p.radar_mode = c.radar_mode; p.sum_reward = c.sum_reward; p.ep_len = c.episode_length; p.out_flags = c.out_flags;
+    p.dt = c.dt; p.vmax = c.vmax; p.acc_max = c.acc_max; p.prot = c.prot; p.ray_len = c.ray_len; p.goal_r = c.goal_r;
+    p.env_id_base = c.env_id_base; p.seed = c.seed;
+    p.maps = env->d_maps; p.n_maps = env->n_maps; p.ray_dir = env->d_ray;
+    p.bank_cells = env->d_bank_cells; p.bank_w = env->d_bank_w; p.bank_map = env->d_bank_map; p.n_scen = env->n_scen;
+    p.mask = mask; p.actions = actions; p.stats = env->d_stats;
+    p.st = env->st; p.out = *out; p.L = env->layout;
+    cudaError_t e = launch_env_kernel(c.variant, p, mode, env->threads, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "env_kernel launch");
+    env->launches += 1;
+    return 0;
+}
+
+extern "C" int aac_reset(AacEnv *env, const uint8_t *mask_dev, const AacOut *out, void *stream) {
+    return launch(env, MODE_RESET, mask_dev, nullptr, out, stream);
+}
+extern "C" int aac_observe(AacEnv *env, const AacOut *out, void *stream) { return launch(env, MODE_OBSERVE, nullptr, nullptr, out, stream); }
+extern "C" int aac_step(AacEnv *env, const float *actions_dev, const AacOut *out, void *stream) {
+    return launch(env, MODE_STEP, nullptr, actions_dev, out, stream);
+}
+extern "C" int aac_autoreset(AacEnv *env, const AacOut *out, void *stream) {
+    if (!out || !out->terminated) return fail(AAC_ERR_ARG, "aac_autoreset: out->terminated is NULL");
+    return launch(env, MODE_RESET, out->terminated, nullptr, out, stream);
+}
+
+extern "C" int aac_step_host(AacEnv *env, const float *actions_host, const AacOut *od, const AacOut *oh, int32_t autoreset, void *stream_) {
+    if (!env || !actions_host || !od || !oh) return fail(AAC_ERR_ARG, "aac_step_host: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t E = env->cfg.n_envs, N = env->cfg.n_agents, A = E * N, M = N - 1, R = env->cfg.n_rays;
+    const size_t D = own_dim(env->cfg.variant, (int)N);
+    if (!env->d_actions) CU(cudaMalloc(&env->d_actions, A * 2 * sizeof(float)));
+    CU(cudaMemcpyAsync(env->d_actions, actions_host, A * 2 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    int rc = aac_step(env, env->d_actions, od, stream);
+    if (rc) return rc;
+#define D2H(field, bytes)                                                                                   \
+    if (oh->field) {                                                                                        \
+        if (!od->field) return fail(AAC_ERR_ARG, "aac_step_host: host buffer without a device buffer: %s", #field); \
+        CU(cudaMemcpyAsync(oh->field, od->field, (bytes), cudaMemcpyDeviceToHost, stream));                 \
+    }
+    // the terminal transition is copied out before the reset observation overwrites its rows
+    D2H(reward, A * 4) D2H(done, A) D2H(check_goal, A) D2H(bbc, E * 4) D2H(terminated, E) D2H(tcpa_min, A * 16)
+    if (autoreset) {
+        rc = aac_autoreset(env, od, stream);
+        if (rc) return rc;
+    }
+    D2H(norm_own, A * D * 4) D2H(norm_nbr, A * 5 * M * 4) D2H(radar, A * R * 4) D2H(norm_nbr6, A * M * 24)
+    D2H(raw_own, A * D * 4) D2H(raw_nbr, A * 5 * M * 4) D2H(raw_nbr6, A * M * 24)
+    D2H(tcpa_pair, A * M * 16) D2H(nbr_order, A * M) D2H(radar_min, A * R * 4) D2H(radar_hit, A * R * 2)
+    D2H(parts, A * 32) D2H(branch, A)
+#undef D2H
+    CU(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+extern "C" int aac_read_stats(AacEnv *env, double *stats_host, int32_t reset, void *stream_) {
+    if (!env || !stats_host) return fail(AAC_ERR_ARG, "aac_read_stats: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CU(cudaMemcpyAsync(stats_host, env->d_stats, sizeof(double) * AAC_N_STATS, cudaMemcpyDeviceToHost, stream));
+    if (reset) CU(cudaMemsetAsync(env->d_stats, 0, sizeof(double) * AAC_N_STATS, stream));
+    CU(cudaStreamSynchronize(stream));
+    return 0;
+}

@@ -31,7 +31,7 @@ class OracleCfg(C.Structure):
 _STATE_FIELDS = ["pos", "vel", "heading", "reach", "wp_cur", "wall_cnt", "prev_nn", "vflags", "ref_line", "ref_w"]
 _OUT_FIELDS = ["raw_own", "norm_own", "raw_nbr", "norm_nbr", "radar", "radar_min", "radar_hit", "raw_nbr6",
                "norm_nbr6", "nbr_order", "tcpa", "conflict", "reward", "done", "check_goal", "bbc", "parts",
-               "margin", "branch"]
+               "margin", "branch", "tcpa_min"]
 
 
 class _State(C.Structure):
@@ -98,7 +98,7 @@ class OracleEnv:
             "nbr_order": np.zeros((E, N, M), i), "tcpa": np.zeros((E, N, M, 4), f), "conflict": np.zeros((E, N, 2), i),
             "reward": np.zeros((E, N), f), "done": np.zeros((E, N), i), "check_goal": np.zeros((E, N), i),
             "bbc": np.zeros((E, 4), i), "parts": np.zeros((E, N, 8), f), "margin": np.zeros((E, N), f),
-            "branch": np.zeros((E, N), i),
+            "branch": np.zeros((E, N), i), "tcpa_min": np.zeros((E, N, 4), f),
         }
         self._s = _State(*[self.state[n].ctypes.data for n in _STATE_FIELDS])
         self._o = _Out(*[self.out[n].ctypes.data for n in _OUT_FIELDS])
@@ -132,3 +132,11 @@ class OracleEnv:
         lib().oracle_step(C.byref(self.cfg), self.occ.ctypes.data_as(C.c_void_p), C.c_int(self.E),
                           C.byref(self._s), a.ctypes.data_as(C.c_void_p), C.byref(self._o))
         return self.out
+
+    def radar_probe(self, pos, i):
+        """Radar of drone `i` for the position set pos[N,2] -> (stored value[R], true min[R], hit id[R])."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        out, omin, hit = np.zeros(self.R), np.zeros(self.R), np.zeros(self.R, dtype=np.int32)
+        lib().oracle_radar(C.byref(self.cfg), self.occ.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p), C.c_int(i),
+                           out.ctypes.data_as(C.c_void_p), omin.ctypes.data_as(C.c_void_p), hit.ctypes.data_as(C.c_void_p))
+        return out, omin, hit

@@ -1,0 +1,326 @@
+"""Parity harness: the CUDA env (through the C ABI) against the float64 oracle.
+
+Two drivers:
+  * `GpuGoldenAdapter` lets tests/replay.py replay the committed reference rollouts (tests/golden/*.npz)
+    through the CUDA env with teacher forcing (float32 state is re-seeded from the float64 rollout
+    after every compared step);
+  * `lockstep()` steps a batched CUDA env and the oracle side by side on identical inputs: after every
+    step the oracle's state is overwritten with the CUDA env's (float32 values are exact in float64),
+    so every comparison isolates one step of arithmetic.
+
+Tolerances (north_star: 1e-4 relative for ranges, tdCPA, rewards and states; flags bit-exact except
+counted boundary-epsilon ties):
+  * real-valued outputs: |got - want| <= RTOL * |want| + atol, RTOL = 1e-4, atol a per-quantity floor that
+    covers float32 resolution of the inputs (positions are float32 in a +-150 m local frame: 1.5e-5 m);
+  * a step of an env is a TIE and its flag / reward comparisons are skipped (and counted) when the
+    oracle's own `margin` (smallest |quantity - threshold| over all predicates of that drone) is below
+    TIE_EPS, or two neighbour distances of a drone differ by less than TIE_EPS (V2 sort order);
+  * a radar mismatch is a tie when the oracle itself returns the CUDA value for the drone displaced by
+    +-TIE_EPS (a grazing ray); anything else is a failure.
+"""
+import numpy as np
+import torch
+
+from multi_agent_aac_b200 import _capi as K
+from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+from multi_agent_aac_b200.maps import synthetic_map
+from multi_agent_aac_b200.reset import ScenarioBank
+from oracle.oracle import OracleEnv, RADAR_LAST_HIT, RADAR_MIN
+
+RTOL = 1e-4
+TIE_EPS = 2e-4
+ALL_OUT = K.OUT_RAW | K.OUT_NBR6 | K.OUT_TCPA_PAIR | K.OUT_RADAR_AUX | K.OUT_PARTS
+ATOL = {"norm_own": 2e-6, "norm_nbr": 2e-6, "norm_nbr6": 2e-6, "raw_own": 1e-4, "raw_nbr": 1e-4, "raw_nbr6": 1e-4, "radar": 2e-4,
+        "radar_min": 2e-4, "reward": 2e-4, "parts": 5e-4, "pos": 5e-5, "vel": 5e-6, "heading": 5e-6}
+
+
+def np_out(env):
+    return {k: v.detach().cpu().numpy() for k, v in env.out.items()}
+
+
+class GpuGoldenAdapter:
+    """OracleEnv surface (set_episode / observe / step / .state) over a 1-env BatchedDroneEnv."""
+
+    def __init__(self, variant, gmap, n_agents, n_rays, device="cuda:0"):
+        cfg = preset("att" if variant == "att" else "tdcpa_v2", n_envs=1, n_agents=n_agents, n_rays=n_rays, w_max=32, out_flags=ALL_OUT)
+        self.env = BatchedDroneEnv(cfg, gmap, device=device)
+        self.variant = variant
+        self.state = {}
+
+    def _collect(self):
+        o = np_out(self.env)
+        s = self.env.agent_state()
+        self.state = {"pos": s["pos"], "vel": s["vel"], "heading": s["heading"], "reach": s["reach"], "wp_cur": s["wp_cur"]}
+        return o
+
+    def set_episode(self, e, starts, lines, headings):
+        self.env.set_episode(e, starts, lines, headings)
+
+    def observe(self):
+        self.env.observe()
+        return self._collect()
+
+    def step(self, actions):
+        a = torch.tensor(np.asarray(actions, dtype=np.float32), device=self.env.device).contiguous()
+        self.env.step(a)
+        return self._collect()
+
+    def resync(self, env, d, t):
+        """Teacher forcing from the golden float64 rollout."""
+        self.env.load_agent_state(d["pos"][t][None], d["vel"][t][None],
+                                  heading=d["heading"][t][None] if self.variant == "v2" else None)
+
+
+def cells_to_lines(gmap, ref_cells, ref_w):
+    """uint16 cell codes [.., W] -> float64 vertex coordinates [.., W, 2]."""
+    c = ref_cells.astype(np.int64) & 0xFFFF
+    x = gmap.x0c + (c >> 8) * gmap.grid_length
+    y = gmap.y0c + (c & 255) * gmap.grid_length
+    return np.stack([x, y], -1).astype(np.float64)
+
+
+def sync_oracle(orc, env, envs=None, full=False):
+    """Copy the CUDA env's state into the oracle (all envs, or the listed ones)."""
+    s = env.agent_state()
+    sel = slice(None) if envs is None else envs
+    st = orc.state
+    st["pos"][sel] = s["pos"][sel]
+    st["vel"][sel] = s["vel"][sel]
+    st["heading"][sel] = s["heading"][sel]
+    st["reach"][sel] = s["reach"][sel]
+    st["wp_cur"][sel] = s["wp_cur"][sel]
+    st["wall_cnt"][sel] = s["wall_cnt"][sel]
+    st["vflags"][sel] = s["vflags"][sel]
+    pn = s["prev_nn"].copy()
+    pn[pn == 255] = -1
+    st["prev_nn"][sel] = pn[sel]
+    if full:
+        cells = env.state["ref_cells"].cpu().numpy().view(np.uint16)
+        st["ref_line"][sel] = cells_to_lines(env.gmap, cells, None)[sel][..., :orc.w_max, :]
+        st["ref_w"][sel] = s["ref_w"][sel]
+    return s
+
+
+class Tally:
+    def __init__(self):
+        self.n = {}
+        self.ties = {}
+        self.worst = {}
+        self.fail = []
+
+    def count(self, key, n=1):
+        self.n[key] = self.n.get(key, 0) + int(n)
+
+    def tie(self, key, n=1):
+        self.ties[key] = self.ties.get(key, 0) + int(n)
+
+    def close(self, key, got, want, where, atol, rtol=RTOL, mask=None):
+        got = np.asarray(got, dtype=np.float64)
+        want = np.asarray(want, dtype=np.float64).reshape(got.shape)
+        both_nan = np.isnan(got) & np.isnan(want)
+        err = np.abs(got - want) - rtol * np.abs(want) - atol
+        err = np.where(both_nan | ((got == want)), -1.0, err)
+        err = np.where(np.isnan(err), np.inf, err)
+        if mask is not None:
+            err = np.where(mask, err, -1.0)
+        self.count(key, err.size if mask is None else int(np.sum(mask)))
+        w = float(np.max(np.abs(got - want)[np.isfinite(got - want)])) if np.isfinite(got - want).any() else 0.0
+        self.worst[key] = max(self.worst.get(key, 0.0), w)
+        bad = err > 0
+        if bad.any():
+            idx = np.unravel_index(np.argmax(err), err.shape)
+            if len(self.fail) < 50:
+                self.fail.append("%s %s idx=%s got=%r want=%r (%d bad)" % (key, where, idx, got[idx], want[idx], int(bad.sum())))
+        return bad
+
+    def equal(self, key, got, want, where, mask=None):
+        got = np.asarray(got).astype(np.int64)
+        want = np.asarray(want).astype(np.int64).reshape(got.shape)
+        bad = got != want
+        if mask is not None:
+            bad &= mask
+        self.count(key, got.size if mask is None else int(np.sum(mask)))
+        if bad.any() and len(self.fail) < 50:
+            idx = np.unravel_index(np.argmax(bad), bad.shape)
+            self.fail.append("%s %s idx=%s got=%r want=%r (%d bad)" % (key, where, idx, got[idx], want[idx], int(bad.sum())))
+        return bad
+
+    def summary(self):
+        return {"compared": self.n, "ties": self.ties, "worst_abs_err": {k: float("%.3g" % v) for k, v in self.worst.items()},
+                "failures": len(self.fail)}
+
+
+def _bcast(mask_env, shape):
+    m = np.asarray(mask_env)
+    return np.broadcast_to(m.reshape(m.shape + (1,) * (len(shape) - m.ndim)), shape)
+
+
+def compare_obs(T, variant, g, o, where, env_ok, s_gpu, orc, rows=None):
+    """Observation blocks + radar.  env_ok[e] False => order-dependent blocks of env e are skipped."""
+    E = g["norm_own"].shape[0]
+    rows = np.ones(E, dtype=bool) if rows is None else rows
+    ok = env_ok & rows
+    keys = ["norm_own", "raw_own", "norm_nbr6", "raw_nbr6"] + (["norm_nbr", "raw_nbr"] if variant == "v2" else [])
+    for k in keys:
+        if k in g:
+            T.close(k, g[k], o[k], where, ATOL[k], mask=_bcast(ok, g[k].shape))
+    # radar: every mismatch must be explained by a grazing ray
+    for k in ("radar", "radar_min"):
+        bad = T.close(k + "(pre-tie)", g[k], o[k], where, ATOL[k], mask=_bcast(rows, g[k].shape))
+        T.fail = [f for f in T.fail if not f.startswith(k + "(pre-tie)")]
+        radar_tie_env = np.zeros(E, dtype=bool)
+        for e, i in {(int(e), int(i)) for e, i, _ in zip(*np.nonzero(bad))}:
+            explained = np.zeros(g[k].shape[2], dtype=bool)
+            for dx, dy in ((TIE_EPS, 0), (-TIE_EPS, 0), (0, TIE_EPS), (0, -TIE_EPS), (TIE_EPS, TIE_EPS), (-TIE_EPS, -TIE_EPS),
+                           (TIE_EPS, -TIE_EPS), (-TIE_EPS, TIE_EPS)):
+                pos = orc.state["pos"][e].copy()
+                pos[i] += (dx, dy)
+                out, omin, _ = orc.radar_probe(pos, i)
+                ref = out if k == "radar" else omin
+                gv = g[k][e, i].astype(np.float64)
+                explained |= (np.abs(gv - ref) <= RTOL * np.abs(ref) + 10 * ATOL[k]) | (np.isnan(gv) & np.isnan(ref))
+            still = bad[e, i] & ~explained
+            T.tie(k, int((bad[e, i] & explained).sum()))
+            radar_tie_env[e] = True
+            if still.any() and len(T.fail) < 50:
+                r = int(np.argmax(still))
+                T.fail.append("%s %s env=%d drone=%d ray=%d got=%r want=%r pos=%r" % (k, where, e, i, r, g[k][e, i, r], o[k][e, i, r],
+                                                                                      orc.state["pos"][e, i].tolist()))
+        T.count(k, int(rows.sum()) * g[k].shape[1] * g[k].shape[2])
+    hit_ok = (np.abs(g["radar"].astype(np.float64) - o["radar"]) <= 1e-3) & _bcast(rows & ~radar_tie_env, g["radar"].shape)
+    badh = (g["radar_hit"].astype(np.int64) != o["radar_hit"]) & hit_ok
+    # equal-distance hits (a ray through a corner shared by two cells) may name either cell
+    T.count("radar_hit", int(hit_ok.sum()))
+    if badh.any():
+        T.tie("radar_hit", int(badh.sum()))
+    return radar_tie_env
+
+
+def lockstep(variant, n_envs, n_agents, n_rays, steps, seed=0, radar_mode=None, n_scen=128, cluster=None, map_seed=0,
+             device="cuda:0", autoreset=True, tile_envs=0, block_threads=0, action_scale=1.0):
+    """Returns a Tally.  `cluster` = radius (m): after every reset drones 1.. are moved next to drone 0 so
+    that drone-radar / near-drone / collision branches fire."""
+    gmap = synthetic_map(seed=map_seed)
+    E, N, R, M = n_envs, n_agents, n_rays, n_agents - 1
+    if radar_mode is None:
+        radar_mode = RADAR_LAST_HIT if variant == "v2" else RADAR_MIN
+    cfg = preset("att" if variant == "att" else "tdcpa_v2", n_envs=E, n_agents=N, n_rays=R, w_max=32, out_flags=ALL_OUT,
+                 radar_mode=radar_mode, seed=seed, tile_envs=tile_envs, block_threads=block_threads)
+    env = BatchedDroneEnv(cfg, gmap, device=device)
+    env.set_bank(ScenarioBank(gmap, N, n_scen, w_max=32, seed=seed))
+    orc = OracleEnv(variant, gmap, E, N, R, w_max=32, radar_mode=radar_mode)
+    rng = np.random.default_rng(seed + 1)
+    T = Tally()
+
+    def scatter_cluster(envs):
+        if cluster is None or N < 2:
+            return
+        st = env.state
+        px, py = st["px"].cpu().numpy(), st["py"].cpu().numpy()
+        for e in envs:
+            for i in range(1, N):
+                px[e, i] = px[e, 0] + rng.uniform(-cluster, cluster)
+                py[e, i] = py[e, 0] + rng.uniform(-cluster, cluster)
+        st["px"].copy_(torch.tensor(px, device=env.device))
+        st["py"].copy_(torch.tensor(py, device=env.device))
+
+    def check_reset(envs, where):
+        scatter_cluster(envs)
+        env.observe()
+        g = np_out(env)
+        sync_oracle(orc, env, full=True)
+        orc.state["prev_nn"][envs] = -1
+        o = {k: v.copy() for k, v in orc.observe().items()}
+        rows = np.zeros(E, dtype=bool)
+        rows[envs] = True
+        env_ok = sort_ok(orc, o)
+        compare_obs(T, variant, g, o, where, env_ok, None, orc, rows=rows)
+        if M > 0:
+            T.equal("nbr_order", g["nbr_order"], o["nbr_order"], where, mask=_bcast(env_ok & rows, g["nbr_order"].shape))
+
+    def sort_ok(orc_, o):
+        if variant != "v2" or M < 2:
+            return np.ones(E, dtype=bool)
+        pos = orc_.state["pos"]
+        d = np.linalg.norm(pos[:, :, None, :] - pos[:, None, :, :], axis=-1)          # [E,N,N]
+        order = o["nbr_order"].astype(np.int64)                                      # [E,N,M]
+        ds = np.take_along_axis(d, order, axis=2)
+        gap = np.min(np.diff(ds, axis=2), axis=(1, 2))
+        bad = gap < TIE_EPS
+        T.tie("sort_order", int(bad.sum()))
+        return ~bad
+
+    env.reset()
+    check_reset(np.arange(E), "reset")
+    for t in range(steps):
+        act = (rng.uniform(-1.0, 1.0, size=(E, N, 2)) * action_scale).astype(np.float32)
+        where = "t%d" % t
+        env.step(torch.tensor(act, device=env.device))
+        g = np_out(env)
+        s_gpu = env.agent_state()
+        o = {k: v.copy() for k, v in orc.step(act.astype(np.float64)).items()}
+        so = {k: v.copy() for k, v in orc.state.items()}
+        env_ok = sort_ok(orc, o)
+        # kinematics
+        T.close("pos", s_gpu["pos"], so["pos"], where, ATOL["pos"])
+        T.close("vel", s_gpu["vel"], so["vel"], where, ATOL["vel"])
+        if variant == "v2":
+            # heading = atan2 of a float32 displacement: compare as an angle difference, skip stopped drones
+            dh = np.abs(np.angle(np.exp(1j * (s_gpu["heading"] - so["heading"]))))
+            moving = np.linalg.norm(so["vel"], axis=-1) > 1e-3
+            T.close("heading", np.where(moving, dh, 0.0), np.zeros_like(dh), where, 2e-5)
+        radar_tie_env = compare_obs(T, variant, g, o, where, env_ok, s_gpu, orc)
+        if M > 0:
+            T.equal("nbr_order", g["nbr_order"], o["nbr_order"], where, mask=_bcast(env_ok, g["nbr_order"].shape))
+            # tdCPA: t = (r.w)/|w|^2 is ill-conditioned for nearly equal velocities; scale the floor by 1/|w|
+            tp_g, tp_o = g["tcpa_pair"].astype(np.float64), o["tcpa"]
+            order = o["nbr_order"].astype(np.int64)
+            vel = so["vel"]
+            w = np.linalg.norm(np.take_along_axis(vel[:, None, :, :].repeat(N, 1), order[..., None].repeat(2, -1), axis=2) - vel[:, :, None, :], axis=-1)
+            cond = 1.0 + 1.0 / np.maximum(w, 1e-6)
+            okp = _bcast(env_ok, tp_g.shape[:3])
+            for c, name in ((0, "tcpa"), (1, "d_tcpa")):
+                err = np.abs(tp_g[..., c] - tp_o[..., c]) - RTOL * np.abs(tp_o[..., c]) * cond - 2e-4 * cond
+                T.count(name, int(okp.sum()))
+                T.worst[name] = max(T.worst.get(name, 0.0), float(np.max(np.where(okp, np.abs(tp_g[..., c] - tp_o[..., c]) / cond, 0.0))))
+                badp = (err > 0) & okp
+                if badp.any() and len(T.fail) < 50:
+                    idx = np.unravel_index(np.argmax(np.where(okp, err, -1)), err.shape)
+                    T.fail.append("%s %s idx=%s got=%r want=%r |w|=%r" % (name, where, idx, tp_g[idx + (c,)], tp_o[idx + (c,)], w[idx]))
+        # flags and rewards: skip envs with a predicate within TIE_EPS of its threshold
+        margin_ok = (o["margin"] >= TIE_EPS).all(axis=1)
+        T.tie("predicate_margin", int((~margin_ok).sum()))
+        flag_ok = margin_ok & env_ok & ~radar_tie_env
+        fm = _bcast(flag_ok, (E, N))
+        bad_env = np.zeros(E, dtype=bool)
+        for key, gv, ov in (("done", g["done"], o["done"]), ("check_goal", g["check_goal"], o["check_goal"]),
+                            ("branch", g["branch"], o["branch"]), ("reach", s_gpu["reach"], so["reach"]),
+                            ("wp_cur", s_gpu["wp_cur"], so["wp_cur"]), ("wall_cnt", s_gpu["wall_cnt"], so["wall_cnt"])):
+            bad_env |= T.equal(key, gv, ov, where, mask=fm).any(axis=1)
+        if variant == "v2":
+            T.equal("vflags", s_gpu["vflags"], so["vflags"], where, mask=fm)
+        T.equal("bbc", g["bbc"], o["bbc"], where, mask=_bcast(flag_ok, (E, 4)))
+        T.close("reward", g["reward"], o["reward"], where, ATOL["reward"], mask=fm)
+        T.close("parts", g["parts"], o["parts"], where, ATOL["parts"], mask=_bcast(flag_ok, g["parts"].shape))
+        if M > 0:
+            tm_g, tm_o = g["tcpa_min"].astype(np.float64), o["tcpa_min"]
+            # conflict counters flip when d_tcpa crosses 2*prot or tcpa crosses 0 / 1: compare away from those
+            tp = o["tcpa"]
+            near = (np.abs(tp[..., 1] - 5.0) < 5e-3) | (np.abs(tp[..., 3] - 5.0) < 5e-3) | (np.abs(tp[..., 0]) < 1e-3) | \
+                   (np.abs(tp[..., 0] - 1.0) < 1e-3) | (np.abs(tp[..., 2]) < 1e-3) | (np.abs(tp[..., 2] - 1.0) < 1e-3)
+            cm = fm & ~near.any(axis=2)
+            T.equal("conflict_counts", tm_g[..., 3], tm_o[..., 3], where, mask=cm)
+        # terminated: step cap | any done | all reached
+        term_o = ((env.state["ep_step"].cpu().numpy() > cfg.episode_length).astype(np.int64)
+                  | (o["done"].any(axis=1).astype(np.int64) << 1) | (so["reach"].all(axis=1).astype(np.int64) << 2))
+        T.equal("terminated", g["terminated"], term_o, where, mask=flag_ok)
+        # lock step: the oracle continues from the CUDA env's float32 state
+        sync_oracle(orc, env)
+        if autoreset:
+            term = np.nonzero(g["terminated"])[0]
+            if len(term):
+                env.autoreset()
+                check_reset(term, where + ".reset")
+    T.launches = env.launch_count
+    env.close()
+    return T

@@ -1,0 +1,152 @@
+"""CPU: host-side logic (maps, reset planner, scenario bank), the C-ABI library's exports, the
+multi-rank statistics reduction (gloo, world_size 2).  No CUDA calls."""
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from multi_agent_aac_b200 import _capi
+from multi_agent_aac_b200.maps import MULTIMAP_BOUNDS, GridMap, grid_shape, multimap_set, synthetic_map
+from multi_agent_aac_b200.reset import ScenarioBank, plan_path, prune_collinear, sample_episode_reference_order
+from multi_agent_aac_b200.stats import reduce_episode_stats, shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_default_grid_shape_matches_survey():
+    assert grid_shape([455, 680, 255, 385]) == (23, 13)      # 23 x 13 = 299 cells
+    m = synthetic_map(seed=0)
+    assert m.occ.shape == (23, 13) and 0.1 < m.occ.mean() < 0.5
+    assert m.occ[0].sum() == 0 and m.occ[:, 0].sum() == 0     # border ring free
+    assert all(len(p) > 0 for p in m.target_pools())
+
+
+def test_multimap_set_fits_device_limits():
+    maps = multimap_set(seed=0)
+    assert len(maps) == len(MULTIMAP_BOUNDS) == 14
+    for m in maps:
+        assert m.gx * m.gy <= _capi.MAP_STRIDE and (m.gx + 8) * (m.gy + 8) + 32 <= 2048
+
+
+def test_plan_path_and_prune():
+    occ = np.zeros((6, 5), dtype=np.uint8)
+    occ[2, 0:4] = 1
+    path = plan_path(occ, (0, 0), (5, 0))
+    assert path[0] == (0, 0) and path[-1] == (5, 0)
+    assert all(abs(a[0] - b[0]) + abs(a[1] - b[1]) == 1 for a, b in zip(path, path[1:]))
+    assert all(occ[c] == 0 for c in path)
+    pruned = prune_collinear(path)
+    assert pruned[0] == path[0] and pruned[-1] == path[-1]
+    for a, b in zip(pruned, pruned[1:]):
+        assert a[0] == b[0] or a[1] == b[1]
+    occ[:, 4] = 0
+    occ[2, :] = 1
+    assert plan_path(occ, (0, 0), (5, 0)) is None
+
+
+def test_reference_order_reset_is_seeded_and_separated():
+    m = synthetic_map(seed=0)
+    a = sample_episode_reference_order(random.Random(5), m, 4)
+    b = sample_episode_reference_order(random.Random(5), m, 4)
+    assert a.starts == b.starts and a.cells == b.cells
+    for i in range(4):
+        for j in range(i):
+            assert np.hypot(a.starts[i][0] - a.starts[j][0], a.starts[i][1] - a.starts[j][1]) > 5.0
+    for line, c in zip(a.lines, a.cells):
+        assert len(line) == len(c) >= 2
+
+
+def test_scenario_bank_packing():
+    m = synthetic_map(seed=0)
+    bank = ScenarioBank(m, 3, 16, w_max=32, seed=1)
+    assert bank.cells.shape == (16, 3, 32) and bank.cells.dtype == np.uint16 and bank.w.min() >= 2
+    for s in range(16):
+        for i in range(3):
+            w = bank.w[s, i]
+            ix, iy = bank.cells[s, i, :w] >> 8, bank.cells[s, i, :w] & 255
+            assert (m.occ[ix, iy] == 0).all()
+            assert ((np.diff(ix.astype(int)) == 0) | (np.diff(iy.astype(int)) == 0)).all()
+
+
+def test_library_exports_every_declared_symbol():
+    _capi.build()
+    header = open(os.path.join(ROOT, "include", "aac_env.h")).read()
+    declared = set(re.findall(r"\b(aac_[a-z_]+)\s*\(", header))
+    assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    lib.aac_own_dim.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    assert lib.aac_own_dim(0, 3) == 14 and lib.aac_own_dim(1, 10) == 7      # pure host helper
+    lib.aac_last_error.restype = ctypes.c_char_p
+    h = ctypes.c_void_p()
+    cfg = _capi.AacConfig()
+    cfg.abi_version = 999
+    lib.aac_create.argtypes = [ctypes.POINTER(_capi.AacConfig), ctypes.POINTER(ctypes.c_void_p)]
+    assert lib.aac_create(ctypes.byref(cfg), ctypes.byref(h)) == -1 and b"abi_version" in lib.aac_last_error()
+
+
+def test_struct_sizes_match_header_layout():
+    assert ctypes.sizeof(_capi.AacConfig) == 12 * 4 + 16 + 6 * 4
+    assert ctypes.sizeof(_capi.AacState) == 13 * 8 and ctypes.sizeof(_capi.AacOut) == 19 * 8
+    assert ctypes.sizeof(_capi.AacMapDesc) == 2 * 4 + 4 * 4 + 5 * 4
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "multi_agent_aac_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f
+
+
+def test_env_requires_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    with pytest.raises(_capi.AacError):
+        BatchedDroneEnv(preset("att"), synthetic_map(seed=0))
+
+
+def test_shard_range_partitions():
+    for world in (1, 2, 3, 8):
+        spans = [shard_range(r, world, 65536 + 5) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == 65541
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def _stats_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    local = np.zeros(_capi.N_STATS)
+    local[0], local[1], local[2], local[3 + rank] = 10 * (rank + 1), 500.0, -3.0 * (rank + 1), 4
+    lo, hi = shard_range(rank, world, 1001)
+    out = reduce_episode_stats(local)
+    out["span"] = (lo, hi)
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_episode_stats_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_stats_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in (0, 1):
+        assert res[r]["episodes"] == 30 and res[r]["steps"] == 1000 and res[r]["return_sum"] == -9
+        assert res[r]["bound_crash"] == 4 and res[r]["building_crash"] == 4
+        assert abs(res[r]["mean_return"] + 0.3) < 1e-12
+    assert res[0]["span"] == (0, 501) and res[1]["span"] == (501, 1001)

@@ -1,0 +1,98 @@
+"""CPU: the float64 oracle against the rollouts recorded from the UNMODIFIED reference classes
+(tests/golden/*.npz, made by tests/golden/gen_golden.py), plus properties the domain offers."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from multi_agent_aac_b200.maps import synthetic_map
+from oracle.oracle import OracleEnv, RADAR_MIN
+from tests.replay import GOLDEN_DIR, load_case, replay
+
+GOLDEN = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def test_fixture_inventory():
+    assert len(GOLDEN) >= 10
+    assert any(n.startswith("att") for n in GOLDEN) and any(n.startswith("v2") for n in GOLDEN)
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_oracle_replays_reference_rollout(name):
+    d, variant, n, rays, ep_len, gmap = load_case(name)
+    env = OracleEnv(variant, gmap, 1, n, rays)
+    diff = replay(env, d, variant, rtol=1e-9, atol=1e-9)
+    assert not diff.fail, "\n".join(diff.fail[:10])
+
+
+def _two_drone_env(variant, p0, p1, goal0=(640.0, 320.0), rays=18):
+    gmap = synthetic_map(seed=0)
+    gmap.occ[:] = 0
+    env = OracleEnv(variant, gmap, 1, 2, rays)
+    lines = [np.array([[470.0, 270.0], goal0]), np.array([[470.0, 370.0], [640.0, 370.0]])]
+    env.set_episode(0, [p0, p1], lines, [0.0, 0.0])
+    return env
+
+
+def test_kat_geometry_test_sample_reaches_goal():
+    """ATT/geometry_test.py:12-14: cur=(534.12,355.86), goal=(536,356): centre distance 1.885 < 3.5."""
+    env = _two_drone_env("att", (534.12, 355.86), (600.0, 300.0), goal0=(536.0, 356.0))
+    env.state["ref_line"][0, 0, 1] = (536.0, 356.0)
+    env.observe()
+    out = env.step(np.zeros((1, 2, 2)))
+    assert out["check_goal"][0, 0] == 1 and out["branch"][0, 0] == 3 and out["done"][0, 0] == 0
+    assert env.state["reach"][0, 0] == 1
+
+
+def test_goal_polygon_band():
+    """64-gon(2.5) n 64-gon(1) is non-empty up to 3.5*cos(pi/64) in every direction, empty
+    beyond 3.5, and reaches 3.5 exactly along the shared vertex directions (angle 0)."""
+    for dist, ang, want in ((3.4957, 0.3, 1), (3.5001, 0.0, 0), (3.4999, 0.0, 1), (3.4990, np.pi / 64, 0)):
+        g = (500.0, 300.0)
+        p = (g[0] + dist * np.cos(ang), g[1] + dist * np.sin(ang))
+        env = _two_drone_env("att", p, (600.0, 350.0), goal0=g)
+        env.observe()
+        out = env.step(np.zeros((1, 2, 2)))
+        assert out["check_goal"][0, 0] == want, (dist, ang)
+
+
+def test_tcpa_special_value_iff_zero_relative_velocity():
+    env = _two_drone_env("att", (500.0, 300.0), (520.0, 300.0))
+    env.observe()
+    out = env.step(np.zeros((1, 2, 2)))          # both at rest
+    assert (out["tcpa"][0, :, 0, 0] == -10.0).all()
+    assert np.allclose(out["tcpa"][0, :, 0, 1], 20.0)
+    act = np.zeros((1, 2, 2))
+    act[0, 0, 0] = 1.0                           # drone 0 accelerates towards drone 1
+    out = env.step(act)
+    assert (out["tcpa"][0, :, 0, 0] != -10.0).all()
+    v = env.state["vel"][0, 0, 0]
+    assert np.isclose(out["tcpa"][0, 0, 0, 0], (20.0 - v * 0.5) / v)
+
+
+def test_radar_properties_and_crash_flags():
+    rng = np.random.default_rng(0)
+    gmap = synthetic_map(seed=0)
+    from multi_agent_aac_b200.reset import ScenarioBank
+    for variant in ("att", "v2"):
+        E, N, R = 32, 4, 36
+        bank = ScenarioBank(gmap, N, E, w_max=32, seed=3)
+        env = OracleEnv(variant, gmap, E, N, R, radar_mode=RADAR_MIN)
+        g = gmap.grid_length
+        for e in range(E):
+            lines = []
+            for i in range(N):
+                w = int(bank.w[e, i])
+                c = bank.cells[e, i, :w].astype(np.int64)
+                lines.append(np.stack([gmap.x0c + (c >> 8) * g, gmap.y0c + (c & 255) * g], -1).astype(np.float64))
+            env.set_episode(e, [l[0] for l in lines], lines, [0.0] * N)
+        env.observe()
+        for t in range(40):
+            out = env.step(rng.uniform(-1, 1, size=(E, N, 2)))
+            r = out["radar"]
+            assert np.nanmax(r) <= 15.0 + 1e-9 and np.nanmin(r) >= 0.0
+            done_env = out["done"].any(axis=1)
+            assert (out["bbc"][done_env, :3].any(axis=1)).all(), "done implies a bound/building/drone flag"
+            assert (~out["bbc"][~done_env, :3].any(axis=1)).all()
+            assert np.all(np.linalg.norm(env.state["vel"], axis=-1) <= 5.0 + 1e-9)
