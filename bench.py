@@ -3,8 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl reference]
 
-One "step" = env.step + ss_reward for every env of the shard followed by the auto-reset of finished
-episodes: two kernel launches through the C ABI (aac_step, aac_autoreset).  Prints ONE JSON line.
+One "step" = env.step + ss_reward for every env of the shard, fused with the auto-reset of the episodes
+that finish: ONE kernel launch through the C ABI (aac_step_autoreset).  Prints ONE JSON line.
 Workloads: c2 = one_model_att 4096 envs x 3 drones x 36 rays; c3 (default, the
 configuration the 1/2/4/8-GPU metric and the north-star target are quoted on) = tdCPA_forV2 65536 envs x
 10 drones x 36 rays per GPU; c5 = 131072 envs x 20 drones x 72 rays per GPU (the 8-GPU 1M-env sweep).
@@ -201,20 +201,17 @@ def main():
     if sampler:
         sampler.start()
     K_ = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K_)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K_)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record(stream)
     for k in range(K_):
         ev[k][0].record(stream)
-        env.step(acts[k % n_act], autoreset=False)
+        env.step(acts[k % n_act], autoreset=True)     # ONE launch: step + reward + fused auto-reset
         ev[k][1].record(stream)
-        env.autoreset()
-        ev[k][2].record(stream)
     t_end.record(stream)
     barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
     step_kernel_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    reset_kernel_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     launches = env.launch_count - launches0
     clocks = sampler.summary() if sampler else None
     if world > 1:
@@ -260,7 +257,7 @@ def main():
             "e2e": {"value": agents_total * args.e2e_steps / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
             "gpu_launches": int(launches),
-            "kernels": {"env_kernel(step)_ms": step_kernel_ms, "env_kernel(autoreset)_ms": reset_kernel_ms},
+            "kernels": {"env_kernel(step+autoreset)_ms": step_kernel_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_kind": peak_kind, "bytes_per_agent_step": bytes_per,
                          "kernel": "env_kernel<V2> step" if variant == "v2" else "env_kernel<ATT> step"},

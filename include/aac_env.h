@@ -71,7 +71,7 @@ typedef struct {
     int32_t sum_reward;     /* full_observable_critic_flag    (ATT:2602; ATT/ma_main:77) */
     int32_t episode_length; /* step cap                       (ATT/ma_main:914 => 50, V2: 100) */
     int32_t out_flags;      /* AAC_OUT_* */
-    int32_t tile_envs;      /* envs per CTA; 0 = pick */
+    int32_t tile_envs;      /* envs per warp (tile_envs * n_agents <= 32); 0 = pick 32 / n_agents */
     int32_t block_threads;  /* threads per CTA; 0 = pick */
     int64_t env_id_base;    /* global id of env 0 of this shard (scenario hashing) */
     uint64_t seed;
@@ -156,6 +156,10 @@ int aac_reset(AacEnv *env, const uint8_t *mask_dev, const AacOut *out, void *cud
 int aac_observe(AacEnv *env, const AacOut *out, void *cuda_stream);
 /* env.step + ss_reward / ss_reward_Mar (ATT:2627 + :2105, V2:3703 + :2995, MM:2016 + :1674) */
 int aac_step(AacEnv *env, const float *actions_dev /* [E,N,2] */, const AacOut *out, void *cuda_stream);
+/* aac_step fused with the caller's episode rule (ATT/ma_main:448-462 -> reset_world) in ONE launch: the
+ * envs that terminate in this step keep their terminal reward / done / check_goal / bbc / terminated
+ * and are re-initialised from the scenario bank; their observation rows carry the reset observation */
+int aac_step_autoreset(AacEnv *env, const float *actions_dev /* [E,N,2] */, const AacOut *out, void *cuda_stream);
 /* the caller's episode rule (ATT/ma_main:448-462 -> reset_world): reset every env whose
  * out->terminated byte is non-zero, overwrite its observation rows with the reset observation */
 int aac_autoreset(AacEnv *env, const AacOut *out, void *cuda_stream);

@@ -15,11 +15,12 @@ using namespace aac;
 struct AacEnv {
     AacConfig cfg;
     int device = 0;
-    int te = 0, threads = 0;
-    SmemLayout layout{};
+    int group = 0, threads = 0;   // envs per warp, threads per CTA
+    WarpLayout wl{};
+    CtaLayout cl{};
     MapDev *d_maps = nullptr;
     int n_maps = 0;
-    float2 *d_ray = nullptr;
+    float4 *d_ray = nullptr;
     uint16_t *d_bank_cells = nullptr;
     uint8_t *d_bank_w = nullptr;
     int32_t *d_bank_map = nullptr;
@@ -67,36 +68,35 @@ extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
     if (!env) return fail(AAC_ERR_STATE, "aac_create: out of host memory");
     env->cfg = *cfg;
     CU(cudaGetDevice(&env->device));
-    // tile: whole envs per CTA, about a hundred drones, a multiple of 4 envs so every output row block
-    // of a tile starts 16-byte aligned
-    int te = cfg->tile_envs > 0 ? cfg->tile_envs : ((96 + cfg->n_agents - 1) / cfg->n_agents + 3) / 4 * 4;
-    if (te < 1) te = 1;
-    const int optin = max_smem_optin();
-    SmemLayout L = make_layout(cfg->variant, te, cfg->n_agents, cfg->n_rays, cfg->w_max, cfg->out_flags);
-    while (te > 1 && (int)L.total > (optin > 0 ? optin / 2 : 100 * 1024)) {
-        te = te > 4 ? te - 4 : te - 1;
-        L = make_layout(cfg->variant, te, cfg->n_agents, cfg->n_rays, cfg->w_max, cfg->out_flags);
-    }
-    if (optin > 0 && (int)L.total > optin) { delete env; return fail(AAC_ERR_ARG, "aac_create: one env does not fit in shared memory"); }
-    env->te = te;
-    env->layout = L;
+    // a warp owns G = 32 / N whole envs; a CTA is a handful of independent warps sharing the map
+    env->group = cfg->tile_envs > 0 ? cfg->tile_envs : (32 / cfg->n_agents > 0 ? 32 / cfg->n_agents : 1);
+    if (env->group * cfg->n_agents > 32) { delete env; return fail(AAC_ERR_ARG, "aac_create: tile_envs * n_agents must not exceed 32"); }
     env->threads = cfg->block_threads > 0 ? cfg->block_threads : MAX_THREADS;
     if (env->threads > MAX_THREADS || env->threads % 32) { delete env; return fail(AAC_ERR_ARG, "aac_create: block_threads must be a multiple of 32, <= 256"); }
+    env->wl = make_warp_layout(cfg->variant, cfg->n_agents, cfg->out_flags);
+    const int optin = max_smem_optin();
+    while (true) {
+        env->cl = make_cta_layout(env->wl, cfg->n_rays, env->threads / 32);
+        if (optin <= 0 || (int)env->cl.total <= optin || env->threads == 32) break;
+        env->threads -= 32;
+    }
+    if (optin > 0 && (int)env->cl.total > optin) { delete env; return fail(AAC_ERR_ARG, "aac_create: one warp's envs do not fit in shared memory"); }
     cudaError_t e = upload_constants();
     if (e != cudaSuccess) { delete env; return cuda_fail(e, "upload_constants"); }
     // ray table: direction k*(360/R) degrees (ATT:1058-1066).  The reference adds 15*cos to a
     // coordinate of a few hundred metres, so components below ~1e-14 vanish: axis rays are exact.
-    std::vector<float2> rays(cfg->n_rays);
+    std::vector<float4> rays(cfg->n_rays);
     const int step_deg = 360 / cfg->n_rays;
     for (int k = 0; k < cfg->n_rays; ++k) {
         const double rad = (double)(k * step_deg) * (M_PI / 180.0);
         double c = cos(rad), s = sin(rad);
         if (fabs(c) < 1e-12) c = 0.0;
         if (fabs(s) < 1e-12) s = 0.0;
-        rays[k] = make_float2((float)c, (float)s);
+        const float dx = (float)(cfg->ray_len * c), dy = (float)(cfg->ray_len * s);
+        rays[k] = make_float4(dx, dy, dx != 0.0f ? 1.0f / dx : INFINITY, dy != 0.0f ? 1.0f / dy : INFINITY);
     }
-    CU(cudaMalloc(&env->d_ray, sizeof(float2) * cfg->n_rays));
-    CU(cudaMemcpy(env->d_ray, rays.data(), sizeof(float2) * cfg->n_rays, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&env->d_ray, sizeof(float4) * cfg->n_rays));
+    CU(cudaMemcpy(env->d_ray, rays.data(), sizeof(float4) * cfg->n_rays, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&env->d_stats, sizeof(double) * AAC_N_STATS));
     CU(cudaMemset(env->d_stats, 0, sizeof(double) * AAC_N_STATS));
     *out = env;
@@ -134,6 +134,7 @@ extern "C" int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *
         o.ex0 = (d.x0c - 0.5f * d.cell) - d.origin_x; o.ey0 = (d.y0c - 0.5f * d.cell) - d.origin_y;
         o.xmin_g = d.bound[0]; o.ymin_g = d.bound[2];
         o.cell = d.cell; o.inv_cell = 1.0f / d.cell;
+        o.ihx = 1.0f / o.hx; o.ihy = 1.0f / o.hy;
         for (int ix = 0; ix < d.gx; ++ix)
             for (int iy = 0; iy < d.gy; ++iy)
                 if (occ[(size_t)m * AAC_MAP_STRIDE + ix * d.gy + iy]) {
@@ -182,37 +183,38 @@ extern "C" int aac_bind_state(AacEnv *env, const AacState *s) {
 static int check_out(const AacEnv *env, const AacOut *o, int mode) {
     const int f = env->cfg.out_flags;
     const bool v2 = env->cfg.variant == AAC_VARIANT_V2;
+    const bool pairs = env->cfg.n_agents > 1;   // a single drone has no neighbour blocks (zero-size tensors)
     if (!o) return fail(AAC_ERR_ARG, "output block is NULL");
-    if (!o->norm_own || !o->radar || (v2 && env->cfg.n_agents > 1 && !o->norm_nbr)) return fail(AAC_ERR_ARG, "norm_own / norm_nbr / radar must be provided");
+    if (!o->norm_own || !o->radar || (v2 && pairs && !o->norm_nbr)) return fail(AAC_ERR_ARG, "norm_own / norm_nbr / radar must be provided");
     if (mode == MODE_STEP && (!o->reward || !o->done || !o->check_goal || !o->bbc || !o->terminated || !o->tcpa_min))
         return fail(AAC_ERR_ARG, "reward / done / check_goal / bbc / terminated / tcpa_min must be provided");
-    if ((f & AAC_OUT_NBR6) && !o->norm_nbr6) return fail(AAC_ERR_ARG, "AAC_OUT_NBR6 set but norm_nbr6 is NULL");
-    if ((f & AAC_OUT_RAW) && (!o->raw_own || (v2 && !o->raw_nbr) || ((f & AAC_OUT_NBR6) && !o->raw_nbr6))) return fail(AAC_ERR_ARG, "AAC_OUT_RAW set but a raw_* pointer is NULL");
-    if ((f & AAC_OUT_TCPA_PAIR) && (!o->tcpa_pair || !o->nbr_order)) return fail(AAC_ERR_ARG, "AAC_OUT_TCPA_PAIR set but tcpa_pair / nbr_order is NULL");
+    if ((f & AAC_OUT_NBR6) && pairs && !o->norm_nbr6) return fail(AAC_ERR_ARG, "AAC_OUT_NBR6 set but norm_nbr6 is NULL");
+    if ((f & AAC_OUT_RAW) && (!o->raw_own || (v2 && pairs && !o->raw_nbr) || ((f & AAC_OUT_NBR6) && pairs && !o->raw_nbr6))) return fail(AAC_ERR_ARG, "AAC_OUT_RAW set but a raw_* pointer is NULL");
+    if ((f & AAC_OUT_TCPA_PAIR) && pairs && (!o->tcpa_pair || !o->nbr_order)) return fail(AAC_ERR_ARG, "AAC_OUT_TCPA_PAIR set but tcpa_pair / nbr_order is NULL");
     if ((f & AAC_OUT_RADAR_AUX) && (!o->radar_min || !o->radar_hit)) return fail(AAC_ERR_ARG, "AAC_OUT_RADAR_AUX set but radar_min / radar_hit is NULL");
     if ((f & AAC_OUT_PARTS) && mode == MODE_STEP && (!o->parts || !o->branch)) return fail(AAC_ERR_ARG, "AAC_OUT_PARTS set but parts / branch is NULL");
     return 0;
 }
 
-static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actions, const AacOut *out, void *stream) {
+static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actions, const AacOut *out, void *stream, int autoreset = 0) {
     if (!env) return fail(AAC_ERR_ARG, "null handle");
     if (!env->bound) return fail(AAC_ERR_STATE, "aac_bind_state has not been called");
     if (!env->d_maps) return fail(AAC_ERR_STATE, "aac_set_maps has not been called");
-    if (mode == MODE_RESET && !env->d_bank_cells) return fail(AAC_ERR_STATE, "aac_set_bank has not been called");
+    if ((mode == MODE_RESET || autoreset) && !env->d_bank_cells) return fail(AAC_ERR_STATE, "aac_set_bank has not been called");
     if (mode == MODE_STEP && !actions) return fail(AAC_ERR_ARG, "actions is NULL");
     const int rc = check_out(env, out, mode);
     if (rc) return rc;
     KParams p;
     memset(&p, 0, sizeof(p));
     const AacConfig &c = env->cfg;
-    p.E = c.n_envs; p.N = c.n_agents; p.R = c.n_rays; p.W = c.w_max; p.TE = env->te;
+    p.E = c.n_envs; p.N = c.n_agents; p.R = c.n_rays; p.W = c.w_max; p.G = env->group;
     p.radar_mode = c.radar_mode; p.sum_reward = c.sum_reward; p.ep_len = c.episode_length; p.out_flags = c.out_flags;
     p.dt = c.dt; p.vmax = c.vmax; p.acc_max = c.acc_max; p.prot = c.prot; p.ray_len = c.ray_len; p.goal_r = c.goal_r;
     p.env_id_base = c.env_id_base; p.seed = c.seed;
-    p.maps = env->d_maps; p.n_maps = env->n_maps; p.ray_dir = env->d_ray;
+    p.maps = env->d_maps; p.n_maps = env->n_maps; p.ray_tab = env->d_ray; p.autoreset = autoreset;
     p.bank_cells = env->d_bank_cells; p.bank_w = env->d_bank_w; p.bank_map = env->d_bank_map; p.n_scen = env->n_scen;
     p.mask = mask; p.actions = actions; p.stats = env->d_stats;
-    p.st = env->st; p.out = *out; p.L = env->layout;
+    p.st = env->st; p.out = *out; p.CL = env->cl; p.WL = env->wl;
     cudaError_t e = launch_env_kernel(c.variant, p, mode, env->threads, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "env_kernel launch");
     env->launches += 1;
@@ -226,6 +228,9 @@ extern "C" int aac_observe(AacEnv *env, const AacOut *out, void *stream) { retur
 extern "C" int aac_step(AacEnv *env, const float *actions_dev, const AacOut *out, void *stream) {
     return launch(env, MODE_STEP, nullptr, actions_dev, out, stream);
 }
+extern "C" int aac_step_autoreset(AacEnv *env, const float *actions_dev, const AacOut *out, void *stream) {
+    return launch(env, MODE_STEP, nullptr, actions_dev, out, stream, 1);
+}
 extern "C" int aac_autoreset(AacEnv *env, const AacOut *out, void *stream) {
     if (!out || !out->terminated) return fail(AAC_ERR_ARG, "aac_autoreset: out->terminated is NULL");
     return launch(env, MODE_RESET, out->terminated, nullptr, out, stream);
@@ -238,19 +243,16 @@ extern "C" int aac_step_host(AacEnv *env, const float *actions_host, const AacOu
     const size_t D = own_dim(env->cfg.variant, (int)N);
     if (!env->d_actions) CU(cudaMalloc(&env->d_actions, A * 2 * sizeof(float)));
     CU(cudaMemcpyAsync(env->d_actions, actions_host, A * 2 * sizeof(float), cudaMemcpyHostToDevice, stream));
-    int rc = aac_step(env, env->d_actions, od, stream);
+    // one launch: with autoreset the terminal transition's reward / done / flags are kept and the
+    // observation rows of the finished envs carry their reset observation
+    int rc = autoreset ? aac_step_autoreset(env, env->d_actions, od, stream) : aac_step(env, env->d_actions, od, stream);
     if (rc) return rc;
 #define D2H(field, bytes)                                                                                   \
     if (oh->field) {                                                                                        \
         if (!od->field) return fail(AAC_ERR_ARG, "aac_step_host: host buffer without a device buffer: %s", #field); \
         CU(cudaMemcpyAsync(oh->field, od->field, (bytes), cudaMemcpyDeviceToHost, stream));                 \
     }
-    // the terminal transition is copied out before the reset observation overwrites its rows
     D2H(reward, A * 4) D2H(done, A) D2H(check_goal, A) D2H(bbc, E * 4) D2H(terminated, E) D2H(tcpa_min, A * 16)
-    if (autoreset) {
-        rc = aac_autoreset(env, od, stream);
-        if (rc) return rc;
-    }
     D2H(norm_own, A * D * 4) D2H(norm_nbr, A * 5 * M * 4) D2H(radar, A * R * 4) D2H(norm_nbr6, A * M * 24)
     D2H(raw_own, A * D * 4) D2H(raw_nbr, A * 5 * M * 4) D2H(raw_nbr6, A * M * 24)
     D2H(tcpa_pair, A * M * 16) D2H(nbr_order, A * M) D2H(radar_min, A * R * 4) D2H(radar_hit, A * R * 2)

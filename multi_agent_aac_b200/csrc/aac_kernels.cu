@@ -1,7 +1,18 @@
 // Batched multi-drone environment step for sm_100a: kinematics, neighbour ordering, radar, tdCPA,
-// observation assembly, reward / done.  One CTA owns a tile of TE whole environments; every phase is
-// a strided loop over that tile's work items (agents, ordered pairs, rays), results are staged in
-// shared memory and leave the SM as coalesced row stores.
+// observation assembly, reward / done, auto-reset.
+//
+// Execution model: WARP-AUTONOMOUS.  Each warp owns a group of G = 32 / N whole environments (G * N <= 32
+// drones) and runs the entire pipeline for them with __syncwarp only; there is no CTA barrier on the
+// step path, so warps of one CTA drift apart and the SM overlaps their latencies.
+//   lane = drone     load + action integration, neighbour sort + 4x4 occupancy window, own block,
+//                    reward / collision / goal
+//   lane = item      ordered pairs (tdCPA + neighbour blocks) and rays (radar), flattened over the group
+//   lane = env       crash-penalty chain, summed reward, flags, episode end
+// Outputs leave as coalesced stores: radar / tdCPA items are item-major already; 5- and 6-float pair
+// blocks and the own rows pass through a small per-warp staging buffer.  The only CTA-wide data are the
+// map (occupancy bitmap + constants, one TMA bulk copy per CTA) and the ray table.
+// Envs that terminate are re-initialised from the scenario bank by the same warp and the observation
+// pipeline runs again over those envs only (fused auto-reset).
 //
 // Reference behaviour (file:line; ATT / V2 as in include/aac_env.h, UA / UV2 = Utilities_own_*.py):
 //   kinematics            ATT:2639-2713, V2:3729-3787
@@ -10,6 +21,7 @@
 //   tdCPA                 UA:308-329 == UV2:337-358
 //   observation layout    ATT:1285-1296,1357-1493; V2:1417-1429,1490-1713; NormalizeData UA:554-607
 //   reward / done         ATT:2105-2618 (ss_reward), V2:2995-3684 (ss_reward_Mar, train mode)
+//   reset                 ATT:301-372 (state after reset_world), episode rule ATT/ma_main:448-462
 // Geometry: every shapely "circle" is the regular 64-gon GEOS builds for Point.buffer(r);
 // because all of them share vertex angles, polygon-polygon and polygon-square emptiness tests reduce
 // to a support-function test over the 16 first-quadrant edge normals (Minkowski sum of two such
@@ -50,10 +62,64 @@ int max_smem_optin() {
     return v;
 }
 
+// ------------------------------------------------------------------------------------ TMA / mbarrier
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on the mbarrier (bytes % 16 == 0, 16-B aligned)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------ helpers
 
-constexpr unsigned F_DONE = 1u, F_GOAL = 2u, F_BRANCH_SHIFT = 2u, F_BBC3 = 32u, F_DOUBLE = 64u, F_ATGOAL = 128u;
+constexpr unsigned F_DONE = 1u, F_GOAL = 2u, F_BRANCH_SHIFT = 2u, F_BBC3 = 32u, F_DOUBLE = 64u;
 constexpr unsigned M_REACH = 1u << 8, M_VBOUND = 1u << 9, M_VBLDG = 1u << 10, M_VDRONE = 1u << 11;
+// occupancy-window flags (upper half of the window word)
+constexpr unsigned W_NEAR_BOUND = 1u << 16;  // a boundary line is within ray reach (or the drone is outside)
+constexpr unsigned W_SLOW = 1u << 17;        // drone centre inside an occupied cell / window clamped: generic path
+
+// (hi, lo) = divmod(index, n) advanced by a fixed stride without dividing again
+struct Walk {
+    int hi, lo, dhi, dlo, n;
+    __device__ __forceinline__ Walk(int start, int stride, int n_) : n(n_) {
+        hi = start / n_; lo = start - hi * n_;
+        dhi = stride / n_; dlo = stride - dhi * n_;
+    }
+    __device__ __forceinline__ void next() {
+        lo += dlo; hi += dhi;
+        if (lo >= n) { lo -= n; ++hi; }
+    }
+};
 
 __device__ __forceinline__ float cell_cx(const MapDev &m, int ix) { return m.ex0 + (ix + 0.5f) * m.cell; }
 __device__ __forceinline__ float cell_cy(const MapDev &m, int iy) { return m.ey0 + (iy + 0.5f) * m.cell; }
@@ -103,9 +169,7 @@ __device__ __forceinline__ float cap_extent(float t0) {
 
 // LineString([p0, p1]).buffer(r) vertex bounding box against the 4 boundary lines (ATT:2172-2173,
 // :2507).  Local frame: the lines are x = -hx, hx and y = -hy, hy.
-__device__ bool capsule_hits_bound(float x0, float y0, float x1, float y1, float r, float hx, float hy) {
-    const float lox = fminf(x0, x1) - r, hix = fmaxf(x0, x1) + r, loy = fminf(y0, y1) - r, hiy = fmaxf(y0, y1) + r;
-    if (lox > -hx && hix < hx && loy > -hy && hiy < hy) return false;  // cannot reach any line
+__device__ __noinline__ bool capsule_hits_bound_exact(float x0, float y0, float x1, float y1, float r, float hx, float hy) {
     float mnx, mxx, mny, mxy;
     if (x0 == x1 && y0 == y1) {  // GEOS drops the repeated point: plain 64-gon, vertices on the axes
         mnx = x0 - r; mxx = x0 + r; mny = y0 - r; mxy = y0 + r;
@@ -119,6 +183,11 @@ __device__ bool capsule_hits_bound(float x0, float y0, float x1, float y1, float
     }
     return (mnx <= -hx && -hx <= mxx) || (mnx <= hx && hx <= mxx) || (mny <= -hy && -hy <= mxy) || (mny <= hy && hy <= mxy);
 }
+__device__ __forceinline__ bool capsule_hits_bound(float x0, float y0, float x1, float y1, float r, float hx, float hy) {
+    const float lox = fminf(x0, x1) - r, hix = fmaxf(x0, x1) + r, loy = fminf(y0, y1) - r, hiy = fmaxf(y0, y1) + r;
+    if (lox > -hx && hix < hx && loy > -hy && hiy < hy) return false;  // cannot reach any line
+    return capsule_hits_bound_exact(x0, y0, x1, y1, r, hx, hy);
+}
 
 // UA:308-329: returns tcpa, d_tcpa and whether the pair counts as a potential conflict
 __device__ __forceinline__ void tcpa_dcpa(float hpx, float hpy, float hvx, float hvy, float opx, float opy, float ovx, float ovy,
@@ -126,7 +195,6 @@ __device__ __forceinline__ void tcpa_dcpa(float hpx, float hpy, float hvx, float
     const float rx = hpx - opx, ry = hpy - opy;
     const float wx = ovx - hvx, wy = ovy - hvy;
     const float w2 = wx * wx + wy * wy;
-    conf = false;
     if (w2 == 0.0f) {
         tcpa = -10.0f;
         d = sqrtf(rx * rx + ry * ry);  // both advance by the same velocity: separation is unchanged
@@ -155,83 +223,113 @@ __device__ __forceinline__ unsigned pick_scenario(long long gid, int episode, un
 
 // ------------------------------------------------------------------------------------ radar
 
-// one ray against the occupied cells of the agent's 4x4 window and the 4 boundary lines
-// (V2:1210-1300).  `sensed` = last hit in ascending cell order then L,R,B,T.
-__device__ __forceinline__ void radar_grid_ray(const MapDev &mp, float px, float py, float2 dir, float ray_len, unsigned win,
-                                               int wix0, int wiy0, bool last_hit, float &out, float &out_min, int &out_id) {
-    const float dx = ray_len * dir.x, dy = ray_len * dir.y, len = ray_len;
-    const float ex = px + dx, ey = py + dy;
-    const float idx = dx != 0.0f ? 1.0f / dx : 0.0f, idy = dy != 0.0f ? 1.0f / dy : 0.0f;
-    int r0 = (int)floorf((fminf(px, ex) - mp.ex0) * mp.inv_cell) - wix0, r1 = (int)floorf((fmaxf(px, ex) - mp.ex0) * mp.inv_cell) - wix0;
-    int c0 = (int)floorf((fminf(py, ey) - mp.ey0) * mp.inv_cell) - wiy0, c1 = (int)floorf((fmaxf(py, ey) - mp.ey0) * mp.inv_cell) - wiy0;
-    r0 = max(r0, 0); r1 = min(r1, 3); c0 = max(c0, 0); c1 = min(c1, 3);
-    unsigned m = 0;
-    if (r0 <= r1 && c0 <= c1) {
-        const unsigned rows = (0xFFFFu >> (4 * (3 - r1))) & (0xFFFFu << (4 * r0));
-        const unsigned cols = ((0xFu >> (3 - c1)) & (0xFu << c0)) * 0x1111u;
-        m = win & rows & cols;
-    }
-    float shortest = CUDART_INF_F, sensed = len;
-    int shortest_id = -1, sensed_id = -1;
-    while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const int ix = wix0 + (b >> 2), iy = wiy0 + (b & 3);
-        const float x0 = mp.ex0 + ix * mp.cell, x1 = x0 + mp.cell, y0 = mp.ey0 + iy * mp.cell, y1 = y0 + mp.cell;
-        float ent = -CUDART_INF_F, ext = CUDART_INF_F;
-        if (dx != 0.0f) {
-            const float t0 = (x0 - px) * idx, t1 = (x1 - px) * idx;
-            ent = fminf(t0, t1); ext = fmaxf(t0, t1);
-        } else if (px < x0 || px > x1) continue;
-        if (dy != 0.0f) {
-            const float t0 = (y0 - py) * idy, t1 = (y1 - py) * idy;
-            ent = fmaxf(ent, fminf(t0, t1)); ext = fminf(ext, fmaxf(t0, t1));
-        } else if (py < y0 || py > y1) continue;
-        const float lo = fmaxf(ent, 0.0f), hi = fminf(ext, 1.0f);
-        if (lo > hi) continue;
-        // nearest point of segment n cell BOUNDARY (V2:1258-1265): the entry point, or the exit point
-        // when the drone centre is strictly inside the cell, or nothing (nan) when the whole ray is
-        const bool inside = px > x0 && px < x1 && py > y0 && py < y1;
-        const float d = !inside ? lo * len : (ext <= 1.0f ? ext * len : CUDART_NAN_F);
-        const int id = ix * mp.gy + iy;
-        sensed = d; sensed_id = id;
-        if (d < shortest) { shortest = d; shortest_id = id; }
-    }
+// the 4 boundary lines in the reference's order L, R, B, T (V2:145-152); ray = (dx, dy, 1/dx, 1/dy)
+template <bool AUX>
+__device__ __forceinline__ void radar_bounds(const MapDev &mp, float px, float py, float4 ray, float len, float &shortest, float &sensed,
+                                             int &shortest_id, int &sensed_id) {
     const int nb = mp.gx * mp.gy;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-        const float dd = b < 2 ? dx : dy, pp = b < 2 ? px : py, inv = b < 2 ? idx : idy;
+        const float dd = b < 2 ? ray.x : ray.y, pp = b < 2 ? px : py, inv = b < 2 ? ray.z : ray.w;
         const float lim = b < 2 ? mp.hx : mp.hy, line = (b & 1) ? lim : -lim;
         if (dd != 0.0f) {
             const float t = (line - pp) * inv;
             if (t >= 0.0f && t <= 1.0f) {
                 const float d = t * len;
-                sensed = d; sensed_id = nb + b;
-                if (d < shortest) { shortest = d; shortest_id = nb + b; }
+                sensed = d;
+                if (AUX) sensed_id = nb + b;
+                if (d < shortest) { shortest = d; if (AUX) shortest_id = nb + b; }
             }
         } else if (pp == line) {  // ray runs along the boundary: GEOS returns the whole overlap
-            sensed = len; sensed_id = nb + b;
-            if (0.0f < shortest) { shortest = 0.0f; shortest_id = nb + b; }
+            sensed = len;
+            if (AUX) sensed_id = nb + b;
+            if (0.0f < shortest) { shortest = 0.0f; if (AUX) shortest_id = nb + b; }
         }
     }
-    out_min = shortest == CUDART_INF_F ? len : shortest;
-    if (last_hit) { out = sensed; out_id = sensed_id; }
-    else { out = out_min; out_id = shortest_id; }
+}
+
+// Fast path.  One ray against the occupied cells of the drone's 4x4 window (V2:1210-1300).  The slab
+// parameters of the 5 + 5 grid lines bounding the window are computed once per ray; every occupied
+// cell then costs two max/min pairs.  `wrel` = window origin relative to the drone.  Visiting order is
+// ascending (ix, iy) = ascending cell index, so `sensed` ends as the reference's last hit.
+// Axis-parallel rays carry 1/d = +inf: the products are +-inf (or NaN exactly on a grid line, which
+// fminf / fmaxf drop), i.e. no constraint from that axis.
+template <bool AUX>
+__device__ __forceinline__ void radar_window(const MapDev &mp, float2 wrel, unsigned win, int wix0, int wiy0, float4 ray, float len,
+                                             float &shortest, float &sensed, int &shortest_id, int &sensed_id) {
+    float tx[5], ty[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        tx[q] = fmaf((float)q, mp.cell, wrel.x) * ray.z;
+        ty[q] = fmaf((float)q, mp.cell, wrel.y) * ray.w;
+    }
+    float eny[4], exy[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { eny[c] = fminf(ty[c], ty[c + 1]); exy[c] = fmaxf(ty[c], ty[c + 1]); }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (!((win >> (4 * r)) & 0xFu)) continue;
+        const float enx = fmaxf(fminf(tx[r], tx[r + 1]), 0.0f), exx = fminf(fmaxf(tx[r], tx[r + 1]), 1.0f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (!((win >> (4 * r + c)) & 1u)) continue;
+            const float lo = fmaxf(enx, eny[c]), hi = fminf(exx, exy[c]);
+            if (lo <= hi) {
+                const float d = lo * len;
+                sensed = d;
+                if (AUX) sensed_id = (wix0 + r) * mp.gy + wiy0 + c;
+                if (d < shortest) { shortest = d; if (AUX) shortest_id = (wix0 + r) * mp.gy + wiy0 + c; }
+            }
+        }
+    }
+}
+
+// Generic path (drone centre inside an occupied cell, or outside the padded grid): tests every occupied
+// cell whose box overlaps the ray's box, with the reference's inside-the-cell semantics: the nearest
+// point of segment n cell BOUNDARY is the exit point, or nothing (nan) when the whole ray is inside
+// (V2:1258-1265).
+template <bool AUX>
+__device__ __noinline__ void radar_generic(const MapDev &mp, float px, float py, float4 ray, float len, float &shortest, float &sensed,
+                                           int &shortest_id, int &sensed_id) {
+    const float ex = px + ray.x, ey = py + ray.y;
+    const int ixa = (int)floorf((fminf(px, ex) - mp.ex0) * mp.inv_cell), ixb = (int)floorf((fmaxf(px, ex) - mp.ex0) * mp.inv_cell);
+    const int iya = (int)floorf((fminf(py, ey) - mp.ey0) * mp.inv_cell), iyb = (int)floorf((fmaxf(py, ey) - mp.ey0) * mp.inv_cell);
+    for (int ix = max(ixa, 0); ix <= min(ixb, mp.gx - 1); ++ix)
+        for (int iy = max(iya, 0); iy <= min(iyb, mp.gy - 1); ++iy) {
+            if (!occupied(mp, ix, iy)) continue;
+            const float x0 = mp.ex0 + ix * mp.cell, x1 = x0 + mp.cell, y0 = mp.ey0 + iy * mp.cell, y1 = y0 + mp.cell;
+            float ent = -CUDART_INF_F, ext = CUDART_INF_F;
+            if (ray.x != 0.0f) {
+                const float t0 = (x0 - px) * ray.z, t1 = (x1 - px) * ray.z;
+                ent = fminf(t0, t1); ext = fmaxf(t0, t1);
+            } else if (px < x0 || px > x1) continue;
+            if (ray.y != 0.0f) {
+                const float t0 = (y0 - py) * ray.w, t1 = (y1 - py) * ray.w;
+                ent = fmaxf(ent, fminf(t0, t1)); ext = fminf(ext, fmaxf(t0, t1));
+            } else if (py < y0 || py > y1) continue;
+            const float lo = fmaxf(ent, 0.0f), hi = fminf(ext, 1.0f);
+            if (lo > hi) continue;
+            const bool inside = px > x0 && px < x1 && py > y0 && py < y1;
+            const float d = !inside ? lo * len : (ext <= 1.0f ? ext * len : CUDART_NAN_F);
+            sensed = d;
+            if (AUX) sensed_id = ix * mp.gy + iy;
+            if (d < shortest) { shortest = d; if (AUX) shortest_id = ix * mp.gy + iy; }
+        }
 }
 
 // one ray against the other drones' protective 64-gons (ATT:1052-1170): entry distance, 0 inside
-__device__ __forceinline__ void radar_drones_ray(const float *s_px, const float *s_py, int env_base, int N, int i, float2 dir,
-                                                 float ray_len, float r, int id_base, float &out, int &out_id) {
-    const float dx = ray_len * dir.x, dy = ray_len * dir.y, len = ray_len;
+__device__ __forceinline__ void radar_drones_ray(const float *s_px, const float *s_py, int env_base, int N, int i, float4 ray, float len,
+                                                 float r, int id_base, float &out, int &out_id) {
+    const float dx = ray.x, dy = ray.y;
     const float px = s_px[env_base + i], py = s_py[env_base + i];
-    const float apo = r * c_apo;
+    const float apo = r * c_apo, inv_l2 = 1.0f / (len * len);
     float best = len, shortest = CUDART_INF_F;
     int best_id = -1;
     for (int j = 0; j < N; ++j) {
         if (j == i) continue;
         const float qx = px - s_px[env_base + j], qy = py - s_py[env_base + j];
         // distance from the polygon centre to the segment; beyond r the ray cannot touch it
-        float tt = -(qx * dx + qy * dy) / (len * len);
+        float tt = -(qx * dx + qy * dy) * inv_l2;
         tt = fminf(fmaxf(tt, 0.0f), 1.0f);
         const float cx = fmaf(tt, dx, qx), cy = fmaf(tt, dy, qy);
         if (cx * cx + cy * cy > r * r * 1.00001f) continue;
@@ -255,136 +353,70 @@ __device__ __forceinline__ void radar_drones_ray(const float *s_px, const float 
 
 // ------------------------------------------------------------------------------------ kernel
 
-template <int VAR>
-__global__ void __launch_bounds__(MAX_THREADS) env_kernel(const __grid_constant__ KParams p, const int mode) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout &L = p.L;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int N = p.N, M = N - 1, R = p.R, W = p.W;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+// per-warp shared-memory slice (32 drone slots) and the handles a warp needs
+struct Warp {
+    const MapDev *map;
+    const float4 *ray;
+    int lane;
+    int e_lo, ng, a0, nA;   // first env of the group, envs / drones in it, global index of its first drone
+    float *px, *py, *vx, *vy, *hd, *ppx, *ppy, *pvx, *pvy;
+    unsigned *meta, *meta2, *minr, *agf;
+    float *agr, *d2, *stg, *own, *raw_own;
+    uint8_t *order, *pflag, *atgoal, *refw, *rs;
+    uint2 *win;
+    float2 *wrel, *tc;
+};
+
+// lanes hold PI floats each for the items [0, n_valid) of one warp iteration; the block leaves as
+// n_valid * PI consecutive floats at dst
+template <int PI>
+__device__ __forceinline__ void flush_items(float *dst, int n_valid, const float (&v)[PI], float *stg, int lane) {
+    if (lane < n_valid) {
+#pragma unroll
+        for (int c = 0; c < PI; ++c) stg[lane * PI + c] = v[c];
+    }
+    __syncwarp();
+    for (int f = lane; f < n_valid * PI; f += 32) dst[f] = stg[f];
+    __syncwarp();
+}
+
+// observation pipeline for the drones [a_lo, a_lo + n_ag) of the warp's group (whole envs):
+// neighbour order + window -> { pairs | rays | own block }.  `cells` = the lane's reference-line row.
+template <int VAR, bool AUX>
+__device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, const int a_lo, const int n_ag, const uint16_t *cells) {
+    const int lane = w.lane;
+    const int N = p.N, M = N - 1, R = p.R, Mp = M | 1;
     const int D = own_dim(VAR, N);
-    const int e0 = blockIdx.x * p.TE;
-    const int ne = min(p.TE, p.E - e0);
-    const int A = ne * N, a0 = e0 * N;
     const int flags = p.out_flags;
+    const MapDev &mp = *w.map;
+    const float inv_vmax = 1.0f / p.vmax;
+    const bool mine = lane < n_ag;
+    const int a = a_lo + lane;           // the lane's drone in the drone-per-lane phases
+    const int eb = mine ? (a / N) * N : 0;  // first drone of its env
 
-    MapDev *s_maps = reinterpret_cast<MapDev *>(smem + L.maps);
-    float2 *s_ray = reinterpret_cast<float2 *>(smem + L.ray);
-    int4 *s_envi = reinterpret_cast<int4 *>(smem + L.envi);  // x active, y scenario, z map row, w result bits
-    float *s_px = reinterpret_cast<float *>(smem + L.cur), *s_py = s_px + p.TE * N, *s_vx = s_py + p.TE * N, *s_vy = s_vx + p.TE * N,
-          *s_hd = s_vy + p.TE * N;
-    float *s_ppx = reinterpret_cast<float *>(smem + L.pre), *s_ppy = s_ppx + p.TE * N, *s_pvx = s_ppy + p.TE * N, *s_pvy = s_pvx + p.TE * N;
-    unsigned *s_meta = reinterpret_cast<unsigned *>(smem + L.meta), *s_meta2 = reinterpret_cast<unsigned *>(smem + L.meta2);
-    uint16_t *s_cells = reinterpret_cast<uint16_t *>(smem + L.cells);
-    uint8_t *s_refw = smem + L.refw;
-    float *s_d2 = reinterpret_cast<float *>(smem + L.d2);
-    uint8_t *s_order = smem + L.order;
-    uint2 *s_win = reinterpret_cast<uint2 *>(smem + L.win);
-    float2 *s_tc = reinterpret_cast<float2 *>(smem + L.tc);
-    uint8_t *s_pflag = smem + L.pflag;
-    unsigned *s_agf = reinterpret_cast<unsigned *>(smem + L.agf);
-    float *s_agr = reinterpret_cast<float *>(smem + L.agr);
-    float *s_own = reinterpret_cast<float *>(smem + L.own), *s_nbr = reinterpret_cast<float *>(smem + L.nbr);
-    float *s_radar = reinterpret_cast<float *>(smem + L.radar), *s_nbr6 = reinterpret_cast<float *>(smem + L.nbr6);
-    float *s_raw_own = reinterpret_cast<float *>(smem + L.raw_own), *s_raw_nbr = reinterpret_cast<float *>(smem + L.raw_nbr);
-    float *s_raw_nbr6 = reinterpret_cast<float *>(smem + L.raw_nbr6);
-    float4 *s_tmin = reinterpret_cast<float4 *>(smem + L.tmin), *s_tpair = reinterpret_cast<float4 *>(smem + L.tpair);
-    float *s_rmin = reinterpret_cast<float *>(smem + L.rmin);
-    int16_t *s_rhit = reinterpret_cast<int16_t *>(smem + L.rhit);
-    float *s_parts = reinterpret_cast<float *>(smem + L.parts);
-
-    // ---- phase 0: which envs of the tile take part; scenario / map row per env; ray table
-    bool any_active = false;
-    for (int e = tid; e < ne; e += nt) {
-        const int ge = e0 + e;
-        int active = 1, scen = 0, map_row = 0;
-        if (mode == MODE_RESET) {
-            active = p.mask ? (p.mask[ge] != 0) : 1;
-            if (active) {
-                scen = (int)pick_scenario(p.env_id_base + ge, p.st.ep_index[ge], p.seed, p.n_scen);
-                map_row = p.bank_map ? p.bank_map[scen] : 0;
-                if (p.st.map_id) p.st.map_id[ge] = map_row;
-            }
-        } else if (p.st.map_id) {
-            map_row = p.st.map_id[ge];
+    // ---- neighbour iteration order (ATT: index order; V2: stable insertion sort by distance), window
+    if (mine) {
+        const int i = a - eb;
+        const float px = w.px[a], py = w.py[a];
+        float *dist = w.d2 + a * Mp;
+        uint8_t *ord = w.order + a * M;
+        int m = 0;
+        for (int j = 0; j < N; ++j) {
+            if (j == i) continue;
+            const float dx = w.px[eb + j] - px, dy = w.py[eb + j] - py;
+            const float d2 = dx * dx + dy * dy;
+            int q = m;
+            if (VAR == AAC_VARIANT_V2)
+                while (q > 0 && dist[q - 1] > d2) { dist[q] = dist[q - 1]; ord[q] = ord[q - 1]; --q; }
+            dist[q] = d2; ord[q] = (uint8_t)j;
+            ++m;
         }
-        s_envi[e] = make_int4(active, scen, map_row, 0);
-        any_active |= active != 0;
-    }
-    if (mode == MODE_RESET && !__syncthreads_or(any_active)) return;
-    for (int k = tid; k < R; k += nt) s_ray[k] = p.ray_dir[k];
-    __syncthreads();
-    {   // stage the map(s) this tile uses (one shared map unless VAR == MM)
-        const int nmap = VAR == AAC_VARIANT_MM ? ne : 1;
-        constexpr int WORDS = sizeof(MapDev) / 4;
-        for (int k = tid; k < nmap * WORDS; k += nt) {
-            const int mi = k / WORDS, w = k - mi * WORDS;
-            const int row = VAR == AAC_VARIANT_MM ? s_envi[mi].z : 0;
-            reinterpret_cast<unsigned *>(s_maps)[k] = reinterpret_cast<const unsigned *>(p.maps + row)[w];
-        }
-    }
-    __syncthreads();
-
-    // ---- phase A: load (or re-initialise) the per-drone records, integrate the action
-    for (int a = tid; a < A; a += nt) {
-        const int ga = a0 + a, e = a / N, i = a - e * N;
-        const MapDev &mp = s_maps[VAR == AAC_VARIANT_MM ? e : 0];
-        float px, py, vx, vy, hd;
-        unsigned meta;
-        if (mode == MODE_RESET && s_envi[e].x) {
-            const size_t src = ((size_t)s_envi[e].y * N + i) * W;
-            for (int k = 0; k < W; ++k) {
-                const uint16_t c = p.bank_cells[src + k];
-                p.st.ref_cells[(size_t)ga * W + k] = c;
-                s_cells[a * W + k] = c;
-            }
-            const int w = p.bank_w[(size_t)s_envi[e].y * N + i];
-            p.st.ref_w[ga] = (uint8_t)w;
-            s_refw[a] = (uint8_t)w;
-            const uint16_t c0 = s_cells[a * W], c1 = s_cells[a * W + 1];
-            px = cell_cx(mp, c0 >> 8); py = cell_cy(mp, c0 & 255);
-            vx = 0.0f; vy = 0.0f;
-            hd = atan2f(cell_cy(mp, c1 & 255) - py, cell_cx(mp, c1 >> 8) - px);  // ATT:359
-            meta = 0xFFFF0000u;
-            if (p.st.wall_count) p.st.wall_count[ga] = 0;
-        } else {
-            px = p.st.px[ga]; py = p.st.py[ga]; vx = p.st.vx[ga]; vy = p.st.vy[ga]; hd = p.st.heading[ga];
-            meta = p.st.meta[ga];
-            const int w = p.st.ref_w[ga];
-            s_refw[a] = (uint8_t)w;
-            for (int k = 0; k < w; ++k) s_cells[a * W + k] = p.st.ref_cells[(size_t)ga * W + k];
-        }
-        s_ppx[a] = px; s_ppy[a] = py; s_pvx[a] = vx; s_pvy[a] = vy;
-        if (mode == MODE_STEP) {  // ATT:2655-2713
-            const float2 act = reinterpret_cast<const float2 *>(p.actions)[ga];
-            const float cvx = fmaf(act.x * p.acc_max, p.dt, vx), cvy = fmaf(act.y * p.acc_max, p.dt, vy);
-            const float sp = sqrtf(cvx * cvx + cvy * cvy);
-            if (sp >= p.vmax) { const float s = p.vmax / sp; vx = cvx * s; vy = cvy * s; }
-            else { vx = cvx; vy = cvy; }
-            float ddx = vx * p.dt, ddy = vy * p.dt;
-            if (VAR == AAC_VARIANT_V2) {
-                if (meta & M_REACH) { ddx = 0.0f; ddy = 0.0f; }  // V2:3770-3775
-                hd = atan2f(ddy, ddx);                            // V2:3783
-            }
-            px += ddx; py += ddy;
-        }
-        s_px[a] = px; s_py[a] = py; s_vx[a] = vx; s_vy[a] = vy; s_hd[a] = hd;
-        s_meta[a] = meta;
-    }
-    __syncthreads();
-
-    // ---- phase B1: squared distance matrix, occupancy window per drone
-    for (int w = tid; w < A * N; w += nt) {
-        const int a = w / N, j = w - a * N, e = a / N, i = a - e * N;
-        const float dx = s_px[e * N + j] - s_px[a], dy = s_py[e * N + j] - s_py[a];
-        s_d2[w] = j == i ? CUDART_INF_F : dx * dx + dy * dy;
-    }
-    for (int a = tid; a < A; a += nt) {
-        const int e = a / N;
-        const MapDev &mp = s_maps[VAR == AAC_VARIANT_MM ? e : 0];
-        int ix0 = (int)floorf((s_px[a] - p.ray_len - mp.ex0) * mp.inv_cell);
-        int iy0 = (int)floorf((s_py[a] - p.ray_len - mp.ey0) * mp.inv_cell);
-        ix0 = min(max(ix0, -MAP_PAD), mp.gx + MAP_PAD - 4);
-        iy0 = min(max(iy0, -MAP_PAD), mp.gy + MAP_PAD - 4);
+        // 4x4 occupancy window covering the square the rays can reach
+        const float fx = (px - p.ray_len - mp.ex0) * mp.inv_cell, fy = (py - p.ray_len - mp.ey0) * mp.inv_cell;
+        const int rx0 = (int)floorf(fx), ry0 = (int)floorf(fy);
+        const int ix0 = min(max(rx0, -MAP_PAD), mp.gx + MAP_PAD - 4), iy0 = min(max(ry0, -MAP_PAD), mp.gy + MAP_PAD - 4);
         unsigned mask = 0;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -392,382 +424,565 @@ __global__ void __launch_bounds__(MAX_THREADS) env_kernel(const __grid_constant_
             const unsigned lo = mp.bits[b >> 5], hi = mp.bits[min((b >> 5) + 1, MAP_WORDS - 1)];
             mask |= (__funnelshift_r(lo, hi, b & 31) & 0xFu) << (4 * r);
         }
-        s_win[a] = make_uint2(mask, (unsigned)(ix0 & 0xFFFF) | ((unsigned)iy0 << 16));
-    }
-    __syncthreads();
-
-    // ---- phase B2: neighbour iteration order (ATT: index order; V2: stable sort by distance)
-    for (int w = tid; w < A * N; w += nt) {
-        const int a = w / N, j = w - a * N, e = a / N, i = a - e * N;
-        if (j == i) continue;
-        int rank;
-        if (VAR == AAC_VARIANT_V2) {
-            const float dj = s_d2[w];
-            rank = 0;
-            for (int q = 0; q < N; ++q) {
-                const float dq = s_d2[a * N + q];
-                rank += (dq < dj) || (dq == dj && q < j);  // the self entry is +inf and never counts
+        const float wx = mp.ex0 + ix0 * mp.cell - px, wy = mp.ey0 + iy0 * mp.cell - py;
+        // drop the corner cells no ray of length ray_len can reach; flag the rare geometries
+        unsigned keep = 0, slow = (ix0 != rx0 || iy0 != ry0) ? W_SLOW : 0u;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float nx = fmaxf(fmaxf(wx + r * mp.cell, -(wx + (r + 1) * mp.cell)), 0.0f);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float ny = fmaxf(fmaxf(wy + c * mp.cell, -(wy + (c + 1) * mp.cell)), 0.0f);
+                if (nx * nx + ny * ny <= p.ray_len * p.ray_len * 1.0001f) keep |= 1u << (4 * r + c);
+                if (nx == 0.0f && ny == 0.0f && ((mask >> (4 * r + c)) & 1u)) slow = W_SLOW;  // centre inside (or on) an occupied cell
             }
-        } else {
-            rank = j < i ? j : j - 1;
         }
-        s_order[a * M + rank] = (uint8_t)j;
+        mask &= keep;
+        const bool near_bound = !(px - p.ray_len > -mp.hx && px + p.ray_len < mp.hx && py - p.ray_len > -mp.hy && py + p.ray_len < mp.hy);
+        w.win[a] = make_uint2(mask | (near_bound ? W_NEAR_BOUND : 0u) | slow, (unsigned)(ix0 & 0xFFFF) | ((unsigned)iy0 << 16));
+        w.wrel[a] = make_float2(wx, wy);
+        w.minr[a] = 0x7F800000u;
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- phase C: ordered pairs -> tdCPA (cur, pre) and the neighbour blocks of the observation
-    const float inv_vmax = 1.0f / p.vmax;
-    for (int w = tid; w < A * M; w += nt) {
-        const int a = w / M, k = w - a * M, e = a / N;
-        const MapDev &mp = s_maps[VAR == AAC_VARIANT_MM ? e : 0];
-        const int b = e * N + s_order[w];
-        const float px = s_px[a], py = s_py[a], ox = s_px[b], oy = s_py[b], ovx = s_vx[b], ovy = s_vy[b];
-        const float dx = ox - px, dy = oy - py;
-        float t1, d1, t2, d2;
-        bool c1, c2;
-        tcpa_dcpa(px, py, s_vx[a], s_vy[a], ox, oy, ovx, ovy, 2.0f * p.prot, t1, d1, c1);
-        tcpa_dcpa(s_ppx[a], s_ppy[a], s_pvx[a], s_pvy[a], s_ppx[b], s_ppy[b], s_pvx[b], s_pvy[b], 2.0f * p.prot, t2, d2, c2);
-        s_tc[w] = make_float2(t1, d1);
-        s_pflag[w] = (uint8_t)((c1 ? 1 : 0) | (c2 ? 2 : 0));
-        if (flags & AAC_OUT_TCPA_PAIR) s_tpair[w] = make_float4(t1, d1, t2, d2);
-        const float ihx = 1.0f / mp.hx, ihy = 1.0f / mp.hy;
-        if (VAR == AAC_VARIANT_ATT) {
-            float *r = s_own + a * D + 6 + 4 * k;  // scale_pos applied to a delta (ATT:1374)
-            r[0] = (dx - mp.xmin_g) * ihx - 1.0f; r[1] = (dy - mp.ymin_g) * ihy - 1.0f; r[2] = ovx * inv_vmax; r[3] = ovy * inv_vmax;
-            if (flags & AAC_OUT_RAW) { float *q = s_raw_own + a * D + 6 + 4 * k; q[0] = dx; q[1] = dy; q[2] = ovx; q[3] = ovy; }
-        } else if (VAR == AAC_VARIANT_V2) {
-            float *r = s_nbr + a * 5 * M + 5 * k;  // host - neighbour, host heading (V2:1519,1571)
-            r[0] = -dx * ihx; r[1] = -dy * ihy; r[2] = ovx * inv_vmax; r[3] = ovy * inv_vmax; r[4] = s_hd[a];
-            if (flags & AAC_OUT_RAW) { float *q = s_raw_nbr + a * 5 * M + 5 * k; q[0] = dx; q[1] = dy; q[2] = ovx; q[3] = ovy; q[4] = s_hd[b]; }
-        }
-        if (flags & AAC_OUT_NBR6) {  // legacy block built from [px,py,vx,vy,2.5] (ATT:1396-1410)
-            const float oxg = ox + mp.ox, oyg = oy + mp.oy;
-            float *r = s_nbr6 + w * 6;
-            r[0] = dx * 0.5f * ihx; r[1] = dy * 0.5f * ihy; r[2] = (ovy - oxg) * 0.5f * ihx; r[3] = (p.prot - oyg) * 0.5f * ihy;
-            r[4] = ovx * inv_vmax; r[5] = ovy * inv_vmax;
-            if (flags & AAC_OUT_RAW) { float *q = s_raw_nbr6 + w * 6; q[0] = dx; q[1] = dy; q[2] = ovy - oxg; q[3] = p.prot - oyg; q[4] = ovx; q[5] = ovy; }
+    // ---- ordered pairs -> tdCPA (cur, pre) and the neighbour blocks of the observation
+    if (M > 0) {
+        const int n_items = n_ag * M;
+        const size_t pg0 = (size_t)(w.a0 + a_lo) * M;  // global index of the range's first pair
+        for (Walk it(lane, 32, M); it.hi * M + it.lo - lane < n_items; it.next()) {
+            const int idx = it.hi * M + it.lo, base = idx - lane;   // base = first item of this warp iteration
+            const int n_valid = min(32, n_items - base);
+            const bool ok = idx < n_items;
+            const int aa = a_lo + (ok ? it.hi : 0), k = ok ? it.lo : 0, pi = aa * M + k;
+            const int ebb = (aa / N) * N, b = ebb + w.order[pi];
+            const float px = w.px[aa], py = w.py[aa], ox = w.px[b], oy = w.py[b], ovx = w.vx[b], ovy = w.vy[b];
+            const float dx = ox - px, dy = oy - py;
+            float t1, d1, t2, d2;
+            bool c1, c2;
+            tcpa_dcpa(px, py, w.vx[aa], w.vy[aa], ox, oy, ovx, ovy, 2.0f * p.prot, t1, d1, c1);
+            tcpa_dcpa(w.ppx[aa], w.ppy[aa], w.pvx[aa], w.pvy[aa], w.ppx[b], w.ppy[b], w.pvx[b], w.pvy[b], 2.0f * p.prot, t2, d2, c2);
+            if (ok) {
+                w.tc[pi] = make_float2(t1, d1);
+                w.pflag[pi] = (uint8_t)((c1 ? 1 : 0) | (c2 ? 2 : 0));
+                if (flags & AAC_OUT_TCPA_PAIR) {
+                    reinterpret_cast<float4 *>(p.out.tcpa_pair)[pg0 + idx] = make_float4(t1, d1, t2, d2);
+                    p.out.nbr_order[pg0 + idx] = (int8_t)w.order[pi];
+                }
+            }
+            if (VAR == AAC_VARIANT_ATT) {
+                if (ok) {
+                    float *r = w.own + aa * D + 6 + 4 * k;  // scale_pos applied to a delta (ATT:1374)
+                    r[0] = (dx - mp.xmin_g) * mp.ihx - 1.0f; r[1] = (dy - mp.ymin_g) * mp.ihy - 1.0f; r[2] = ovx * inv_vmax; r[3] = ovy * inv_vmax;
+                    if (flags & AAC_OUT_RAW) { float *q = w.raw_own + aa * D + 6 + 4 * k; q[0] = dx; q[1] = dy; q[2] = ovx; q[3] = ovy; }
+                }
+            } else if (VAR == AAC_VARIANT_V2) {
+                // host - neighbour, host heading (V2:1519,1571)
+                const float v[5] = {-dx * mp.ihx, -dy * mp.ihy, ovx * inv_vmax, ovy * inv_vmax, w.hd[aa]};
+                flush_items<5>(p.out.norm_nbr + (pg0 + base) * 5, n_valid, v, w.stg, lane);
+                if (flags & AAC_OUT_RAW) {
+                    const float q[5] = {dx, dy, ovx, ovy, w.hd[b]};
+                    flush_items<5>(p.out.raw_nbr + (pg0 + base) * 5, n_valid, q, w.stg, lane);
+                }
+            }
+            if (flags & AAC_OUT_NBR6) {  // legacy block built from [px,py,vx,vy,2.5] (ATT:1396-1410)
+                const float oxg = ox + mp.ox, oyg = oy + mp.oy;
+                const float v[6] = {dx * 0.5f * mp.ihx, dy * 0.5f * mp.ihy, (ovy - oxg) * 0.5f * mp.ihx, (p.prot - oyg) * 0.5f * mp.ihy,
+                                    ovx * inv_vmax, ovy * inv_vmax};
+                flush_items<6>(p.out.norm_nbr6 + (pg0 + base) * 6, n_valid, v, w.stg, lane);
+                if (flags & AAC_OUT_RAW) {
+                    const float q[6] = {dx, dy, ovy - oxg, p.prot - oyg, ovx, ovy};
+                    flush_items<6>(p.out.raw_nbr6 + (pg0 + base) * 6, n_valid, q, w.stg, lane);
+                }
+            }
         }
     }
 
-    // ---- phase D: radar, one work item per (drone, ray)
-    for (int w = tid; w < A * R; w += nt) {
-        const int a = w / R, k = w - a * R, e = a / N, i = a - e * N;
-        const MapDev &mp = s_maps[VAR == AAC_VARIANT_MM ? e : 0];
-        float out, out_min;
-        int id;
-        if (VAR == AAC_VARIANT_ATT) {
-            radar_drones_ray(s_px, s_py, e * N, N, i, s_ray[k], p.ray_len, p.prot, mp.gx * mp.gy + 4, out, id);
-            out_min = out;
-        } else {
-            const uint2 wn = s_win[a];
-            radar_grid_ray(mp, s_px[a], s_py[a], s_ray[k], p.ray_len, wn.x, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16),
-                           VAR == AAC_VARIANT_V2 && p.radar_mode == AAC_RADAR_LAST_HIT, out, out_min, id);
+    // ---- radar, one work item per (drone, ray); stores are item-major, i.e. already coalesced
+    {
+        const int n_items = n_ag * R;
+        const size_t rg0 = (size_t)(w.a0 + a_lo) * R;
+        for (Walk it(lane, 32, R); it.hi * R + it.lo - lane < n_items; it.next()) {
+            const int idx = it.hi * R + it.lo;
+            const bool ok = idx < n_items;
+            const int aa = a_lo + (ok ? it.hi : 0), k = ok ? it.lo : 0;
+            const float4 ray = w.ray[k];
+            const float len = p.ray_len;
+            float out, out_min;
+            int id = -1;
+            if (VAR == AAC_VARIANT_ATT) {
+                const int ebb = (aa / N) * N;
+                radar_drones_ray(w.px, w.py, ebb, N, aa - ebb, ray, len, p.prot, mp.gx * mp.gy + 4, out, id);
+                out_min = out;
+            } else {
+                const uint2 wn = w.win[aa];
+                float shortest = CUDART_INF_F, sensed = len;
+                int shortest_id = -1, sensed_id = -1;
+                if (!(wn.x & W_SLOW))
+                    radar_window<AUX>(mp, w.wrel[aa], wn.x & 0xFFFFu, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16), ray, len, shortest,
+                                      sensed, shortest_id, sensed_id);
+                else
+                    radar_generic<AUX>(mp, w.px[aa], w.py[aa], ray, len, shortest, sensed, shortest_id, sensed_id);
+                if (wn.x & (W_NEAR_BOUND | W_SLOW)) radar_bounds<AUX>(mp, w.px[aa], w.py[aa], ray, len, shortest, sensed, shortest_id, sensed_id);
+                out_min = shortest == CUDART_INF_F ? len : shortest;
+                const bool last_hit = VAR == AAC_VARIANT_V2 && p.radar_mode == AAC_RADAR_LAST_HIT;
+                out = last_hit ? sensed : out_min;
+                if (AUX) id = last_hit ? sensed_id : shortest_id;
+            }
+            if (ok) {
+                p.out.radar[rg0 + idx] = out;
+                if (AUX) { p.out.radar_min[rg0 + idx] = out_min; p.out.radar_hit[rg0 + idx] = (int16_t)id; }
+            }
+            // per-drone minimum of the stored ranges (the reward's min_radar): ranges are >= 0, so their
+            // bit patterns order like unsigned integers and nan (0x7FC00000) sorts above every number
+            const unsigned key = ok ? __float_as_uint(out) : 0xFFFFFFFFu;
+            const int a_first = __shfl_sync(FULL, aa, 0), a_last = __shfl_sync(FULL, aa, min(31, n_items - (idx - lane) - 1));
+            for (int q = a_first; q <= a_last; ++q) {
+                const unsigned m = __reduce_min_sync(FULL, aa == q ? key : 0xFFFFFFFFu);
+                if (lane == 0) w.minr[q] = min(w.minr[q], m);
+            }
         }
-        s_radar[w] = out;
-        if (flags & AAC_OUT_RADAR_AUX) { s_rmin[w] = out_min; s_rhit[w] = (int16_t)id; }
     }
+    __syncwarp();
 
-    // ---- phase E1: own block of the observation, goal contact
-    for (int a = tid; a < A; a += nt) {
-        const int e = a / N;
-        const MapDev &mp = s_maps[VAR == AAC_VARIANT_MM ? e : 0];
-        const int w = s_refw[a];
-        const uint16_t cg = s_cells[a * W + w - 1];
+    // ---- own block of the observation, goal contact
+    if (mine) {
+        const int nw = w.refw[a];
+        const uint16_t cg = cells[nw - 1];
         const float gx = cell_cx(mp, cg >> 8), gy = cell_cy(mp, cg & 255);
-        const float px = s_px[a], py = s_py[a];
-        const float ihx = 1.0f / mp.hx, ihy = 1.0f / mp.hy;
-        float nvx = s_vx[a] * inv_vmax, nvy = s_vy[a] * inv_vmax;
-        if (VAR == AAC_VARIANT_MM) { nvx = s_vx[a] * ihx; nvy = s_vy[a] * ihy; }
+        const float px = w.px[a], py = w.py[a];
+        float nvx = w.vx[a] * inv_vmax, nvy = w.vy[a] * inv_vmax;
+        if (VAR == AAC_VARIANT_MM) { nvx = w.vx[a] * mp.ihx; nvy = w.vy[a] * mp.ihy; }
         else if (M > 0) {
             // `norm_vel` is re-bound inside the neighbour loop (ATT:1408, V2:1586) before the own block
             // is assembled (ATT:1463, V2:1672): the slot carries the LAST neighbour's velocity
-            const int b = e * N + s_order[a * M + M - 1];
-            nvx = s_vx[b] * inv_vmax; nvy = s_vy[b] * inv_vmax;
+            const int b = eb + w.order[a * M + M - 1];
+            nvx = w.vx[b] * inv_vmax; nvy = w.vy[b] * inv_vmax;
         }
-        float *r = s_own + a * D;
-        r[0] = px * ihx; r[1] = py * ihy; r[2] = nvx; r[3] = nvy; r[4] = gx * ihx - r[0]; r[5] = gy * ihy - r[1];
-        if (VAR == AAC_VARIANT_V2) r[6] = s_hd[a];
+        float *r = w.own + a * D;
+        r[0] = px * mp.ihx; r[1] = py * mp.ihy; r[2] = nvx; r[3] = nvy; r[4] = gx * mp.ihx - r[0]; r[5] = gy * mp.ihy - r[1];
+        if (VAR == AAC_VARIANT_V2) r[6] = w.hd[a];
         if (flags & AAC_OUT_RAW) {
-            float *q = s_raw_own + a * D;
-            q[0] = px + mp.ox; q[1] = py + mp.oy; q[2] = s_vx[a]; q[3] = s_vy[a]; q[4] = gx - px; q[5] = gy - py;
-            if (VAR == AAC_VARIANT_V2) q[6] = s_hd[a];
+            float *q = w.raw_own + a * D;
+            q[0] = px + mp.ox; q[1] = py + mp.oy; q[2] = w.vx[a]; q[3] = w.vy[a]; q[4] = gx - px; q[5] = gy - py;
+            if (VAR == AAC_VARIANT_V2) q[6] = w.hd[a];
         }
-        s_agf[a] = gons_touch(gx - px, gy - py, p.prot + p.goal_r) ? F_ATGOAL : 0u;
-        s_agr[a] = 0.0f;
+        w.atgoal[a] = gons_touch(gx - px, gy - py, p.prot + p.goal_r) ? 1 : 0;
     }
+    __syncwarp();
+    {   // own rows of the range are contiguous: coalesced copy
+        float *dst = p.out.norm_own + (size_t)(w.a0 + a_lo) * D;
+        const float *src = w.own + a_lo * D;
+        for (int f = lane; f < n_ag * D; f += 32) dst[f] = src[f];
+        if (flags & AAC_OUT_RAW) {
+            float *dr = p.out.raw_own + (size_t)(w.a0 + a_lo) * D;
+            const float *sr = w.raw_own + a_lo * D;
+            for (int f = lane; f < n_ag * D; f += 32) dr[f] = sr[f];
+        }
+    }
+    __syncwarp();
+}
+
+// re-initialise env g of the warp's group from the scenario bank: what reset_world leaves behind
+// (ATT:301-372).  Returns the lane's reference-line row (bank memory) for the drones of that env.
+__device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp &w, const int g) {
+    const int lane = w.lane, N = p.N, W = p.W;
+    const MapDev &mp = *w.map;
+    const int ge = w.e_lo + g;
+    const int ep = p.st.ep_index[ge];
+    const unsigned scen = pick_scenario(p.env_id_base + ge, ep, p.seed, p.n_scen);
+    __syncwarp();
+    if (lane == 0) {
+        p.st.ep_index[ge] = ep + 1;
+        p.st.ep_step[ge] = 0;
+        p.st.ep_return[ge] = 0.0f;
+    }
+    // reference lines: 16-byte chunks bank -> global state (W is a multiple of 8)
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.bank_cells + (size_t)scen * N * W);
+    uint4 *dst = reinterpret_cast<uint4 *>(p.st.ref_cells + (size_t)ge * N * W);
+    for (int c = lane; c < N * W / 8; c += 32) dst[c] = src[c];
+    const uint16_t *row = nullptr;
+    if (lane < N) {
+        const int a = g * N + lane;
+        row = p.bank_cells + ((size_t)scen * N + lane) * W;
+        const int nw = p.bank_w[(size_t)scen * N + lane];
+        w.refw[a] = (uint8_t)nw;
+        p.st.ref_w[(size_t)ge * N + lane] = (uint8_t)nw;
+        const uint16_t c0 = row[0], c1 = row[1];
+        const float px = cell_cx(mp, c0 >> 8), py = cell_cy(mp, c0 & 255);
+        w.px[a] = px; w.py[a] = py; w.vx[a] = 0.0f; w.vy[a] = 0.0f;
+        w.hd[a] = atan2f(cell_cy(mp, c1 & 255) - py, cell_cx(mp, c1 >> 8) - px);  // ATT:359
+        w.ppx[a] = px; w.ppy[a] = py; w.pvx[a] = 0.0f; w.pvy[a] = 0.0f;
+        w.meta[a] = 0xFFFF0000u;
+        if (p.st.wall_count) p.st.wall_count[(size_t)ge * N + lane] = 0;
+    }
+    __syncwarp();
+    return row;
+}
+
+// distance to the reference polyline and arc length of the nearest point: first segment attaining the
+// minimum wins (ATT:3203-3214, V2:4286-4297, UV2:413-441).  Vertices come 8 per 16-byte load.
+__device__ __forceinline__ void polyline_nearest(const MapDev &mp, const uint16_t *cells, int nw, float px, float py, float &best2, float &arc,
+                                                 float &total) {
+    best2 = CUDART_INF_F; arc = 0.0f;
+    float run = 0.0f, ax = 0.0f, ay = 0.0f;
+    for (int c8 = 0; c8 < nw; c8 += 8) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(cells + c8);
+        const unsigned wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k = c8 + q;
+            if (k >= nw) break;
+            const unsigned c = (wd[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
+            const float bx = cell_cx(mp, c >> 8), by = cell_cy(mp, c & 255);
+            if (k > 0) {
+                const float sx = bx - ax, sy = by - ay, len2 = sx * sx + sy * sy;
+                const float sl = sqrtf(len2);
+                float rr = len2 > 0.0f ? __fdividef((px - ax) * sx + (py - ay) * sy, len2) : 0.0f;
+                rr = fminf(fmaxf(rr, 0.0f), 1.0f);
+                const float qx = fmaf(rr, sx, ax) - px, qy = fmaf(rr, sy, ay) - py;
+                const float dq = qx * qx + qy * qy;
+                if (dq < best2) { best2 = dq; arc = fmaf(rr, sl, run); }
+                run += sl;
+            }
+            ax = bx; ay = by;
+        }
+    }
+    total = run;
+}
+
+template <int VAR, bool AUX>
+__global__ void __launch_bounds__(MAX_THREADS) env_kernel(const __grid_constant__ KParams p, const int mode) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpc = blockDim.x >> 5;
+    const int N = p.N, M = N - 1, W = p.W, G = p.G;
+    const int Mp = M | 1;
+    const int flags = p.out_flags;
+    const CtaLayout &CL = p.CL;
+    const WarpLayout &WL = p.WL;
+
+    MapDev *s_map = reinterpret_cast<MapDev *>(smem + CL.map);
+    float4 *s_ray = reinterpret_cast<float4 *>(smem + CL.ray);
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem + CL.bar);
+    int *s_cnt = reinterpret_cast<int *>(smem + CL.cnt);
+
+    // ---- CTA prologue: the map arrives by one TMA bulk copy, the ray table by plain loads
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(s_bar, sizeof(MapDev));
+        bulk_g2s(s_map, p.maps, sizeof(MapDev), s_bar);
+    }
+    for (int k = tid; k < p.R; k += blockDim.x) s_ray[k] = p.ray_tab[k];
+    if (tid < 16) s_cnt[tid] = 0;
     __syncthreads();
+    mbar_wait(s_bar, 0);
 
-    // ---- phase E2: reward / collision / goal per drone
-    if (mode == MODE_STEP) {
-        for (int a = tid; a < A; a += nt) {
-            const int e = a / N, i = a - e * N, eb = e * N;
-            const MapDev &mp = s_maps[VAR == AAC_VARIANT_MM ? e : 0];
-            const float px = s_px[a], py = s_py[a];
-            const int w = s_refw[a];
-            unsigned meta = s_meta[a];
-            const bool at_goal = s_agf[a] & F_ATGOAL;
-            if (VAR == AAC_VARIANT_V2 && at_goal) meta |= M_REACH;  // top of the drone's iteration (V2:3025-3033)
-            const bool reach_i = meta & M_REACH;
-            // neighbour scan (ATT:2187-2236, V2:3092-3168)
-            int nearest = -1, n_coll = 0, last_coll = -1, imm_key = -1, conf_cur = 0, conf_pre = 0;
-            bool prev2 = false;
-            float shortest = CUDART_INF_F, imm_tcpa = CUDART_INF_F, imm_d = CUDART_INF_F;
-            const int pn0 = (meta >> 16) & 0xFF, pn1 = (meta >> 24) & 0xFF;
-            for (int k = 0; k < M; ++k) {
-                const int j = s_order[a * M + k];
-                const float2 tc = s_tc[a * M + k];
-                const unsigned pf = s_pflag[a * M + k];
-                conf_cur += pf & 1; conf_pre += (pf >> 1) & 1;
-                if (tc.x >= 0.0f && tc.x < imm_tcpa) { imm_tcpa = tc.x; imm_d = tc.y; imm_key = j; }
-                else if (tc.x == -10.0f && tc.y < imm_tcpa) { imm_tcpa = tc.x; imm_d = tc.y; imm_key = j; }
-                const float d = sqrtf(s_d2[a * N + j]);
-                if (d < shortest) { shortest = d; nearest = j; }
-                if (d <= 2.0f * p.prot) {
-                    if (VAR == AAC_VARIANT_V2) {
-                        // reach_target of drone j as drone i sees it: set in earlier steps, or earlier in
-                        // this step's loop when j < i (V2:3160)
-                        const bool reach_j = (s_meta[eb + j] & M_REACH) || (j < i && (s_agf[eb + j] & F_ATGOAL));
-                        if (reach_j || reach_i) continue;
-                        prev2 |= (j == pn0) || (M > 1 && j == pn1);  // V2:3170-3179
-                    }
-                    ++n_coll; last_coll = j;
+    unsigned char *ws = smem + CL.warps + (size_t)warp * WL.total;
+    Warp w;
+    w.map = s_map; w.ray = s_ray; w.lane = lane;
+    w.e_lo = (blockIdx.x * wpc + warp) * G;
+    w.ng = min(G, p.E - w.e_lo);
+    w.a0 = w.e_lo * N;
+    w.nA = w.ng * N;
+    w.px = reinterpret_cast<float *>(ws + WL.cur); w.py = w.px + 32; w.vx = w.py + 32; w.vy = w.vx + 32; w.hd = w.vy + 32;
+    w.ppx = reinterpret_cast<float *>(ws + WL.pre); w.ppy = w.ppx + 32; w.pvx = w.ppy + 32; w.pvy = w.pvx + 32;
+    w.meta = reinterpret_cast<unsigned *>(ws + WL.meta); w.meta2 = w.meta + 32; w.minr = w.meta2 + 32; w.agf = w.minr + 32;
+    w.agr = reinterpret_cast<float *>(ws + WL.agr);
+    w.d2 = reinterpret_cast<float *>(ws + WL.d2);
+    w.stg = reinterpret_cast<float *>(ws + WL.stg);
+    w.own = reinterpret_cast<float *>(ws + WL.own);
+    w.raw_own = reinterpret_cast<float *>(ws + WL.raw_own);
+    w.order = ws + WL.order; w.pflag = ws + WL.pflag; w.atgoal = ws + WL.bytes; w.refw = w.atgoal + 32; w.rs = w.refw + 32;
+    w.win = reinterpret_cast<uint2 *>(ws + WL.win);
+    w.wrel = reinterpret_cast<float2 *>(ws + WL.wrel);
+    w.tc = reinterpret_cast<float2 *>(ws + WL.tc);
+    const MapDev &mp = *s_map;
+
+    if (w.ng > 0) {
+        const int nA = w.nA, a0 = w.a0;
+        const bool mine = lane < nA;
+        const int a = lane, ga = a0 + lane;
+        const int my_env = mine ? a / N : 0;
+        const uint16_t *cells = p.st.ref_cells + (size_t)(mine ? ga : a0) * W;
+
+        // ---- load the per-drone records; integrate the action (ATT:2655-2713)
+        if (mine) {
+            float px = p.st.px[ga], py = p.st.py[ga], vx = p.st.vx[ga], vy = p.st.vy[ga], hd = p.st.heading[ga];
+            const unsigned meta = p.st.meta[ga];
+            w.ppx[a] = px; w.ppy[a] = py; w.pvx[a] = vx; w.pvy[a] = vy;
+            if (mode == MODE_STEP) {
+                const float2 act = reinterpret_cast<const float2 *>(p.actions)[ga];
+                const float cvx = fmaf(act.x * p.acc_max, p.dt, vx), cvy = fmaf(act.y * p.acc_max, p.dt, vy);
+                const float sp = sqrtf(cvx * cvx + cvy * cvy);
+                if (sp >= p.vmax) { const float s = p.vmax / sp; vx = cvx * s; vy = cvy * s; }
+                else { vx = cvx; vy = cvy; }
+                float ddx = vx * p.dt, ddy = vy * p.dt;
+                if (VAR == AAC_VARIANT_V2) {
+                    if (meta & M_REACH) { ddx = 0.0f; ddy = 0.0f; }  // V2:3770-3775
+                    hd = atan2f(ddy, ddx);                            // V2:3783
                 }
+                px += ddx; py += ddy;
             }
-            s_tmin[a] = make_float4(imm_tcpa, imm_d, (float)imm_key, (float)(conf_cur + 256 * conf_pre));
-            if (VAR == AAC_VARIANT_V2 && n_coll > 0) meta |= M_VDRONE;
-            // building contact: the protective 64-gon against the (at most 2x2) cells it can reach
-            bool collide_building = false;
-            {
-                const int ixa = (int)floorf((px - p.prot - mp.ex0) * mp.inv_cell), ixb = (int)floorf((px + p.prot - mp.ex0) * mp.inv_cell);
-                const int iya = (int)floorf((py - p.prot - mp.ey0) * mp.inv_cell), iyb = (int)floorf((py + p.prot - mp.ey0) * mp.inv_cell);
-                for (int ix = ixa; ix <= ixb; ++ix)
-                    for (int iy = iya; iy <= iyb; ++iy)
-                        if (occupied(mp, ix, iy) && gon_square_touch(px - cell_cx(mp, ix), py - cell_cy(mp, iy), 0.5f * mp.cell, p.prot))
-                            collide_building = true;
-            }
-            if (collide_building && VAR == AAC_VARIANT_V2) meta |= M_VBLDG;
-            // waypoint (ATT:2297-2303)
-            const int cur = meta & 0xFF;
-            const uint16_t cw = s_cells[a * W + 1 + cur], cg = s_cells[a * W + w - 1];
-            const float gx = cell_cx(mp, cg >> 8), gy = cell_cy(mp, cg & 255);
-            const float wdx = px - cell_cx(mp, cw >> 8), wdy = py - cell_cy(mp, cw & 255);
-            const bool wp_flag = sqrtf(wdx * wdx + wdy * wdy) < 5.0f;
-            const float ppx = s_ppx[a], ppy = s_ppy[a];
-            const bool hit_bound = capsule_hits_bound(ppx, ppy, px, py, p.prot, mp.hx, mp.hy);
-            const float spd = sqrtf(s_vx[a] * s_vx[a] + s_vy[a] * s_vy[a]);
-            const float after_hg = sqrtf((px - gx) * (px - gx) + (py - gy) * (py - gy));
-            // nearest point on the reference line: first segment attaining the minimum (ATT:3203-3214)
-            float cross_err = CUDART_INF_F, arc = 0.0f, run = 0.0f;
-            {
-                float ax = cell_cx(mp, s_cells[a * W] >> 8), ay = cell_cy(mp, s_cells[a * W] & 255);
-                for (int k = 1; k < w; ++k) {
-                    const uint16_t c = s_cells[a * W + k];
-                    const float bx = cell_cx(mp, c >> 8), by = cell_cy(mp, c & 255);
-                    const float sx = bx - ax, sy = by - ay, len2 = sx * sx + sy * sy;
-                    float rr = len2 > 0.0f ? ((px - ax) * sx + (py - ay) * sy) / len2 : 0.0f;
-                    rr = fminf(fmaxf(rr, 0.0f), 1.0f);
-                    const float qx = fmaf(rr, sx, ax), qy = fmaf(rr, sy, ay);
-                    const float d = sqrtf((px - qx) * (px - qx) + (py - qy) * (py - qy));
-                    const float sl = sqrtf(len2);
-                    if (d < cross_err) { cross_err = d; arc = fmaf(rr, sl, run); }
-                    run += sl;
-                    ax = bx; ay = by;
-                }
-            }
-            float min_radar = CUDART_INF_F;
-            for (int k = 0; k < R; ++k) { const float v = s_radar[a * R + k]; if (v < min_radar) min_radar = v; }
-            float dist_to_goal, near_drone = 0.0f, near_bldg = 0.0f, small_step, rew = 0.0f;
-            unsigned res = 0, branch;
-            if (VAR == AAC_VARIANT_ATT) {
-                // (|pre-g| - |pos-g|) / vmax without the cancellation: (a-b).(a+b) / (|a|+|b|)  (ATT:2319-2325)
-                const float bx = ppx - gx, by = ppy - gy, cx = px - gx, cy = py - gy;
-                const float before_hg = sqrtf(bx * bx + by * by);
-                const float den = before_hg + after_hg;
-                dist_to_goal = den > 0.0f ? ((bx - cx) * (bx + cx) + (by - cy) * (by + cy)) / den * inv_vmax : 0.0f;
-                const float c_dr = 1.0f + (2.5f / (10.0f - 2.5f)), m_dr = (0.0f - 1.0f) / (10.0f - 2.5f);  // ATT:2420-2426
-                for (int k = 0; k < M; ++k) {  // every in-band neighbour adds the NEAREST one's penalty (ATT:2430-2432)
-                    const float d = sqrtf(s_d2[a * N + s_order[a * M + k]]);
-                    if (d >= 2.5f && d <= 10.0f) near_drone += fmaf(m_dr, shortest, c_dr);
-                }
-                small_step = 0.0f;  // coefficient 0 (ATT:2438)
-                if (hit_bound) { rew = -20.0f - small_step - near_bldg; res |= F_DONE; branch = 0; }
-                else if (n_coll > 0) {
-                    rew = -20.0f - small_step - near_drone; res |= F_DONE; branch = 2;
-                    if (last_coll == nearest) res |= F_BBC3;
-                } else if (at_goal) { res |= F_GOAL; meta |= M_REACH; rew = 20.0f; branch = 3; }
-                else {
-                    if (wp_flag && (w - 1 - cur) > 1) meta = (meta & ~0xFFu) | (unsigned)(cur + 1);  // ATT:2565-2566
-                    rew = dist_to_goal - small_step - near_bldg - near_drone;                           // ATT:2576-2578
-                    branch = 4;
-                }
-            } else {
-                const float dist_left = cross_err + (run - arc);  // UV2:413-441
-                dist_to_goal = 6.0f * (1.0f - dist_left / run);    // V2:3257-3268
-                if (nearest >= 0 && shortest >= 2.5f && shortest <= 6.0f) {  // V2:3365-3386
-                    const float c_dr = 1.0f + (2.5f / (6.0f - 2.5f)), m_dr = (0.0f - 1.0f) / (6.0f - 2.5f);
-                    const float brg = bearing_deg(px, py, s_px[eb + nearest], s_py[eb + nearest]);
-                    const float coef = (brg >= 90.0f && brg <= 180.0f) ? 20.0f : 10.0f;
-                    near_drone = coef * fmaf(m_dr, shortest, c_dr);
-                }
-                const float thr = 0.5f * p.vmax;  // V2:3446-3453
-                small_step = 5.0f * ((thr - fminf(fmaxf(spd, 0.0f), thr)) * (1.0f / thr));
-                if (min_radar >= p.prot && min_radar <= 5.0f) near_bldg = 3.0f * fmaf((0.0f - 1.0f) / (5.0f - p.prot), min_radar, 2.0f);  // V2:3522-3539
-                // crash rewards are filled in by the per-env pass below: the penalty doubles along the
-                // drone loop (V2:3590-3594)
-                if (hit_bound) { meta |= M_VBOUND; res |= F_DONE; branch = 0; }
-                else if (collide_building) { res |= F_DONE; branch = 1; }
-                else if (n_coll > 0) {
-                    res |= F_DONE; branch = 2;
-                    const float brg = bearing_deg(px, py, s_px[eb + last_coll], s_py[eb + last_coll]);
-                    if (brg >= 90.0f && brg <= 180.0f) res |= F_DOUBLE;
-                    if (prev2) res |= F_BBC3;
-                } else if (at_goal) { res |= F_GOAL; rew = 20.0f; branch = 3; }
-                else {
-                    if (wp_flag && (w - 1 - cur) > 1) meta = (meta & ~0xFFu) | (unsigned)(cur + 1);
-                    rew = dist_to_goal - small_step - near_bldg - near_drone;  // V2:3631-3633
-                    branch = 4;
-                }
-            }
-            if (collide_building && p.st.wall_count) p.st.wall_count[a0 + a] += 1;
-            // s_agf is read by the other drones of this env for F_ATGOAL only; keep that bit
-            atomicOr(&s_agf[a], res | (branch << F_BRANCH_SHIFT));
-            s_agr[a] = rew;
-            if (flags & AAC_OUT_PARTS) {
-                float *q = s_parts + a * 8;
-                q[0] = dist_to_goal; q[1] = near_drone; q[2] = near_bldg; q[3] = small_step; q[4] = cross_err; q[5] = after_hg;
-                q[6] = min_radar; q[7] = shortest;
-            }
-            // other drones read s_meta[j] & M_REACH (the record as it stood before this step) in the loop
-            // above: publish the new record only after every drone of the tile is through
-            s_meta2[a] = meta;
+            w.px[a] = px; w.py[a] = py; w.vx[a] = vx; w.vy[a] = vy; w.hd[a] = hd;
+            w.meta[a] = meta;
+            w.refw[a] = p.st.ref_w[ga];
         }
-        __syncthreads();
-        for (int a = tid; a < A; a += nt) s_meta[a] = s_meta2[a];
-        __syncthreads();
-    }
+        __syncwarp();
 
-    // ---- phase E3: per env -- crash penalties, summed reward, bound_building_check, episode end
-    for (int e = tid; e < ne; e += nt) {
-        if (mode == MODE_RESET && !s_envi[e].x) continue;
-        const int ge = e0 + e, eb = e * N;
-        if (mode == MODE_STEP) {
-            float cp = 20.0f, sum = 0.0f;
-            unsigned bbc = 0, any_done = 0, all_reach = 1, n_reach = 0;
-            for (int i = 0; i < N; ++i) {
-                const unsigned f = s_agf[eb + i], br = (f >> F_BRANCH_SHIFT) & 7u;
-                if (VAR == AAC_VARIANT_V2 && br <= 2) {
-                    if (f & F_DOUBLE) cp *= 2.0f;
-                    s_agr[eb + i] = -cp;
-                }
-                if (br <= 2) bbc |= 1u << br;
-                if (f & F_BBC3) bbc |= 8u;
-                any_done |= f & F_DONE;
-                const unsigned reached = (s_meta[eb + i] & M_REACH) ? 1u : 0u;
-                all_reach &= reached;
-                n_reach += reached;
-                sum += s_agr[eb + i];
-            }
-            if (p.sum_reward) {  // reward = [sum(reward)] * N (ATT:2602-2603)
-                for (int i = 0; i < N; ++i) s_agr[eb + i] = sum;
-                sum *= (float)N;
-            }
-            const int step = p.st.ep_step[ge] + 1;
-            p.st.ep_step[ge] = step;
-            const float ret = p.st.ep_return[ge] + sum;
-            p.st.ep_return[ge] = ret;
-            const unsigned term = (step > p.ep_len ? 1u : 0u) | (any_done ? 2u : 0u) | (all_reach ? 4u : 0u);
-            reinterpret_cast<uchar4 *>(p.out.bbc)[ge] = make_uchar4(bbc & 1, (bbc >> 1) & 1, (bbc >> 2) & 1, (bbc >> 3) & 1);
-            p.out.terminated[ge] = (uint8_t)term;
-            if (term && p.stats) {  // episode statistics (ATT/ma_main:581-637)
-                atomicAdd(p.stats + 0, 1.0);
-                atomicAdd(p.stats + 1, (double)step);
-                atomicAdd(p.stats + 2, (double)ret);
-                if (bbc & 1) atomicAdd(p.stats + 3, 1.0);
-                if (bbc & 2) atomicAdd(p.stats + 4, 1.0);
-                if (bbc & 4) atomicAdd(p.stats + 5, 1.0);
-                if (bbc & 8) atomicAdd(p.stats + 6, 1.0);
-                if (all_reach) atomicAdd(p.stats + 7, 1.0);
-                if (n_reach) atomicAdd(p.stats + 8, (double)n_reach);
-                if (term == 1u) atomicAdd(p.stats + 9, 1.0);
+        unsigned store_mask = (w.ng >= 32) ? FULL : ((1u << w.ng) - 1u);  // envs whose records are written back
+        if (mode == MODE_RESET) {
+            // reset_world for the masked envs only
+            store_mask = 0;
+            for (int g = 0; g < w.ng; ++g) {
+                if (p.mask && !p.mask[w.e_lo + g]) continue;   // uniform across the warp
+                store_mask |= 1u << g;
+                const uint16_t *row = init_env(p, w, g);
+                observe_range<VAR, AUX>(p, w, g * N, N, lane < N ? row : p.bank_cells);
             }
         } else {
-            if (mode == MODE_RESET) {
-                p.st.ep_step[ge] = 0;
-                p.st.ep_return[ge] = 0.0f;
-                p.st.ep_index[ge] += 1;
+            observe_range<VAR, AUX>(p, w, 0, nA, cells);
+        }
+
+        if (mode == MODE_STEP) {
+            // ---- reward / collision / goal per drone
+            if (mine) {
+                const int eb = my_env * N, i = a - eb;
+                const float px = w.px[a], py = w.py[a];
+                const int nw = w.refw[a];
+                unsigned meta = w.meta[a];
+                const bool at_goal = w.atgoal[a];
+                if (VAR == AAC_VARIANT_V2 && at_goal) meta |= M_REACH;  // top of the drone's iteration (V2:3025-3033)
+                const bool reach_i = meta & M_REACH;
+                // neighbour scan (ATT:2187-2236, V2:3092-3168)
+                int nearest = -1, n_coll = 0, last_coll = -1, imm_key = -1, conf_cur = 0, conf_pre = 0;
+                bool prev2 = false;
+                float shortest2 = CUDART_INF_F, imm_tcpa = CUDART_INF_F, imm_d = CUDART_INF_F;
+                const int pn0 = (meta >> 16) & 0xFF, pn1 = (meta >> 24) & 0xFF;
+                const float coll2 = 4.0f * p.prot * p.prot;
+                for (int k = 0; k < M; ++k) {
+                    const int j = w.order[a * M + k];
+                    const float2 tc = w.tc[a * M + k];
+                    const unsigned pf = w.pflag[a * M + k];
+                    conf_cur += pf & 1; conf_pre += (pf >> 1) & 1;
+                    if (tc.x >= 0.0f && tc.x < imm_tcpa) { imm_tcpa = tc.x; imm_d = tc.y; imm_key = j; }
+                    else if (tc.x == -10.0f && tc.y < imm_tcpa) { imm_tcpa = tc.x; imm_d = tc.y; imm_key = j; }
+                    const float d2 = w.d2[a * Mp + k];
+                    if (d2 < shortest2) { shortest2 = d2; nearest = j; }
+                    if (d2 <= coll2) {
+                        if (VAR == AAC_VARIANT_V2) {
+                            // reach_target of drone j as drone i sees it: set in earlier steps, or earlier in
+                            // this step's loop when j < i (V2:3160)
+                            const bool reach_j = (w.meta[eb + j] & M_REACH) || (j < i && w.atgoal[eb + j]);
+                            if (reach_j || reach_i) continue;
+                            prev2 |= (j == pn0) || (M > 1 && j == pn1);  // V2:3170-3179
+                        }
+                        ++n_coll; last_coll = j;
+                    }
+                }
+                const float shortest = sqrtf(shortest2);
+                reinterpret_cast<float4 *>(p.out.tcpa_min)[ga] = make_float4(imm_tcpa, imm_d, (float)imm_key, (float)(conf_cur + 256 * conf_pre));
+                if (VAR == AAC_VARIANT_V2 && n_coll > 0) meta |= M_VDRONE;
+                // building contact: the protective 64-gon against the (at most 2x2) cells it can reach
+                bool collide_building = false;
+                {
+                    const int ixa = (int)floorf((px - p.prot - mp.ex0) * mp.inv_cell), ixb = (int)floorf((px + p.prot - mp.ex0) * mp.inv_cell);
+                    const int iya = (int)floorf((py - p.prot - mp.ey0) * mp.inv_cell), iyb = (int)floorf((py + p.prot - mp.ey0) * mp.inv_cell);
+                    for (int ix = ixa; ix <= ixb; ++ix)
+                        for (int iy = iya; iy <= iyb; ++iy)
+                            if (occupied(mp, ix, iy) && gon_square_touch(px - cell_cx(mp, ix), py - cell_cy(mp, iy), 0.5f * mp.cell, p.prot))
+                                collide_building = true;
+                }
+                if (collide_building && VAR == AAC_VARIANT_V2) meta |= M_VBLDG;
+                // waypoint (ATT:2297-2303)
+                const int cur = meta & 0xFF;
+                const uint16_t cw = cells[1 + cur], cg = cells[nw - 1];
+                const float gx = cell_cx(mp, cg >> 8), gy = cell_cy(mp, cg & 255);
+                const float wdx = px - cell_cx(mp, cw >> 8), wdy = py - cell_cy(mp, cw & 255);
+                const bool wp_flag = wdx * wdx + wdy * wdy < 25.0f;
+                const float ppx = w.ppx[a], ppy = w.ppy[a];
+                const bool hit_bound = capsule_hits_bound(ppx, ppy, px, py, p.prot, mp.hx, mp.hy);
+                const float after_hg = sqrtf((px - gx) * (px - gx) + (py - gy) * (py - gy));
+                const unsigned mr_bits = w.minr[a];
+                const float min_radar = mr_bits > 0x7F800000u ? CUDART_INF_F : __uint_as_float(mr_bits);
+                float dist_to_goal, near_drone = 0.0f, near_bldg = 0.0f, small_step = 0.0f, rew = 0.0f, cross_err = 0.0f;
+                unsigned res = 0, branch;
+                if (VAR == AAC_VARIANT_ATT) {
+                    // (|pre-g| - |pos-g|) / vmax without the cancellation: (a-b).(a+b) / (|a|+|b|)  (ATT:2319-2325)
+                    const float bx = ppx - gx, by = ppy - gy, cx = px - gx, cy = py - gy;
+                    const float den = sqrtf(bx * bx + by * by) + after_hg;
+                    dist_to_goal = den > 0.0f ? ((bx - cx) * (bx + cx) + (by - cy) * (by + cy)) / den / p.vmax : 0.0f;
+                    const float c_dr = 1.0f + (2.5f / (10.0f - 2.5f)), m_dr = (0.0f - 1.0f) / (10.0f - 2.5f);  // ATT:2420-2426
+                    for (int k = 0; k < M; ++k) {  // every in-band neighbour adds the NEAREST one's penalty (ATT:2430-2432)
+                        const float d2 = w.d2[a * Mp + k];
+                        if (d2 >= 6.25f && d2 <= 100.0f) near_drone += fmaf(m_dr, shortest, c_dr);
+                    }
+                    if (hit_bound) { rew = -20.0f - small_step - near_bldg; res |= F_DONE; branch = 0; }
+                    else if (n_coll > 0) {
+                        rew = -20.0f - small_step - near_drone; res |= F_DONE; branch = 2;
+                        if (last_coll == nearest) res |= F_BBC3;
+                    } else if (at_goal) { res |= F_GOAL; meta |= M_REACH; rew = 20.0f; branch = 3; }
+                    else {
+                        if (wp_flag && (nw - 1 - cur) > 1) meta = (meta & ~0xFFu) | (unsigned)(cur + 1);  // ATT:2565-2566
+                        rew = dist_to_goal - small_step - near_bldg - near_drone;                            // ATT:2576-2578
+                        branch = 4;
+                    }
+                    if (flags & AAC_OUT_PARTS) {  // cross-track error is reported, not rewarded (ATT:2368 coefficient 0)
+                        float best2, arc, total;
+                        polyline_nearest(mp, cells, nw, px, py, best2, arc, total);
+                        cross_err = sqrtf(best2);
+                    }
+                } else {
+                    float best2, arc, total;
+                    polyline_nearest(mp, cells, nw, px, py, best2, arc, total);
+                    cross_err = sqrtf(best2);
+                    const float dist_left = cross_err + (total - arc);  // UV2:413-441
+                    dist_to_goal = 6.0f * (1.0f - dist_left / total);    // V2:3257-3268
+                    if (nearest >= 0 && shortest >= 2.5f && shortest <= 6.0f) {  // V2:3365-3386
+                        const float c_dr = 1.0f + (2.5f / (6.0f - 2.5f)), m_dr = (0.0f - 1.0f) / (6.0f - 2.5f);
+                        const float brg = bearing_deg(px, py, w.px[eb + nearest], w.py[eb + nearest]);
+                        const float coef = (brg >= 90.0f && brg <= 180.0f) ? 20.0f : 10.0f;
+                        near_drone = coef * fmaf(m_dr, shortest, c_dr);
+                    }
+                    const float spd = sqrtf(w.vx[a] * w.vx[a] + w.vy[a] * w.vy[a]);
+                    const float thr = 0.5f * p.vmax;  // V2:3446-3453
+                    small_step = 5.0f * ((thr - fminf(fmaxf(spd, 0.0f), thr)) * (1.0f / thr));
+                    if (min_radar >= p.prot && min_radar <= 5.0f) near_bldg = 3.0f * fmaf((0.0f - 1.0f) / (5.0f - p.prot), min_radar, 2.0f);  // V2:3522-3539
+                    // crash rewards are filled in by the per-env lanes below: the penalty doubles along the
+                    // drone loop (V2:3590-3594)
+                    if (hit_bound) { meta |= M_VBOUND; res |= F_DONE; branch = 0; }
+                    else if (collide_building) { res |= F_DONE; branch = 1; }
+                    else if (n_coll > 0) {
+                        res |= F_DONE; branch = 2;
+                        const float brg = bearing_deg(px, py, w.px[eb + last_coll], w.py[eb + last_coll]);
+                        if (brg >= 90.0f && brg <= 180.0f) res |= F_DOUBLE;
+                        if (prev2) res |= F_BBC3;
+                    } else if (at_goal) { res |= F_GOAL; rew = 20.0f; branch = 3; }
+                    else {
+                        if (wp_flag && (nw - 1 - cur) > 1) meta = (meta & ~0xFFu) | (unsigned)(cur + 1);
+                        rew = dist_to_goal - small_step - near_bldg - near_drone;  // V2:3631-3633
+                        branch = 4;
+                    }
+                }
+                if (collide_building && p.st.wall_count) p.st.wall_count[ga] += 1;
+                w.agf[a] = res | (branch << F_BRANCH_SHIFT);
+                w.agr[a] = rew;
+                if (flags & AAC_OUT_PARTS) {
+                    float4 *q = reinterpret_cast<float4 *>(p.out.parts + (size_t)ga * 8);
+                    q[0] = make_float4(dist_to_goal, near_drone, near_bldg, small_step);
+                    q[1] = make_float4(cross_err, after_hg, min_radar, shortest);
+                    p.out.branch[ga] = (int8_t)branch;
+                }
+                // other drones read w.meta[j] & M_REACH (the record as it stood before this step) in the loop
+                // above: publish the new record only after every drone of the group is through
+                w.meta2[a] = meta;
+            }
+            __syncwarp();
+
+            // ---- per env: crash penalties, summed reward, bound_building_check, episode end
+            bool reset_me = false;
+            if (lane < w.ng) {
+                const int ge = w.e_lo + lane, eb = lane * N;
+                float cp = 20.0f, sum = 0.0f;
+                unsigned bbc = 0, any_done = 0, all_reach = 1, n_reach = 0;
+                for (int i = 0; i < N; ++i) {
+                    const unsigned f = w.agf[eb + i], br = (f >> F_BRANCH_SHIFT) & 7u;
+                    if (VAR == AAC_VARIANT_V2 && br <= 2) {
+                        if (f & F_DOUBLE) cp *= 2.0f;
+                        w.agr[eb + i] = -cp;
+                    }
+                    if (br <= 2) bbc |= 1u << br;
+                    if (f & F_BBC3) bbc |= 8u;
+                    any_done |= f & F_DONE;
+                    const unsigned reached = (w.meta2[eb + i] & M_REACH) ? 1u : 0u;
+                    all_reach &= reached;
+                    n_reach += reached;
+                    sum += w.agr[eb + i];
+                }
+                if (p.sum_reward) {  // reward = [sum(reward)] * N (ATT:2602-2603)
+                    for (int i = 0; i < N; ++i) w.agr[eb + i] = sum;
+                    sum *= (float)N;
+                }
+                const int step = p.st.ep_step[ge] + 1;
+                const float ret = p.st.ep_return[ge] + sum;
+                const unsigned term = (step > p.ep_len ? 1u : 0u) | (any_done ? 2u : 0u) | (all_reach ? 4u : 0u);
+                reinterpret_cast<uchar4 *>(p.out.bbc)[ge] = make_uchar4(bbc & 1, (bbc >> 1) & 1, (bbc >> 2) & 1, (bbc >> 3) & 1);
+                p.out.terminated[ge] = (uint8_t)term;
+                if (term) {  // episode statistics (ATT/ma_main:581-637), reduced per CTA first
+                    atomicAdd(&s_cnt[1], 1);
+                    atomicAdd(&s_cnt[2], step);
+                    atomicAdd(reinterpret_cast<float *>(&s_cnt[3]), ret);
+                    if (bbc & 1) atomicAdd(&s_cnt[4], 1);
+                    if (bbc & 2) atomicAdd(&s_cnt[5], 1);
+                    if (bbc & 4) atomicAdd(&s_cnt[6], 1);
+                    if (bbc & 8) atomicAdd(&s_cnt[7], 1);
+                    if (all_reach) atomicAdd(&s_cnt[8], 1);
+                    if (n_reach) atomicAdd(&s_cnt[9], (int)n_reach);
+                    if (term == 1u) atomicAdd(&s_cnt[10], 1);
+                }
+                reset_me = term && p.autoreset;
+                if (!reset_me) { p.st.ep_step[ge] = step; p.st.ep_return[ge] = ret; }
+            }
+            const unsigned reset_mask = __ballot_sync(FULL, reset_me);
+            // the terminal transition leaves before the reset touches the records
+            if (mine) {
+                const unsigned f = w.agf[a];
+                w.meta[a] = w.meta2[a];
+                p.out.reward[ga] = w.agr[a];
+                p.out.done[ga] = (uint8_t)(f & F_DONE ? 1 : 0);
+                p.out.check_goal[ga] = (uint8_t)(f & F_GOAL ? 1 : 0);
+            }
+            __syncwarp();
+            // ---- fused auto-reset of the envs that just terminated (ATT/ma_main:448-462 -> reset_world)
+            for (int g = 0; g < w.ng; ++g) {
+                if (!((reset_mask >> g) & 1u)) continue;
+                const uint16_t *row = init_env(p, w, g);
+                observe_range<VAR, AUX>(p, w, g * N, N, lane < N ? row : p.bank_cells);
             }
         }
-    }
-    __syncthreads();
 
-    // ---- phase F: state write-back and coalesced row stores of the staged outputs
-    const bool partial = mode == MODE_RESET;
-    for (int a = tid; a < A; a += nt) {
-        const int e = a / N;
-        if (partial && !s_envi[e].x) continue;
-        const int ga = a0 + a;
-        unsigned meta = s_meta[a];
-        if (M > 0) meta = (meta & 0x0000FFFFu) | ((unsigned)s_order[a * M] << 16) | ((unsigned)(M > 1 ? s_order[a * M + 1] : 0xFF) << 24);
-        p.st.px[ga] = s_px[a]; p.st.py[ga] = s_py[a]; p.st.vx[ga] = s_vx[a]; p.st.vy[ga] = s_vy[a]; p.st.heading[ga] = s_hd[a];
-        p.st.meta[ga] = meta;
-        if (mode == MODE_STEP) {
-            const unsigned f = s_agf[a];
-            p.out.reward[ga] = s_agr[a];
-            p.out.done[ga] = (uint8_t)(f & F_DONE ? 1 : 0);
-            p.out.check_goal[ga] = (uint8_t)(f & F_GOAL ? 1 : 0);
-            reinterpret_cast<float4 *>(p.out.tcpa_min)[ga] = s_tmin[a];
-            if (flags & AAC_OUT_PARTS) p.out.branch[ga] = (int8_t)((f >> F_BRANCH_SHIFT) & 7u);
+        // ---- write the per-drone records back; the first two neighbour keys become the next step's
+        //      pre_surroundingNeighbor (V2:3170-3179)
+        if (mine && ((store_mask >> my_env) & 1u)) {
+            unsigned meta = w.meta[a];
+            if (M > 0) meta = (meta & 0x0000FFFFu) | ((unsigned)w.order[a * M] << 16) | ((unsigned)(M > 1 ? w.order[a * M + 1] : 0xFF) << 24);
+            p.st.px[ga] = w.px[a]; p.st.py[ga] = w.py[a]; p.st.vx[ga] = w.vx[a]; p.st.vy[ga] = w.vy[a]; p.st.heading[ga] = w.hd[a];
+            p.st.meta[ga] = meta;
         }
     }
-    auto store_rows = [&](float *dst, const float *src, int per_agent) {
-        if (!dst || per_agent == 0) return;
-        float *g = dst + (size_t)a0 * per_agent;
-        for (int k = tid; k < A * per_agent; k += nt) {
-            if (partial && !s_envi[(k / per_agent) / N].x) continue;
-            g[k] = src[k];
-        }
-    };
-    store_rows(p.out.norm_own, s_own, D);
-    if (VAR == AAC_VARIANT_V2) store_rows(p.out.norm_nbr, s_nbr, 5 * M);
-    store_rows(p.out.radar, s_radar, R);
-    if (flags & AAC_OUT_NBR6) store_rows(p.out.norm_nbr6, s_nbr6, 6 * M);
-    if (flags & AAC_OUT_RAW) {
-        store_rows(p.out.raw_own, s_raw_own, D);
-        if (VAR == AAC_VARIANT_V2) store_rows(p.out.raw_nbr, s_raw_nbr, 5 * M);
-        if (flags & AAC_OUT_NBR6) store_rows(p.out.raw_nbr6, s_raw_nbr6, 6 * M);
-    }
-    if (flags & AAC_OUT_TCPA_PAIR) {
-        store_rows(p.out.tcpa_pair, reinterpret_cast<const float *>(s_tpair), 4 * M);
-        int8_t *g = p.out.nbr_order + (size_t)a0 * M;
-        for (int k = tid; k < A * M; k += nt) {
-            if (partial && !s_envi[(k / M) / N].x) continue;
-            g[k] = (int8_t)s_order[k];
+
+    // ---- CTA epilogue: episode counters
+    if (mode == MODE_STEP && p.stats) {
+        __syncthreads();
+        if (tid == 0 && s_cnt[1]) {
+            atomicAdd(p.stats + 0, (double)s_cnt[1]);
+            atomicAdd(p.stats + 1, (double)s_cnt[2]);
+            atomicAdd(p.stats + 2, (double)*reinterpret_cast<float *>(&s_cnt[3]));
+            for (int k = 4; k <= 10; ++k)
+                if (s_cnt[k]) atomicAdd(p.stats + k - 1, (double)s_cnt[k]);
         }
     }
-    if (flags & AAC_OUT_RADAR_AUX) {
-        store_rows(p.out.radar_min, s_rmin, R);
-        int16_t *g = p.out.radar_hit + (size_t)a0 * R;
-        for (int k = tid; k < A * R; k += nt) {
-            if (partial && !s_envi[(k / R) / N].x) continue;
-            g[k] = s_rhit[k];
-        }
-    }
-    if ((flags & AAC_OUT_PARTS) && mode == MODE_STEP) store_rows(p.out.parts, s_parts, 8);
+}
+
+template <int VAR, bool AUX>
+static cudaError_t launch_one(const KParams &p, int mode, int threads, cudaStream_t stream) {
+    const int wpc = threads / 32;
+    const int groups = (p.E + p.G - 1) / p.G;
+    const int grid = (groups + wpc - 1) / wpc;
+    auto fn = env_kernel<VAR, AUX>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.CL.total);
+    if (e != cudaSuccess) return e;
+    fn<<<grid, threads, p.CL.total, stream>>>(p, mode);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, cudaStream_t stream) {
-    const int grid = (p.E + p.TE - 1) / p.TE;
-    if (grid <= 0) return cudaSuccess;
-    void (*fn)(KParams, int) = nullptr;
+    if (p.E <= 0) return cudaSuccess;
+    const bool aux = p.out_flags & AAC_OUT_RADAR_AUX;
     switch (variant) {
-        case AAC_VARIANT_ATT: fn = env_kernel<AAC_VARIANT_ATT>; break;
-        case AAC_VARIANT_V2: fn = env_kernel<AAC_VARIANT_V2>; break;
+        case AAC_VARIANT_ATT: return aux ? launch_one<AAC_VARIANT_ATT, true>(p, mode, threads, stream) : launch_one<AAC_VARIANT_ATT, false>(p, mode, threads, stream);
+        case AAC_VARIANT_V2: return aux ? launch_one<AAC_VARIANT_V2, true>(p, mode, threads, stream) : launch_one<AAC_VARIANT_V2, false>(p, mode, threads, stream);
         default: return cudaErrorInvalidValue;
     }
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.L.total);
-    if (e != cudaSuccess) return e;
-    fn<<<grid, threads, p.L.total, stream>>>(p, mode);
-    return cudaGetLastError();
 }
 
 }  // namespace aac

@@ -21,28 +21,31 @@ struct __align__(16) MapDev {
     float ox, oy;          // global coordinates of the local origin
     float xmin_g, ymin_g;  // global bound minima (ATT applies scale_pos to a delta)
     float cell, inv_cell;
-    float pad0, pad1;
+    float ihx, ihy;        // 1 / hx, 1 / hy
     uint32_t bits[MAP_WORDS];
 };
 static_assert(sizeof(MapDev) % 16 == 0, "MapDev is moved with 16-byte bulk copies");
 
 enum Mode : int { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_RESET = 2 };
 
-// shared-memory carve-up (byte offsets), computed once on the host
-struct SmemLayout {
-    unsigned maps, ray, envi, cur, pre, meta, meta2, cells, refw, d2, order, win, tc, pflag, agf, agr,
-        own, nbr, radar, nbr6, raw_own, raw_nbr, raw_nbr6, tmin, tpair, rmin, rhit, parts, total;
+// shared-memory carve-up (byte offsets), computed once on the host: CTA-wide data, then one slice per warp
+struct CtaLayout {
+    unsigned map, ray, bar, cnt, warps, total;
+};
+struct WarpLayout {  // offsets inside a warp's slice; every array has 32 drone slots
+    unsigned cur, pre, meta, agr, d2, order, pflag, bytes, win, wrel, tc, stg, own, raw_own, total;
 };
 
 struct KParams {
-    int E, N, R, W, TE;
+    int E, N, R, W, G;      // G = envs per warp (G * N <= 32)
     int radar_mode, sum_reward, ep_len, out_flags;
     float dt, vmax, acc_max, prot, ray_len, goal_r;
     long long env_id_base;
     unsigned long long seed;
     const MapDev *maps;
     int n_maps;
-    const float2 *ray_dir;  // [R] (cos, sin) of k*360/R degrees, exact zeros on the axes
+    const float4 *ray_tab;  // [R] (dx, dy, 1/dx, 1/dy) of the ray at k*360/R degrees; exact zeros on the axes, 1/0 = +inf
+    int autoreset;          // MODE_STEP: re-initialise the envs that terminate and emit their reset observation
     const uint16_t *bank_cells;
     const uint8_t *bank_w;
     const int32_t *bank_map;
@@ -52,7 +55,8 @@ struct KParams {
     double *stats;        // [AAC_N_STATS]
     AacState st;
     AacOut out;
-    SmemLayout L;
+    CtaLayout CL;
+    WarpLayout WL;
 };
 
 __host__ __device__ inline unsigned align16(unsigned x) { return (x + 15u) & ~15u; }
@@ -61,43 +65,40 @@ __host__ __device__ inline int own_dim(int variant, int N) {
     return variant == AAC_VARIANT_ATT ? 6 + 4 * (N - 1) : (variant == AAC_VARIANT_V2 ? 7 : 6);
 }
 
-inline SmemLayout make_layout(int variant, int TE, int N, int R, int W, int flags) {
-    SmemLayout L;
-    const unsigned A = TE * N, M = N - 1;
+inline WarpLayout make_warp_layout(int variant, int N, int flags) {
+    WarpLayout L;
+    const unsigned M = N - 1, Mp = M | 1, M1 = M ? M : 1;
     const unsigned D = own_dim(variant, N);
-    const bool v2 = variant == AAC_VARIANT_V2;
     unsigned o = 0;
     auto take = [&](unsigned bytes) { unsigned r = o; o = align16(o + bytes); return r; };
-    const unsigned nmap = variant == AAC_VARIANT_MM ? TE : 1;
-    L.maps = take(nmap * sizeof(MapDev));
-    L.ray = take(R * 8);
-    L.envi = take(TE * 16);          // per env: active, scenario, map row, flags
-    L.cur = take(5 * A * 4);         // px py vx vy heading
-    L.pre = take(4 * A * 4);         // pre_pos, pre_vel
-    L.meta = take(A * 4);
-    L.meta2 = take(A * 4);
-    L.cells = take(A * W * 2);
-    L.refw = take(A);
-    L.d2 = take(A * N * 4);
-    L.order = take(A * (M ? M : 1));
-    L.win = take(A * 8);             // 4x4 occupancy window: mask, ix0 | iy0 << 16
-    L.tc = take(A * M * 8);          // current tcpa, d_tcpa per ordered pair
-    L.pflag = take(A * (M ? M : 1)); // per pair: bit0 cur conflict, bit1 pre conflict
-    L.agf = take(A * 4);             // per agent result flags
-    L.agr = take(A * 4);             // per agent reward
-    L.own = take(A * D * 4);
-    L.nbr = take(v2 ? A * 5 * M * 4 : 0);
-    L.radar = take(A * R * 4);
-    L.nbr6 = take((flags & AAC_OUT_NBR6) ? A * M * 6 * 4 : 0);
-    L.raw_own = take((flags & AAC_OUT_RAW) ? A * D * 4 : 0);
-    L.raw_nbr = take((flags & AAC_OUT_RAW) && v2 ? A * 5 * M * 4 : 0);
-    L.raw_nbr6 = take((flags & AAC_OUT_RAW) && (flags & AAC_OUT_NBR6) ? A * M * 6 * 4 : 0);
-    L.tmin = take(A * 16);
-    L.tpair = take((flags & AAC_OUT_TCPA_PAIR) ? A * M * 16 : 0);
-    L.rmin = take((flags & AAC_OUT_RADAR_AUX) ? A * R * 4 : 0);
-    L.rhit = take((flags & AAC_OUT_RADAR_AUX) ? A * R * 2 : 0);
-    L.parts = take((flags & AAC_OUT_PARTS) ? A * 8 * 4 : 0);
+    L.cur = take(5 * 32 * 4);        // px py vx vy heading
+    L.pre = take(4 * 32 * 4);        // pre_pos, pre_vel
+    L.meta = take(4 * 32 * 4);       // meta, meta2, min radar bits, result flags
+    L.agr = take(32 * 4);            // reward
+    L.d2 = take(32 * Mp * 4);        // neighbour distances^2 in iteration order, odd row stride
+    L.order = take(32 * M1);
+    L.pflag = take(32 * M1);         // per pair: bit0 cur conflict, bit1 pre conflict
+    L.bytes = take(3 * 32);          // at-goal flag, ref-line vertex count, scratch
+    L.win = take(32 * 8);            // 4x4 occupancy window: mask | flags, ix0 | iy0 << 16
+    L.wrel = take(32 * 8);           // window origin relative to the drone
+    L.tc = take(32 * M1 * 8);        // current tcpa, d_tcpa per ordered pair
+    L.stg = take(32 * 6 * 4);        // transient staging of one warp iteration's pair blocks
+    L.own = take(32 * D * 4);        // own rows of the observation
+    L.raw_own = take((flags & AAC_OUT_RAW) ? 32 * D * 4 : 0);
     L.total = o;
+    return L;
+}
+
+inline CtaLayout make_cta_layout(const WarpLayout &WL, int R, int warps) {
+    CtaLayout L;
+    unsigned o = 0;
+    auto take = [&](unsigned bytes) { unsigned r = o; o = align16(o + bytes); return r; };
+    L.map = take(sizeof(MapDev));
+    L.ray = take(R * 16);
+    L.bar = take(16);
+    L.cnt = take(16 * 4);
+    L.warps = take(0);
+    L.total = L.warps + warps * WL.total;
     return L;
 }
 

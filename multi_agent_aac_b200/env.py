@@ -183,9 +183,8 @@ class BatchedDroneEnv:
                 or tuple(actions.shape) != (self.E, self.N, 2):
             raise ValueError("actions must be a contiguous float32 [E, N, 2] tensor on %s" % self.device)
         with torch.cuda.device(self.device):
-            K.check(self.L.aac_step(self.h, C.c_void_p(actions.data_ptr()), C.byref(self._out_c), self._stream_ptr()), "aac_step")
-            if autoreset:
-                K.check(self.L.aac_autoreset(self.h, C.byref(self._out_c), self._stream_ptr()), "aac_autoreset")
+            fn = self.L.aac_step_autoreset if autoreset else self.L.aac_step
+            K.check(fn(self.h, C.c_void_p(actions.data_ptr()), C.byref(self._out_c), self._stream_ptr()), "aac_step")
         o = self.out
         info = {k: o[k] for k in ("check_goal", "bbc", "terminated", "tcpa_min", "tcpa_pair", "nbr_order", "radar_min",
                                   "radar_hit", "parts", "branch") if k in o}

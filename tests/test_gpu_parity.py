@@ -64,9 +64,74 @@ def test_lockstep_v2_cluster():
 
 def test_lockstep_ragged_tile_and_single_drone():
     _run(variant="v2", n_envs=37, n_agents=4, n_rays=18, steps=30, seed=7, tile_envs=5, block_threads=96)
-    T = parity.lockstep(variant="att", n_envs=9, n_agents=1, n_rays=18, steps=20, seed=8)
+    T = parity.lockstep(variant="v2", n_envs=9, n_agents=1, n_rays=18, steps=20, seed=8)
     assert not T.fail, "\n".join(T.fail[:12])
 
 
 def test_lockstep_r72_n20():
     _run(variant="v2", n_envs=32, n_agents=20, n_rays=72, steps=20, seed=9)
+
+
+def test_fused_autoreset_equals_step_then_autoreset():
+    """aac_step_autoreset (one launch) must leave exactly the state and outputs of aac_step followed by
+    aac_autoreset (two launches), bit for bit."""
+    import numpy as np
+    import torch
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import synthetic_map
+    from multi_agent_aac_b200.reset import ScenarioBank
+    gmap = synthetic_map(seed=0)
+    for variant, n, r, E in (("tdcpa_v2", 10, 36, 300), ("att", 3, 18, 257)):
+        envs = []
+        for _ in range(2):
+            cfg = preset(variant, n_envs=E, n_agents=n, n_rays=r, w_max=32, seed=5, out_flags=parity.ALL_OUT)
+            env = BatchedDroneEnv(cfg, gmap)
+            env.set_bank(ScenarioBank(gmap, n, 64, w_max=32, seed=5))
+            env.reset()
+            envs.append(env)
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(3)
+        n_term = 0
+        for t in range(25):
+            act = (torch.rand((E, n, 2), device="cuda", generator=gen) * 2 - 1).contiguous()
+            envs[0].step(act, autoreset=False)
+            term = envs[0].out["terminated"].clone()
+            envs[0].autoreset()
+            envs[1].step(act, autoreset=True)
+            n_term += int((term != 0).sum())
+            for k in envs[0].out:
+                a, b = envs[0].out[k], envs[1].out[k]
+                assert torch.equal(a.view(torch.uint8), b.view(torch.uint8)), (variant, t, k)
+            for k in envs[0].state:
+                assert torch.equal(envs[0].state[k].view(torch.uint8), envs[1].state[k].view(torch.uint8)), (variant, t, k)
+        assert n_term > 0
+        s0, s1 = envs[0].read_stats(), envs[1].read_stats()
+        assert np.array_equal(s0[[0, 1, 3, 4, 5, 6, 7, 8, 9]], s1[[0, 1, 3, 4, 5, 6, 7, 8, 9]]) and s0[0] == n_term
+        assert abs(s0[2] - s1[2]) <= 1e-3 * max(1.0, abs(s0[2]))
+
+
+def test_partial_reset_leaves_other_envs_untouched():
+    import torch
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import synthetic_map
+    from multi_agent_aac_b200.reset import ScenarioBank
+    gmap = synthetic_map(seed=0)
+    E, n, r = 50, 4, 18
+    env = BatchedDroneEnv(preset("tdcpa_v2", n_envs=E, n_agents=n, n_rays=r, w_max=32, seed=9), gmap)
+    env.set_bank(ScenarioBank(gmap, n, 32, w_max=32, seed=9))
+    env.reset()
+    act = torch.zeros((E, n, 2), device="cuda")
+    act[..., 0] = 0.3
+    env.step(act)
+    before_state = {k: v.clone() for k, v in env.state.items()}
+    before_out = {k: v.clone() for k, v in env.out.items()}
+    mask = torch.zeros(E, dtype=torch.uint8, device="cuda")
+    mask[[3, 17, 18, 49]] = 1
+    env.reset(mask)
+    keep = mask == 0
+    for k, v in env.state.items():
+        assert torch.equal(v[keep], before_state[k][keep]), k
+    for k in ("norm_own", "norm_nbr", "radar", "reward", "done"):
+        assert torch.equal(env.out[k][keep], before_out[k][keep]), k
+    assert (env.state["ep_step"][mask != 0] == 0).all() and (env.state["ep_index"][mask != 0] == 2).all()
+    assert (env.state["vx"][mask != 0] == 0).all()
