@@ -68,7 +68,7 @@ def nvcc_command(out=LIB_PATH):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-prec-div=false", "-prec-sqrt=false",
             "-Xcompiler", "-fPIC", "-shared", "-o", out] + SOURCES
 
 

@@ -3,6 +3,7 @@
 // except where the header says so.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -27,6 +28,8 @@ struct AacEnv {
     int n_scen = 0;
     float *d_actions = nullptr;  // staging for aac_step_host
     double *d_stats = nullptr;
+    int *d_work = nullptr;       // ping-pong group counters of the persistent kernel
+    int sms = 0;
     AacState st{};
     bool bound = false;
     int64_t launches = 0;
@@ -97,6 +100,9 @@ extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
     }
     CU(cudaMalloc(&env->d_ray, sizeof(float4) * cfg->n_rays));
     CU(cudaMemcpy(env->d_ray, rays.data(), sizeof(float4) * cfg->n_rays, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&env->d_work, 2 * sizeof(int)));
+    CU(cudaMemset(env->d_work, 0, 2 * sizeof(int)));
+    CU(cudaDeviceGetAttribute(&env->sms, cudaDevAttrMultiProcessorCount, env->device));
     CU(cudaMalloc(&env->d_stats, sizeof(double) * AAC_N_STATS));
     CU(cudaMemset(env->d_stats, 0, sizeof(double) * AAC_N_STATS));
     *out = env;
@@ -112,6 +118,7 @@ extern "C" void aac_destroy(AacEnv *env) {
     cudaFree(env->d_bank_map);
     cudaFree(env->d_actions);
     cudaFree(env->d_stats);
+    cudaFree(env->d_work);
     delete env;
 }
 
@@ -214,8 +221,10 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     p.maps = env->d_maps; p.n_maps = env->n_maps; p.ray_tab = env->d_ray; p.autoreset = autoreset;
     p.bank_cells = env->d_bank_cells; p.bank_w = env->d_bank_w; p.bank_map = env->d_bank_map; p.n_scen = env->n_scen;
     p.mask = mask; p.actions = actions; p.stats = env->d_stats;
+    p.work = env->d_work; p.parity = (int)(env->launches & 1);
+    { const char *v = getenv("AAC_CTA_SYNC"); p.cta_sync = v ? atoi(v) : 0; }
     p.st = env->st; p.out = *out; p.CL = env->cl; p.WL = env->wl;
-    cudaError_t e = launch_env_kernel(c.variant, p, mode, env->threads, (cudaStream_t)stream);
+    cudaError_t e = launch_env_kernel(c.variant, p, mode, env->threads, env->sms, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "env_kernel launch");
     env->launches += 1;
     return 0;

@@ -134,7 +134,7 @@ __device__ __forceinline__ bool occupied(const MapDev &m, int ix, int iy) {
 // max over the 64 edge normals of n . (ax, ay) for ax, ay >= 0 (attained in the first quadrant)
 __device__ __forceinline__ float support64_q1(float ax, float ay) {
     float m = -CUDART_INF_F;
-#pragma unroll
+#pragma unroll 2
     for (int i = 0; i < 16; ++i) m = fmaxf(m, fmaf(c_n16[i].x, ax, c_n16[i].y * ay));
     return m;
 }
@@ -208,7 +208,7 @@ __device__ __forceinline__ void tcpa_dcpa(float hpx, float hpy, float hvx, float
 }
 
 // UV2:31-44
-__device__ __forceinline__ float bearing_deg(float xh, float yh, float xi, float yi) {
+__device__ __noinline__ float bearing_deg(float xh, float yh, float xi, float yi) {
     const float th = atan2f(yi - yh, xi - xh) * 57.29577951308232f;
     return th < 0.0f ? -th : 360.0f - th;
 }
@@ -248,38 +248,30 @@ __device__ __forceinline__ void radar_bounds(const MapDev &mp, float px, float p
     }
 }
 
-// Fast path.  One ray against the occupied cells of the drone's 4x4 window (V2:1210-1300).  The slab
-// parameters of the 5 + 5 grid lines bounding the window are computed once per ray; every occupied
-// cell then costs two max/min pairs.  `wrel` = window origin relative to the drone.  Visiting order is
-// ascending (ix, iy) = ascending cell index, so `sensed` ends as the reference's last hit.
+// Fast path.  One ray against the occupied cells of the drone's 4x4 window (V2:1210-1300): a slab test per
+// set bit of the window mask, lowest bit first = ascending (ix, iy) = ascending cell index, so `sensed`
+// ends as the reference's last hit.  `wrel` = window origin relative to the drone.  The loop
+// is deliberately not unrolled: all lanes of a warp iteration work on the same drone, so the trip count
+// is warp-uniform and the body stays resident in the instruction cache.
 // Axis-parallel rays carry 1/d = +inf: the products are +-inf (or NaN exactly on a grid line, which
 // fminf / fmaxf drop), i.e. no constraint from that axis.
 template <bool AUX>
 __device__ __forceinline__ void radar_window(const MapDev &mp, float2 wrel, unsigned win, int wix0, int wiy0, float4 ray, float len,
                                              float &shortest, float &sensed, int &shortest_id, int &sensed_id) {
-    float tx[5], ty[5];
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        tx[q] = fmaf((float)q, mp.cell, wrel.x) * ray.z;
-        ty[q] = fmaf((float)q, mp.cell, wrel.y) * ray.w;
-    }
-    float eny[4], exy[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) { eny[c] = fminf(ty[c], ty[c + 1]); exy[c] = fmaxf(ty[c], ty[c + 1]); }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        if (!((win >> (4 * r)) & 0xFu)) continue;
-        const float enx = fmaxf(fminf(tx[r], tx[r + 1]), 0.0f), exx = fminf(fmaxf(tx[r], tx[r + 1]), 1.0f);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (!((win >> (4 * r + c)) & 1u)) continue;
-            const float lo = fmaxf(enx, eny[c]), hi = fminf(exx, exy[c]);
-            if (lo <= hi) {
-                const float d = lo * len;
-                sensed = d;
-                if (AUX) sensed_id = (wix0 + r) * mp.gy + wiy0 + c;
-                if (d < shortest) { shortest = d; if (AUX) shortest_id = (wix0 + r) * mp.gy + wiy0 + c; }
-            }
+#pragma unroll 1
+    while (win) {
+        const int b = __ffs(win) - 1;
+        win &= win - 1;
+        const int r = b >> 2, c = b & 3;
+        const float x0 = fmaf((float)r, mp.cell, wrel.x), y0 = fmaf((float)c, mp.cell, wrel.y);
+        const float tx0 = x0 * ray.z, tx1 = (x0 + mp.cell) * ray.z, ty0 = y0 * ray.w, ty1 = (y0 + mp.cell) * ray.w;
+        const float lo = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), 0.0f);
+        const float hi = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), 1.0f);
+        if (lo <= hi) {
+            const float d = lo * len;
+            sensed = d;
+            if (AUX) sensed_id = (wix0 + r) * mp.gy + wiy0 + c;
+            if (d < shortest) { shortest = d; if (AUX) shortest_id = (wix0 + r) * mp.gy + wiy0 + c; }
         }
     }
 }
@@ -367,6 +359,7 @@ struct Warp {
     uint8_t *order, *pflag, *atgoal, *refw, *rs;
     uint2 *win;
     float2 *wrel, *tc;
+    const uint16_t *cells[1];  // unused placeholder (cells are read from global rows, see cells_of)
 };
 
 // lanes hold PI floats each for the items [0, n_valid) of one warp iteration; the block leaves as
@@ -427,7 +420,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
         const float wx = mp.ex0 + ix0 * mp.cell - px, wy = mp.ey0 + iy0 * mp.cell - py;
         // drop the corner cells no ray of length ray_len can reach; flag the rare geometries
         unsigned keep = 0, slow = (ix0 != rx0 || iy0 != ry0) ? W_SLOW : 0u;
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < 4; ++r) {
             const float nx = fmaxf(fmaxf(wx + r * mp.cell, -(wx + (r + 1) * mp.cell)), 0.0f);
 #pragma unroll
@@ -497,18 +490,16 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
         }
     }
 
-    // ---- radar, one work item per (drone, ray); stores are item-major, i.e. already coalesced
+    // ---- radar.  A warp iteration covers 32 rays of ONE drone (window mask, bounds flag and position are
+    //      then warp-uniform: no divergence in the cell loop); the R % 32 leftover rays of several drones
+    //      are packed into shared iterations.  Ranges are >= 0, so their bit patterns order like unsigned
+    //      integers and nan (0x7FC00000) sorts above every number: the per-drone minimum the reward needs
+    //      (min_radar) is one redux.sync per drone and iteration.
     {
-        const int n_items = n_ag * R;
-        const size_t rg0 = (size_t)(w.a0 + a_lo) * R;
-        for (Walk it(lane, 32, R); it.hi * R + it.lo - lane < n_items; it.next()) {
-            const int idx = it.hi * R + it.lo;
-            const bool ok = idx < n_items;
-            const int aa = a_lo + (ok ? it.hi : 0), k = ok ? it.lo : 0;
+        const float len = p.ray_len;
+        auto cast = [&](const int aa, const int k, float &out_min, int &id) -> float {
             const float4 ray = w.ray[k];
-            const float len = p.ray_len;
-            float out, out_min;
-            int id = -1;
+            float out;
             if (VAR == AAC_VARIANT_ATT) {
                 const int ebb = (aa / N) * N;
                 radar_drones_ray(w.px, w.py, ebb, N, aa - ebb, ray, len, p.prot, mp.gx * mp.gy + 4, out, id);
@@ -528,17 +519,48 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
                 out = last_hit ? sensed : out_min;
                 if (AUX) id = last_hit ? sensed_id : shortest_id;
             }
-            if (ok) {
-                p.out.radar[rg0 + idx] = out;
-                if (AUX) { p.out.radar_min[rg0 + idx] = out_min; p.out.radar_hit[rg0 + idx] = (int16_t)id; }
+            return out;
+        };
+        const int full = R >> 5, rem = R & 31;
+        const size_t rg0 = (size_t)(w.a0 + a_lo) * R;
+        float *g_out = p.out.radar + rg0;
+        // full chunks: lanes = rays 32c .. 32c+31 of drone q
+#pragma unroll 1
+        for (int q = 0; q < n_ag; ++q) {
+#pragma unroll 1
+            for (int c = 0; c < full; ++c) {
+                const int k = (c << 5) + lane;
+                float out_min;
+                int id = -1;
+                const float out = cast(a_lo + q, k, out_min, id);
+                g_out[q * R + k] = out;
+                if (AUX) { p.out.radar_min[rg0 + q * R + k] = out_min; p.out.radar_hit[rg0 + q * R + k] = (int16_t)id; }
+                const unsigned m = __reduce_min_sync(FULL, __float_as_uint(out));
+                if (lane == 0) w.minr[a_lo + q] = min(w.minr[a_lo + q], m);
             }
-            // per-drone minimum of the stored ranges (the reward's min_radar): ranges are >= 0, so their
-            // bit patterns order like unsigned integers and nan (0x7FC00000) sorts above every number
-            const unsigned key = ok ? __float_as_uint(out) : 0xFFFFFFFFu;
-            const int a_first = __shfl_sync(FULL, aa, 0), a_last = __shfl_sync(FULL, aa, min(31, n_items - (idx - lane) - 1));
-            for (int q = a_first; q <= a_last; ++q) {
-                const unsigned m = __reduce_min_sync(FULL, aa == q ? key : 0xFFFFFFFFu);
-                if (lane == 0) w.minr[q] = min(w.minr[q], m);
+        }
+        // leftover rays: `per` drones share an iteration, `rem` lanes each
+        if (rem) {
+            const int per = 32 / rem;
+            const int sub = lane / rem, k = (full << 5) + lane - sub * rem;
+#pragma unroll 1
+            for (int q0 = 0; q0 < n_ag; q0 += per) {
+                const int nsub = min(per, n_ag - q0);
+                const bool ok = sub < nsub;
+                const int q = q0 + (ok ? sub : 0);
+                float out_min;
+                int id = -1;
+                const float out = cast(a_lo + q, k, out_min, id);
+                if (ok) {
+                    g_out[q * R + k] = out;
+                    if (AUX) { p.out.radar_min[rg0 + q * R + k] = out_min; p.out.radar_hit[rg0 + q * R + k] = (int16_t)id; }
+                }
+                const unsigned key = ok ? __float_as_uint(out) : 0xFFFFFFFFu;
+#pragma unroll 1
+                for (int s2 = 0; s2 < nsub; ++s2) {
+                    const unsigned m = __reduce_min_sync(FULL, sub == s2 ? key : 0xFFFFFFFFu);
+                    if (lane == s2) w.minr[a_lo + q0 + s2] = min(w.minr[a_lo + q0 + s2], m);
+                }
             }
         }
     }
@@ -624,36 +646,30 @@ __device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp
 __device__ __forceinline__ void polyline_nearest(const MapDev &mp, const uint16_t *cells, int nw, float px, float py, float &best2, float &arc,
                                                  float &total) {
     best2 = CUDART_INF_F; arc = 0.0f;
-    float run = 0.0f, ax = 0.0f, ay = 0.0f;
-    for (int c8 = 0; c8 < nw; c8 += 8) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(cells + c8);
-        const unsigned wd[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int k = c8 + q;
-            if (k >= nw) break;
-            const unsigned c = (wd[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
-            const float bx = cell_cx(mp, c >> 8), by = cell_cy(mp, c & 255);
-            if (k > 0) {
-                const float sx = bx - ax, sy = by - ay, len2 = sx * sx + sy * sy;
-                const float sl = sqrtf(len2);
-                float rr = len2 > 0.0f ? __fdividef((px - ax) * sx + (py - ay) * sy, len2) : 0.0f;
-                rr = fminf(fmaxf(rr, 0.0f), 1.0f);
-                const float qx = fmaf(rr, sx, ax) - px, qy = fmaf(rr, sy, ay) - py;
-                const float dq = qx * qx + qy * qy;
-                if (dq < best2) { best2 = dq; arc = fmaf(rr, sl, run); }
-                run += sl;
-            }
-            ax = bx; ay = by;
-        }
+    float run = 0.0f;
+    unsigned c = cells[0];
+    float ax = cell_cx(mp, c >> 8), ay = cell_cy(mp, c & 255);
+#pragma unroll 1
+    for (int k = 1; k < nw; ++k) {
+        c = cells[k];
+        const float bx = cell_cx(mp, c >> 8), by = cell_cy(mp, c & 255);
+        const float sx = bx - ax, sy = by - ay, len2 = sx * sx + sy * sy;
+        const float sl = sqrtf(len2);
+        float rr = len2 > 0.0f ? __fdividef((px - ax) * sx + (py - ay) * sy, len2) : 0.0f;
+        rr = fminf(fmaxf(rr, 0.0f), 1.0f);
+        const float qx = fmaf(rr, sx, ax) - px, qy = fmaf(rr, sy, ay) - py;
+        const float dq = qx * qx + qy * qy;
+        if (dq < best2) { best2 = dq; arc = fmaf(rr, sl, run); }
+        run += sl;
+        ax = bx; ay = by;
     }
     total = run;
 }
 
 template <int VAR, bool AUX>
-__global__ void __launch_bounds__(MAX_THREADS) env_kernel(const __grid_constant__ KParams p, const int mode) {
+__global__ void __launch_bounds__(MAX_THREADS, 3) env_kernel(const __grid_constant__ KParams p, const int mode) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpc = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, M = N - 1, W = p.W, G = p.G;
     const int Mp = M | 1;
     const int flags = p.out_flags;
@@ -663,27 +679,23 @@ __global__ void __launch_bounds__(MAX_THREADS) env_kernel(const __grid_constant_
     MapDev *s_map = reinterpret_cast<MapDev *>(smem + CL.map);
     float4 *s_ray = reinterpret_cast<float4 *>(smem + CL.ray);
     unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem + CL.bar);
-    int *s_cnt = reinterpret_cast<int *>(smem + CL.cnt);
 
-    // ---- CTA prologue: the map arrives by one TMA bulk copy, the ray table by plain loads
+    // ---- CTA prologue: the map arrives by one TMA bulk copy, the ray table by plain loads.  This is the
+    //      only CTA-wide synchronisation of the kernel.
     if (tid == 0) {
         mbar_init(s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(s_bar, sizeof(MapDev));
         bulk_g2s(s_map, p.maps, sizeof(MapDev), s_bar);
+        if (blockIdx.x == 0) p.work[p.parity ^ 1] = 0;   // the next launch's group counter
     }
     for (int k = tid; k < p.R; k += blockDim.x) s_ray[k] = p.ray_tab[k];
-    if (tid < 16) s_cnt[tid] = 0;
     __syncthreads();
     mbar_wait(s_bar, 0);
 
     unsigned char *ws = smem + CL.warps + (size_t)warp * WL.total;
     Warp w;
     w.map = s_map; w.ray = s_ray; w.lane = lane;
-    w.e_lo = (blockIdx.x * wpc + warp) * G;
-    w.ng = min(G, p.E - w.e_lo);
-    w.a0 = w.e_lo * N;
-    w.nA = w.ng * N;
     w.px = reinterpret_cast<float *>(ws + WL.cur); w.py = w.px + 32; w.vx = w.py + 32; w.vy = w.vx + 32; w.hd = w.vy + 32;
     w.ppx = reinterpret_cast<float *>(ws + WL.pre); w.ppy = w.ppx + 32; w.pvx = w.ppy + 32; w.pvy = w.pvx + 32;
     w.meta = reinterpret_cast<unsigned *>(ws + WL.meta); w.meta2 = w.meta + 32; w.minr = w.meta2 + 32; w.agf = w.minr + 32;
@@ -698,7 +710,29 @@ __global__ void __launch_bounds__(MAX_THREADS) env_kernel(const __grid_constant_
     w.tc = reinterpret_cast<float2 *>(ws + WL.tc);
     const MapDev &mp = *s_map;
 
-    if (w.ng > 0) {
+    // episode counters of this lane's envs (ATT/ma_main:581-637), flushed once per warp
+    int st_ep = 0, st_steps = 0, st_bits[7] = {0, 0, 0, 0, 0, 0, 0};
+    float st_ret = 0.0f;
+
+    // ---- persistent warp: fetch a group of G whole envs, run the pipeline, fetch the next
+    const int n_groups = (p.E + G - 1) / G;
+    for (;;) {
+        int gi = 0;
+        if (p.cta_sync) {   // whole CTA fetches together: warps stay in phase (instruction-cache locality)
+            __syncthreads();
+            if (tid == 0) *reinterpret_cast<int *>(s_bar + 1) = atomicAdd(&p.work[p.parity], (int)(blockDim.x >> 5));
+            __syncthreads();
+            gi = *reinterpret_cast<int *>(s_bar + 1) + warp;
+            if (gi - warp >= n_groups) break;
+        } else {
+            if (lane == 0) gi = atomicAdd(&p.work[p.parity], 1);
+            gi = __shfl_sync(FULL, gi, 0);
+            if (gi >= n_groups) break;
+        }
+        w.e_lo = gi * G;
+        w.ng = max(0, min(G, p.E - w.e_lo));
+        w.a0 = w.e_lo * N;
+        w.nA = w.ng * N;
         const int nA = w.nA, a0 = w.a0;
         const bool mine = lane < nA;
         const int a = lane, ga = a0 + lane;
@@ -729,21 +763,28 @@ __global__ void __launch_bounds__(MAX_THREADS) env_kernel(const __grid_constant_
         }
         __syncwarp();
 
-        unsigned store_mask = (w.ng >= 32) ? FULL : ((1u << w.ng) - 1u);  // envs whose records are written back
+        // Jobs of a group: job 0 = the whole group (step / observe), job g+1 = env g alone after it has been
+        // re-initialised (reset mode: the masked envs; step mode: the envs that just terminated).  One copy
+        // of the pipeline serves them all.
+        unsigned reset_mask = 0, store_mask = (w.ng >= 32) ? FULL : ((1u << w.ng) - 1u);
         if (mode == MODE_RESET) {
-            // reset_world for the masked envs only
-            store_mask = 0;
-            for (int g = 0; g < w.ng; ++g) {
-                if (p.mask && !p.mask[w.e_lo + g]) continue;   // uniform across the warp
-                store_mask |= 1u << g;
-                const uint16_t *row = init_env(p, w, g);
-                observe_range<VAR, AUX>(p, w, g * N, N, lane < N ? row : p.bank_cells);
-            }
-        } else {
-            observe_range<VAR, AUX>(p, w, 0, nA, cells);
+            bool m = lane < w.ng && (!p.mask || p.mask[w.e_lo + lane]);
+            reset_mask = __ballot_sync(FULL, m);
+            store_mask = reset_mask;
         }
+        for (int job = (mode == MODE_RESET ? 1 : 0); job <= w.ng; ++job) {
+            int a_lo = 0, n_ag = nA;
+            const uint16_t *cl = cells;
+            if (job > 0) {
+                const int g = job - 1;
+                if (!((reset_mask >> g) & 1u)) continue;
+                const uint16_t *row = init_env(p, w, g);
+                a_lo = g * N; n_ag = N;
+                cl = lane < N ? row : p.bank_cells;
+            }
+            observe_range<VAR, AUX>(p, w, a_lo, n_ag, cl);
+            if (job > 0 || mode != MODE_STEP) continue;
 
-        if (mode == MODE_STEP) {
             // ---- reward / collision / goal per drone
             if (mine) {
                 const int eb = my_env * N, i = a - eb;
@@ -884,6 +925,7 @@ __global__ void __launch_bounds__(MAX_THREADS) env_kernel(const __grid_constant_
                 const int ge = w.e_lo + lane, eb = lane * N;
                 float cp = 20.0f, sum = 0.0f;
                 unsigned bbc = 0, any_done = 0, all_reach = 1, n_reach = 0;
+#pragma unroll 1
                 for (int i = 0; i < N; ++i) {
                     const unsigned f = w.agf[eb + i], br = (f >> F_BRANCH_SHIFT) & 7u;
                     if (VAR == AAC_VARIANT_V2 && br <= 2) {
@@ -899,6 +941,7 @@ __global__ void __launch_bounds__(MAX_THREADS) env_kernel(const __grid_constant_
                     sum += w.agr[eb + i];
                 }
                 if (p.sum_reward) {  // reward = [sum(reward)] * N (ATT:2602-2603)
+#pragma unroll 1
                     for (int i = 0; i < N; ++i) w.agr[eb + i] = sum;
                     sum *= (float)N;
                 }
@@ -907,22 +950,15 @@ __global__ void __launch_bounds__(MAX_THREADS) env_kernel(const __grid_constant_
                 const unsigned term = (step > p.ep_len ? 1u : 0u) | (any_done ? 2u : 0u) | (all_reach ? 4u : 0u);
                 reinterpret_cast<uchar4 *>(p.out.bbc)[ge] = make_uchar4(bbc & 1, (bbc >> 1) & 1, (bbc >> 2) & 1, (bbc >> 3) & 1);
                 p.out.terminated[ge] = (uint8_t)term;
-                if (term) {  // episode statistics (ATT/ma_main:581-637), reduced per CTA first
-                    atomicAdd(&s_cnt[1], 1);
-                    atomicAdd(&s_cnt[2], step);
-                    atomicAdd(reinterpret_cast<float *>(&s_cnt[3]), ret);
-                    if (bbc & 1) atomicAdd(&s_cnt[4], 1);
-                    if (bbc & 2) atomicAdd(&s_cnt[5], 1);
-                    if (bbc & 4) atomicAdd(&s_cnt[6], 1);
-                    if (bbc & 8) atomicAdd(&s_cnt[7], 1);
-                    if (all_reach) atomicAdd(&s_cnt[8], 1);
-                    if (n_reach) atomicAdd(&s_cnt[9], (int)n_reach);
-                    if (term == 1u) atomicAdd(&s_cnt[10], 1);
+                if (term) {
+                    st_ep += 1; st_steps += step; st_ret += ret;
+                    st_bits[0] += bbc & 1; st_bits[1] += (bbc >> 1) & 1; st_bits[2] += (bbc >> 2) & 1; st_bits[3] += (bbc >> 3) & 1;
+                    st_bits[4] += all_reach; st_bits[5] += n_reach; st_bits[6] += term == 1u;
                 }
                 reset_me = term && p.autoreset;
                 if (!reset_me) { p.st.ep_step[ge] = step; p.st.ep_return[ge] = ret; }
             }
-            const unsigned reset_mask = __ballot_sync(FULL, reset_me);
+            reset_mask = __ballot_sync(FULL, reset_me);
             // the terminal transition leaves before the reset touches the records
             if (mine) {
                 const unsigned f = w.agf[a];
@@ -932,12 +968,6 @@ __global__ void __launch_bounds__(MAX_THREADS) env_kernel(const __grid_constant_
                 p.out.check_goal[ga] = (uint8_t)(f & F_GOAL ? 1 : 0);
             }
             __syncwarp();
-            // ---- fused auto-reset of the envs that just terminated (ATT/ma_main:448-462 -> reset_world)
-            for (int g = 0; g < w.ng; ++g) {
-                if (!((reset_mask >> g) & 1u)) continue;
-                const uint16_t *row = init_env(p, w, g);
-                observe_range<VAR, AUX>(p, w, g * N, N, lane < N ? row : p.bank_cells);
-            }
         }
 
         // ---- write the per-drone records back; the first two neighbour keys become the next step's
@@ -948,39 +978,58 @@ __global__ void __launch_bounds__(MAX_THREADS) env_kernel(const __grid_constant_
             p.st.px[ga] = w.px[a]; p.st.py[ga] = w.py[a]; p.st.vx[ga] = w.vx[a]; p.st.vy[ga] = w.vy[a]; p.st.heading[ga] = w.hd[a];
             p.st.meta[ga] = meta;
         }
+        __syncwarp();
     }
 
-    // ---- CTA epilogue: episode counters
+    // ---- warp epilogue: episode counters (ATT/ma_main:581-637), one set of atomics per warp
     if (mode == MODE_STEP && p.stats) {
-        __syncthreads();
-        if (tid == 0 && s_cnt[1]) {
-            atomicAdd(p.stats + 0, (double)s_cnt[1]);
-            atomicAdd(p.stats + 1, (double)s_cnt[2]);
-            atomicAdd(p.stats + 2, (double)*reinterpret_cast<float *>(&s_cnt[3]));
-            for (int k = 4; k <= 10; ++k)
-                if (s_cnt[k]) atomicAdd(p.stats + k - 1, (double)s_cnt[k]);
+        const int ep = __reduce_add_sync(FULL, st_ep);
+        if (ep) {
+            const int steps = __reduce_add_sync(FULL, st_steps);
+            float ret = st_ret;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ret += __shfl_xor_sync(FULL, ret, o);
+            int b[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) b[k] = __reduce_add_sync(FULL, st_bits[k]);
+            if (lane == 0) {
+                atomicAdd(p.stats + 0, (double)ep);
+                atomicAdd(p.stats + 1, (double)steps);
+                atomicAdd(p.stats + 2, (double)ret);
+#pragma unroll
+                for (int k = 0; k < 7; ++k)
+                    if (b[k]) atomicAdd(p.stats + 3 + k, (double)b[k]);
+            }
         }
     }
 }
 
 template <int VAR, bool AUX>
-static cudaError_t launch_one(const KParams &p, int mode, int threads, cudaStream_t stream) {
+static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, cudaStream_t stream) {
     const int wpc = threads / 32;
     const int groups = (p.E + p.G - 1) / p.G;
-    const int grid = (groups + wpc - 1) / wpc;
     auto fn = env_kernel<VAR, AUX>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.CL.total);
     if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, p.CL.total);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    // persistent warps: as many CTAs as fit on the device at once (a multiple of the SM count), never
+    // more than there are groups to hand out
+    int grid = sms * per_sm;
+    const int need = (groups + wpc - 1) / wpc;
+    if (grid > need) grid = need;
     fn<<<grid, threads, p.CL.total, stream>>>(p, mode);
     return cudaGetLastError();
 }
 
-cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, cudaStream_t stream) {
+cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, int sms, cudaStream_t stream) {
     if (p.E <= 0) return cudaSuccess;
     const bool aux = p.out_flags & AAC_OUT_RADAR_AUX;
     switch (variant) {
-        case AAC_VARIANT_ATT: return aux ? launch_one<AAC_VARIANT_ATT, true>(p, mode, threads, stream) : launch_one<AAC_VARIANT_ATT, false>(p, mode, threads, stream);
-        case AAC_VARIANT_V2: return aux ? launch_one<AAC_VARIANT_V2, true>(p, mode, threads, stream) : launch_one<AAC_VARIANT_V2, false>(p, mode, threads, stream);
+        case AAC_VARIANT_ATT: return aux ? launch_one<AAC_VARIANT_ATT, true>(p, mode, threads, sms, stream) : launch_one<AAC_VARIANT_ATT, false>(p, mode, threads, sms, stream);
+        case AAC_VARIANT_V2: return aux ? launch_one<AAC_VARIANT_V2, true>(p, mode, threads, sms, stream) : launch_one<AAC_VARIANT_V2, false>(p, mode, threads, sms, stream);
         default: return cudaErrorInvalidValue;
     }
 }

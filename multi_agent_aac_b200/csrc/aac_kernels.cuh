@@ -30,7 +30,7 @@ enum Mode : int { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_RESET = 2 };
 
 // shared-memory carve-up (byte offsets), computed once on the host: CTA-wide data, then one slice per warp
 struct CtaLayout {
-    unsigned map, ray, bar, cnt, warps, total;
+    unsigned map, ray, bar, warps, total;
 };
 struct WarpLayout {  // offsets inside a warp's slice; every array has 32 drone slots
     unsigned cur, pre, meta, agr, d2, order, pflag, bytes, win, wrel, tc, stg, own, raw_own, total;
@@ -53,6 +53,9 @@ struct KParams {
     const uint8_t *mask;  // MODE_RESET: per-env byte, NULL = every env
     const float *actions;
     double *stats;        // [AAC_N_STATS]
+    int *work;            // [2] group counters of the persistent warps, ping-pong between launches
+    int cta_sync;         // 1: the warps of a CTA fetch their groups together (stay in phase)
+    int parity;           // which counter this launch consumes (it zeroes the other one)
     AacState st;
     AacOut out;
     CtaLayout CL;
@@ -96,7 +99,6 @@ inline CtaLayout make_cta_layout(const WarpLayout &WL, int R, int warps) {
     L.map = take(sizeof(MapDev));
     L.ray = take(R * 16);
     L.bar = take(16);
-    L.cnt = take(16 * 4);
     L.warps = take(0);
     L.total = L.warps + warps * WL.total;
     return L;
@@ -104,7 +106,7 @@ inline CtaLayout make_cta_layout(const WarpLayout &WL, int R, int warps) {
 
 // fills the __constant__ polygon tables of the current device (call once per device)
 cudaError_t upload_constants();
-cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, cudaStream_t stream);
+cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, int sms, cudaStream_t stream);
 int max_smem_optin();
 
 }  // namespace aac
