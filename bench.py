@@ -204,11 +204,13 @@ def main():
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K_)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record(stream)
+    host_t0 = time.perf_counter()
     for k in range(K_):
         ev[k][0].record(stream)
         env.step(acts[k % n_act], autoreset=True)     # ONE launch: step + reward + fused auto-reset
         ev[k][1].record(stream)
     t_end.record(stream)
+    host_issue_ms = (time.perf_counter() - host_t0) * 1e3 / K_
     barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
     step_kernel_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
@@ -257,7 +259,7 @@ def main():
             "e2e": {"value": agents_total * args.e2e_steps / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
             "gpu_launches": int(launches),
-            "kernels": {"env_kernel(step+autoreset)_ms": step_kernel_ms},
+            "kernels": {"env_kernel(step+autoreset)_ms": step_kernel_ms, "host_issue_ms_per_step": host_issue_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_kind": peak_kind, "bytes_per_agent_step": bytes_per,
                          "kernel": "env_kernel<V2> step" if variant == "v2" else "env_kernel<ATT> step"},

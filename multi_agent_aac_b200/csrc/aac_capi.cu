@@ -30,6 +30,7 @@ struct AacEnv {
     double *d_stats = nullptr;
     int *d_work = nullptr;       // ping-pong group counters of the persistent kernel
     int sms = 0;
+    int grid = 0;                // persistent grid size, fixed at the first launch
     AacState st{};
     bool bound = false;
     int64_t launches = 0;
@@ -224,7 +225,7 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     p.work = env->d_work; p.parity = (int)(env->launches & 1);
     { const char *v = getenv("AAC_CTA_SYNC"); p.cta_sync = v ? atoi(v) : 0; }
     p.st = env->st; p.out = *out; p.CL = env->cl; p.WL = env->wl;
-    cudaError_t e = launch_env_kernel(c.variant, p, mode, env->threads, env->sms, (cudaStream_t)stream);
+    cudaError_t e = launch_env_kernel(c.variant, p, mode, env->threads, env->sms, &env->grid, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "env_kernel launch");
     env->launches += 1;
     return 0;

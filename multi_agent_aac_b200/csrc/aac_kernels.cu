@@ -105,8 +105,9 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 constexpr unsigned F_DONE = 1u, F_GOAL = 2u, F_BRANCH_SHIFT = 2u, F_BBC3 = 32u, F_DOUBLE = 64u;
 constexpr unsigned M_REACH = 1u << 8, M_VBOUND = 1u << 9, M_VBLDG = 1u << 10, M_VDRONE = 1u << 11;
 // occupancy-window flags (upper half of the window word)
-constexpr unsigned W_NEAR_BOUND = 1u << 16;  // a boundary line is within ray reach (or the drone is outside)
 constexpr unsigned W_SLOW = 1u << 17;        // drone centre inside an occupied cell / window clamped: generic path
+constexpr unsigned W_LINE_SHIFT = 20;        // bits 20..23: boundary line L, R, B, T is within ray reach
+constexpr unsigned W_NEAR_BOUND = 0xFu << W_LINE_SHIFT;
 
 // (hi, lo) = divmod(index, n) advanced by a fixed stride without dividing again
 struct Walk {
@@ -223,13 +224,16 @@ __device__ __forceinline__ unsigned pick_scenario(long long gid, int episode, un
 
 // ------------------------------------------------------------------------------------ radar
 
-// the 4 boundary lines in the reference's order L, R, B, T (V2:145-152); ray = (dx, dy, 1/dx, 1/dy)
+// the boundary lines in the reference's order L, R, B, T (V2:145-152); ray = (dx, dy, 1/dx, 1/dy).  `lines` has
+// one bit per line that can be reached at all from the drone's position.
 template <bool AUX>
-__device__ __forceinline__ void radar_bounds(const MapDev &mp, float px, float py, float4 ray, float len, float &shortest, float &sensed,
-                                             int &shortest_id, int &sensed_id) {
+__device__ __forceinline__ void radar_bounds(const MapDev &mp, float px, float py, float4 ray, float len, unsigned lines, float &shortest,
+                                             float &sensed, int &shortest_id, int &sensed_id) {
     const int nb = mp.gx * mp.gy;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
+#pragma unroll 1
+    while (lines) {
+        const int b = __ffs(lines) - 1;
+        lines &= lines - 1;
         const float dd = b < 2 ? ray.x : ray.y, pp = b < 2 ? px : py, inv = b < 2 ? ray.z : ray.w;
         const float lim = b < 2 ? mp.hx : mp.hy, line = (b & 1) ? lim : -lim;
         if (dd != 0.0f) {
@@ -356,9 +360,9 @@ struct Warp {
     float *px, *py, *vx, *vy, *hd, *ppx, *ppy, *pvx, *pvy;
     unsigned *meta, *meta2, *minr, *agf;
     float *agr, *d2, *stg, *own, *raw_own;
-    uint8_t *order, *pflag, *atgoal, *refw, *rs;
+    uint8_t *order, *atgoal, *refw, *rs;
     uint2 *win;
-    float2 *wrel, *tc;
+    float2 *wrel;
     const uint16_t *cells[1];  // unused placeholder (cells are read from global rows, see cells_of)
 };
 
@@ -431,8 +435,13 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
             }
         }
         mask &= keep;
-        const bool near_bound = !(px - p.ray_len > -mp.hx && px + p.ray_len < mp.hx && py - p.ray_len > -mp.hy && py + p.ray_len < mp.hy);
-        w.win[a] = make_uint2(mask | (near_bound ? W_NEAR_BOUND : 0u) | slow, (unsigned)(ix0 & 0xFFFF) | ((unsigned)iy0 << 16));
+        // a line can only be crossed if it lies within ray reach along its axis
+        unsigned lines = 0;
+        if (fabsf(px + mp.hx) <= p.ray_len) lines |= 1u;
+        if (fabsf(px - mp.hx) <= p.ray_len) lines |= 2u;
+        if (fabsf(py + mp.hy) <= p.ray_len) lines |= 4u;
+        if (fabsf(py - mp.hy) <= p.ray_len) lines |= 8u;
+        w.win[a] = make_uint2(mask | (lines << W_LINE_SHIFT) | slow, (unsigned)(ix0 & 0xFFFF) | ((unsigned)iy0 << 16));
         w.wrel[a] = make_float2(wx, wy);
         w.minr[a] = 0x7F800000u;
     }
@@ -450,17 +459,13 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
             const int ebb = (aa / N) * N, b = ebb + w.order[pi];
             const float px = w.px[aa], py = w.py[aa], ox = w.px[b], oy = w.py[b], ovx = w.vx[b], ovy = w.vy[b];
             const float dx = ox - px, dy = oy - py;
-            float t1, d1, t2, d2;
-            bool c1, c2;
-            tcpa_dcpa(px, py, w.vx[aa], w.vy[aa], ox, oy, ovx, ovy, 2.0f * p.prot, t1, d1, c1);
-            tcpa_dcpa(w.ppx[aa], w.ppy[aa], w.pvx[aa], w.pvy[aa], w.ppx[b], w.ppy[b], w.pvx[b], w.pvy[b], 2.0f * p.prot, t2, d2, c2);
-            if (ok) {
-                w.tc[pi] = make_float2(t1, d1);
-                w.pflag[pi] = (uint8_t)((c1 ? 1 : 0) | (c2 ? 2 : 0));
-                if (flags & AAC_OUT_TCPA_PAIR) {
-                    reinterpret_cast<float4 *>(p.out.tcpa_pair)[pg0 + idx] = make_float4(t1, d1, t2, d2);
-                    p.out.nbr_order[pg0 + idx] = (int8_t)w.order[pi];
-                }
+            if (ok && (flags & AAC_OUT_TCPA_PAIR)) {
+                float t1, d1, t2, d2;
+                bool c1, c2;
+                tcpa_dcpa(px, py, w.vx[aa], w.vy[aa], ox, oy, ovx, ovy, 2.0f * p.prot, t1, d1, c1);
+                tcpa_dcpa(w.ppx[aa], w.ppy[aa], w.pvx[aa], w.pvy[aa], w.ppx[b], w.ppy[b], w.pvx[b], w.pvy[b], 2.0f * p.prot, t2, d2, c2);
+                reinterpret_cast<float4 *>(p.out.tcpa_pair)[pg0 + idx] = make_float4(t1, d1, t2, d2);
+                p.out.nbr_order[pg0 + idx] = (int8_t)w.order[pi];
             }
             if (VAR == AAC_VARIANT_ATT) {
                 if (ok) {
@@ -513,7 +518,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
                                       sensed, shortest_id, sensed_id);
                 else
                     radar_generic<AUX>(mp, w.px[aa], w.py[aa], ray, len, shortest, sensed, shortest_id, sensed_id);
-                if (wn.x & (W_NEAR_BOUND | W_SLOW)) radar_bounds<AUX>(mp, w.px[aa], w.py[aa], ray, len, shortest, sensed, shortest_id, sensed_id);
+                if (wn.x & W_NEAR_BOUND) radar_bounds<AUX>(mp, w.px[aa], w.py[aa], ray, len, (wn.x >> W_LINE_SHIFT) & 0xFu, shortest, sensed, shortest_id, sensed_id);
                 out_min = shortest == CUDART_INF_F ? len : shortest;
                 const bool last_hit = VAR == AAC_VARIANT_V2 && p.radar_mode == AAC_RADAR_LAST_HIT;
                 out = last_hit ? sensed : out_min;
@@ -667,7 +672,7 @@ __device__ __forceinline__ void polyline_nearest(const MapDev &mp, const uint16_
 }
 
 template <int VAR, bool AUX>
-__global__ void __launch_bounds__(MAX_THREADS, 3) env_kernel(const __grid_constant__ KParams p, const int mode) {
+__global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_constant__ KParams p, const int mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, M = N - 1, W = p.W, G = p.G;
@@ -704,10 +709,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 3) env_kernel(const __grid_consta
     w.stg = reinterpret_cast<float *>(ws + WL.stg);
     w.own = reinterpret_cast<float *>(ws + WL.own);
     w.raw_own = reinterpret_cast<float *>(ws + WL.raw_own);
-    w.order = ws + WL.order; w.pflag = ws + WL.pflag; w.atgoal = ws + WL.bytes; w.refw = w.atgoal + 32; w.rs = w.refw + 32;
+    w.order = ws + WL.order; w.atgoal = ws + WL.bytes; w.refw = w.atgoal + 32; w.rs = w.refw + 32;
     w.win = reinterpret_cast<uint2 *>(ws + WL.win);
     w.wrel = reinterpret_cast<float2 *>(ws + WL.wrel);
-    w.tc = reinterpret_cast<float2 *>(ws + WL.tc);
     const MapDev &mp = *s_map;
 
     // episode counters of this lane's envs (ATT/ma_main:581-637), flushed once per warp
@@ -800,13 +804,18 @@ __global__ void __launch_bounds__(MAX_THREADS, 3) env_kernel(const __grid_consta
                 float shortest2 = CUDART_INF_F, imm_tcpa = CUDART_INF_F, imm_d = CUDART_INF_F;
                 const int pn0 = (meta >> 16) & 0xFF, pn1 = (meta >> 24) & 0xFF;
                 const float coll2 = 4.0f * p.prot * p.prot;
+                const float hvx = w.vx[a], hvy = w.vy[a], hppx = w.ppx[a], hppy = w.ppy[a], hpvx = w.pvx[a], hpvy = w.pvy[a];
+#pragma unroll 1
                 for (int k = 0; k < M; ++k) {
-                    const int j = w.order[a * M + k];
-                    const float2 tc = w.tc[a * M + k];
-                    const unsigned pf = w.pflag[a * M + k];
-                    conf_cur += pf & 1; conf_pre += (pf >> 1) & 1;
-                    if (tc.x >= 0.0f && tc.x < imm_tcpa) { imm_tcpa = tc.x; imm_d = tc.y; imm_key = j; }
-                    else if (tc.x == -10.0f && tc.y < imm_tcpa) { imm_tcpa = tc.x; imm_d = tc.y; imm_key = j; }
+                    const int j = w.order[a * M + k], b = eb + j;
+                    // tdCPA against every neighbour for the current and the previous state (ATT:2189-2196)
+                    float t1, d1, t2, dd2;
+                    bool c1, c2;
+                    tcpa_dcpa(px, py, hvx, hvy, w.px[b], w.py[b], w.vx[b], w.vy[b], 2.0f * p.prot, t1, d1, c1);
+                    tcpa_dcpa(hppx, hppy, hpvx, hpvy, w.ppx[b], w.ppy[b], w.pvx[b], w.pvy[b], 2.0f * p.prot, t2, dd2, c2);
+                    conf_cur += c1; conf_pre += c2;
+                    if (t1 >= 0.0f && t1 < imm_tcpa) { imm_tcpa = t1; imm_d = d1; imm_key = j; }
+                    else if (t1 == -10.0f && d1 < imm_tcpa) { imm_tcpa = t1; imm_d = d1; imm_key = j; }
                     const float d2 = w.d2[a * Mp + k];
                     if (d2 < shortest2) { shortest2 = d2; nearest = j; }
                     if (d2 <= coll2) {
@@ -1005,31 +1014,38 @@ __global__ void __launch_bounds__(MAX_THREADS, 3) env_kernel(const __grid_consta
 }
 
 template <int VAR, bool AUX>
-static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, cudaStream_t stream) {
+static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     const int wpc = threads / 32;
     const int groups = (p.E + p.G - 1) / p.G;
     auto fn = env_kernel<VAR, AUX>;
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.CL.total);
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, p.CL.total);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    // persistent warps: as many CTAs as fit on the device at once (a multiple of the SM count), never
-    // more than there are groups to hand out
-    int grid = sms * per_sm;
-    const int need = (groups + wpc - 1) / wpc;
-    if (grid > need) grid = need;
-    fn<<<grid, threads, p.CL.total, stream>>>(p, mode);
+    if (*grid_cache <= 0) {   // first launch of this handle: opt in to the shared memory, size the persistent grid
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.CL.total);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, p.CL.total);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        // persistent warps: as many CTAs as fit on the device at once (a multiple of the SM count), never
+        // more than there are groups to hand out
+        int grid = sms * per_sm;
+        const int need = (groups + wpc - 1) / wpc;
+        if (grid > need) grid = need;
+        *grid_cache = grid;
+    }
+    fn<<<*grid_cache, threads, p.CL.total, stream>>>(p, mode);
     return cudaGetLastError();
 }
 
-cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, int sms, cudaStream_t stream) {
+cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     if (p.E <= 0) return cudaSuccess;
     const bool aux = p.out_flags & AAC_OUT_RADAR_AUX;
     switch (variant) {
-        case AAC_VARIANT_ATT: return aux ? launch_one<AAC_VARIANT_ATT, true>(p, mode, threads, sms, stream) : launch_one<AAC_VARIANT_ATT, false>(p, mode, threads, sms, stream);
-        case AAC_VARIANT_V2: return aux ? launch_one<AAC_VARIANT_V2, true>(p, mode, threads, sms, stream) : launch_one<AAC_VARIANT_V2, false>(p, mode, threads, sms, stream);
+        case AAC_VARIANT_ATT:
+            return aux ? launch_one<AAC_VARIANT_ATT, true>(p, mode, threads, sms, grid_cache, stream)
+                       : launch_one<AAC_VARIANT_ATT, false>(p, mode, threads, sms, grid_cache, stream);
+        case AAC_VARIANT_V2:
+            return aux ? launch_one<AAC_VARIANT_V2, true>(p, mode, threads, sms, grid_cache, stream)
+                       : launch_one<AAC_VARIANT_V2, false>(p, mode, threads, sms, grid_cache, stream);
         default: return cudaErrorInvalidValue;
     }
 }

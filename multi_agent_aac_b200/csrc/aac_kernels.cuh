@@ -33,7 +33,7 @@ struct CtaLayout {
     unsigned map, ray, bar, warps, total;
 };
 struct WarpLayout {  // offsets inside a warp's slice; every array has 32 drone slots
-    unsigned cur, pre, meta, agr, d2, order, pflag, bytes, win, wrel, tc, stg, own, raw_own, total;
+    unsigned cur, pre, meta, agr, d2, order, bytes, win, wrel, stg, own, raw_own, total;
 };
 
 struct KParams {
@@ -80,11 +80,9 @@ inline WarpLayout make_warp_layout(int variant, int N, int flags) {
     L.agr = take(32 * 4);            // reward
     L.d2 = take(32 * Mp * 4);        // neighbour distances^2 in iteration order, odd row stride
     L.order = take(32 * M1);
-    L.pflag = take(32 * M1);         // per pair: bit0 cur conflict, bit1 pre conflict
     L.bytes = take(3 * 32);          // at-goal flag, ref-line vertex count, scratch
     L.win = take(32 * 8);            // 4x4 occupancy window: mask | flags, ix0 | iy0 << 16
     L.wrel = take(32 * 8);           // window origin relative to the drone
-    L.tc = take(32 * M1 * 8);        // current tcpa, d_tcpa per ordered pair
     L.stg = take(32 * 6 * 4);        // transient staging of one warp iteration's pair blocks
     L.own = take(32 * D * 4);        // own rows of the observation
     L.raw_own = take((flags & AAC_OUT_RAW) ? 32 * D * 4 : 0);
@@ -106,7 +104,7 @@ inline CtaLayout make_cta_layout(const WarpLayout &WL, int R, int warps) {
 
 // fills the __constant__ polygon tables of the current device (call once per device)
 cudaError_t upload_constants();
-cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, int sms, cudaStream_t stream);
+cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream);
 int max_smem_optin();
 
 }  // namespace aac
