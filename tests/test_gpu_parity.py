@@ -135,3 +135,41 @@ def test_partial_reset_leaves_other_envs_untouched():
         assert torch.equal(env.out[k][keep], before_out[k][keep]), k
     assert (env.state["ep_step"][mask != 0] == 0).all() and (env.state["ep_index"][mask != 0] == 2).all()
     assert (env.state["vx"][mask != 0] == 0).all()
+
+
+@pytest.mark.parametrize("name", ["att_n3_plain", "v2_n3_plain"])
+def test_ref_compat_env_reproduces_reference_episode(name):
+    """The drop-in class (reference method names / nested-list tuples, E = 1): with `random.seed(k)` it draws
+    the reference's first episode, and free-running on the recorded actions it tracks the reference's
+    float64 rollout for that episode."""
+    import random
+    import numpy as np
+    from multi_agent_aac_b200.ref_compat import RefCompatEnv, RefCompatEnvV2
+    d, variant, n, rays, ep_len, gmap = load_case(name)
+    seed = int(d["meta"][1])
+    cls = RefCompatEnv if variant == "att" else RefCompatEnvV2
+    env = cls(gmap.occ.astype(float), [], gmap.grid_length, list(gmap.bound), None, None, n_rays=rays)
+    env.create_world(n, 2, 0.95, 0.01, 1, 0.15, 0.05, 0.15, (1800, 1300), 5, [-8, 8])
+    random.seed(seed)
+    state, norm_state = env.reset_world(n, None if variant == "att" else False, 0)
+    assert np.allclose(np.array([env.all_agents[i].pos for i in range(n)]), d["ep_start"][0])
+    for i in range(n):
+        w = int(d["ep_ref_w"][0, i])
+        assert np.allclose(env.all_agents[i].ref_line, d["ep_ref_line"][0, i, :w])
+    assert len(state) == (3 if variant == "att" else 4) and len(state[0]) == n
+    assert np.allclose(np.stack(norm_state[0]), d["ep_norm_0"][0], rtol=1e-4, atol=1e-5)
+    T = int(np.sum(d["episode_id"] == 0))
+    for t in range(T):
+        srr, scr = [None] * n, [[] for _ in range(n)]
+        if variant == "att":
+            out = env.step(d["actions"][t], t + 1, 8, None)
+            rw = env.ss_reward(t + 1, srr, [None] * n, scr, (None, None), True, None)
+        else:
+            out = env.step(d["actions"][t], t + 1, 8, None, True, False)
+            rw = env.ss_reward_Mar(t + 1, srr, scr, (None, None), False, None, True)
+        assert len(out) == 8 and len(rw) == 7
+        reward, done, check_goal, _, _, _, bbc = rw
+        assert np.allclose(np.stack(out[0][0])[:, :4], d["raw_own"][t][:, :4], rtol=1e-4, atol=2e-3), t
+        assert np.allclose([float(r) for r in reward], d["reward"][t], rtol=1e-3, atol=5e-3), t
+        assert list(done) == [bool(v) for v in d["done"][t]] and list(bbc) == [bool(v) for v in d["bbc"][t]], t
+        assert isinstance(reward[0], np.ndarray) and reward[0].ndim == 0 and isinstance(done[0], bool)
