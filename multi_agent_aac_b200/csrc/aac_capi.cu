@@ -99,6 +99,13 @@ extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
         const float dx = (float)(cfg->ray_len * c), dy = (float)(cfg->ray_len * s);
         rays[k] = make_float4(dx, dy, dx != 0.0f ? 1.0f / dx : INFINITY, dy != 0.0f ? 1.0f / dy : INFINITY);
     }
+    // an even fan is made exactly antisymmetric: the kernel casts ray k and ray k + R/2 from one set of
+    // slab products (cos(x + pi) and -cos(x) agree to 1e-16 in the reference's float64)
+    if (cfg->n_rays % 2 == 0)
+        for (int k = 0; k < cfg->n_rays / 2; ++k) {
+            const float4 r = rays[k];
+            rays[k + cfg->n_rays / 2] = make_float4(-r.x, -r.y, r.x != 0.0f ? -r.z : r.z, r.y != 0.0f ? -r.w : r.w);
+        }
     CU(cudaMalloc(&env->d_ray, sizeof(float4) * cfg->n_rays));
     CU(cudaMemcpy(env->d_ray, rays.data(), sizeof(float4) * cfg->n_rays, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&env->d_work, 2 * sizeof(int)));
@@ -223,7 +230,6 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     p.bank_cells = env->d_bank_cells; p.bank_w = env->d_bank_w; p.bank_map = env->d_bank_map; p.n_scen = env->n_scen;
     p.mask = mask; p.actions = actions; p.stats = env->d_stats;
     p.work = env->d_work; p.parity = (int)(env->launches & 1);
-    { const char *v = getenv("AAC_CTA_SYNC"); p.cta_sync = v ? atoi(v) : 0; }
     p.st = env->st; p.out = *out; p.CL = env->cl; p.WL = env->wl;
     cudaError_t e = launch_env_kernel(c.variant, p, mode, env->threads, env->sms, &env->grid, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "env_kernel launch");

@@ -722,17 +722,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
     const int n_groups = (p.E + G - 1) / G;
     for (;;) {
         int gi = 0;
-        if (p.cta_sync) {   // whole CTA fetches together: warps stay in phase (instruction-cache locality)
-            __syncthreads();
-            if (tid == 0) *reinterpret_cast<int *>(s_bar + 1) = atomicAdd(&p.work[p.parity], (int)(blockDim.x >> 5));
-            __syncthreads();
-            gi = *reinterpret_cast<int *>(s_bar + 1) + warp;
-            if (gi - warp >= n_groups) break;
-        } else {
-            if (lane == 0) gi = atomicAdd(&p.work[p.parity], 1);
-            gi = __shfl_sync(FULL, gi, 0);
-            if (gi >= n_groups) break;
-        }
+        if (lane == 0) gi = atomicAdd(&p.work[p.parity], 1);
+        gi = __shfl_sync(FULL, gi, 0);
+        if (gi >= n_groups) break;
         w.e_lo = gi * G;
         w.ng = max(0, min(G, p.E - w.e_lo));
         w.a0 = w.e_lo * N;

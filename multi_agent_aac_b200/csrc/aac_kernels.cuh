@@ -54,7 +54,6 @@ struct KParams {
     const float *actions;
     double *stats;        // [AAC_N_STATS]
     int *work;            // [2] group counters of the persistent warps, ping-pong between launches
-    int cta_sync;         // 1: the warps of a CTA fetch their groups together (stay in phase)
     int parity;           // which counter this launch consumes (it zeroes the other one)
     AacState st;
     AacOut out;
