@@ -122,6 +122,10 @@ class _CoordSeq(list):
 
 class BaseGeometry:
     geom_type = "GeometryCollection"
+
+    @property
+    def type(self):   # shapely 2.0's deprecated alias of geom_type (used at MM:932)
+        return self.geom_type
     is_empty = False
 
     def __bool__(self):

@@ -28,7 +28,7 @@ class OracleCfg(C.Structure):
                 ("x0c", C.c_double), ("y0c", C.c_double), ("cell", C.c_double)]
 
 
-_STATE_FIELDS = ["pos", "vel", "heading", "reach", "wp_cur", "wall_cnt", "prev_nn", "vflags", "ref_line", "ref_w"]
+_STATE_FIELDS = ["pos", "vel", "heading", "reach", "wp_cur", "wall_cnt", "prev_nn", "vflags", "ref_line", "ref_w", "wp_mask"]
 _OUT_FIELDS = ["raw_own", "norm_own", "raw_nbr", "norm_nbr", "radar", "radar_min", "radar_hit", "raw_nbr6",
                "norm_nbr6", "nbr_order", "tcpa", "conflict", "reward", "done", "check_goal", "bbc", "parts",
                "margin", "branch", "tcpa_min"]
@@ -63,31 +63,41 @@ def own_dim(variant, n):
 
 
 class OracleEnv:
-    """E independent envs on one map, float64, stepping through oracle_step()."""
+    """E independent envs, float64, stepping through oracle_step_maps().  `gmap` is one GridMap or, for the
+    multipleMap variant, a list of them (env e lives on maps[env_map[e]])."""
 
     def __init__(self, variant, gmap, n_envs, n_agents, n_rays=18, w_max=32, radar_mode=None, sum_reward=None,
-                 vmax=5.0, acc_max=8.0):
-        self.variant, self.gmap, self.E, self.N, self.R, self.w_max = variant, gmap, n_envs, n_agents, n_rays, w_max
+                 vmax=5.0, acc_max=None):
+        maps = list(gmap) if isinstance(gmap, (list, tuple)) else [gmap]
+        self.variant, self.maps, self.gmap = variant, maps, maps[0]
+        self.E, self.N, self.R, self.w_max = n_envs, n_agents, n_rays, w_max
         if radar_mode is None:
             radar_mode = RADAR_LAST_HIT if variant == "v2" else RADAR_MIN
         if sum_reward is None:
             sum_reward = 1 if variant == "att" else 0   # ATT/ma_main:77 vs V2/ma_main:81
-        cfg = OracleCfg()
-        cfg.variant, cfg.n_agents, cfg.n_rays, cfg.w_max = VARIANT_IDS[variant], n_agents, n_rays, w_max
-        cfg.radar_mode, cfg.sum_reward, cfg.gx, cfg.gy = radar_mode, sum_reward, gmap.gx, gmap.gy
-        cfg.dt, cfg.vmax, cfg.acc_max, cfg.prot, cfg.ray_len, cfg.goal_r = 0.5, vmax, acc_max, 2.5, 15.0, 1.0
-        for k in range(4):
-            cfg.bound[k] = float(gmap.bound[k])
-        cfg.x0c, cfg.y0c, cfg.cell = gmap.x0c, gmap.y0c, float(gmap.grid_length)
-        self.cfg = cfg
-        self.occ = np.ascontiguousarray(gmap.occ, dtype=np.uint8)
+        if acc_max is None:
+            acc_max = 20.0 if variant == "mm" else 8.0  # MM.step hard-codes coe_a = 20 (MM:2025)
+        self.cfgs = (OracleCfg * len(maps))()
+        self.occ_stride = max(m.gx * m.gy for m in maps)
+        self.occ = np.zeros((len(maps), self.occ_stride), dtype=np.uint8)
+        for k, m in enumerate(maps):
+            cfg = self.cfgs[k]
+            cfg.variant, cfg.n_agents, cfg.n_rays, cfg.w_max = VARIANT_IDS[variant], n_agents, n_rays, w_max
+            cfg.radar_mode, cfg.sum_reward, cfg.gx, cfg.gy = radar_mode, sum_reward, m.gx, m.gy
+            cfg.dt, cfg.vmax, cfg.acc_max, cfg.prot, cfg.ray_len, cfg.goal_r = 0.5, vmax, acc_max, 2.5, 15.0, 1.0
+            for q in range(4):
+                cfg.bound[q] = float(m.bound[q])
+            cfg.x0c, cfg.y0c, cfg.cell = m.x0c, m.y0c, float(m.grid_length)
+            self.occ[k, :m.gx * m.gy] = np.ascontiguousarray(m.occ, dtype=np.uint8).reshape(-1)
+        self.cfg = self.cfgs[0]
+        self.env_map = np.zeros(n_envs, dtype=np.int32)
         E, N, R, M = n_envs, n_agents, n_rays, n_agents - 1
         f, i = np.float64, np.int32
         self.state = {
             "pos": np.zeros((E, N, 2), f), "vel": np.zeros((E, N, 2), f), "heading": np.zeros((E, N), f),
             "reach": np.zeros((E, N), i), "wp_cur": np.zeros((E, N), i), "wall_cnt": np.zeros((E, N), i),
             "prev_nn": np.full((E, N, 2), -1, i), "vflags": np.zeros((E, N), i),
-            "ref_line": np.zeros((E, N, w_max, 2), f), "ref_w": np.full((E, N), 2, i),
+            "ref_line": np.zeros((E, N, w_max, 2), f), "ref_w": np.full((E, N), 2, i), "wp_mask": np.full((E, N), 2, i),
         }
         d = own_dim(variant, N)
         self.out = {
@@ -104,9 +114,10 @@ class OracleEnv:
         self._o = _Out(*[self.out[n].ctypes.data for n in _OUT_FIELDS])
 
     # ---- reset ---------------------------------------------------------------------------------
-    def set_episode(self, e, starts, lines, headings):
+    def set_episode(self, e, starts, lines, headings, map_id=0):
         """Install reset data for env `e` (what reset_world leaves behind, ATT:301-372)."""
         s = self.state
+        self.env_map[e] = map_id
         for i in range(self.N):
             w = len(lines[i])
             assert w <= self.w_max
@@ -115,6 +126,7 @@ class OracleEnv:
             s["heading"][e, i] = headings[i]
             s["ref_line"][e, i, :w] = lines[i]
             s["ref_w"][e, i] = w
+            s["wp_mask"][e, i] = (1 << w) - 2      # every vertex after the start is a waypoint (MM:345)
         s["reach"][e] = 0
         s["wp_cur"][e] = 0
         s["wall_cnt"][e] = 0
@@ -122,21 +134,22 @@ class OracleEnv:
         s["prev_nn"][e] = -1
 
     def observe(self):
-        lib().oracle_observe(C.byref(self.cfg), self.occ.ctypes.data_as(C.c_void_p), C.c_int(self.E),
-                             C.byref(self._s), C.byref(self._o))
+        lib().oracle_observe_maps(self.cfgs, self.occ.ctypes.data_as(C.c_void_p), C.c_int(self.occ_stride),
+                                  self.env_map.ctypes.data_as(C.c_void_p), C.c_int(self.E), C.byref(self._s), C.byref(self._o))
         return self.out
 
     def step(self, actions):
         a = np.ascontiguousarray(actions, dtype=np.float64)
         assert a.shape == (self.E, self.N, 2)
-        lib().oracle_step(C.byref(self.cfg), self.occ.ctypes.data_as(C.c_void_p), C.c_int(self.E),
-                          C.byref(self._s), a.ctypes.data_as(C.c_void_p), C.byref(self._o))
+        lib().oracle_step_maps(self.cfgs, self.occ.ctypes.data_as(C.c_void_p), C.c_int(self.occ_stride),
+                               self.env_map.ctypes.data_as(C.c_void_p), C.c_int(self.E), C.byref(self._s),
+                               a.ctypes.data_as(C.c_void_p), C.byref(self._o))
         return self.out
 
-    def radar_probe(self, pos, i):
+    def radar_probe(self, pos, i, map_id=0):
         """Radar of drone `i` for the position set pos[N,2] -> (stored value[R], true min[R], hit id[R])."""
         pos = np.ascontiguousarray(pos, dtype=np.float64)
         out, omin, hit = np.zeros(self.R), np.zeros(self.R), np.zeros(self.R, dtype=np.int32)
-        lib().oracle_radar(C.byref(self.cfg), self.occ.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p), C.c_int(i),
+        lib().oracle_radar(C.byref(self.cfgs[map_id]), self.occ[map_id].ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p), C.c_int(i),
                            out.ctypes.data_as(C.c_void_p), omin.ctypes.data_as(C.c_void_p), hit.ctypes.data_as(C.c_void_p))
         return out, omin, hit

@@ -31,6 +31,14 @@ CASES = {
 }
 
 
+MM_CASES = {
+    # name: (N, seed, steps, episode_length, n_rays, map_seed, n_maps, policy, cluster_radius)
+    "mm_n3_seek": (3, 20, 260, 150, 18, 0, 14, "seek", None),
+    "mm_n3_random": (3, 21, 160, 150, 18, 0, 14, "random", None),
+    "mm_n4_seek_r36": (4, 22, 160, 150, 36, 1, 6, "seek", None),
+}
+
+
 def pack(r):
     out = {k: v for k, v in r.items() if k != "episodes"}
     eps = r["episodes"]
@@ -52,6 +60,37 @@ def pack(r):
     return out
 
 
+def main_mm(names=None):
+    from multi_agent_aac_b200.maps import multimap_set
+    for name, (n, seed, steps, ep_len, rays, mseed, n_maps, policy, cl) in MM_CASES.items():
+        if names and name not in names:
+            continue
+        t = time.time()
+        maps = multimap_set(seed=mseed)[:n_maps]
+        r = H.rollout_mm(maps, n, seed, steps, ep_len, n_rays=rays, policy=policy, cluster_radius=cl)
+        eps = r.pop("episodes")
+        d = dict(r)
+        wmax = max(len(l) for e in eps for l in e["ref_lines"])
+        lines = np.zeros((len(eps), n, wmax, 2))
+        w = np.zeros((len(eps), n), dtype=np.int32)
+        for ei, e in enumerate(eps):
+            for i, l in enumerate(e["ref_lines"]):
+                lines[ei, i, :len(l)] = l
+                w[ei, i] = len(l)
+        d["ep_start"] = np.stack([e["start"] for e in eps])
+        d["ep_heading"] = np.stack([e["heading"] for e in eps])
+        d["ep_ref_line"], d["ep_ref_w"] = lines, w
+        d["ep_map"] = np.array([e["map"] for e in eps])
+        d["ep_raw_own"] = np.stack([e["raw"][0] for e in eps])
+        d["ep_norm_own"] = np.stack([e["norm"][0] for e in eps])
+        d["ep_radar"] = np.stack([e["raw"][1] for e in eps])
+        d["meta_variant"] = np.array("mm")
+        d["meta"] = np.array([n, seed, steps, ep_len, rays, mseed, n_maps])
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+        print("%s: %d steps, %d episodes, done=%d goal=%d maps=%s (%.1fs)" % (
+            name, steps, len(eps), int(r["done"].any(1).sum()), int(r["check_goal"].sum()), sorted(set(d["ep_map"].tolist())), time.time() - t))
+
+
 def main(names=None):
     for name, (variant, n, seed, steps, ep_len, cl, sep, rays, mseed, policy) in CASES.items():
         if names and name not in names:
@@ -71,3 +110,4 @@ def main(names=None):
 
 if __name__ == "__main__":
     main(sys.argv[1:])
+    main_mm(sys.argv[1:])

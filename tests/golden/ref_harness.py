@@ -70,10 +70,31 @@ def grid_polys(gmap):
     return [[ones, zeros]]
 
 
+def make_reference_env_mm(maps, n_agents, max_spd=5, acc_range=(-4, 4)):
+    """multipleMap variant: the constructor takes per-map collections (MM:42) and the reset plans on cropped
+    grid indices looked up through `cropped_coord_match_actual_coord` (MM:330-340)."""
+    mod = load_reference_module("mm")
+    world, bounds, polys, cropped = {}, {}, {}, {}
+    for k, gmap in enumerate(maps):
+        world[k] = gmap.occ.astype(float)
+        bounds[k] = list(gmap.bound)
+        polys[k] = grid_polys(gmap)
+        cropped[k] = {}
+        for ix in range(gmap.gx):
+            for iy in range(gmap.gy):
+                cx, cy = gmap.cell_centre(ix, iy)
+                c = geos_lite.Point(cx, cy).buffer(gmap.grid_length / 2, cap_style=3).centroid
+                cropped[k][(ix, iy)] = [c.x, c.y]
+    env = mod.env_simulator(world, [], maps[0].grid_length, bounds, polys, None, cropped)
+    env.current_observable_space = lambda agent: []
+    env.create_world(n_agents, 2, 0.95, 0.01, 1, 0.15, 0.05, 0.15, (1800, 1300), max_spd, list(acc_range))
+    return env, mod
+
+
 def make_reference_env(variant, gmap, n_agents, max_spd=5, acc_max=8):
     mod = load_reference_module(variant)
     if variant == "mm":
-        raise NotImplementedError
+        raise NotImplementedError("use make_reference_env_mm")
     env = mod.env_simulator(gmap.occ.astype(float), [], gmap.grid_length, list(gmap.bound), grid_polys(gmap), None)
     # current_observable_space (ATT:1607) only fills agent.observableSpace at reset, which
     # cur_state_norm_state_v3 overwrites (ATT:1170) before anything reads it.
@@ -92,7 +113,7 @@ def snapshot_agents(env, variant):
         "pos": np.array([env.all_agents[i].pos for i in range(n)], dtype=np.float64),
         "vel": np.array([env.all_agents[i].vel for i in range(n)], dtype=np.float64),
         "reach": np.array([bool(env.all_agents[i].reach_target) for i in range(n)]),
-        "n_wp": np.array([len(env.all_agents[i].waypoints) for i in range(n)]),
+        "n_wp": np.array([len(getattr(env.all_agents[i], "waypoints", None) or env.all_agents[i].goal) for i in range(n)]),
         "wall": np.array([env.all_agents[i].collide_wall_count for i in range(n)]),
         "heading": np.array([env.all_agents[i].heading for i in range(n)], dtype=np.float64),
     }
@@ -222,6 +243,110 @@ def rollout(variant, gmap, n_agents, seed, n_steps, episode_length, action_scale
             rec["step_in_ep"].append(ep_step)
             all_reach = all(env.all_agents[i].reach_target for i in range(n_agents))
             if ep_step > episode_length or (True in done) or all(check_goal) or all_reach:
+                do_reset()
+                ep_step = 0
+    finally:
+        sys.stdout = old_stdout
+        devnull.close()
+    out = {k: np.stack(v) for k, v in rec.items() if len(v)}
+    out["episodes"] = episodes
+    return out
+
+
+def pack_state_mm(state, n):
+    """MM state list -> (own[N,6], radar[N,R]).  The third part (legacy neighbour block) is ragged: MM only
+    lists neighbours within 17.5 m and never clears the dict (MM:754-770); its actors do not read it
+    (MM/maddpg_agent:361-362, :399), so it is not part of the path."""
+    own = np.stack([flat(a) for a in state[0]])
+    radar = np.stack([flat(a) for a in state[1]])
+    return own, radar
+
+
+def rollout_mm(maps, n_agents, seed, n_steps, episode_length, n_rays=18, policy="random", max_spd=5, quiet=True,
+               cluster_radius=None):
+    """Seeded rollout of the multipleMap reference: a map is drawn per episode as in MM/ma_main:464."""
+    env, mod = make_reference_env_mm(maps, n_agents, max_spd)
+    if n_rays != 18:
+        import builtins
+        step = 360 // n_rays
+        mod.range = lambda *a: builtins.range(0, 360, step) if a == (0, 360, 20) else builtins.range(*a)
+    rng = np.random.default_rng(seed)
+    crng = np.random.default_rng(seed + 7919)
+    random.seed(seed)
+    keys = ("actions", "reward", "done", "check_goal", "bbc", "pos", "vel", "reach", "wp_mask", "episode_id", "step_in_ep", "map_id",
+            "raw_own", "norm_own", "radar", "wall")
+    rec = {k: [] for k in keys}
+    episodes = []
+    state = {"map": 0}
+
+    def wp_mask(i):
+        ag = env.all_agents[i]
+        line = list(ag.ref_line.coords)
+        m = 0
+        for g in ag.goal:
+            k = [q for q in range(len(line)) if abs(line[q][0] - g[0]) < 1e-9 and abs(line[q][1] - g[1]) < 1e-9]
+            m |= 1 << k[0]
+        return m
+
+    def do_reset():
+        state["map"] = random.randrange(len(maps))
+        st, nst = env.reset_world(n_agents, state["map"], 0)
+        if cluster_radius is not None:
+            gm = maps[state["map"]]
+            c = env.all_agents[0].pos.astype(float)
+            for i in range(1, n_agents):
+                p = c + crng.uniform(-cluster_radius, cluster_radius, size=2)
+                env.all_agents[i].pos = p.copy()
+                env.all_agents[i].pre_pos = p.copy()
+            for i in range(n_agents):
+                env.all_agents[i].surroundingNeighbor = {}
+                env.all_agents[i].pre_surroundingNeighbor = {}
+            out = env.cur_state_norm_state_v3({}, state["map"])
+            st, nst = out[0], out[1]
+        snap = snapshot_agents(env, "mm")
+        episodes.append({"start": snap["pos"].copy(), "heading": snap["heading"].copy(), "ref_lines": ref_lines(env),
+                         "raw": pack_state_mm(st, n_agents), "norm": pack_state_mm(nst, n_agents), "map": state["map"]})
+
+    devnull = open(os.devnull, "w")
+    old_stdout = sys.stdout
+    if quiet:
+        sys.stdout = devnull
+    try:
+        do_reset()
+        ep_step = 0
+        for t in range(n_steps):
+            act = rng.uniform(-1.0, 1.0, size=(n_agents, 2))
+            if policy == "seek":   # steer at the first remaining waypoint; coe_a = 20 is hard-coded in MM.step
+                for i in range(n_agents):
+                    ag = env.all_agents[i]
+                    to = np.array(ag.goal[0], dtype=float) - ag.pos
+                    want = to / max(np.linalg.norm(to), 1e-9) * max_spd * 0.9
+                    act[i] = np.clip((want - ag.vel) / (20 * 0.5) + 0.1 * act[i], -1.0, 1.0)
+            ep_step += 1
+            srr = [None] * n_agents
+            scr = [[] for _ in range(n_agents)]
+            esh = [None] * n_agents
+            out = env.step(act, ep_step, state["map"])
+            rw = env.ss_reward(ep_step, srr, esh, scr, state["map"])
+            st, nst = out[0], out[1]
+            reward, done, check_goal, _, _, _, bbc = rw
+            own, radar = pack_state_mm(st, n_agents)
+            nown, _ = pack_state_mm(nst, n_agents)
+            snap = snapshot_agents(env, "mm")
+            rec["actions"].append(act)
+            rec["reward"].append(np.array([float(r) for r in reward]))
+            rec["done"].append(np.array(done, dtype=bool))
+            rec["check_goal"].append(np.array(check_goal, dtype=bool))
+            rec["bbc"].append(np.array(bbc, dtype=bool))
+            rec["raw_own"].append(own); rec["norm_own"].append(nown); rec["radar"].append(radar)
+            for k in ("pos", "vel", "reach", "wall"):
+                rec[k].append(snap[k])
+            rec["wp_mask"].append(np.array([wp_mask(i) for i in range(n_agents)], dtype=np.int64))
+            rec["episode_id"].append(len(episodes) - 1)
+            rec["step_in_ep"].append(ep_step)
+            rec["map_id"].append(state["map"])
+            all_reach = all(env.all_agents[i].reach_target for i in range(n_agents))
+            if ep_step > episode_length or (True in done) or all_reach:
                 do_reset()
                 ep_step = 0
     finally:

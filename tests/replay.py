@@ -91,3 +91,42 @@ def replay(env, d, variant, rtol=1e-9, atol=1e-9, resync=None, max_steps=None):
         if resync is not None:
             resync(env, d, t)
     return diff
+
+
+def load_case_mm(name):
+    from multi_agent_aac_b200.maps import multimap_set
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    n, seed, steps, ep_len, rays, mseed, n_maps = [int(v) for v in d["meta"]]
+    return d, n, rays, ep_len, multimap_set(seed=mseed)[:n_maps]
+
+
+def replay_mm(env, d, rtol=1e-9, atol=1e-9, resync=None):
+    """multipleMap rollouts: a map per episode, observation = own block + radar, waypoint mask in the state."""
+    diff = Diff(rtol, atol)
+    T, N = d["actions"].shape[0], d["actions"].shape[1]
+    ep = -1
+    for t in range(T):
+        if int(d["episode_id"][t]) != ep:
+            ep = int(d["episode_id"][t])
+            w = d["ep_ref_w"][ep]
+            lines = [d["ep_ref_line"][ep, i, :w[i]] for i in range(N)]
+            env.set_episode(0, d["ep_start"][ep], lines, d["ep_heading"][ep], map_id=int(d["ep_map"][ep]))
+            out = env.observe()
+            diff.close("reset.raw_own", out["raw_own"][0], d["ep_raw_own"][ep], "ep%d" % ep)
+            diff.close("reset.norm_own", out["norm_own"][0], d["ep_norm_own"][ep], "ep%d" % ep)
+            diff.close("reset.radar", out["radar"][0], d["ep_radar"][ep], "ep%d" % ep)
+        out = env.step(d["actions"][t][None])
+        where = "t%d(ep%d,s%d,map%d)" % (t, ep, int(d["step_in_ep"][t]), int(d["map_id"][t]))
+        for k in ("raw_own", "norm_own", "radar", "reward"):
+            diff.close(k, out[k][0], d[k][t], where)
+        diff.equal("done", out["done"][0], d["done"][t], where)
+        diff.equal("check_goal", out["check_goal"][0], d["check_goal"][t], where)
+        diff.equal("bbc", np.asarray(out["bbc"][0])[:2], d["bbc"][t], where)
+        diff.close("pos", env.state["pos"][0], d["pos"][t], where)
+        diff.close("vel", env.state["vel"][0], d["vel"][t], where)
+        diff.equal("reach", env.state["reach"][0], d["reach"][t], where)
+        diff.equal("wp_mask", env.state["wp_mask"][0], d["wp_mask"][t], where)
+        diff.equal("wall", env.state["wall_cnt"][0], d["wall"][t], where)
+        if resync is not None:
+            resync(env, d, t)
+    return diff

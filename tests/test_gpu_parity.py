@@ -9,7 +9,9 @@ from tests.replay import GOLDEN_DIR, load_case, replay
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+ALL_GOLDEN = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+GOLDEN = [n for n in ALL_GOLDEN if not n.startswith("mm_")]
+GOLDEN_MM = [n for n in ALL_GOLDEN if n.startswith("mm_")]
 
 
 @pytest.fixture(scope="module", autouse=True)

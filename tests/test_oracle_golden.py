@@ -8,13 +8,15 @@ import pytest
 
 from multi_agent_aac_b200.maps import synthetic_map
 from oracle.oracle import OracleEnv, RADAR_MIN
-from tests.replay import GOLDEN_DIR, load_case, replay
+from tests.replay import GOLDEN_DIR, load_case, load_case_mm, replay, replay_mm
 
-GOLDEN = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+GOLDEN = [n for n in ALL if not n.startswith("mm_")]
+GOLDEN_MM = [n for n in ALL if n.startswith("mm_")]
 
 
 def test_fixture_inventory():
-    assert len(GOLDEN) >= 10
+    assert len(GOLDEN) >= 10 and len(GOLDEN_MM) >= 3
     assert any(n.startswith("att") for n in GOLDEN) and any(n.startswith("v2") for n in GOLDEN)
 
 
@@ -24,6 +26,15 @@ def test_oracle_replays_reference_rollout(name):
     env = OracleEnv(variant, gmap, 1, n, rays)
     diff = replay(env, d, variant, rtol=1e-9, atol=1e-9)
     assert not diff.fail, "\n".join(diff.fail[:10])
+
+
+@pytest.mark.parametrize("name", GOLDEN_MM)
+def test_oracle_replays_multimap_reference_rollout(name):
+    d, n, rays, ep_len, maps = load_case_mm(name)
+    env = OracleEnv("mm", maps, 1, n, rays)
+    diff = replay_mm(env, d, rtol=1e-9, atol=1e-9)
+    assert not diff.fail, "\n".join(diff.fail[:10])
+    assert len(set(d["ep_map"].tolist())) >= 4          # several maps per rollout
 
 
 def _two_drone_env(variant, p0, p1, goal0=(640.0, 320.0), rays=18):
