@@ -106,10 +106,12 @@ typedef struct {
     int32_t *ep_step;     /* [E] steps taken in the running episode */
     int32_t *ep_index;    /* [E] episodes finished */
     float *ep_return;     /* [E] sum of all drones' rewards in the running episode */
-    int32_t *map_id;      /* [E] row of the map table, NULL => 0 */
+    int32_t *map_id;      /* [E] row of the map table (required for AAC_VARIANT_MM, else may be NULL => 0) */
+    uint32_t *wp_mask;    /* [E*N] AAC_VARIANT_MM: bit k = ref-line vertex k is still in agent.goal (MM:1747-1762) */
 } AacState;
 
-/* outputs of one step / reset; D_own = 6+4(N-1) ATT, 7 V2, 6 MM */
+/* outputs of one step / reset; D_own = 6+4(N-1) ATT, 7 V2, 6 MM.  AAC_VARIANT_MM emits norm_own, radar (and raw_own):
+ * its legacy neighbour block is ragged and not read by its actors (MM:754-770, MM/maddpg_agent:361-399) */
 typedef struct {
     float *norm_own;      /* [E,N,D_own]     norm state p1          (ATT:1463-1479, V2:1672-1694) */
     float *norm_nbr;      /* [E,N,5(N-1)]    V2 norm p2, else NULL  (V2:1570-1571,1697) */

@@ -42,7 +42,7 @@ class AacMapDesc(C.Structure):
 
 
 STATE_FIELDS = ["px", "py", "vx", "vy", "heading", "meta", "ref_cells", "ref_w", "wall_count", "ep_step", "ep_index",
-                "ep_return", "map_id"]
+                "ep_return", "map_id", "wp_mask"]
 OUT_FIELDS = ["norm_own", "norm_nbr", "radar", "norm_nbr6", "raw_own", "raw_nbr", "raw_nbr6", "reward", "done",
               "check_goal", "bbc", "terminated", "tcpa_min", "tcpa_pair", "nbr_order", "radar_min", "radar_hit", "parts",
               "branch"]

@@ -61,8 +61,10 @@ extern "C" int64_t aac_launch_count(const AacEnv *env) { return env ? env->launc
 extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
     if (!cfg || !out) return fail(AAC_ERR_ARG, "aac_create: null argument");
     if (cfg->abi_version != AAC_ABI_VERSION) return fail(AAC_ERR_ARG, "aac_create: abi_version mismatch");
-    if (cfg->variant != AAC_VARIANT_ATT && cfg->variant != AAC_VARIANT_V2)
-        return fail(AAC_ERR_ARG, "aac_create: variant must be AAC_VARIANT_ATT or AAC_VARIANT_V2");
+    if (cfg->variant != AAC_VARIANT_ATT && cfg->variant != AAC_VARIANT_V2 && cfg->variant != AAC_VARIANT_MM)
+        return fail(AAC_ERR_ARG, "aac_create: unknown variant");
+    if (cfg->variant == AAC_VARIANT_MM && (cfg->out_flags & (AAC_OUT_NBR6 | AAC_OUT_TCPA_PAIR)))
+        return fail(AAC_ERR_ARG, "aac_create: the multipleMap variant has no neighbour outputs");
     if (cfg->n_envs < 1) return fail(AAC_ERR_ARG, "aac_create: n_envs < 1");
     if (cfg->n_agents < 1 || cfg->n_agents > AAC_MAX_AGENTS) return fail(AAC_ERR_ARG, "aac_create: n_agents out of range");
     if (cfg->n_rays < 1 || cfg->n_rays > AAC_MAX_RAYS || 360 % cfg->n_rays) return fail(AAC_ERR_ARG, "aac_create: n_rays must divide 360");
@@ -133,6 +135,7 @@ extern "C" void aac_destroy(AacEnv *env) {
 extern "C" int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *occ, int32_t n_maps) {
     if (!env || !maps || !occ || n_maps < 1) return fail(AAC_ERR_ARG, "aac_set_maps: bad argument");
     if (env->cfg.variant != AAC_VARIANT_MM && n_maps != 1) return fail(AAC_ERR_ARG, "aac_set_maps: this variant uses exactly one map");
+    if (n_maps > 255) return fail(AAC_ERR_ARG, "aac_set_maps: at most 255 maps");
     std::vector<MapDev> host(n_maps);
     for (int m = 0; m < n_maps; ++m) {
         const AacMapDesc &d = maps[m];
@@ -190,6 +193,7 @@ extern "C" int aac_bind_state(AacEnv *env, const AacState *s) {
     if (!env || !s) return fail(AAC_ERR_ARG, "aac_bind_state: null argument");
     if (!s->px || !s->py || !s->vx || !s->vy || !s->heading || !s->meta || !s->ref_cells || !s->ref_w || !s->ep_step || !s->ep_index || !s->ep_return)
         return fail(AAC_ERR_ARG, "aac_bind_state: a required state array is NULL");
+    if (env->cfg.variant == AAC_VARIANT_MM && (!s->map_id || !s->wp_mask)) return fail(AAC_ERR_ARG, "aac_bind_state: the multipleMap variant needs map_id and wp_mask");
     env->st = *s;
     env->bound = true;
     return 0;

@@ -358,9 +358,9 @@ struct Warp {
     int lane;
     int e_lo, ng, a0, nA;   // first env of the group, envs / drones in it, global index of its first drone
     float *px, *py, *vx, *vy, *hd, *ppx, *ppy, *pvx, *pvy;
-    unsigned *meta, *meta2, *minr, *agf;
+    unsigned *meta, *meta2, *minr, *agf, *wpm;   // wpm: multipleMap waypoint mask
     float *agr, *d2, *stg, *own, *raw_own;
-    uint8_t *order, *atgoal, *refw, *rs;
+    uint8_t *order, *atgoal, *refw, *rs, *amap;   // amap: map row per drone (multipleMap)
     uint2 *win;
     float2 *wrel;
     const uint16_t *cells[1];  // unused placeholder (cells are read from global rows, see cells_of)
@@ -387,11 +387,13 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
     const int N = p.N, M = N - 1, R = p.R, Mp = M | 1;
     const int D = own_dim(VAR, N);
     const int flags = p.out_flags;
-    const MapDev &mp = *w.map;
+    // one map staged in shared memory, or (multipleMap) the env's own map read through L1
+    auto map_of = [&](const int aa) -> const MapDev & { return VAR == AAC_VARIANT_MM ? p.maps[w.amap[aa]] : *w.map; };
     const float inv_vmax = 1.0f / p.vmax;
     const bool mine = lane < n_ag;
     const int a = a_lo + lane;           // the lane's drone in the drone-per-lane phases
     const int eb = mine ? (a / N) * N : 0;  // first drone of its env
+    const MapDev &mp = map_of(mine ? a : a_lo);
 
     // ---- neighbour iteration order (ATT: index order; V2: stable insertion sort by distance), window
     if (mine) {
@@ -400,7 +402,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
         float *dist = w.d2 + a * Mp;
         uint8_t *ord = w.order + a * M;
         int m = 0;
-        for (int j = 0; j < N; ++j) {
+        for (int j = 0; j < N && VAR != AAC_VARIANT_MM; ++j) {   // multipleMap has no neighbour terms on the path
             if (j == i) continue;
             const float dx = w.px[eb + j] - px, dy = w.py[eb + j] - py;
             const float d2 = dx * dx + dy * dy;
@@ -448,7 +450,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
     __syncwarp();
 
     // ---- ordered pairs -> tdCPA (cur, pre) and the neighbour blocks of the observation
-    if (M > 0) {
+    if (M > 0 && VAR != AAC_VARIANT_MM) {
         const int n_items = n_ag * M;
         const size_t pg0 = (size_t)(w.a0 + a_lo) * M;  // global index of the range's first pair
         for (Walk it(lane, 32, M); it.hi * M + it.lo - lane < n_items; it.next()) {
@@ -504,21 +506,22 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
         const float len = p.ray_len;
         auto cast = [&](const int aa, const int k, float &out_min, int &id) -> float {
             const float4 ray = w.ray[k];
+            const MapDev &mr = map_of(aa);
             float out;
             if (VAR == AAC_VARIANT_ATT) {
                 const int ebb = (aa / N) * N;
-                radar_drones_ray(w.px, w.py, ebb, N, aa - ebb, ray, len, p.prot, mp.gx * mp.gy + 4, out, id);
+                radar_drones_ray(w.px, w.py, ebb, N, aa - ebb, ray, len, p.prot, mr.gx * mr.gy + 4, out, id);
                 out_min = out;
             } else {
                 const uint2 wn = w.win[aa];
                 float shortest = CUDART_INF_F, sensed = len;
                 int shortest_id = -1, sensed_id = -1;
                 if (!(wn.x & W_SLOW))
-                    radar_window<AUX>(mp, w.wrel[aa], wn.x & 0xFFFFu, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16), ray, len, shortest,
+                    radar_window<AUX>(mr, w.wrel[aa], wn.x & 0xFFFFu, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16), ray, len, shortest,
                                       sensed, shortest_id, sensed_id);
                 else
-                    radar_generic<AUX>(mp, w.px[aa], w.py[aa], ray, len, shortest, sensed, shortest_id, sensed_id);
-                if (wn.x & W_NEAR_BOUND) radar_bounds<AUX>(mp, w.px[aa], w.py[aa], ray, len, (wn.x >> W_LINE_SHIFT) & 0xFu, shortest, sensed, shortest_id, sensed_id);
+                    radar_generic<AUX>(mr, w.px[aa], w.py[aa], ray, len, shortest, sensed, shortest_id, sensed_id);
+                if (wn.x & W_NEAR_BOUND) radar_bounds<AUX>(mr, w.px[aa], w.py[aa], ray, len, (wn.x >> W_LINE_SHIFT) & 0xFu, shortest, sensed, shortest_id, sensed_id);
                 out_min = shortest == CUDART_INF_F ? len : shortest;
                 const bool last_hit = VAR == AAC_VARIANT_V2 && p.radar_mode == AAC_RADAR_LAST_HIT;
                 out = last_hit ? sensed : out_min;
@@ -574,7 +577,10 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
     // ---- own block of the observation, goal contact
     if (mine) {
         const int nw = w.refw[a];
-        const uint16_t cg = cells[nw - 1];
+        // agent.goal[-1]: the last vertex, or (multipleMap, where waypoints are popped from anywhere in the list,
+        // MM:1757) the highest vertex still in the list
+        const int glast = VAR == AAC_VARIANT_MM ? 31 - __clz(w.wpm[a] | 1u) : nw - 1;
+        const uint16_t cg = cells[glast];
         const float gx = cell_cx(mp, cg >> 8), gy = cell_cy(mp, cg & 255);
         const float px = w.px[a], py = w.py[a];
         float nvx = w.vx[a] * inv_vmax, nvy = w.vy[a] * inv_vmax;
@@ -611,17 +617,20 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
 
 // re-initialise env g of the warp's group from the scenario bank: what reset_world leaves behind
 // (ATT:301-372).  Returns the lane's reference-line row (bank memory) for the drones of that env.
+template <int VAR>
 __device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp &w, const int g) {
     const int lane = w.lane, N = p.N, W = p.W;
-    const MapDev &mp = *w.map;
     const int ge = w.e_lo + g;
     const int ep = p.st.ep_index[ge];
     const unsigned scen = pick_scenario(p.env_id_base + ge, ep, p.seed, p.n_scen);
+    const int map_row = (VAR == AAC_VARIANT_MM && p.bank_map) ? p.bank_map[scen] : 0;   // a map is drawn per episode (MM/ma_main:464)
+    const MapDev &mp = VAR == AAC_VARIANT_MM ? p.maps[map_row] : *w.map;
     __syncwarp();
     if (lane == 0) {
         p.st.ep_index[ge] = ep + 1;
         p.st.ep_step[ge] = 0;
         p.st.ep_return[ge] = 0.0f;
+        if (VAR == AAC_VARIANT_MM) p.st.map_id[ge] = map_row;
     }
     // reference lines: 16-byte chunks bank -> global state (W is a multiple of 8)
     const uint4 *src = reinterpret_cast<const uint4 *>(p.bank_cells + (size_t)scen * N * W);
@@ -640,6 +649,7 @@ __device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp
         w.hd[a] = atan2f(cell_cy(mp, c1 & 255) - py, cell_cx(mp, c1 >> 8) - px);  // ATT:359
         w.ppx[a] = px; w.ppy[a] = py; w.pvx[a] = 0.0f; w.pvy[a] = 0.0f;
         w.meta[a] = 0xFFFF0000u;
+        if (VAR == AAC_VARIANT_MM) { w.amap[a] = (uint8_t)map_row; w.wpm[a] = (1u << nw) - 2u; }   // every vertex after the start (MM:345)
         if (p.st.wall_count) p.st.wall_count[(size_t)ge * N + lane] = 0;
     }
     __syncwarp();
@@ -703,13 +713,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
     w.map = s_map; w.ray = s_ray; w.lane = lane;
     w.px = reinterpret_cast<float *>(ws + WL.cur); w.py = w.px + 32; w.vx = w.py + 32; w.vy = w.vx + 32; w.hd = w.vy + 32;
     w.ppx = reinterpret_cast<float *>(ws + WL.pre); w.ppy = w.ppx + 32; w.pvx = w.ppy + 32; w.pvy = w.pvx + 32;
-    w.meta = reinterpret_cast<unsigned *>(ws + WL.meta); w.meta2 = w.meta + 32; w.minr = w.meta2 + 32; w.agf = w.minr + 32;
+    w.meta = reinterpret_cast<unsigned *>(ws + WL.meta); w.meta2 = w.meta + 32; w.minr = w.meta2 + 32; w.agf = w.minr + 32; w.wpm = w.agf + 32;
     w.agr = reinterpret_cast<float *>(ws + WL.agr);
     w.d2 = reinterpret_cast<float *>(ws + WL.d2);
     w.stg = reinterpret_cast<float *>(ws + WL.stg);
     w.own = reinterpret_cast<float *>(ws + WL.own);
     w.raw_own = reinterpret_cast<float *>(ws + WL.raw_own);
-    w.order = ws + WL.order; w.atgoal = ws + WL.bytes; w.refw = w.atgoal + 32; w.rs = w.refw + 32;
+    w.order = ws + WL.order; w.atgoal = ws + WL.bytes; w.refw = w.atgoal + 32; w.rs = w.refw + 32; w.amap = w.rs + 32;
     w.win = reinterpret_cast<uint2 *>(ws + WL.win);
     w.wrel = reinterpret_cast<float2 *>(ws + WL.wrel);
     const MapDev &mp = *s_map;
@@ -756,6 +766,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
             w.px[a] = px; w.py[a] = py; w.vx[a] = vx; w.vy[a] = vy; w.hd[a] = hd;
             w.meta[a] = meta;
             w.refw[a] = p.st.ref_w[ga];
+            if (VAR == AAC_VARIANT_MM) { w.amap[a] = (uint8_t)p.st.map_id[w.e_lo + my_env]; w.wpm[a] = p.st.wp_mask[ga]; }
         }
         __syncwarp();
 
@@ -774,7 +785,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
             if (job > 0) {
                 const int g = job - 1;
                 if (!((reset_mask >> g) & 1u)) continue;
-                const uint16_t *row = init_env(p, w, g);
+                const uint16_t *row = init_env<VAR>(p, w, g);
                 a_lo = g * N; n_ag = N;
                 cl = lane < N ? row : p.bank_cells;
             }
@@ -783,6 +794,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
 
             // ---- reward / collision / goal per drone
             if (mine) {
+                const MapDev &mp = VAR == AAC_VARIANT_MM ? p.maps[w.amap[a]] : *s_map;
                 const int eb = my_env * N, i = a - eb;
                 const float px = w.px[a], py = w.py[a];
                 const int nw = w.refw[a];
@@ -798,7 +810,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                 const float coll2 = 4.0f * p.prot * p.prot;
                 const float hvx = w.vx[a], hvy = w.vy[a], hppx = w.ppx[a], hppy = w.ppy[a], hpvx = w.pvx[a], hpvy = w.pvy[a];
 #pragma unroll 1
-                for (int k = 0; k < M; ++k) {
+                for (int k = 0; k < M && VAR != AAC_VARIANT_MM; ++k) {
                     const int j = w.order[a * M + k], b = eb + j;
                     // tdCPA against every neighbour for the current and the previous state (ATT:2189-2196)
                     float t1, d1, t2, dd2;
@@ -821,7 +833,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                         ++n_coll; last_coll = j;
                     }
                 }
-                const float shortest = sqrtf(shortest2);
+                float shortest = sqrtf(shortest2);
                 reinterpret_cast<float4 *>(p.out.tcpa_min)[ga] = make_float4(imm_tcpa, imm_d, (float)imm_key, (float)(conf_cur + 256 * conf_pre));
                 if (VAR == AAC_VARIANT_V2 && n_coll > 0) meta |= M_VDRONE;
                 // building contact: the protective 64-gon against the (at most 2x2) cells it can reach
@@ -843,12 +855,70 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                 const bool wp_flag = wdx * wdx + wdy * wdy < 25.0f;
                 const float ppx = w.ppx[a], ppy = w.ppy[a];
                 const bool hit_bound = capsule_hits_bound(ppx, ppy, px, py, p.prot, mp.hx, mp.hy);
-                const float after_hg = sqrtf((px - gx) * (px - gx) + (py - gy) * (py - gy));
+                float after_hg = sqrtf((px - gx) * (px - gx) + (py - gy) * (py - gy));
                 const unsigned mr_bits = w.minr[a];
                 const float min_radar = mr_bits > 0x7F800000u ? CUDART_INF_F : __uint_as_float(mr_bits);
                 float dist_to_goal, near_drone = 0.0f, near_bldg = 0.0f, small_step = 0.0f, rew = 0.0f, cross_err = 0.0f;
                 unsigned res = 0, branch;
-                if (VAR == AAC_VARIANT_ATT) {
+                if (VAR == AAC_VARIANT_MM) {
+                    // ss_reward of the multipleMap variant (MM:1674-2007): no drone-collision branch
+                    unsigned mask = w.wpm[a];
+                    const uint16_t cl = cells[31 - __clz(mask | 1u)];   // goal[-1] before this step's pop (MM:1735)
+                    const float glx = cell_cx(mp, cl >> 8), gly = cell_cy(mp, cl & 255);
+                    after_hg = sqrtf((px - glx) * (px - glx) + (py - gly) * (py - gly));
+                    // waypoint scan (MM:1742-1762): walk the remaining waypoints in order; every new running minimum
+                    // becomes next_wp; the first running minimum closer than 5 m is popped (unless it is the only
+                    // one left) and next_wp becomes the nearest remaining waypoint
+                    int n_goal = __popc(mask);
+                    float smallest2 = CUDART_INF_F, nwx = 0.0f, nwy = 0.0f;
+                    bool wpf = false;
+                    unsigned scan = mask;
+#pragma unroll 1
+                    while (scan) {
+                        const int k = __ffs(scan) - 1;
+                        scan &= scan - 1;
+                        const uint16_t c = cells[k];
+                        const float wx = cell_cx(mp, c >> 8), wy = cell_cy(mp, c & 255);
+                        const float d2 = (px - wx) * (px - wx) + (py - wy) * (py - wy);
+                        if (d2 < smallest2) {
+                            smallest2 = d2; nwx = wx; nwy = wy;
+                            if (d2 < 25.0f) {
+                                wpf = true;
+                                if (n_goal > 1) {
+                                    mask &= ~(1u << k); --n_goal;
+                                    float best = CUDART_INF_F;
+                                    unsigned s2 = mask;
+#pragma unroll 1
+                                    while (s2) {
+                                        const int q = __ffs(s2) - 1;
+                                        s2 &= s2 - 1;
+                                        const uint16_t cq = cells[q];
+                                        const float qx = cell_cx(mp, cq >> 8), qy = cell_cy(mp, cq & 255);
+                                        const float dq = (px - qx) * (px - qx) + (py - qy) * (py - qy);
+                                        if (dq < best) { best = dq; nwx = qx; nwy = qy; }
+                                    }
+                                }
+                                break;
+                            }
+                        }
+                    }
+                    w.wpm[a] = mask;
+                    shortest = sqrtf(smallest2);
+                    // |pre - wp| - |pos - wp| without the cancellation (MM:1779-1795)
+                    const float bx = ppx - nwx, by = ppy - nwy, cx = px - nwx, cy = py - nwy;
+                    const float den = sqrtf(bx * bx + by * by) + sqrtf(cx * cx + cy * cy);
+                    dist_to_goal = den > 0.0f ? ((bx - cx) * (bx + cx) + (by - cy) * (by + cy)) / den : 0.0f;
+                    float best2, arc, total;
+                    polyline_nearest(mp, cells, nw, px, py, best2, arc, total);
+                    cross_err = sqrtf(best2);
+                    const float dist_to_ref = cross_err <= p.prot ? 3.0f * (1.0f - cross_err / p.prot) : -3.0f;   // MM:1812-1817
+                    near_drone = dist_to_ref;   // reported in the `near_drone` slot of the parts record
+                    if (min_radar >= p.prot && min_radar <= 10.0f) near_bldg = 3.0f * fmaf((0.0f - 1.0f) / (10.0f - p.prot), min_radar, 10.0f / 7.5f);  // MM:1845-1860
+                    if (hit_bound) { rew = dist_to_ref - 5.0f + dist_to_goal - near_bldg; res |= F_DONE; branch = 0; }          // MM:1962-1969
+                    else if (collide_building) { rew = dist_to_ref - 5.0f + dist_to_goal - near_bldg; res |= F_DONE; branch = 1; }
+                    else if (at_goal) { res |= F_GOAL; meta |= M_REACH; rew = 5.0f; branch = 3; }
+                    else { rew = ((wpf && n_goal > 1) ? 3.0f : 0.0f) + dist_to_ref + dist_to_goal - near_bldg; branch = 4; }    // MM:1987-1993
+                } else if (VAR == AAC_VARIANT_ATT) {
                     // (|pre-g| - |pos-g|) / vmax without the cancellation: (a-b).(a+b) / (|a|+|b|)  (ATT:2319-2325)
                     const float bx = ppx - gx, by = ppy - gy, cx = px - gx, cy = py - gy;
                     const float den = sqrtf(bx * bx + by * by) + after_hg;
@@ -925,7 +995,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
             if (lane < w.ng) {
                 const int ge = w.e_lo + lane, eb = lane * N;
                 float cp = 20.0f, sum = 0.0f;
-                unsigned bbc = 0, any_done = 0, all_reach = 1, n_reach = 0;
+                unsigned bbc = 0, any_done = 0, all_reach = 1, n_reach = 0, any_goal = 0;
 #pragma unroll 1
                 for (int i = 0; i < N; ++i) {
                     const unsigned f = w.agf[eb + i], br = (f >> F_BRANCH_SHIFT) & 7u;
@@ -936,6 +1006,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                     if (br <= 2) bbc |= 1u << br;
                     if (f & F_BBC3) bbc |= 8u;
                     any_done |= f & F_DONE;
+                    any_goal |= f & F_GOAL;
                     const unsigned reached = (w.meta2[eb + i] & M_REACH) ? 1u : 0u;
                     all_reach &= reached;
                     n_reach += reached;
@@ -956,17 +1027,22 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                     st_bits[0] += bbc & 1; st_bits[1] += (bbc >> 1) & 1; st_bits[2] += (bbc >> 2) & 1; st_bits[3] += (bbc >> 3) & 1;
                     st_bits[4] += all_reach; st_bits[5] += n_reach; st_bits[6] += term == 1u;
                 }
+                w.rs[lane] = any_goal ? 1 : 0;
                 reset_me = term && p.autoreset;
                 if (!reset_me) { p.st.ep_step[ge] = step; p.st.ep_return[ge] = ret; }
             }
             reset_mask = __ballot_sync(FULL, reset_me);
+            __syncwarp();
             // the terminal transition leaves before the reset touches the records
             if (mine) {
                 const unsigned f = w.agf[a];
                 w.meta[a] = w.meta2[a];
                 p.out.reward[ga] = w.agr[a];
                 p.out.done[ga] = (uint8_t)(f & F_DONE ? 1 : 0);
-                p.out.check_goal[ga] = (uint8_t)(f & F_GOAL ? 1 : 0);
+                // multipleMap raises check_goal[reward_record_idx] with an index that is never incremented
+                // (MM:1680, :1958): slot 0 of the env stands for "some drone touched its goal"
+                if (VAR == AAC_VARIANT_MM) p.out.check_goal[ga] = (uint8_t)(a == my_env * N ? w.rs[my_env] : 0);
+                else p.out.check_goal[ga] = (uint8_t)(f & F_GOAL ? 1 : 0);
             }
             __syncwarp();
         }
@@ -975,9 +1051,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
         //      pre_surroundingNeighbor (V2:3170-3179)
         if (mine && ((store_mask >> my_env) & 1u)) {
             unsigned meta = w.meta[a];
-            if (M > 0) meta = (meta & 0x0000FFFFu) | ((unsigned)w.order[a * M] << 16) | ((unsigned)(M > 1 ? w.order[a * M + 1] : 0xFF) << 24);
+            if (M > 0 && VAR != AAC_VARIANT_MM) meta = (meta & 0x0000FFFFu) | ((unsigned)w.order[a * M] << 16) | ((unsigned)(M > 1 ? w.order[a * M + 1] : 0xFF) << 24);
             p.st.px[ga] = w.px[a]; p.st.py[ga] = w.py[a]; p.st.vx[ga] = w.vx[a]; p.st.vy[ga] = w.vy[a]; p.st.heading[ga] = w.hd[a];
             p.st.meta[ga] = meta;
+            if (VAR == AAC_VARIANT_MM) p.st.wp_mask[ga] = w.wpm[a];
         }
         __syncwarp();
     }
@@ -1038,6 +1115,9 @@ cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threa
         case AAC_VARIANT_V2:
             return aux ? launch_one<AAC_VARIANT_V2, true>(p, mode, threads, sms, grid_cache, stream)
                        : launch_one<AAC_VARIANT_V2, false>(p, mode, threads, sms, grid_cache, stream);
+        case AAC_VARIANT_MM:
+            return aux ? launch_one<AAC_VARIANT_MM, true>(p, mode, threads, sms, grid_cache, stream)
+                       : launch_one<AAC_VARIANT_MM, false>(p, mode, threads, sms, grid_cache, stream);
         default: return cudaErrorInvalidValue;
     }
 }

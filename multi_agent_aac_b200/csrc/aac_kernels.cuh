@@ -75,11 +75,11 @@ inline WarpLayout make_warp_layout(int variant, int N, int flags) {
     auto take = [&](unsigned bytes) { unsigned r = o; o = align16(o + bytes); return r; };
     L.cur = take(5 * 32 * 4);        // px py vx vy heading
     L.pre = take(4 * 32 * 4);        // pre_pos, pre_vel
-    L.meta = take(4 * 32 * 4);       // meta, meta2, min radar bits, result flags
+    L.meta = take(5 * 32 * 4);       // meta, meta2, min radar bits, result flags, waypoint mask
     L.agr = take(32 * 4);            // reward
     L.d2 = take(32 * Mp * 4);        // neighbour distances^2 in iteration order, odd row stride
     L.order = take(32 * M1);
-    L.bytes = take(3 * 32);          // at-goal flag, ref-line vertex count, scratch
+    L.bytes = take(4 * 32);          // at-goal flag, ref-line vertex count, per-env scratch, map row
     L.win = take(32 * 8);            // 4x4 occupancy window: mask | flags, ix0 | iy0 << 16
     L.wrel = take(32 * 8);           // window origin relative to the drone
     L.stg = take(32 * 6 * 4);        // transient staging of one warp iteration's pair blocks

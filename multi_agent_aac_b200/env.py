@@ -21,13 +21,13 @@ from . import _capi as K
 from .maps import GridMap
 from .reset import ScenarioBank
 
-VARIANTS = {"att": K.VARIANT_ATT, "v2": K.VARIANT_V2}
+VARIANTS = {"att": K.VARIANT_ATT, "v2": K.VARIANT_V2, "mm": K.VARIANT_MM}
 
 
 @dataclass(frozen=True)
 class EnvConfig:
     """Constants the reference hard-codes in source (SURVEY.md section 5 "config / flags")."""
-    variant: str = "att"          # "att" | "v2"
+    variant: str = "att"          # "att" | "v2" | "mm"
     n_envs: int = 1
     n_agents: int = 3             # ATT/ma_main:100
     n_rays: int = 18              # range(0, 360, 20) (ATT:1058)
@@ -49,24 +49,34 @@ class EnvConfig:
 
 
 def preset(name, **kw) -> EnvConfig:
-    """`att`: one_model_att defaults; `tdcpa_v2`: tdCPA_forV2 defaults (last-hit radar as in the source)."""
+    """`att`: one_model_att defaults; `tdcpa_v2`: tdCPA_forV2 defaults (last-hit radar as in the source);
+    `multimap`: radar_multipleMap defaults."""
     if name == "att":
         base = EnvConfig(variant="att", sum_reward=True, episode_length=50, out_flags=K.OUT_NBR6)
     elif name in ("tdcpa_v2", "v2"):
         base = EnvConfig(variant="v2", sum_reward=False, episode_length=100, radar_mode=K.RADAR_LAST_HIT)
+    elif name in ("multimap", "mm"):
+        # radar_multipleMap: per-episode maps, true-min radar, coe_a = 20 hard-coded in step (MM:2025),
+        # 150-step episodes (MM/ma_main:970)
+        base = EnvConfig(variant="mm", sum_reward=False, episode_length=150, acc_max=20.0)
     else:
         raise ValueError("unknown preset %r" % (name,))
     return replace(base, **kw)
 
 
 def own_dim(variant, n_agents):
-    return 6 + 4 * (n_agents - 1) if variant == "att" else 7
+    return {"att": 6 + 4 * (n_agents - 1), "v2": 7, "mm": 6}[variant]
 
 
 class BatchedDroneEnv:
-    def __init__(self, cfg: EnvConfig, gmap: GridMap, device="cuda:0", stream=None):
+    def __init__(self, cfg: EnvConfig, gmap, device="cuda:0", stream=None):
+        """`gmap`: one GridMap, or a list of them for the multipleMap variant (env e lives on maps[map_id[e]])."""
         if not torch.cuda.is_available():
             raise K.AacError("BatchedDroneEnv needs a CUDA device; there is no CPU path")
+        self.maps = list(gmap) if isinstance(gmap, (list, tuple)) else [gmap]
+        if cfg.variant != "mm" and len(self.maps) != 1:
+            raise ValueError("only the multipleMap variant takes several maps")
+        gmap = self.maps[0]
         self.cfg, self.gmap = cfg, gmap
         self.device = torch.device(device)
         self.L = K.lib()
@@ -75,6 +85,7 @@ class BatchedDroneEnv:
         D = own_dim(cfg.variant, N)
         self.D = D
         self.origin = gmap.origin
+        self.origins = np.array([m.origin for m in self.maps], dtype=np.float64)   # local-frame origin per map
         with torch.cuda.device(self.device):
             c = K.AacConfig(K.ABI_VERSION, VARIANTS[cfg.variant], E, N, R, W, cfg.radar_mode, int(cfg.sum_reward),
                             cfg.episode_length, cfg.out_flags, cfg.tile_envs, cfg.block_threads, cfg.env_id_base, cfg.seed,
@@ -82,7 +93,7 @@ class BatchedDroneEnv:
             h = C.c_void_p()
             K.check(self.L.aac_create(C.byref(c), C.byref(h)), "aac_create")
             self.h = h
-            self._set_map(gmap)
+            self._set_maps(self.maps)
             dev = self.device
             f32, i32, u8 = torch.float32, torch.int32, torch.uint8
             z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
@@ -92,6 +103,9 @@ class BatchedDroneEnv:
                 "ref_w": torch.full((E, N), 2, dtype=u8, device=dev), "wall_count": z((E, N), i32), "ep_step": z((E,), i32),
                 "ep_index": z((E,), i32), "ep_return": z((E,), f32),
             }
+            if cfg.variant == "mm":
+                self.state["map_id"] = z((E,), i32)
+                self.state["wp_mask"] = torch.full((E, N), 2, dtype=i32, device=dev)
             self.state["meta"].fill_(-65536)  # 0xFFFF0000: no previous neighbours
             st = K.AacState(*[self.state[n].data_ptr() if n in self.state else None for n in K.STATE_FIELDS])
             K.check(self.L.aac_bind_state(self.h, C.byref(st)), "aac_bind_state")
@@ -102,16 +116,18 @@ class BatchedDroneEnv:
         self._host_out = None
 
     # ------------------------------------------------------------------ setup helpers
-    def _set_map(self, gmap):
-        d = K.AacMapDesc()
-        d.gx, d.gy = gmap.gx, gmap.gy
-        for k in range(4):
-            d.bound[k] = float(gmap.bound[k])
-        d.x0c, d.y0c, d.cell = gmap.x0c, gmap.y0c, float(gmap.grid_length)
-        d.origin_x, d.origin_y = gmap.origin
-        occ = np.zeros(K.MAP_STRIDE, dtype=np.uint8)
-        occ[:gmap.gx * gmap.gy] = np.ascontiguousarray(gmap.occ, dtype=np.uint8).reshape(-1)
-        K.check(self.L.aac_set_maps(self.h, C.byref(d), occ.ctypes.data_as(C.c_void_p), 1), "aac_set_maps")
+    def _set_maps(self, maps):
+        descs = (K.AacMapDesc * len(maps))()
+        occ = np.zeros((len(maps), K.MAP_STRIDE), dtype=np.uint8)
+        for k, gmap in enumerate(maps):
+            d = descs[k]
+            d.gx, d.gy = gmap.gx, gmap.gy
+            for q in range(4):
+                d.bound[q] = float(gmap.bound[q])
+            d.x0c, d.y0c, d.cell = gmap.x0c, gmap.y0c, float(gmap.grid_length)
+            d.origin_x, d.origin_y = gmap.origin
+            occ[k, :gmap.gx * gmap.gy] = np.ascontiguousarray(gmap.occ, dtype=np.uint8).reshape(-1)
+        K.check(self.L.aac_set_maps(self.h, descs, occ.ctypes.data_as(C.c_void_p), len(maps)), "aac_set_maps")
 
     def alloc_out(self, dev, pin=False):
         cfg, E, N, R, M, D = self.cfg, self.E, self.N, self.R, self.M, self.D
@@ -152,11 +168,15 @@ class BatchedDroneEnv:
         s = self.stream if self.stream is not None else torch.cuda.current_stream(self.device)
         return C.c_void_p(s.cuda_stream)
 
-    def set_bank(self, bank: ScenarioBank):
+    def set_bank(self, bank):
+        """`bank`: a ScenarioBank (one map) or a MultiMapBank (scenarios tagged with their map)."""
         assert bank.n_agents == self.N and bank.w_max == self.cfg.w_max
         cells = np.ascontiguousarray(bank.cells, dtype=np.uint16)
         w = np.ascontiguousarray(bank.w, dtype=np.uint8)
-        b = K.AacBank(bank.n_scenarios, cells.ctypes.data, w.ctypes.data, None)
+        map_id = getattr(bank, "map_id", None)
+        if map_id is not None:
+            map_id = np.ascontiguousarray(map_id, dtype=np.int32)
+        b = K.AacBank(bank.n_scenarios, cells.ctypes.data, w.ctypes.data, map_id.ctypes.data if map_id is not None else None)
         with torch.cuda.device(self.device):
             K.check(self.L.aac_set_bank(self.h, C.byref(b)), "aac_set_bank")
         self._bank = bank
@@ -240,11 +260,11 @@ class BatchedDroneEnv:
             pass
 
     # ------------------------------------------------------------------ explicit episode install / readback
-    def set_episode(self, e, starts, lines, headings):
+    def set_episode(self, e, starts, lines, headings, map_id=0):
         """Install reset data for env `e` exactly as reset_world leaves it (ATT:301-372): start positions
         (global metres), reference lines (lists of cell-centre vertices) and headings."""
-        st, g = self.state, self.gmap
-        ox, oy = self.origin
+        st, g = self.state, self.maps[map_id]
+        ox, oy = g.origin
         N, W = self.N, self.cfg.w_max
         cells = np.zeros((N, W), dtype=np.uint16)
         ws = np.zeros(N, dtype=np.uint8)
@@ -272,15 +292,27 @@ class BatchedDroneEnv:
         st["wall_count"][e] = 0
         st["ep_step"][e] = 0
         st["ep_return"][e] = 0.0
+        if self.cfg.variant == "mm":
+            st["map_id"][e] = int(map_id)
+            st["wp_mask"][e] = torch.tensor(((1 << ws.astype(np.int64)) - 2).astype(np.int32), device=dev)
+
+    def _env_origins(self):
+        if self.cfg.variant == "mm":
+            return self.origins[self.state["map_id"].cpu().numpy()]
+        return np.broadcast_to(self.origins[0], (self.E, 2))
 
     def agent_state(self):
         """Host copy of the per-drone records in the reference's terms (global metres)."""
         st = self.state
-        ox, oy = self.origin
+        org = self._env_origins()
         meta = st["meta"].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
-        pos = np.stack([st["px"].cpu().numpy().astype(np.float64) + ox, st["py"].cpu().numpy().astype(np.float64) + oy], -1)
+        pos = np.stack([st["px"].cpu().numpy().astype(np.float64) + org[:, None, 0],
+                        st["py"].cpu().numpy().astype(np.float64) + org[:, None, 1]], -1)
         vel = np.stack([st["vx"].cpu().numpy(), st["vy"].cpu().numpy()], -1).astype(np.float64)
-        return {"pos": pos, "vel": vel, "heading": st["heading"].cpu().numpy().astype(np.float64),
+        extra = {}
+        if self.cfg.variant == "mm":
+            extra = {"wp_mask": st["wp_mask"].cpu().numpy().astype(np.int64) & 0xFFFFFFFF, "map_id": st["map_id"].cpu().numpy()}
+        return {**extra, "pos": pos, "vel": vel, "heading": st["heading"].cpu().numpy().astype(np.float64),
                 "reach": ((meta >> 8) & 1).astype(np.int32), "wp_cur": (meta & 0xFF).astype(np.int32),
                 "vflags": ((meta >> 9) & 7).astype(np.int32), "wall_cnt": st["wall_count"].cpu().numpy(),
                 "prev_nn": np.stack([(meta >> 16) & 0xFF, (meta >> 24) & 0xFF], -1).astype(np.int32),
@@ -290,11 +322,11 @@ class BatchedDroneEnv:
         """Overwrite the kinematic state (global metres) -- used by parity tests to keep the float32
         env on the float64 trajectory."""
         st, dev = self.state, self.device
-        ox, oy = self.origin
+        org = self._env_origins()
         pos = np.asarray(pos, dtype=np.float64)
         vel = np.asarray(vel, dtype=np.float64)
-        st["px"].copy_(torch.tensor(pos[..., 0] - ox, dtype=torch.float32, device=dev))
-        st["py"].copy_(torch.tensor(pos[..., 1] - oy, dtype=torch.float32, device=dev))
+        st["px"].copy_(torch.tensor(pos[..., 0] - org[:, None, 0], dtype=torch.float32, device=dev))
+        st["py"].copy_(torch.tensor(pos[..., 1] - org[:, None, 1], dtype=torch.float32, device=dev))
         st["vx"].copy_(torch.tensor(vel[..., 0], dtype=torch.float32, device=dev))
         st["vy"].copy_(torch.tensor(vel[..., 1], dtype=torch.float32, device=dev))
         if heading is not None:

@@ -179,3 +179,26 @@ class ScenarioBank:
     @property
     def n_scenarios(self):
         return self.cells.shape[0]
+
+
+class MultiMapBank:
+    """Scenario bank over several maps (multipleMap variant): scenario s is planned on maps[map_id[s]], maps
+    are drawn uniformly as MM/ma_main:464 does per episode.  Same packing as ScenarioBank plus `map_id`."""
+
+    def __init__(self, maps, n_agents, n_scenarios, w_max=32, seed=0, prot=2.5):
+        self.maps, self.n_agents, self.w_max = list(maps), n_agents, w_max
+        rng = np.random.default_rng(seed)
+        self.map_id = rng.integers(0, len(self.maps), size=n_scenarios).astype(np.int32)
+        self.cells = np.zeros((n_scenarios, n_agents, w_max), dtype=np.uint16)
+        self.w = np.zeros((n_scenarios, n_agents), dtype=np.uint8)
+        for k, gmap in enumerate(self.maps):
+            idx = np.nonzero(self.map_id == k)[0]
+            if len(idx) == 0:
+                continue
+            sub = ScenarioBank(gmap, n_agents, len(idx), w_max=w_max, seed=seed * 1000 + k, prot=prot)
+            self.cells[idx] = sub.cells
+            self.w[idx] = sub.w
+
+    @property
+    def n_scenarios(self):
+        return self.cells.shape[0]

@@ -24,8 +24,8 @@ import torch
 
 from multi_agent_aac_b200 import _capi as K
 from multi_agent_aac_b200.env import BatchedDroneEnv, preset
-from multi_agent_aac_b200.maps import synthetic_map
-from multi_agent_aac_b200.reset import ScenarioBank
+from multi_agent_aac_b200.maps import multimap_set, synthetic_map
+from multi_agent_aac_b200.reset import MultiMapBank, ScenarioBank
 from oracle.oracle import OracleEnv, RADAR_LAST_HIT, RADAR_MIN
 
 RTOL = 1e-4
@@ -73,6 +73,36 @@ class GpuGoldenAdapter:
                                   heading=d["heading"][t][None] if self.variant == "v2" else None)
 
 
+class GpuGoldenAdapterMM:
+    """OracleEnv surface for tests/replay.replay_mm over a 1-env multipleMap BatchedDroneEnv."""
+
+    def __init__(self, maps, n_agents, n_rays, device="cuda:0"):
+        cfg = preset("multimap", n_envs=1, n_agents=n_agents, n_rays=n_rays, w_max=32, out_flags=K.OUT_RAW | K.OUT_RADAR_AUX | K.OUT_PARTS)
+        self.env = BatchedDroneEnv(cfg, maps, device=device)
+        self.state = {}
+
+    def _collect(self):
+        o = np_out(self.env)
+        s = self.env.agent_state()
+        self.state = {"pos": s["pos"], "vel": s["vel"], "reach": s["reach"], "wp_mask": s["wp_mask"], "wall_cnt": s["wall_cnt"]}
+        return o
+
+    def set_episode(self, e, starts, lines, headings, map_id=0):
+        self.env.set_episode(e, starts, lines, headings, map_id=map_id)
+
+    def observe(self):
+        self.env.observe()
+        return self._collect()
+
+    def step(self, actions):
+        a = torch.tensor(np.asarray(actions, dtype=np.float32), device=self.env.device).contiguous()
+        self.env.step(a)
+        return self._collect()
+
+    def resync(self, env, d, t):
+        self.env.load_agent_state(d["pos"][t][None], d["vel"][t][None])
+
+
 def cells_to_lines(gmap, ref_cells, ref_w):
     """uint16 cell codes [.., W] -> float64 vertex coordinates [.., W, 2]."""
     c = ref_cells.astype(np.int64) & 0xFFFF
@@ -96,9 +126,16 @@ def sync_oracle(orc, env, envs=None, full=False):
     pn = s["prev_nn"].copy()
     pn[pn == 255] = -1
     st["prev_nn"][sel] = pn[sel]
+    if "wp_mask" in s:
+        st["wp_mask"][sel] = s["wp_mask"][sel].astype(np.int32)
+        orc.env_map[sel] = s["map_id"][sel]
     if full:
         cells = env.state["ref_cells"].cpu().numpy().view(np.uint16)
-        st["ref_line"][sel] = cells_to_lines(env.gmap, cells, None)[sel][..., :orc.w_max, :]
+        if "map_id" in s:   # vertices are cell centres of the env's own map
+            lines = np.stack([cells_to_lines(env.maps[int(m)], cells[e], None) for e, m in enumerate(s["map_id"])])
+        else:
+            lines = cells_to_lines(env.gmap, cells, None)
+        st["ref_line"][sel] = lines[sel][..., :orc.w_max, :]
         st["ref_w"][sel] = s["ref_w"][sel]
     return s
 
@@ -162,7 +199,7 @@ def compare_obs(T, variant, g, o, where, env_ok, s_gpu, orc, rows=None):
     E = g["norm_own"].shape[0]
     rows = np.ones(E, dtype=bool) if rows is None else rows
     ok = env_ok & rows
-    keys = ["norm_own", "raw_own", "norm_nbr6", "raw_nbr6"] + (["norm_nbr", "raw_nbr"] if variant == "v2" else [])
+    keys = ["norm_own", "raw_own"] + (["norm_nbr6", "raw_nbr6"] if variant != "mm" else []) + (["norm_nbr", "raw_nbr"] if variant == "v2" else [])
     for k in keys:
         if k in g:
             T.close(k, g[k], o[k], where, ATOL[k], mask=_bcast(ok, g[k].shape))
@@ -181,7 +218,7 @@ def compare_obs(T, variant, g, o, where, env_ok, s_gpu, orc, rows=None):
                            (-RADAR_EPS, -RADAR_EPS), (RADAR_EPS, -RADAR_EPS), (-RADAR_EPS, RADAR_EPS)):
                 pos = orc.state["pos"][e].copy()
                 pos[i] += (dx, dy)
-                out, omin, _ = orc.radar_probe(pos, i)
+                out, omin, _ = orc.radar_probe(pos, i, map_id=int(orc.env_map[e]))
                 ref = out if k == "radar" else omin
                 any_nan |= np.isnan(ref)
                 lo, hi = np.fmin(lo, ref), np.fmax(hi, ref)
@@ -208,14 +245,22 @@ def lockstep(variant, n_envs, n_agents, n_rays, steps, seed=0, radar_mode=None, 
              device="cuda:0", autoreset=True, tile_envs=0, block_threads=0, action_scale=1.0):
     """Returns a Tally.  `cluster` = radius (m): after every reset drones 1.. are moved next to drone 0 so
     that drone-radar / near-drone / collision branches fire."""
-    gmap = synthetic_map(seed=map_seed)
     E, N, R, M = n_envs, n_agents, n_rays, n_agents - 1
     if radar_mode is None:
         radar_mode = RADAR_LAST_HIT if variant == "v2" else RADAR_MIN
-    cfg = preset("att" if variant == "att" else "tdcpa_v2", n_envs=E, n_agents=N, n_rays=R, w_max=32, out_flags=ALL_OUT,
-                 radar_mode=radar_mode, seed=seed, tile_envs=tile_envs, block_threads=block_threads)
+    if variant == "mm":
+        gmap = multimap_set(seed=map_seed)
+        cfg = preset("multimap", n_envs=E, n_agents=N, n_rays=R, w_max=32, out_flags=K.OUT_RAW | K.OUT_RADAR_AUX | K.OUT_PARTS,
+                     seed=seed, tile_envs=tile_envs, block_threads=block_threads)
+        bank = MultiMapBank(gmap, N, n_scen, w_max=32, seed=seed)
+        M = 0   # no neighbour terms on the multipleMap path
+    else:
+        gmap = synthetic_map(seed=map_seed)
+        cfg = preset("att" if variant == "att" else "tdcpa_v2", n_envs=E, n_agents=N, n_rays=R, w_max=32, out_flags=ALL_OUT,
+                     radar_mode=radar_mode, seed=seed, tile_envs=tile_envs, block_threads=block_threads)
+        bank = ScenarioBank(gmap, N, n_scen, w_max=32, seed=seed)
     env = BatchedDroneEnv(cfg, gmap, device=device)
-    env.set_bank(ScenarioBank(gmap, N, n_scen, w_max=32, seed=seed))
+    env.set_bank(bank)
     orc = OracleEnv(variant, gmap, E, N, R, w_max=32, radar_mode=radar_mode)
     rng = np.random.default_rng(seed + 1)
     T = Tally()
@@ -310,16 +355,19 @@ def lockstep(variant, n_envs, n_agents, n_rays, steps, seed=0, radar_mode=None, 
         T.tie("predicate_margin", int((~margin_ok).sum()))
         flag_ok = margin_ok & env_ok & ~radar_tie_env
         fm = _bcast(flag_ok, (E, N))
+        if variant == "mm":   # no coupling between the drones of an env in this variant's reward: mask per drone
+            fm = (o["margin"] >= TIE_EPS) & _bcast(env_ok & ~radar_tie_env, (E, N))
         bad_env = np.zeros(E, dtype=bool)
+        wp_key = ("wp_mask", s_gpu["wp_mask"], so["wp_mask"]) if variant == "mm" else ("wp_cur", s_gpu["wp_cur"], so["wp_cur"])
         for key, gv, ov in (("done", g["done"], o["done"]), ("check_goal", g["check_goal"], o["check_goal"]),
                             ("branch", g["branch"], o["branch"]), ("reach", s_gpu["reach"], so["reach"]),
-                            ("wp_cur", s_gpu["wp_cur"], so["wp_cur"]), ("wall_cnt", s_gpu["wall_cnt"], so["wall_cnt"])):
+                            wp_key, ("wall_cnt", s_gpu["wall_cnt"], so["wall_cnt"])):
             bad_env |= T.equal(key, gv, ov, where, mask=fm).any(axis=1)
         if variant == "v2":
             T.equal("vflags", s_gpu["vflags"], so["vflags"], where, mask=fm)
         T.equal("bbc", g["bbc"], o["bbc"], where, mask=_bcast(flag_ok, (E, 4)))
         T.close("reward", g["reward"], o["reward"], where, ATOL["reward"], mask=fm)
-        T.close("parts", g["parts"], o["parts"], where, ATOL["parts"], mask=_bcast(flag_ok, g["parts"].shape))
+        T.close("parts", g["parts"], o["parts"], where, ATOL["parts"], mask=np.broadcast_to(fm[..., None], g["parts"].shape))
         if M > 0:
             tm_g, tm_o = g["tcpa_min"].astype(np.float64), o["tcpa_min"]
             # conflict counters flip when d_tcpa crosses 2*prot or tcpa crosses 0 / 1: compare away from those
