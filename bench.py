@@ -27,6 +27,7 @@ WORKLOADS = {
     "c2": ("att", 4096, 3, 36, "one_model_att 4096 envs x 3 drones, 36-ray radar, single grid map"),
     "c2r18": ("att", 4096, 3, 18, "one_model_att 4096 envs x 3 drones, 18-ray radar, single grid map"),
     "c3": ("tdcpa_v2", 65536, 10, 36, "tdCPA_forV2 65536 envs x 10 drones per GPU, 36-ray radar, single grid map"),
+    "c4": ("multimap", 65536, 3, 18, "radar_multipleMap 65536 envs x 3 drones per GPU, 18-ray radar, 14 heterogeneous maps, map drawn per episode"),
     "c5": ("tdcpa_v2", 131072, 20, 72, "tdCPA_forV2 131072 envs x 20 drones per GPU, 72-ray radar (1M envs on 8 GPUs)"),
 }
 W_REF = 4  # reference-line vertices assumed by SURVEY.md section 8d's byte count
@@ -34,7 +35,7 @@ W_REF = 4  # reference-line vertices assumed by SURVEY.md section 8d's byte coun
 
 def algorithmic_bytes(variant, n, r):
     """4 * (26 + 2W + obs words) per agent-step, W = 4."""
-    obs = 7 + 5 * (n - 1) + r if variant != "att" else 6 + 4 * (n - 1) + r + 6 * (n - 1)
+    obs = {"att": 6 + 4 * (n - 1) + r + 6 * (n - 1), "v2": 7 + 5 * (n - 1) + r, "mm": 6 + r}[variant]
     return 4 * (26 + 2 * W_REF + obs)
 
 
@@ -57,7 +58,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -88,10 +89,17 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows)}
 
 
+def variant_of(preset_name):
+    return {"att": "att", "tdcpa_v2": "v2", "multimap": "mm"}[preset_name]
+
+
 def build_world(wl, n_scen, seed):
-    from multi_agent_aac_b200.maps import synthetic_map
-    from multi_agent_aac_b200.reset import ScenarioBank
+    from multi_agent_aac_b200.maps import multimap_set, synthetic_map
+    from multi_agent_aac_b200.reset import MultiMapBank, ScenarioBank
     preset_name, envs, n, r, _ = WORKLOADS[wl]
+    if preset_name == "multimap":
+        maps = multimap_set(seed=0)
+        return maps, MultiMapBank(maps, n, n_scen, w_max=32, seed=seed)
     gmap = synthetic_map(seed=0)
     bank = ScenarioBank(gmap, n, n_scen, w_max=32, seed=seed)
     return gmap, bank
@@ -102,22 +110,24 @@ def cpu_reference_run(wl, steps, warmup, sample_envs, threads=None):
     from oracle.oracle import OracleEnv, RADAR_LAST_HIT, RADAR_MIN
     from multi_agent_aac_b200.reset import Episode
     preset_name, _, n, r, desc = WORKLOADS[wl]
-    variant = "att" if preset_name == "att" else "v2"
+    variant = variant_of(preset_name)
     cores = threads or os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(cores)
     gmap, bank = build_world(wl, 64, seed=123)
     E = sample_envs
     orc = OracleEnv(variant, gmap, E, n, r, w_max=32, radar_mode=RADAR_LAST_HIT if variant == "v2" else RADAR_MIN)
-    g = gmap.grid_length
     for e in range(E):
         s = e % bank.n_scenarios
+        mid = int(bank.map_id[s]) if hasattr(bank, "map_id") else 0
+        gm = gmap[mid] if isinstance(gmap, list) else gmap
+        g = gm.grid_length
         lines = []
         for i in range(n):
             w = int(bank.w[s, i])
             c = bank.cells[s, i, :w].astype(np.int64)
-            lines.append(np.stack([gmap.x0c + (c >> 8) * g, gmap.y0c + (c & 255) * g], -1).astype(np.float64))
+            lines.append(np.stack([gm.x0c + (c >> 8) * g, gm.y0c + (c & 255) * g], -1).astype(np.float64))
         heads = [float(np.arctan2(l[1][1] - l[0][1], l[1][0] - l[0][0])) for l in lines]
-        orc.set_episode(e, [l[0] for l in lines], lines, heads)
+        orc.set_episode(e, [l[0] for l in lines], lines, heads, map_id=mid)
     orc.observe()
     rng = np.random.default_rng(0)
     acts = rng.uniform(-1, 1, size=(4, E, n, 2))
@@ -154,7 +164,7 @@ def main():
     preset_name, envs, n, r, desc = WORKLOADS[args.workload]
     if args.envs:
         envs = args.envs
-    variant = "att" if preset_name == "att" else "v2"
+    variant = variant_of(preset_name)
     bytes_per = algorithmic_bytes(variant, n, r)
 
     if args.impl == "reference":
@@ -273,7 +283,7 @@ def main():
             "kernels": {"env_kernel(step+autoreset)_ms": step_kernel_ms, "host_issue_ms_per_step": host_issue_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_kind": peak_kind, "bytes_per_agent_step": bytes_per,
-                         "kernel": "env_kernel<V2> step" if variant == "v2" else "env_kernel<ATT> step"},
+                         "kernel": "env_kernel<%s> step+autoreset" % variant.upper()},
             "clocks": clocks,
             "episode_stats": {k: float(v) for k, v in zip(K.STAT_NAMES, stats)},
         }

@@ -284,9 +284,16 @@ __device__ __forceinline__ void radar_window(const MapDev &mp, float2 wrel, unsi
 // cell whose box overlaps the ray's box, with the reference's inside-the-cell semantics: the nearest
 // point of segment n cell BOUNDARY is the exit point, or nothing (nan) when the whole ray is inside
 // (V2:1258-1265).
+struct GenericHit {
+    float shortest, sensed;
+    int shortest_id, sensed_id;
+};
 template <bool AUX>
-__device__ __noinline__ void radar_generic(const MapDev &mp, float px, float py, float4 ray, float len, float &shortest, float &sensed,
-                                           int &shortest_id, int &sensed_id) {
+__device__ __noinline__ GenericHit radar_generic(const MapDev &mp, float px, float py, float4 ray, float len) {
+    // results travel by value: reference parameters of a non-inlined function would pin the caller's
+    // accumulators in local memory on the hot path
+    float shortest = CUDART_INF_F, sensed = len;
+    int shortest_id = -1, sensed_id = -1;
     const float ex = px + ray.x, ey = py + ray.y;
     const int ixa = (int)floorf((fminf(px, ex) - mp.ex0) * mp.inv_cell), ixb = (int)floorf((fmaxf(px, ex) - mp.ex0) * mp.inv_cell);
     const int iya = (int)floorf((fminf(py, ey) - mp.ey0) * mp.inv_cell), iyb = (int)floorf((fmaxf(py, ey) - mp.ey0) * mp.inv_cell);
@@ -311,6 +318,7 @@ __device__ __noinline__ void radar_generic(const MapDev &mp, float px, float py,
             if (AUX) sensed_id = ix * mp.gy + iy;
             if (d < shortest) { shortest = d; if (AUX) shortest_id = ix * mp.gy + iy; }
         }
+    return GenericHit{shortest, sensed, shortest_id, sensed_id};
 }
 
 // one ray against the other drones' protective 64-gons (ATT:1052-1170): entry distance, 0 inside
@@ -381,10 +389,10 @@ __device__ __forceinline__ void flush_items(float *dst, int n_valid, const float
 
 // observation pipeline for the drones [a_lo, a_lo + n_ag) of the warp's group (whole envs):
 // neighbour order + window -> { pairs | rays | own block }.  `cells` = the lane's reference-line row.
-template <int VAR, bool AUX>
+template <int VAR, bool AUX, int NT>
 __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, const int a_lo, const int n_ag, const uint16_t *cells) {
     const int lane = w.lane;
-    const int N = p.N, M = N - 1, R = p.R, Mp = M | 1;
+    const int N = NT ? NT : p.N, M = N - 1, R = p.R, Mp = M | 1;   // NT > 0: drone count known at compile time
     const int D = own_dim(VAR, N);
     const int flags = p.out_flags;
     // one map staged in shared memory, or (multipleMap) the env's own map read through L1
@@ -401,16 +409,45 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
         const float px = w.px[a], py = w.py[a];
         float *dist = w.d2 + a * Mp;
         uint8_t *ord = w.order + a * M;
-        int m = 0;
-        for (int j = 0; j < N && VAR != AAC_VARIANT_MM; ++j) {   // multipleMap has no neighbour terms on the path
-            if (j == i) continue;
-            const float dx = w.px[eb + j] - px, dy = w.py[eb + j] - py;
-            const float d2 = dx * dx + dy * dy;
-            int q = m;
-            if (VAR == AAC_VARIANT_V2)
-                while (q > 0 && dist[q - 1] > d2) { dist[q] = dist[q - 1]; ord[q] = ord[q - 1]; --q; }
-            dist[q] = d2; ord[q] = (uint8_t)j;
-            ++m;
+        if (VAR == AAC_VARIANT_V2 && NT > 1) {
+            // Stable sort by distance (V2:769-801) with the drone count known at compile time: the keys live in
+            // registers and go through a fixed compare-exchange network (no divergence between lanes).  A key is
+            // the distance's bit pattern with the neighbour slot in the 5 low mantissa bits, so one unsigned
+            // compare orders by (distance, index); distances closer than 32 ulp order by index.
+            constexpr int MC = NT > 1 ? NT - 1 : 1;
+            unsigned key[MC];
+#pragma unroll
+            for (int m = 0; m < MC; ++m) {
+                const int j = m + (m >= i ? 1 : 0);
+                const float dx = w.px[eb + j] - px, dy = w.py[eb + j] - py;
+                key[m] = (__float_as_uint(dx * dx + dy * dy) & ~31u) | (unsigned)m;
+            }
+#pragma unroll
+            for (int s_ = 1; s_ < MC; ++s_) {
+#pragma unroll
+                for (int q = s_; q > 0; --q) {
+                    const unsigned lo = min(key[q - 1], key[q]), hi = max(key[q - 1], key[q]);
+                    key[q - 1] = lo; key[q] = hi;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < MC; ++k) {
+                const int m = key[k] & 31u;
+                dist[k] = __uint_as_float(key[k] & ~31u);
+                ord[k] = (uint8_t)(m + (m >= i ? 1 : 0));
+            }
+        } else {
+            int m = 0;
+            for (int j = 0; j < N && VAR != AAC_VARIANT_MM; ++j) {   // multipleMap has no neighbour terms on the path
+                if (j == i) continue;
+                const float dx = w.px[eb + j] - px, dy = w.py[eb + j] - py;
+                const float d2 = dx * dx + dy * dy;
+                int q = m;
+                if (VAR == AAC_VARIANT_V2)
+                    while (q > 0 && dist[q - 1] > d2) { dist[q] = dist[q - 1]; ord[q] = ord[q - 1]; --q; }
+                dist[q] = d2; ord[q] = (uint8_t)j;
+                ++m;
+            }
         }
         // 4x4 occupancy window covering the square the rays can reach
         const float fx = (px - p.ray_len - mp.ex0) * mp.inv_cell, fy = (py - p.ray_len - mp.ey0) * mp.inv_cell;
@@ -519,8 +556,10 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
                 if (!(wn.x & W_SLOW))
                     radar_window<AUX>(mr, w.wrel[aa], wn.x & 0xFFFFu, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16), ray, len, shortest,
                                       sensed, shortest_id, sensed_id);
-                else
-                    radar_generic<AUX>(mr, w.px[aa], w.py[aa], ray, len, shortest, sensed, shortest_id, sensed_id);
+                else {
+                    const GenericHit h = radar_generic<AUX>(mr, w.px[aa], w.py[aa], ray, len);
+                    shortest = h.shortest; sensed = h.sensed; shortest_id = h.shortest_id; sensed_id = h.sensed_id;
+                }
                 if (wn.x & W_NEAR_BOUND) radar_bounds<AUX>(mr, w.px[aa], w.py[aa], ray, len, (wn.x >> W_LINE_SHIFT) & 0xFu, shortest, sensed, shortest_id, sensed_id);
                 out_min = shortest == CUDART_INF_F ? len : shortest;
                 const bool last_hit = VAR == AAC_VARIANT_V2 && p.radar_mode == AAC_RADAR_LAST_HIT;
@@ -681,11 +720,11 @@ __device__ __forceinline__ void polyline_nearest(const MapDev &mp, const uint16_
     total = run;
 }
 
-template <int VAR, bool AUX>
+template <int VAR, bool AUX, int NT>
 __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_constant__ KParams p, const int mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int N = p.N, M = N - 1, W = p.W, G = p.G;
+    const int N = NT ? NT : p.N, M = N - 1, W = p.W, G = p.G;
     const int Mp = M | 1;
     const int flags = p.out_flags;
     const CtaLayout &CL = p.CL;
@@ -722,8 +761,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
     w.order = ws + WL.order; w.atgoal = ws + WL.bytes; w.refw = w.atgoal + 32; w.rs = w.refw + 32; w.amap = w.rs + 32;
     w.win = reinterpret_cast<uint2 *>(ws + WL.win);
     w.wrel = reinterpret_cast<float2 *>(ws + WL.wrel);
-    const MapDev &mp = *s_map;
-
     // episode counters of this lane's envs (ATT/ma_main:581-637), flushed once per warp
     int st_ep = 0, st_steps = 0, st_bits[7] = {0, 0, 0, 0, 0, 0, 0};
     float st_ret = 0.0f;
@@ -789,7 +826,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                 a_lo = g * N; n_ag = N;
                 cl = lane < N ? row : p.bank_cells;
             }
-            observe_range<VAR, AUX>(p, w, a_lo, n_ag, cl);
+            observe_range<VAR, AUX, NT>(p, w, a_lo, n_ag, cl);
             if (job > 0 || mode != MODE_STEP) continue;
 
             // ---- reward / collision / goal per drone
@@ -1082,11 +1119,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
     }
 }
 
-template <int VAR, bool AUX>
+template <int VAR, bool AUX, int NT>
 static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     const int wpc = threads / 32;
     const int groups = (p.E + p.G - 1) / p.G;
-    auto fn = env_kernel<VAR, AUX>;
+    auto fn = env_kernel<VAR, AUX, NT>;
     if (*grid_cache <= 0) {   // first launch of this handle: opt in to the shared memory, size the persistent grid
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.CL.total);
         if (e != cudaSuccess) return e;
@@ -1105,19 +1142,23 @@ static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, 
     return cudaGetLastError();
 }
 
+template <int VAR, int NT>
+static cudaError_t launch_aux(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
+    return (p.out_flags & AAC_OUT_RADAR_AUX) ? launch_one<VAR, true, NT>(p, mode, threads, sms, grid_cache, stream)
+                                             : launch_one<VAR, false, NT>(p, mode, threads, sms, grid_cache, stream);
+}
+
 cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     if (p.E <= 0) return cudaSuccess;
-    const bool aux = p.out_flags & AAC_OUT_RADAR_AUX;
     switch (variant) {
-        case AAC_VARIANT_ATT:
-            return aux ? launch_one<AAC_VARIANT_ATT, true>(p, mode, threads, sms, grid_cache, stream)
-                       : launch_one<AAC_VARIANT_ATT, false>(p, mode, threads, sms, grid_cache, stream);
+        case AAC_VARIANT_ATT: return launch_aux<AAC_VARIANT_ATT, 0>(p, mode, threads, sms, grid_cache, stream);
+        case AAC_VARIANT_MM: return launch_aux<AAC_VARIANT_MM, 0>(p, mode, threads, sms, grid_cache, stream);
         case AAC_VARIANT_V2:
-            return aux ? launch_one<AAC_VARIANT_V2, true>(p, mode, threads, sms, grid_cache, stream)
-                       : launch_one<AAC_VARIANT_V2, false>(p, mode, threads, sms, grid_cache, stream);
-        case AAC_VARIANT_MM:
-            return aux ? launch_one<AAC_VARIANT_MM, true>(p, mode, threads, sms, grid_cache, stream)
-                       : launch_one<AAC_VARIANT_MM, false>(p, mode, threads, sms, grid_cache, stream);
+            // the drone counts of the benchmark configurations get kernels specialised on N (register-resident
+            // neighbour sort, unrolled neighbour loops); every other count runs the generic kernel
+            if (p.N == 10) return launch_aux<AAC_VARIANT_V2, 10>(p, mode, threads, sms, grid_cache, stream);
+            if (p.N == 20) return launch_aux<AAC_VARIANT_V2, 20>(p, mode, threads, sms, grid_cache, stream);
+            return launch_aux<AAC_VARIANT_V2, 0>(p, mode, threads, sms, grid_cache, stream);
         default: return cudaErrorInvalidValue;
     }
 }
