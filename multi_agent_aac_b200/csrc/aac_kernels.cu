@@ -750,17 +750,21 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
     unsigned char *ws = smem + CL.warps + (size_t)warp * WL.total;
     Warp w;
     w.map = s_map; w.ray = s_ray; w.lane = lane;
-    w.px = reinterpret_cast<float *>(ws + WL.cur); w.py = w.px + 32; w.vx = w.py + 32; w.vy = w.vx + 32; w.hd = w.vy + 32;
-    w.ppx = reinterpret_cast<float *>(ws + WL.pre); w.ppy = w.ppx + 32; w.pvx = w.ppy + 32; w.pvy = w.pvx + 32;
-    w.meta = reinterpret_cast<unsigned *>(ws + WL.meta); w.meta2 = w.meta + 32; w.minr = w.meta2 + 32; w.agf = w.minr + 32; w.wpm = w.agf + 32;
-    w.agr = reinterpret_cast<float *>(ws + WL.agr);
-    w.d2 = reinterpret_cast<float *>(ws + WL.d2);
-    w.stg = reinterpret_cast<float *>(ws + WL.stg);
-    w.own = reinterpret_cast<float *>(ws + WL.own);
-    w.raw_own = reinterpret_cast<float *>(ws + WL.raw_own);
-    w.order = ws + WL.order; w.atgoal = ws + WL.bytes; w.refw = w.atgoal + 32; w.rs = w.refw + 32; w.amap = w.rs + 32;
-    w.win = reinterpret_cast<uint2 *>(ws + WL.win);
-    w.wrel = reinterpret_cast<float2 *>(ws + WL.wrel);
+    w.px = reinterpret_cast<float *>(ws + WS_CUR); w.py = w.px + 32; w.vx = w.py + 32; w.vy = w.vx + 32; w.hd = w.vy + 32;
+    w.ppx = reinterpret_cast<float *>(ws + WS_PRE); w.ppy = w.ppx + 32; w.pvx = w.ppy + 32; w.pvy = w.pvx + 32;
+    w.meta = reinterpret_cast<unsigned *>(ws + WS_META); w.meta2 = w.meta + 32; w.minr = w.meta2 + 32; w.agf = w.minr + 32; w.wpm = w.agf + 32;
+    w.agr = reinterpret_cast<float *>(ws + WS_AGR);
+    w.atgoal = ws + WS_BYTES; w.refw = w.atgoal + 32; w.rs = w.refw + 32; w.amap = w.rs + 32;
+    w.win = reinterpret_cast<uint2 *>(ws + WS_WIN);
+    w.wrel = reinterpret_cast<float2 *>(ws + WS_WREL);
+    w.stg = reinterpret_cast<float *>(ws + WS_STG);
+    // the variable part: compile-time offsets too when the drone count is a template parameter
+    const WarpLayout VL = NT ? make_warp_layout(VAR, NT, 0) : WL;
+    w.d2 = reinterpret_cast<float *>(ws + VL.d2);
+    w.order = ws + VL.order;
+    w.own = reinterpret_cast<float *>(ws + VL.own);
+    w.raw_own = reinterpret_cast<float *>(ws + (NT ? WL.raw_own : VL.raw_own));
+
     // episode counters of this lane's envs (ATT/ma_main:581-637), flushed once per warp
     int st_ep = 0, st_steps = 0, st_bits[7] = {0, 0, 0, 0, 0, 0, 0};
     float st_ret = 0.0f;

@@ -32,8 +32,19 @@ enum Mode : int { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_RESET = 2 };
 struct CtaLayout {
     unsigned map, ray, bar, warps, total;
 };
-struct WarpLayout {  // offsets inside a warp's slice; every array has 32 drone slots
-    unsigned cur, pre, meta, agr, d2, order, bytes, win, wrel, stg, own, raw_own, total;
+// Per-warp slice (32 drone slots).  The fixed-size arrays sit at compile-time offsets so the kernel addresses them
+// as `slice + immediate`; the arrays whose size depends on the drone count follow at WS_VAR.
+constexpr unsigned WS_CUR = 0;                      // px py vx vy heading        5 x 32 floats
+constexpr unsigned WS_PRE = WS_CUR + 5 * 128;       // pre_pos, pre_vel           4 x 32 floats
+constexpr unsigned WS_META = WS_PRE + 4 * 128;      // meta, meta2, min radar bits, result flags, waypoint mask
+constexpr unsigned WS_AGR = WS_META + 5 * 128;      // reward
+constexpr unsigned WS_BYTES = WS_AGR + 128;         // at-goal flag, ref-line vertex count, per-env scratch, map row
+constexpr unsigned WS_WIN = WS_BYTES + 4 * 32;      // 4x4 occupancy window: mask | flags, ix0 | iy0 << 16
+constexpr unsigned WS_WREL = WS_WIN + 256;          // window origin relative to the drone
+constexpr unsigned WS_STG = WS_WREL + 256;          // transient staging of one warp iteration's pair blocks
+constexpr unsigned WS_VAR = WS_STG + 32 * 6 * 4;    // d2 [32][M|1] floats, order [32][M] bytes, own rows, raw own rows
+struct WarpLayout {
+    unsigned d2, order, own, raw_own, total;        // byte offsets of the variable part inside the slice
 };
 
 struct KParams {
@@ -67,24 +78,15 @@ __host__ __device__ inline int own_dim(int variant, int N) {
     return variant == AAC_VARIANT_ATT ? 6 + 4 * (N - 1) : (variant == AAC_VARIANT_V2 ? 7 : 6);
 }
 
-inline WarpLayout make_warp_layout(int variant, int N, int flags) {
+__host__ __device__ inline WarpLayout make_warp_layout(int variant, int N, int flags) {
     WarpLayout L;
     const unsigned M = N - 1, Mp = M | 1, M1 = M ? M : 1;
     const unsigned D = own_dim(variant, N);
-    unsigned o = 0;
-    auto take = [&](unsigned bytes) { unsigned r = o; o = align16(o + bytes); return r; };
-    L.cur = take(5 * 32 * 4);        // px py vx vy heading
-    L.pre = take(4 * 32 * 4);        // pre_pos, pre_vel
-    L.meta = take(5 * 32 * 4);       // meta, meta2, min radar bits, result flags, waypoint mask
-    L.agr = take(32 * 4);            // reward
-    L.d2 = take(32 * Mp * 4);        // neighbour distances^2 in iteration order, odd row stride
-    L.order = take(32 * M1);
-    L.bytes = take(4 * 32);          // at-goal flag, ref-line vertex count, per-env scratch, map row
-    L.win = take(32 * 8);            // 4x4 occupancy window: mask | flags, ix0 | iy0 << 16
-    L.wrel = take(32 * 8);           // window origin relative to the drone
-    L.stg = take(32 * 6 * 4);        // transient staging of one warp iteration's pair blocks
-    L.own = take(32 * D * 4);        // own rows of the observation
-    L.raw_own = take((flags & AAC_OUT_RAW) ? 32 * D * 4 : 0);
+    unsigned o = WS_VAR;
+    L.d2 = o; o = align16(o + 32 * Mp * 4);        // neighbour distances^2 in iteration order, odd row stride
+    L.order = o; o = align16(o + 32 * M1);
+    L.own = o; o = align16(o + 32 * D * 4);        // own rows of the observation
+    L.raw_own = o; o = align16(o + ((flags & AAC_OUT_RAW) ? 32 * D * 4 : 0));
     L.total = o;
     return L;
 }
