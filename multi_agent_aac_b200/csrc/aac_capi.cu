@@ -31,6 +31,7 @@ struct AacEnv {
     int *d_work = nullptr;       // ping-pong group counters of the persistent kernel
     int sms = 0;
     int grid = 0;                // persistent grid size, fixed at the first launch
+    float cell = 0.0f;           // cell size of the maps (all maps of a handle share it)
     AacState st{};
     bool bound = false;
     int64_t launches = 0;
@@ -151,6 +152,7 @@ extern "C" int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *
         o.ox = d.origin_x; o.oy = d.origin_y;
         o.ex0 = (d.x0c - 0.5f * d.cell) - d.origin_x; o.ey0 = (d.y0c - 0.5f * d.cell) - d.origin_y;
         o.xmin_g = d.bound[0]; o.ymin_g = d.bound[2];
+        if (m > 0 && d.cell != maps[0].cell) return fail(AAC_ERR_ARG, "aac_set_maps: every map must use the same cell size");
         o.cell = d.cell; o.inv_cell = 1.0f / d.cell;
         o.ihx = 1.0f / o.hx; o.ihy = 1.0f / o.hy;
         for (int ix = 0; ix < d.gx; ++ix)
@@ -164,6 +166,7 @@ extern "C" int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *
     CU(cudaMalloc(&env->d_maps, sizeof(MapDev) * n_maps));
     CU(cudaMemcpy(env->d_maps, host.data(), sizeof(MapDev) * n_maps, cudaMemcpyHostToDevice));
     env->n_maps = n_maps;
+    env->cell = maps[0].cell;
     return 0;
 }
 
@@ -228,7 +231,7 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     const AacConfig &c = env->cfg;
     p.E = c.n_envs; p.N = c.n_agents; p.R = c.n_rays; p.W = c.w_max; p.G = env->group;
     p.radar_mode = c.radar_mode; p.sum_reward = c.sum_reward; p.ep_len = c.episode_length; p.out_flags = c.out_flags;
-    p.dt = c.dt; p.vmax = c.vmax; p.acc_max = c.acc_max; p.prot = c.prot; p.ray_len = c.ray_len; p.goal_r = c.goal_r;
+    p.cell = env->cell; p.dt = c.dt; p.vmax = c.vmax; p.acc_max = c.acc_max; p.prot = c.prot; p.ray_len = c.ray_len; p.goal_r = c.goal_r;
     p.env_id_base = c.env_id_base; p.seed = c.seed;
     p.maps = env->d_maps; p.n_maps = env->n_maps; p.ray_tab = env->d_ray; p.autoreset = autoreset;
     p.bank_cells = env->d_bank_cells; p.bank_w = env->d_bank_w; p.bank_map = env->d_bank_map; p.n_scen = env->n_scen;

@@ -260,22 +260,22 @@ __device__ __forceinline__ void radar_bounds(const MapDev &mp, float px, float p
 // Axis-parallel rays carry 1/d = +inf: the products are +-inf (or NaN exactly on a grid line, which
 // fminf / fmaxf drop), i.e. no constraint from that axis.
 template <bool AUX>
-__device__ __forceinline__ void radar_window(const MapDev &mp, float2 wrel, unsigned win, int wix0, int wiy0, float4 ray, float len,
-                                             float &shortest, float &sensed, int &shortest_id, int &sensed_id) {
+__device__ __forceinline__ void radar_window(const MapDev &mp, const float2 *lut, float2 wrel, unsigned win, int wix0, int wiy0, float4 ray,
+                                             float len, float &shortest, float &sensed, int &shortest_id, int &sensed_id) {
 #pragma unroll 1
     while (win) {
         const int b = __ffs(win) - 1;
         win &= win - 1;
-        const int r = b >> 2, c = b & 3;
-        const float x0 = fmaf((float)r, mp.cell, wrel.x), y0 = fmaf((float)c, mp.cell, wrel.y);
+        const float2 off = lut[b];   // (row, column) of window cell b times the cell size
+        const float x0 = wrel.x + off.x, y0 = wrel.y + off.y;
         const float tx0 = x0 * ray.z, tx1 = (x0 + mp.cell) * ray.z, ty0 = y0 * ray.w, ty1 = (y0 + mp.cell) * ray.w;
         const float lo = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), 0.0f);
         const float hi = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), 1.0f);
         if (lo <= hi) {
             const float d = lo * len;
             sensed = d;
-            if (AUX) sensed_id = (wix0 + r) * mp.gy + wiy0 + c;
-            if (d < shortest) { shortest = d; if (AUX) shortest_id = (wix0 + r) * mp.gy + wiy0 + c; }
+            if (AUX) sensed_id = (wix0 + (b >> 2)) * mp.gy + wiy0 + (b & 3);
+            if (d < shortest) { shortest = d; if (AUX) shortest_id = (wix0 + (b >> 2)) * mp.gy + wiy0 + (b & 3); }
         }
     }
 }
@@ -363,6 +363,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 struct Warp {
     const MapDev *map;
     const float4 *ray;
+    const float2 *lut;  // [16] window cell (row, column) * cell size
     int lane;
     int e_lo, ng, a0, nA;   // first env of the group, envs / drones in it, global index of its first drone
     float *px, *py, *vx, *vy, *hd, *ppx, *ppy, *pvx, *pvy;
@@ -383,16 +384,22 @@ __device__ __forceinline__ void flush_items(float *dst, int n_valid, const float
         for (int c = 0; c < PI; ++c) stg[lane * PI + c] = v[c];
     }
     __syncwarp();
-    for (int f = lane; f < n_valid * PI; f += 32) dst[f] = stg[f];
+    if (n_valid == 32) {
+#pragma unroll
+        for (int c = 0; c < PI; ++c) dst[c * 32 + lane] = stg[c * 32 + lane];
+    } else {
+        for (int f = lane; f < n_valid * PI; f += 32) dst[f] = stg[f];
+    }
     __syncwarp();
 }
 
 // observation pipeline for the drones [a_lo, a_lo + n_ag) of the warp's group (whole envs):
 // neighbour order + window -> { pairs | rays | own block }.  `cells` = the lane's reference-line row.
-template <int VAR, bool AUX, int NT>
+template <int VAR, bool AUX, int NT, int RT>
 __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, const int a_lo, const int n_ag, const uint16_t *cells) {
     const int lane = w.lane;
-    const int N = NT ? NT : p.N, M = N - 1, R = p.R, Mp = M | 1;   // NT > 0: drone count known at compile time
+    // NT / RT > 0: drone count / ray count known at compile time
+    const int N = NT ? NT : p.N, M = N - 1, R = RT ? RT : p.R, Mp = M | 1;
     const int D = own_dim(VAR, N);
     const int flags = p.out_flags;
     // one map staged in shared memory, or (multipleMap) the env's own map read through L1
@@ -541,8 +548,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
     //      (min_radar) is one redux.sync per drone and iteration.
     {
         const float len = p.ray_len;
-        auto cast = [&](const int aa, const int k, float &out_min, int &id) -> float {
-            const float4 ray = w.ray[k];
+        auto cast = [&](const int aa, const float4 ray, float &out_min, int &id) -> float {
             const MapDev &mr = map_of(aa);
             float out;
             if (VAR == AAC_VARIANT_ATT) {
@@ -554,7 +560,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
                 float shortest = CUDART_INF_F, sensed = len;
                 int shortest_id = -1, sensed_id = -1;
                 if (!(wn.x & W_SLOW))
-                    radar_window<AUX>(mr, w.wrel[aa], wn.x & 0xFFFFu, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16), ray, len, shortest,
+                    radar_window<AUX>(mr, w.lut, w.wrel[aa], wn.x & 0xFFFFu, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16), ray, len, shortest,
                                       sensed, shortest_id, sensed_id);
                 else {
                     const GenericHit h = radar_generic<AUX>(mr, w.px[aa], w.py[aa], ray, len);
@@ -572,6 +578,8 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
         const size_t rg0 = (size_t)(w.a0 + a_lo) * R;
         float *g_out = p.out.radar + rg0;
         // full chunks: lanes = rays 32c .. 32c+31 of drone q
+        // a lane casts the same ray(s) for every drone: the table entry of the first chunk stays in registers
+        const float4 ray0 = w.ray[lane < R ? lane : 0];
 #pragma unroll 1
         for (int q = 0; q < n_ag; ++q) {
 #pragma unroll 1
@@ -579,7 +587,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
                 const int k = (c << 5) + lane;
                 float out_min;
                 int id = -1;
-                const float out = cast(a_lo + q, k, out_min, id);
+                const float out = cast(a_lo + q, c == 0 ? ray0 : w.ray[k], out_min, id);
                 g_out[q * R + k] = out;
                 if (AUX) { p.out.radar_min[rg0 + q * R + k] = out_min; p.out.radar_hit[rg0 + q * R + k] = (int16_t)id; }
                 const unsigned m = __reduce_min_sync(FULL, __float_as_uint(out));
@@ -590,6 +598,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
         if (rem) {
             const int per = 32 / rem;
             const int sub = lane / rem, k = (full << 5) + lane - sub * rem;
+            const float4 rayr = w.ray[k < R ? k : 0];
 #pragma unroll 1
             for (int q0 = 0; q0 < n_ag; q0 += per) {
                 const int nsub = min(per, n_ag - q0);
@@ -597,7 +606,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
                 const int q = q0 + (ok ? sub : 0);
                 float out_min;
                 int id = -1;
-                const float out = cast(a_lo + q, k, out_min, id);
+                const float out = cast(a_lo + q, rayr, out_min, id);
                 if (ok) {
                     g_out[q * R + k] = out;
                     if (AUX) { p.out.radar_min[rg0 + q * R + k] = out_min; p.out.radar_hit[rg0 + q * R + k] = (int16_t)id; }
@@ -720,7 +729,7 @@ __device__ __forceinline__ void polyline_nearest(const MapDev &mp, const uint16_
     total = run;
 }
 
-template <int VAR, bool AUX, int NT>
+template <int VAR, bool AUX, int NT, int RT>
 __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_constant__ KParams p, const int mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -744,12 +753,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
         if (blockIdx.x == 0) p.work[p.parity ^ 1] = 0;   // the next launch's group counter
     }
     for (int k = tid; k < p.R; k += blockDim.x) s_ray[k] = p.ray_tab[k];
+    float2 *s_lut = reinterpret_cast<float2 *>(smem + CL.lut);
+    if (tid < 16) s_lut[tid] = make_float2((float)(tid >> 2) * p.cell, (float)(tid & 3) * p.cell);
     __syncthreads();
     mbar_wait(s_bar, 0);
 
     unsigned char *ws = smem + CL.warps + (size_t)warp * WL.total;
     Warp w;
-    w.map = s_map; w.ray = s_ray; w.lane = lane;
+    w.map = s_map; w.ray = s_ray; w.lut = s_lut; w.lane = lane;
     w.px = reinterpret_cast<float *>(ws + WS_CUR); w.py = w.px + 32; w.vx = w.py + 32; w.vy = w.vx + 32; w.hd = w.vy + 32;
     w.ppx = reinterpret_cast<float *>(ws + WS_PRE); w.ppy = w.ppx + 32; w.pvx = w.ppy + 32; w.pvy = w.pvx + 32;
     w.meta = reinterpret_cast<unsigned *>(ws + WS_META); w.meta2 = w.meta + 32; w.minr = w.meta2 + 32; w.agf = w.minr + 32; w.wpm = w.agf + 32;
@@ -830,7 +841,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                 a_lo = g * N; n_ag = N;
                 cl = lane < N ? row : p.bank_cells;
             }
-            observe_range<VAR, AUX, NT>(p, w, a_lo, n_ag, cl);
+            observe_range<VAR, AUX, NT, RT>(p, w, a_lo, n_ag, cl);
             if (job > 0 || mode != MODE_STEP) continue;
 
             // ---- reward / collision / goal per drone
@@ -1123,11 +1134,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
     }
 }
 
-template <int VAR, bool AUX, int NT>
+template <int VAR, bool AUX, int NT, int RT>
 static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     const int wpc = threads / 32;
     const int groups = (p.E + p.G - 1) / p.G;
-    auto fn = env_kernel<VAR, AUX, NT>;
+    auto fn = env_kernel<VAR, AUX, NT, RT>;
     if (*grid_cache <= 0) {   // first launch of this handle: opt in to the shared memory, size the persistent grid
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.CL.total);
         if (e != cudaSuccess) return e;
@@ -1146,23 +1157,25 @@ static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, 
     return cudaGetLastError();
 }
 
-template <int VAR, int NT>
+template <int VAR, int NT, int RT>
 static cudaError_t launch_aux(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
-    return (p.out_flags & AAC_OUT_RADAR_AUX) ? launch_one<VAR, true, NT>(p, mode, threads, sms, grid_cache, stream)
-                                             : launch_one<VAR, false, NT>(p, mode, threads, sms, grid_cache, stream);
+    return (p.out_flags & AAC_OUT_RADAR_AUX) ? launch_one<VAR, true, NT, RT>(p, mode, threads, sms, grid_cache, stream)
+                                             : launch_one<VAR, false, NT, RT>(p, mode, threads, sms, grid_cache, stream);
 }
 
 cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     if (p.E <= 0) return cudaSuccess;
     switch (variant) {
-        case AAC_VARIANT_ATT: return launch_aux<AAC_VARIANT_ATT, 0>(p, mode, threads, sms, grid_cache, stream);
-        case AAC_VARIANT_MM: return launch_aux<AAC_VARIANT_MM, 0>(p, mode, threads, sms, grid_cache, stream);
+        case AAC_VARIANT_ATT: return launch_aux<AAC_VARIANT_ATT, 0, 0>(p, mode, threads, sms, grid_cache, stream);
+        case AAC_VARIANT_MM: return launch_aux<AAC_VARIANT_MM, 0, 0>(p, mode, threads, sms, grid_cache, stream);
         case AAC_VARIANT_V2:
-            // the drone counts of the benchmark configurations get kernels specialised on N (register-resident
-            // neighbour sort, unrolled neighbour loops); every other count runs the generic kernel
-            if (p.N == 10) return launch_aux<AAC_VARIANT_V2, 10>(p, mode, threads, sms, grid_cache, stream);
-            if (p.N == 20) return launch_aux<AAC_VARIANT_V2, 20>(p, mode, threads, sms, grid_cache, stream);
-            return launch_aux<AAC_VARIANT_V2, 0>(p, mode, threads, sms, grid_cache, stream);
+            // the benchmark configurations get kernels specialised on the drone and ray counts (register-resident
+            // neighbour sort, constant loop bounds and addressing); everything else runs the generic kernel
+            if (p.N == 10 && p.R == 36) return launch_aux<AAC_VARIANT_V2, 10, 36>(p, mode, threads, sms, grid_cache, stream);
+            if (p.N == 20 && p.R == 72) return launch_aux<AAC_VARIANT_V2, 20, 72>(p, mode, threads, sms, grid_cache, stream);
+            if (p.N == 10) return launch_aux<AAC_VARIANT_V2, 10, 0>(p, mode, threads, sms, grid_cache, stream);
+            if (p.N == 20) return launch_aux<AAC_VARIANT_V2, 20, 0>(p, mode, threads, sms, grid_cache, stream);
+            return launch_aux<AAC_VARIANT_V2, 0, 0>(p, mode, threads, sms, grid_cache, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -30,7 +30,7 @@ enum Mode : int { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_RESET = 2 };
 
 // shared-memory carve-up (byte offsets), computed once on the host: CTA-wide data, then one slice per warp
 struct CtaLayout {
-    unsigned map, ray, bar, warps, total;
+    unsigned map, ray, lut, bar, warps, total;
 };
 // Per-warp slice (32 drone slots).  The fixed-size arrays sit at compile-time offsets so the kernel addresses them
 // as `slice + immediate`; the arrays whose size depends on the drone count follow at WS_VAR.
@@ -51,6 +51,7 @@ struct KParams {
     int E, N, R, W, G;      // G = envs per warp (G * N <= 32)
     int radar_mode, sum_reward, ep_len, out_flags;
     float dt, vmax, acc_max, prot, ray_len, goal_r;
+    float cell;             // cell size shared by every map of the handle
     long long env_id_base;
     unsigned long long seed;
     const MapDev *maps;
@@ -97,6 +98,7 @@ inline CtaLayout make_cta_layout(const WarpLayout &WL, int R, int warps) {
     auto take = [&](unsigned bytes) { unsigned r = o; o = align16(o + bytes); return r; };
     L.map = take(sizeof(MapDev));
     L.ray = take(R * 16);
+    L.lut = take(16 * 8);
     L.bar = take(16);
     L.warps = take(0);
     L.total = L.warps + warps * WL.total;
