@@ -30,8 +30,11 @@ struct AacEnv {
     double *d_stats = nullptr;
     int *d_work = nullptr;       // ping-pong group counters of the persistent kernel
     int sms = 0;
-    int grid = 0;                // persistent grid size, fixed at the first launch
+    int grid = 0;                // resident CTAs per SM of the kernel, queried at the first launch
     float cell = 0.0f;           // cell size of the maps (all maps of a handle share it)
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};   // aac_step_host: chunks rotate over these streams
+    cudaEvent_t pipe_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t pair_launches[1 + 16] = {0};                 // launches per group-counter pair (0 = whole range)
     AacState st{};
     bool bound = false;
     int64_t launches = 0;
@@ -111,8 +114,8 @@ extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
         }
     CU(cudaMalloc(&env->d_ray, sizeof(float4) * cfg->n_rays));
     CU(cudaMemcpy(env->d_ray, rays.data(), sizeof(float4) * cfg->n_rays, cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&env->d_work, 2 * sizeof(int)));
-    CU(cudaMemset(env->d_work, 0, 2 * sizeof(int)));
+    CU(cudaMalloc(&env->d_work, 2 * 17 * sizeof(int)));   // one ping-pong pair for whole-range launches, 16 for pipeline chunks
+    CU(cudaMemset(env->d_work, 0, 2 * 17 * sizeof(int)));
     CU(cudaDeviceGetAttribute(&env->sms, cudaDevAttrMultiProcessorCount, env->device));
     CU(cudaMalloc(&env->d_stats, sizeof(double) * AAC_N_STATS));
     CU(cudaMemset(env->d_stats, 0, sizeof(double) * AAC_N_STATS));
@@ -130,6 +133,8 @@ extern "C" void aac_destroy(AacEnv *env) {
     cudaFree(env->d_actions);
     cudaFree(env->d_stats);
     cudaFree(env->d_work);
+    for (auto &s : env->pipe) if (s) cudaStreamDestroy(s);
+    for (auto &e : env->pipe_ev) if (e) cudaEventDestroy(e);
     delete env;
 }
 
@@ -218,7 +223,23 @@ static int check_out(const AacEnv *env, const AacOut *o, int mode) {
     return 0;
 }
 
-static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actions, const AacOut *out, void *stream, int autoreset = 0) {
+// advance every per-env / per-drone pointer of the state and output blocks to env `e_lo`
+static void offset_rows(AacState &s, AacOut &o, size_t e_lo, size_t N, size_t R, size_t W, size_t D) {
+    const size_t a = e_lo * N, M = N - 1;
+#define ADV(ptr, n) if (ptr) ptr += (n)
+    ADV(s.px, a); ADV(s.py, a); ADV(s.vx, a); ADV(s.vy, a); ADV(s.heading, a); ADV(s.meta, a); ADV(s.ref_cells, a * W); ADV(s.ref_w, a);
+    ADV(s.wall_count, a); ADV(s.ep_step, e_lo); ADV(s.ep_index, e_lo); ADV(s.ep_return, e_lo); ADV(s.map_id, e_lo); ADV(s.wp_mask, a);
+    ADV(o.norm_own, a * D); ADV(o.norm_nbr, a * 5 * M); ADV(o.radar, a * R); ADV(o.norm_nbr6, a * 6 * M);
+    ADV(o.raw_own, a * D); ADV(o.raw_nbr, a * 5 * M); ADV(o.raw_nbr6, a * 6 * M);
+    ADV(o.reward, a); ADV(o.done, a); ADV(o.check_goal, a); ADV(o.bbc, e_lo * 4); ADV(o.terminated, e_lo); ADV(o.tcpa_min, a * 4);
+    ADV(o.tcpa_pair, a * 4 * M); ADV(o.nbr_order, a * M); ADV(o.radar_min, a * R); ADV(o.radar_hit, a * R); ADV(o.parts, a * 8); ADV(o.branch, a);
+#undef ADV
+}
+
+// launch over the envs [e_lo, e_lo + e_cnt) of the handle (e_cnt <= 0: all of them).  `pair` selects the
+// ping-pong group-counter pair: launches that may run concurrently must use different pairs.
+static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actions, const AacOut *out, void *stream, int autoreset = 0,
+                  int e_lo = 0, int e_cnt = 0, int pair = 0) {
     if (!env) return fail(AAC_ERR_ARG, "null handle");
     if (!env->bound) return fail(AAC_ERR_STATE, "aac_bind_state has not been called");
     if (!env->d_maps) return fail(AAC_ERR_STATE, "aac_set_maps has not been called");
@@ -236,11 +257,19 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     p.maps = env->d_maps; p.n_maps = env->n_maps; p.ray_tab = env->d_ray; p.autoreset = autoreset;
     p.bank_cells = env->d_bank_cells; p.bank_w = env->d_bank_w; p.bank_map = env->d_bank_map; p.n_scen = env->n_scen;
     p.mask = mask; p.actions = actions; p.stats = env->d_stats;
-    p.work = env->d_work; p.parity = (int)(env->launches & 1);
+    p.work = env->d_work + 2 * pair; p.parity = (int)(env->pair_launches[pair] & 1);
     p.st = env->st; p.out = *out; p.CL = env->cl; p.WL = env->wl;
+    if (e_cnt > 0) {
+        p.E = e_cnt;
+        p.env_id_base += e_lo;
+        if (p.mask) p.mask += e_lo;
+        if (p.actions) p.actions += (size_t)e_lo * c.n_agents * 2;
+        offset_rows(p.st, p.out, e_lo, c.n_agents, c.n_rays, c.w_max, own_dim(c.variant, c.n_agents));
+    }
     cudaError_t e = launch_env_kernel(c.variant, p, mode, env->threads, env->sms, &env->grid, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "env_kernel launch");
     env->launches += 1;
+    env->pair_launches[pair] += 1;
     return 0;
 }
 
@@ -262,25 +291,46 @@ extern "C" int aac_autoreset(AacEnv *env, const AacOut *out, void *stream) {
 extern "C" int aac_step_host(AacEnv *env, const float *actions_host, const AacOut *od, const AacOut *oh, int32_t autoreset, void *stream_) {
     if (!env || !actions_host || !od || !oh) return fail(AAC_ERR_ARG, "aac_step_host: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
-    const size_t E = env->cfg.n_envs, N = env->cfg.n_agents, A = E * N, M = N - 1, R = env->cfg.n_rays;
+    const size_t E = env->cfg.n_envs, N = env->cfg.n_agents, M = N - 1, R = env->cfg.n_rays;
     const size_t D = own_dim(env->cfg.variant, (int)N);
-    if (!env->d_actions) CU(cudaMalloc(&env->d_actions, A * 2 * sizeof(float)));
-    CU(cudaMemcpyAsync(env->d_actions, actions_host, A * 2 * sizeof(float), cudaMemcpyHostToDevice, stream));
-    // one launch: with autoreset the terminal transition's reward / done / flags are kept and the
-    // observation rows of the finished envs carry their reset observation
-    int rc = autoreset ? aac_step_autoreset(env, env->d_actions, od, stream) : aac_step(env, env->d_actions, od, stream);
-    if (rc) return rc;
-#define D2H(field, bytes)                                                                                   \
-    if (oh->field) {                                                                                        \
-        if (!od->field) return fail(AAC_ERR_ARG, "aac_step_host: host buffer without a device buffer: %s", #field); \
-        CU(cudaMemcpyAsync(oh->field, od->field, (bytes), cudaMemcpyDeviceToHost, stream));                 \
+    if (!env->d_actions) CU(cudaMalloc(&env->d_actions, E * N * 2 * sizeof(float)));
+    if (!env->pipe[0]) {
+        for (auto &s : env->pipe) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        for (auto &e : env->pipe_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    D2H(reward, A * 4) D2H(done, A) D2H(check_goal, A) D2H(bbc, E * 4) D2H(terminated, E) D2H(tcpa_min, A * 16)
-    D2H(norm_own, A * D * 4) D2H(norm_nbr, A * 5 * M * 4) D2H(radar, A * R * 4) D2H(norm_nbr6, A * M * 24)
-    D2H(raw_own, A * D * 4) D2H(raw_nbr, A * 5 * M * 4) D2H(raw_nbr6, A * M * 24)
-    D2H(tcpa_pair, A * M * 16) D2H(nbr_order, A * M) D2H(radar_min, A * R * 4) D2H(radar_hit, A * R * 2)
-    D2H(parts, A * 32) D2H(branch, A)
+    // The envs are cut into chunks that rotate over three streams: while chunk c's outputs cross PCIe, chunk c+1
+    // steps and chunk c+2's actions arrive.  Small batches go as one chunk.  With autoreset the terminal
+    // transition's reward / done / flags are kept and the observation rows of the finished envs carry their reset
+    // observation (one fused launch per chunk).
+    const size_t G = env->group;
+    size_t n_chunks = E * N >= 65536 ? 8 : 1;
+    size_t per = ((E + n_chunks - 1) / n_chunks + G - 1) / G * G;
+    n_chunks = (E + per - 1) / per;
+    CU(cudaEventRecord(env->pipe_ev[3], stream));
+    for (size_t ch = 0; ch < n_chunks; ++ch) {
+        const size_t e_lo = ch * per, cnt = (e_lo + per <= E ? per : E - e_lo), a_lo = e_lo * N, A = cnt * N;
+        cudaStream_t s = env->pipe[ch % 3];
+        if (ch < 3) CU(cudaStreamWaitEvent(s, env->pipe_ev[3], 0));
+        CU(cudaMemcpyAsync(env->d_actions + a_lo * 2, actions_host + a_lo * 2, A * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+        const int rc = launch(env, MODE_STEP, nullptr, env->d_actions, od, s, autoreset ? 1 : 0, (int)e_lo, (int)cnt, 1 + (int)ch);
+        if (rc) return rc;
+#define D2H(field, per_env)                                                                                              \
+        if (oh->field) {                                                                                                 \
+            if (!od->field) return fail(AAC_ERR_ARG, "aac_step_host: host buffer without a device buffer: %s", #field);  \
+            CU(cudaMemcpyAsync((char *)oh->field + e_lo * (per_env), (const char *)od->field + e_lo * (per_env), cnt * (per_env), \
+                               cudaMemcpyDeviceToHost, s));                                                              \
+        }
+        D2H(reward, N * 4) D2H(done, N) D2H(check_goal, N) D2H(bbc, 4) D2H(terminated, 1) D2H(tcpa_min, N * 16)
+        D2H(norm_own, N * D * 4) D2H(norm_nbr, N * 5 * M * 4) D2H(radar, N * R * 4) D2H(norm_nbr6, N * M * 24)
+        D2H(raw_own, N * D * 4) D2H(raw_nbr, N * 5 * M * 4) D2H(raw_nbr6, N * M * 24)
+        D2H(tcpa_pair, N * M * 16) D2H(nbr_order, N * M) D2H(radar_min, N * R * 4) D2H(radar_hit, N * R * 2)
+        D2H(parts, N * 32) D2H(branch, N)
 #undef D2H
+    }
+    for (int k = 0; k < 3 && (size_t)k < n_chunks; ++k) {
+        CU(cudaEventRecord(env->pipe_ev[k], env->pipe[k]));
+        CU(cudaStreamWaitEvent(stream, env->pipe_ev[k], 0));
+    }
     CU(cudaStreamSynchronize(stream));
     return 0;
 }

@@ -1139,21 +1139,20 @@ static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, 
     const int wpc = threads / 32;
     const int groups = (p.E + p.G - 1) / p.G;
     auto fn = env_kernel<VAR, AUX, NT, RT>;
-    if (*grid_cache <= 0) {   // first launch of this handle: opt in to the shared memory, size the persistent grid
+    if (*grid_cache <= 0) {   // first launch of this handle: opt in to the shared memory, query the residency
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.CL.total);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, p.CL.total);
         if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        // persistent warps: as many CTAs as fit on the device at once (a multiple of the SM count), never
-        // more than there are groups to hand out
-        int grid = sms * per_sm;
-        const int need = (groups + wpc - 1) / wpc;
-        if (grid > need) grid = need;
-        *grid_cache = grid;
+        *grid_cache = per_sm < 1 ? 1 : per_sm;
     }
-    fn<<<*grid_cache, threads, p.CL.total, stream>>>(p, mode);
+    // persistent warps: as many CTAs as fit on the device at once (a multiple of the SM count), never more than
+    // there are groups to hand out
+    int grid = sms * *grid_cache;
+    const int need = (groups + wpc - 1) / wpc;
+    if (grid > need) grid = need;
+    fn<<<grid, threads, p.CL.total, stream>>>(p, mode);
     return cudaGetLastError();
 }
 

@@ -211,3 +211,33 @@ def test_ref_compat_env_reproduces_reference_episode(name):
         assert np.allclose([float(r) for r in reward], d["reward"][t], rtol=1e-3, atol=5e-3), t
         assert list(done) == [bool(v) for v in d["done"][t]] and list(bbc) == [bool(v) for v in d["bbc"][t]], t
         assert isinstance(reward[0], np.ndarray) and reward[0].ndim == 0 and isinstance(done[0], bool)
+
+
+@pytest.mark.parametrize("n_envs", [100, 7001])
+def test_step_host_pipeline_equals_device_step(n_envs):
+    """aac_step_host (pinned host buffers, chunks pipelined over three streams for large batches) must return
+    exactly what aac_step_autoreset leaves on the device."""
+    import torch
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import synthetic_map
+    from multi_agent_aac_b200.reset import ScenarioBank
+    gmap = synthetic_map(seed=0)
+    n, r = 10, 36
+    envs = []
+    for _ in range(2):
+        env = BatchedDroneEnv(preset("tdcpa_v2", n_envs=n_envs, n_agents=n, n_rays=r, w_max=32, seed=3), gmap)
+        env.set_bank(ScenarioBank(gmap, n, 64, w_max=32, seed=3))
+        env.reset()
+        envs.append(env)
+    host = envs[1].host_buffers(("norm_own", "norm_nbr", "radar", "reward", "done", "check_goal", "bbc", "terminated", "tcpa_min"))
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(1)
+    for t in range(6):
+        act = (torch.rand((n_envs, n, 2), generator=gen) * 2 - 1).contiguous().pin_memory()
+        envs[0].step(act.cuda(), autoreset=True)
+        out = envs[1].step_host(act, autoreset=True)
+        for k, v in out.items():
+            assert torch.equal(v.view(torch.uint8), envs[0].out[k].cpu().view(torch.uint8)), (t, k)
+        for k in envs[0].state:
+            assert torch.equal(envs[0].state[k].view(torch.uint8), envs[1].state[k].view(torch.uint8)), (t, k)
+    assert abs(envs[0].read_stats()[0] - envs[1].read_stats()[0]) == 0
