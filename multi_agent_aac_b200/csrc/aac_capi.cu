@@ -79,9 +79,24 @@ extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
     env->cfg = *cfg;
     CU(cudaGetDevice(&env->device));
     // a warp owns G = 32 / N whole envs; a CTA is a handful of independent warps sharing the map
+    CU(cudaDeviceGetAttribute(&env->sms, cudaDevAttrMultiProcessorCount, env->device));
     env->group = cfg->tile_envs > 0 ? cfg->tile_envs : (32 / cfg->n_agents > 0 ? 32 / cfg->n_agents : 1);
+    if (cfg->tile_envs <= 0) {
+        // small batches are latency-bound (one group's pipeline is a ~60 us dependency chain): give each warp fewer envs
+        // so that there are at least 16 groups per SM, even though lanes idle in the drone-per-lane phases
+        const int want = cfg->n_envs / (16 * (env->sms > 0 ? env->sms : 1));
+        if (want < env->group) env->group = want < 1 ? 1 : want;
+    }
     if (env->group * cfg->n_agents > 32) { delete env; return fail(AAC_ERR_ARG, "aac_create: tile_envs * n_agents must not exceed 32"); }
-    env->threads = cfg->block_threads > 0 ? cfg->block_threads : MAX_THREADS;
+    if (cfg->block_threads > 0) {
+        env->threads = cfg->block_threads;
+    } else {
+        // small batches: fewer warps per CTA so that every SM gets work (a 4096-env x 3-drone batch is only 410 groups)
+        const int groups = (cfg->n_envs + env->group - 1) / env->group;
+        int wpc = (groups + env->sms - 1) / (env->sms > 0 ? env->sms : 1);
+        wpc = wpc < 1 ? 1 : (wpc > MAX_THREADS / 32 ? MAX_THREADS / 32 : wpc);
+        env->threads = 32 * wpc;
+    }
     if (env->threads > MAX_THREADS || env->threads % 32) { delete env; return fail(AAC_ERR_ARG, "aac_create: block_threads must be a multiple of 32, <= 256"); }
     env->wl = make_warp_layout(cfg->variant, cfg->n_agents, cfg->out_flags);
     const int optin = max_smem_optin();
@@ -116,7 +131,6 @@ extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
     CU(cudaMemcpy(env->d_ray, rays.data(), sizeof(float4) * cfg->n_rays, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&env->d_work, 2 * 17 * sizeof(int)));   // one ping-pong pair for whole-range launches, 16 for pipeline chunks
     CU(cudaMemset(env->d_work, 0, 2 * 17 * sizeof(int)));
-    CU(cudaDeviceGetAttribute(&env->sms, cudaDevAttrMultiProcessorCount, env->device));
     CU(cudaMalloc(&env->d_stats, sizeof(double) * AAC_N_STATS));
     CU(cudaMemset(env->d_stats, 0, sizeof(double) * AAC_N_STATS));
     *out = env;
