@@ -142,6 +142,33 @@ def cpu_reference_run(wl, steps, warmup, sample_envs, threads=None):
             "seconds": dt}, dt / steps
 
 
+def quick_device_rate(wl, dev, steps=300, warmup=10):
+    """Device-resident throughput of another workload (reported next to the main line, N = 1 only)."""
+    import torch
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    preset_name, envs, n, r, desc = WORKLOADS[wl]
+    gmap, bank = build_world(wl, 256, seed=1000)
+    env = BatchedDroneEnv(preset(preset_name, n_envs=envs, n_agents=n, n_rays=r, w_max=32, seed=1000), gmap, device=dev)
+    from multi_agent_aac_b200.reset import OdTable
+    env.set_od_tables([OdTable(m, w_max=32) for m in (gmap if isinstance(gmap, list) else [gmap])])
+    env.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7)
+    acts = [(torch.rand((envs, n, 2), device=dev, generator=gen) * 2 - 1).contiguous() for _ in range(4)]
+    for k in range(warmup):
+        env.step(acts[k % 4], autoreset=True)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    t0.record()
+    for k in range(steps):
+        env.step(acts[k % 4], autoreset=True)
+    t1.record()
+    torch.cuda.synchronize(dev)
+    ms = t0.elapsed_time(t1) / steps
+    env.close()
+    return {"workload": desc, "value": envs * n / (ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms, "steps": steps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -151,9 +178,12 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scenarios", type=int, default=512)
+    ap.add_argument("--reset-source", default="od", choices=["od", "bank"],
+                    help="od: origins/destinations drawn on the device from the map's OD table; bank: pre-planned scenario bank")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-envs", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the short runs of the other single-GPU workloads")
     ap.add_argument("--tile-envs", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     args = ap.parse_args()
@@ -198,7 +228,11 @@ def main():
     cfg = preset(preset_name, n_envs=envs, n_agents=n, n_rays=r, w_max=32, seed=1000, env_id_base=rank * envs,
                  tile_envs=args.tile_envs, block_threads=args.threads)
     env = BatchedDroneEnv(cfg, gmap, device=dev)
-    env.set_bank(bank)
+    if args.reset_source == "bank":
+        env.set_bank(bank)
+    else:   # origins / destinations drawn on the device at every reset from the maps' OD tables
+        from multi_agent_aac_b200.reset import OdTable
+        env.set_od_tables([OdTable(m, w_max=32) for m in (gmap if isinstance(gmap, list) else [gmap])])
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(1 + rank)
@@ -274,7 +308,8 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / K_, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "envs_per_gpu": envs, "drones": n, "rays": r, "variant": preset_name,
-                       "radar_mode": "last_hit" if cfg.radar_mode else "min", "scenario_bank": args.scenarios,
+                       "radar_mode": "last_hit" if cfg.radar_mode else "min",
+                       "reset": "device-side OD sampling from the map's origin/destination table" if args.reset_source == "od" else "scenario bank of %d" % args.scenarios,
                        "l2": "state+actions+outputs per step = %.0f MB > 126 MB L2, 8 rotating action buffers; no flush needed" % (envs * n * bytes_per / 1e6),
                        "tile_envs": args.tile_envs, "sharding": "envs by instance, no data-path collective"},
             "e2e": {"value": agents_total * args.e2e_steps / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
@@ -287,6 +322,8 @@ def main():
             "clocks": clocks,
             "episode_stats": {k: float(v) for k, v in zip(K.STAT_NAMES, stats)},
         }
+        if world == 1 and not args.no_aux:   # the other single-GPU configurations of BASELINE.json, device-resident
+            line["other_workloads"] = {w: quick_device_rate(w, dev) for w in ("c2", "c4") if w != args.workload}
         if not args.no_cpu and world == 1:
             sample = args.cpu_envs or max(64, min(4096, 20000 // n))
             base, _ = cpu_reference_run(args.workload, 10, 1, sample)

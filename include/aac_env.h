@@ -144,12 +144,36 @@ typedef struct {
     const int32_t *map_id; /* [S] or NULL (all on map 0) */
 } AacBank;
 
+/* Origin / destination table of one map: every free cell that can be a start or a goal (the four quadrant pools of
+ * create_world, ATT:154-197) and the pruned grid path between every pair of them (reset_world's jps_find_path +
+ * collinear pruning, ATT:317-347), planned once on the host.  With a table installed the device draws origins and
+ * destinations itself, following reset_world's rule (ATT:254-276): a start quadrant, a different target quadrant,
+ * a start cell redrawn until it is more than 2 * protectiveBound from every earlier drone's start, a goal cell. */
+typedef struct {
+    int32_t n_cells;            /* P: pool cells, sorted by quadrant */
+    int32_t pool_off[5];        /* quadrant q owns cells [pool_off[q], pool_off[q+1]) */
+    const uint16_t *cell_code;  /* [P] ix<<8|iy */
+    const uint32_t *path_off;   /* [P*P] offset of path (start, goal) in path_cells, a multiple of 8 (paths are padded to
+                                   8-cell = 16-byte chunks); pairs inside one quadrant unused */
+    const uint8_t *path_len;    /* [P*P] vertices of that path (2..w_max), 0 = unused pair */
+    const uint16_t *path_cells; /* vertex pool */
+    int64_t n_path_cells;
+} AacOdTable;
+
 /* env_simulator.__init__ + create_world (ATT:41,84) */
 int aac_create(const AacConfig *cfg, AacEnv **out);
 void aac_destroy(AacEnv *env);
 /* world_map / bound / allGridPoly constructor arguments (ATT:41; MM:42 takes collections) */
 int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *occ /* [M,AAC_MAP_STRIDE] */, int32_t n_maps);
 int aac_set_bank(AacEnv *env, const AacBank *bank);
+/* one table per map (host pointers, copied); resets draw from the tables instead of the scenario bank */
+int aac_set_od_tables(AacEnv *env, const AacOdTable *tables, int32_t n_maps);
+/* Host-only helper: the reference's grid search (ATT/jps_straight.py:17-70: best-first on f = g + Manhattan, first
+ * minimum in discovery order, neighbours visited in the order (0,-1), (0,1), (-1,0), (1,0), cells never re-opened)
+ * followed by collinear pruning (ATT:321-331).  occ is uint8[gx*gy], ix-major.  Writes up to max_cells codes
+ * ix<<8|iy and returns the vertex count, 0 if the goal is unreachable, -1 if the path needs more than max_cells. */
+int aac_plan_path(const uint8_t *occ, int32_t gx, int32_t gy, int32_t sx, int32_t sy, int32_t tx, int32_t ty, uint16_t *out_cells,
+                  int32_t max_cells);
 int aac_bind_state(AacEnv *env, const AacState *state);
 /* reset_world (ATT:199-511): re-initialise the envs whose mask byte is non-zero (NULL = all) from
  * the scenario bank and emit their first observation */

@@ -26,6 +26,8 @@ struct AacEnv {
     uint8_t *d_bank_w = nullptr;
     int32_t *d_bank_map = nullptr;
     int n_scen = 0;
+    OdDev *d_od = nullptr;       // origin / destination tables (one per map) and the buffers they point into
+    std::vector<void *> od_bufs;
     float *d_actions = nullptr;  // staging for aac_step_host
     double *d_stats = nullptr;
     int *d_work = nullptr;       // ping-pong group counters of the persistent kernel
@@ -147,6 +149,8 @@ extern "C" void aac_destroy(AacEnv *env) {
     cudaFree(env->d_actions);
     cudaFree(env->d_stats);
     cudaFree(env->d_work);
+    cudaFree(env->d_od);
+    for (void *b : env->od_bufs) cudaFree(b);
     for (auto &s : env->pipe) if (s) cudaStreamDestroy(s);
     for (auto &e : env->pipe_ev) if (e) cudaEventDestroy(e);
     delete env;
@@ -211,6 +215,103 @@ extern "C" int aac_set_bank(AacEnv *env, const AacBank *bank) {
     return 0;
 }
 
+extern "C" int aac_set_od_tables(AacEnv *env, const AacOdTable *tables, int32_t n_maps) {
+    if (!env || !tables || n_maps < 1) return fail(AAC_ERR_ARG, "aac_set_od_tables: bad argument");
+    if (n_maps != (env->n_maps ? env->n_maps : 1)) return fail(AAC_ERR_ARG, "aac_set_od_tables: one table per map (call aac_set_maps first)");
+    std::vector<OdDev> host(n_maps);
+    std::vector<void *> bufs;
+    auto upload = [&](const void *src, size_t bytes, const void **dst) -> cudaError_t {
+        void *d = nullptr;
+        cudaError_t e = cudaMalloc(&d, bytes ? bytes : 1);
+        if (e != cudaSuccess) return e;
+        bufs.push_back(d);
+        *dst = d;
+        return cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+    };
+    for (int m = 0; m < n_maps; ++m) {
+        const AacOdTable &t = tables[m];
+        if (t.n_cells < 2 || !t.cell_code || !t.path_off || !t.path_len || !t.path_cells) return fail(AAC_ERR_ARG, "aac_set_od_tables: incomplete table");
+        for (int q = 0; q < 4; ++q)
+            if (t.pool_off[q + 1] <= t.pool_off[q]) return fail(AAC_ERR_ARG, "aac_set_od_tables: every quadrant pool needs at least one cell");
+        if (t.pool_off[0] != 0 || t.pool_off[4] != t.n_cells) return fail(AAC_ERR_ARG, "aac_set_od_tables: pool offsets do not cover the cells");
+        const size_t P = t.n_cells;
+        for (size_t k = 0; k < P * P; ++k)
+            if (t.path_len[k] > env->cfg.w_max || (t.path_len[k] && (t.path_off[k] & 7u))) return fail(AAC_ERR_ARG, "aac_set_od_tables: a path has more than w_max vertices or is not 8-cell aligned");
+        if (t.n_path_cells & 7) return fail(AAC_ERR_ARG, "aac_set_od_tables: path_cells must be padded to a multiple of 8");
+        OdDev &o = host[m];
+        o.n_cells = t.n_cells;
+        for (int q = 0; q < 5; ++q) o.pool_off[q] = t.pool_off[q];
+        cudaError_t e;
+        if ((e = upload(t.cell_code, P * 2, (const void **)&o.cell_code)) != cudaSuccess || (e = upload(t.path_off, P * P * 4, (const void **)&o.path_off)) != cudaSuccess ||
+            (e = upload(t.path_len, P * P, (const void **)&o.path_len)) != cudaSuccess ||
+            (e = upload(t.path_cells, (size_t)t.n_path_cells * 2, (const void **)&o.path_cells)) != cudaSuccess) {
+            for (void *b : bufs) cudaFree(b);
+            return cuda_fail(e, "aac_set_od_tables upload");
+        }
+    }
+    cudaFree(env->d_od);
+    for (void *b : env->od_bufs) cudaFree(b);
+    env->od_bufs = bufs;
+    env->d_od = nullptr;
+    CU(cudaMalloc(&env->d_od, sizeof(OdDev) * n_maps));
+    CU(cudaMemcpy(env->d_od, host.data(), sizeof(OdDev) * n_maps, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// the reference's grid search and collinear pruning, host only (ATT/jps_straight.py:17-70, ATT:321-331)
+extern "C" int aac_plan_path(const uint8_t *occ, int32_t gx, int32_t gy, int32_t sx, int32_t sy, int32_t tx, int32_t ty, uint16_t *out_cells,
+                             int32_t max_cells) {
+    if (!occ || !out_cells || gx < 1 || gy < 1 || gx > 255 || gy > 255) return fail(AAC_ERR_ARG, "aac_plan_path: bad argument");
+    if (sx < 0 || sy < 0 || tx < 0 || ty < 0 || sx >= gx || tx >= gx || sy >= gy || ty >= gy) return fail(AAC_ERR_ARG, "aac_plan_path: cell outside the grid");
+    const int n = gx * gy;
+    std::vector<uint8_t> status(n, 0);   // 0 unseen, 1 open, 2 closed
+    std::vector<int> gcost(n, 0), fcost(n, 0), parent(n, -1), frontier;
+    const int s = sx * gy + sy, t = tx * gy + ty;
+    frontier.push_back(s);
+    status[s] = 1;
+    static const int DX[4] = {0, 0, -1, 1}, DY[4] = {-1, 1, 0, 0};
+    int found = -1;
+    while (!frontier.empty()) {
+        size_t kb = 0;   // first entry, in discovery order, with the smallest f
+        for (size_t k = 1; k < frontier.size(); ++k)
+            if (fcost[frontier[k]] < fcost[frontier[kb]]) kb = k;
+        const int cur = frontier[kb];
+        frontier.erase(frontier.begin() + kb);
+        status[cur] = 2;
+        if (cur == t) { found = cur; break; }
+        const int cx = cur / gy, cy = cur % gy;
+        for (int d = 0; d < 4; ++d) {
+            const int nx = cx + DX[d], ny = cy + DY[d];
+            if (nx < 0 || ny < 0 || nx >= gx || ny >= gy || occ[nx * gy + ny]) continue;
+            const int c = nx * gy + ny;
+            if (status[c]) continue;   // a discovered cell is never re-queued or re-costed
+            gcost[c] = gcost[cur] + 1;
+            fcost[c] = gcost[c] + abs(nx - tx) + abs(ny - ty);
+            parent[c] = cur;
+            status[c] = 1;
+            frontier.push_back(c);
+        }
+    }
+    if (found < 0) return 0;
+    std::vector<int> path;
+    for (int c = found; c != -1; c = parent[c]) path.push_back(c);
+    const int L = (int)path.size();   // path[L-1] = start ... path[0] = goal
+    auto cell = [&](int k) { return path[L - 1 - k]; };
+    std::vector<int> keep;
+    keep.push_back(cell(0));
+    if (L >= 2) {
+        int dx = cell(1) / gy - cell(0) / gy, dy = cell(1) % gy - cell(0) % gy;
+        for (int k = 2; k < L; ++k) {
+            const int ex = cell(k) / gy - cell(k - 1) / gy, ey = cell(k) % gy - cell(k - 1) % gy;
+            if (ex != dx || ey != dy) { keep.push_back(cell(k - 1)); dx = ex; dy = ey; }
+        }
+        keep.push_back(cell(L - 1));
+    }
+    if ((int)keep.size() > max_cells) return -1;
+    for (size_t k = 0; k < keep.size(); ++k) out_cells[k] = (uint16_t)(((keep[k] / gy) << 8) | (keep[k] % gy));
+    return (int)keep.size();
+}
+
 extern "C" int aac_bind_state(AacEnv *env, const AacState *s) {
     if (!env || !s) return fail(AAC_ERR_ARG, "aac_bind_state: null argument");
     if (!s->px || !s->py || !s->vx || !s->vy || !s->heading || !s->meta || !s->ref_cells || !s->ref_w || !s->ep_step || !s->ep_index || !s->ep_return)
@@ -257,7 +358,7 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     if (!env) return fail(AAC_ERR_ARG, "null handle");
     if (!env->bound) return fail(AAC_ERR_STATE, "aac_bind_state has not been called");
     if (!env->d_maps) return fail(AAC_ERR_STATE, "aac_set_maps has not been called");
-    if ((mode == MODE_RESET || autoreset) && !env->d_bank_cells) return fail(AAC_ERR_STATE, "aac_set_bank has not been called");
+    if ((mode == MODE_RESET || autoreset) && !env->d_bank_cells && !env->d_od) return fail(AAC_ERR_STATE, "neither aac_set_bank nor aac_set_od_tables has been called");
     if (mode == MODE_STEP && !actions) return fail(AAC_ERR_ARG, "actions is NULL");
     const int rc = check_out(env, out, mode);
     if (rc) return rc;
@@ -269,7 +370,7 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     p.cell = env->cell; p.dt = c.dt; p.vmax = c.vmax; p.acc_max = c.acc_max; p.prot = c.prot; p.ray_len = c.ray_len; p.goal_r = c.goal_r;
     p.env_id_base = c.env_id_base; p.seed = c.seed;
     p.maps = env->d_maps; p.n_maps = env->n_maps; p.ray_tab = env->d_ray; p.autoreset = autoreset;
-    p.bank_cells = env->d_bank_cells; p.bank_w = env->d_bank_w; p.bank_map = env->d_bank_map; p.n_scen = env->n_scen;
+    p.bank_cells = env->d_bank_cells; p.bank_w = env->d_bank_w; p.bank_map = env->d_bank_map; p.n_scen = env->n_scen; p.od = env->d_od;
     p.mask = mask; p.actions = actions; p.stats = env->d_stats;
     p.work = env->d_work + 2 * pair; p.parity = (int)(env->pair_launches[pair] & 1);
     p.st = env->st; p.out = *out; p.CL = env->cl; p.WL = env->wl;

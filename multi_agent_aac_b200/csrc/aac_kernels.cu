@@ -663,15 +663,39 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
     __syncwarp();
 }
 
-// re-initialise env g of the warp's group from the scenario bank: what reset_world leaves behind
-// (ATT:301-372).  Returns the lane's reference-line row (bank memory) for the drones of that env.
+// counter-based random draws for (env, episode, draw index): independent of how envs are sharded over GPUs.
+// `episode_key` folds seed, global env id and episode index once; a draw is one multiply-xorshift finaliser on top.
+__device__ __forceinline__ unsigned episode_key(unsigned long long seed, long long gid, int episode) {
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(gid + 1) + 0xD1B54A32D192ED03ull * (unsigned long long)(episode + 1);
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (unsigned)(x >> 32) ^ (unsigned)x;
+}
+__device__ __forceinline__ unsigned draw(unsigned key, unsigned ctr) {
+    unsigned h = key ^ (ctr * 0x9E3779B1u);
+    h ^= h >> 16; h *= 0x7FEB352Du;
+    h ^= h >> 15; h *= 0x846CA68Bu;
+    h ^= h >> 16;
+    return h;
+}
+
+// re-initialise env g of the warp's group: what reset_world leaves behind (ATT:251-372).  Origins, destinations and
+// reference lines come from the map's origin / destination table when one is installed (the device draws them with
+// reset_world's rule, ATT:254-276), else from a pre-planned scenario of the bank.  Returns the lane's reference-line
+// row for the drones of that env.
 template <int VAR>
 __device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp &w, const int g) {
     const int lane = w.lane, N = p.N, W = p.W;
     const int ge = w.e_lo + g;
+    const long long gid = p.env_id_base + ge;
     const int ep = p.st.ep_index[ge];
-    const unsigned scen = pick_scenario(p.env_id_base + ge, ep, p.seed, p.n_scen);
-    const int map_row = (VAR == AAC_VARIANT_MM && p.bank_map) ? p.bank_map[scen] : 0;   // a map is drawn per episode (MM/ma_main:464)
+    const bool use_od = p.od != nullptr;
+    const unsigned scen = use_od ? 0u : pick_scenario(gid, ep, p.seed, p.n_scen);
+    // a map is drawn per episode (MM/ma_main:464)
+    int map_row = 0;
+    const unsigned key = use_od ? episode_key(p.seed, gid, ep) : 0u;
+    if (VAR == AAC_VARIANT_MM) map_row = use_od ? (int)(draw(key, 0) % (unsigned)p.n_maps) : (p.bank_map ? p.bank_map[scen] : 0);
     const MapDev &mp = VAR == AAC_VARIANT_MM ? p.maps[map_row] : *w.map;
     __syncwarp();
     if (lane == 0) {
@@ -680,15 +704,61 @@ __device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp
         p.st.ep_return[ge] = 0.0f;
         if (VAR == AAC_VARIANT_MM) p.st.map_id[ge] = map_row;
     }
-    // reference lines: 16-byte chunks bank -> global state (W is a multiple of 8)
-    const uint4 *src = reinterpret_cast<const uint4 *>(p.bank_cells + (size_t)scen * N * W);
-    uint4 *dst = reinterpret_cast<uint4 *>(p.st.ref_cells + (size_t)ge * N * W);
-    for (int c = lane; c < N * W / 8; c += 32) dst[c] = src[c];
     const uint16_t *row = nullptr;
+    int nw = 0;
+    if (use_od) {
+        const OdDev &od = p.od[map_row];
+        // Lane i draws for drone i.  reset_world draws drone by drone and redraws a start until it is more than
+        // 2 * protectiveBound from every EARLIER drone's start (ATT:254-270): the candidates are drawn in parallel
+        // (each drone has its own counter stream), the accept / redraw decisions run drone by drone with the
+        // earlier drones' lanes voting.
+        const float sep2 = 4.0f * p.prot * p.prot * mp.inv_cell * mp.inv_cell;   // (2 * protectiveBound)^2 in cells^2
+        auto candidate = [&](const int i, const int attempt, int &s_idx, int &tq) -> int {
+            const unsigned base = 1u + 256u * (unsigned)i + 4u * (unsigned)attempt;
+            const int sq = draw(key, base) >> 30;
+            tq = (int)(draw(key, base + 1) % 3u);
+            if (tq >= sq) ++tq;                               // a different quadrant for the goal (ATT:256-258)
+            const int n_s = od.pool_off[sq + 1] - od.pool_off[sq];
+            s_idx = od.pool_off[sq] + (int)(draw(key, base + 2) % (unsigned)n_s);
+            return od.cell_code[s_idx];
+        };
+        int s_idx = 0, tq = 0, code = 0;
+        if (lane < N) code = candidate(lane, 0, s_idx, tq);
+        for (int i = 1; i < N; ++i) {                         // drone 0 keeps its first draw
+            for (int attempt = 1; attempt < 48; ++attempt) {
+                const int ci = __shfl_sync(FULL, code, i);
+                const float dx = (float)((ci >> 8) - (code >> 8)), dy = (float)((ci & 255) - (code & 255));
+                if (!__ballot_sync(FULL, lane < i && dx * dx + dy * dy <= sep2)) break;
+                if (lane == i) code = candidate(i, attempt, s_idx, tq);
+            }
+        }
+        int pr = 0;
+        if (lane < N) {
+            const int n_t = od.pool_off[tq + 1] - od.pool_off[tq];
+            const int t_idx = od.pool_off[tq] + (int)(draw(key, 1u + 256u * (unsigned)lane + 3u) % (unsigned)n_t);
+            pr = s_idx * od.n_cells + t_idx;
+        }
+        if (lane < N) {
+            nw = od.path_len[pr];
+            const uint16_t *src = od.path_cells + od.path_off[pr];   // 16-byte aligned: paths are padded to 8 cells
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+            uint4 *d4 = reinterpret_cast<uint4 *>(p.st.ref_cells + ((size_t)ge * N + lane) * W);
+            for (int k = 0; k < (nw + 7) >> 3; ++k) d4[k] = s4[k];
+            row = src;
+        }
+        __syncwarp();
+    } else {
+        // reference lines: 16-byte chunks bank -> global state (W is a multiple of 8)
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.bank_cells + (size_t)scen * N * W);
+        uint4 *dst = reinterpret_cast<uint4 *>(p.st.ref_cells + (size_t)ge * N * W);
+        for (int c = lane; c < N * W / 8; c += 32) dst[c] = src[c];
+        if (lane < N) {
+            row = p.bank_cells + ((size_t)scen * N + lane) * W;
+            nw = p.bank_w[(size_t)scen * N + lane];
+        }
+    }
     if (lane < N) {
         const int a = g * N + lane;
-        row = p.bank_cells + ((size_t)scen * N + lane) * W;
-        const int nw = p.bank_w[(size_t)scen * N + lane];
         w.refw[a] = (uint8_t)nw;
         p.st.ref_w[(size_t)ge * N + lane] = (uint8_t)nw;
         const uint16_t c0 = row[0], c1 = row[1];
@@ -839,7 +909,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                 if (!((reset_mask >> g) & 1u)) continue;
                 const uint16_t *row = init_env<VAR>(p, w, g);
                 a_lo = g * N; n_ag = N;
-                cl = lane < N ? row : p.bank_cells;
+                cl = lane < N ? row : p.st.ref_cells;
             }
             observe_range<VAR, AUX, NT, RT>(p, w, a_lo, n_ag, cl);
             if (job > 0 || mode != MODE_STEP) continue;
@@ -1139,9 +1209,16 @@ static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, 
     const int wpc = threads / 32;
     const int groups = (p.E + p.G - 1) / p.G;
     auto fn = env_kernel<VAR, AUX, NT, RT>;
-    if (*grid_cache <= 0) {   // first launch of this handle: opt in to the shared memory, query the residency
+    static int opted_in[64] = {0};   // dynamic shared memory this instantiation has opted in to, per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if ((int)p.CL.total > opted_in[dev & 63]) {   // handles of different shapes share the function attribute
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.CL.total);
         if (e != cudaSuccess) return e;
+        opted_in[dev & 63] = (int)p.CL.total;
+    }
+    if (*grid_cache <= 0) {   // first launch of this handle: query the residency
+        cudaError_t e;
         int per_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, p.CL.total);
         if (e != cudaSuccess) return e;

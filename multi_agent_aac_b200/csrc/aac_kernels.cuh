@@ -26,6 +26,16 @@ struct __align__(16) MapDev {
 };
 static_assert(sizeof(MapDev) % 16 == 0, "MapDev is moved with 16-byte bulk copies");
 
+// origin / destination table of one map on the device (AacOdTable with device pointers)
+struct OdDev {
+    int n_cells;
+    int pool_off[5];
+    const uint16_t *cell_code;
+    const uint32_t *path_off;
+    const uint8_t *path_len;
+    const uint16_t *path_cells;
+};
+
 enum Mode : int { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_RESET = 2 };
 
 // shared-memory carve-up (byte offsets), computed once on the host: CTA-wide data, then one slice per warp
@@ -62,6 +72,7 @@ struct KParams {
     const uint8_t *bank_w;
     const int32_t *bank_map;
     int n_scen;
+    const OdDev *od;        // [n_maps] origin / destination tables, or NULL (resets then use the scenario bank)
     const uint8_t *mask;  // MODE_RESET: per-env byte, NULL = every env
     const float *actions;
     double *stats;        // [AAC_N_STATS]

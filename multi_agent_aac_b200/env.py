@@ -181,6 +181,23 @@ class BatchedDroneEnv:
             K.check(self.L.aac_set_bank(self.h, C.byref(b)), "aac_set_bank")
         self._bank = bank
 
+    def set_od_tables(self, tables):
+        """Install one OdTable per map: resets then draw origins / destinations on the device (ATT:254-276)."""
+        tables = list(tables) if isinstance(tables, (list, tuple)) else [tables]
+        assert len(tables) == len(self.maps)
+        arr = (K.AacOdTable * len(tables))()
+        for k, t in enumerate(tables):
+            assert t.w_max <= self.cfg.w_max
+            arr[k].n_cells = t.n_cells
+            for q in range(5):
+                arr[k].pool_off[q] = int(t.pool_off[q])
+            arr[k].cell_code, arr[k].path_off = t.cell_code.ctypes.data, t.path_off.ctypes.data
+            arr[k].path_len, arr[k].path_cells = t.path_len.ctypes.data, t.path_cells.ctypes.data
+            arr[k].n_path_cells = int(t.path_cells.size)
+        with torch.cuda.device(self.device):
+            K.check(self.L.aac_set_od_tables(self.h, arr, len(tables)), "aac_set_od_tables")
+        self._od = tables
+
     # ------------------------------------------------------------------ the env surface
     def reset(self, mask=None):
         """reset_world for the masked envs (all when mask is None) from the scenario bank."""

@@ -202,3 +202,51 @@ class MultiMapBank:
     @property
     def n_scenarios(self):
         return self.cells.shape[0]
+
+
+class OdTable:
+    """Origin / destination table of one map (include/aac_env.h AacOdTable): the four quadrant pools of free cells
+    (ATT:154-197) and the pruned grid path between every start / goal pair in different quadrants, planned by the
+    library's host planner `aac_plan_path` (the reference's search and tie-breaking, ATT/jps_straight.py:17-70).
+    With a table installed the device draws origins and destinations itself at every reset (ATT:254-276)."""
+
+    def __init__(self, gmap: GridMap, w_max=32):
+        import ctypes as C
+        from . import _capi as K
+        lib = K.lib()
+        self.gmap, self.w_max = gmap, w_max
+        pools = gmap.target_pools()
+        cells, pool_off, quad = [], [0], []
+        for q in range(4):
+            for cx, cy in pools[q]:
+                cells.append(gmap.cell_of(cx, cy))
+                quad.append(q)
+            pool_off.append(len(cells))
+        P = len(cells)
+        self.n_cells, self.pool_off = P, np.array(pool_off, dtype=np.int32)
+        self.cell_code = np.array([ix * 256 + iy for ix, iy in cells], dtype=np.uint16)
+        self.path_off = np.zeros(P * P, dtype=np.uint32)
+        self.path_len = np.zeros(P * P, dtype=np.uint8)
+        occ = np.ascontiguousarray(gmap.occ, dtype=np.uint8)
+        buf = np.zeros(w_max, dtype=np.uint16)
+        chunks, total = [], 0
+        for s in range(P):
+            for t in range(P):
+                if quad[s] == quad[t]:
+                    continue
+                n = lib.aac_plan_path(occ.ctypes.data, gmap.gx, gmap.gy, cells[s][0], cells[s][1], cells[t][0], cells[t][1],
+                                      buf.ctypes.data, w_max)
+                if n == 0:
+                    raise ValueError("cell %s is unreachable from %s" % (cells[t], cells[s]))
+                if n < 0:
+                    raise ValueError("a reference line needs more than w_max=%d vertices" % w_max)
+                self.path_off[s * P + t] = total
+                self.path_len[s * P + t] = n
+                pad = (n + 7) // 8 * 8                      # the device copies paths in 16-byte chunks
+                chunks.append(np.concatenate([buf[:n], np.zeros(pad - n, dtype=np.uint16)]))
+                total += pad
+        self.path_cells = np.concatenate(chunks) if chunks else np.zeros(1, dtype=np.uint16)
+
+    def path(self, s, t):
+        k = s * self.n_cells + t
+        return self.path_cells[self.path_off[k]:self.path_off[k] + self.path_len[k]]

@@ -241,3 +241,60 @@ def test_step_host_pipeline_equals_device_step(n_envs):
         for k in envs[0].state:
             assert torch.equal(envs[0].state[k].view(torch.uint8), envs[1].state[k].view(torch.uint8)), (t, k)
     assert abs(envs[0].read_stats()[0] - envs[1].read_stats()[0]) == 0
+
+
+@pytest.mark.parametrize("variant", ["tdcpa_v2", "multimap"])
+def test_device_side_origin_destination_sampling(variant):
+    """With an origin / destination table the device draws every episode itself (ATT:254-276): starts in the quadrant
+    pools, more than 2 * protectiveBound apart, goal in a different quadrant, reference line = the host planner's
+    path for that pair; every pool cell gets used; results do not depend on how envs are sharded."""
+    import numpy as np
+    import torch
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import multimap_set, synthetic_map
+    from multi_agent_aac_b200.reset import OdTable, ref_line_cells
+    maps = multimap_set(seed=0)[:5] if variant == "multimap" else [synthetic_map(seed=0)]
+    tabs = [OdTable(m, w_max=32) for m in maps]
+    E, n, r = 4096, 4, 18
+
+    def make(n_envs, base):
+        env = BatchedDroneEnv(preset(variant, n_envs=n_envs, n_agents=n, n_rays=r, w_max=32, seed=77, env_id_base=base),
+                              maps if variant == "multimap" else maps[0])
+        env.set_od_tables(tabs)
+        env.reset()
+        return env
+    env = make(E, 0)
+    s = env.agent_state()
+    cells = env.state["ref_cells"].cpu().numpy().view(np.uint16)
+    map_id = s["map_id"] if variant == "multimap" else np.zeros(E, dtype=np.int64)
+    used = [set() for _ in maps]
+    for e in range(0, E, 7):
+        m, tab = maps[map_id[e]], tabs[map_id[e]]
+        pool_of = {int(c): int(np.searchsorted(tab.pool_off, k, side="right") - 1) for k, c in enumerate(tab.cell_code)}
+        starts = []
+        for i in range(n):
+            w = int(s["ref_w"][e, i])
+            line = [divmod(int(c), 256) for c in cells[e, i, :w]]
+            c0, c1 = int(cells[e, i, 0]), int(cells[e, i, w - 1])
+            assert c0 in pool_of and c1 in pool_of and pool_of[c0] != pool_of[c1]
+            assert line == [tuple(c) for c in ref_line_cells(m, m.cell_centre(*line[0]), m.cell_centre(*line[-1]))]
+            assert np.allclose(s["pos"][e, i], m.cell_centre(*line[0]), atol=1e-4)
+            starts.append(np.array(m.cell_centre(*line[0])))
+            used[map_id[e]].add(c0)
+        for i in range(n):
+            for j in range(i):
+                assert np.hypot(*(starts[i] - starts[j])) > 5.0
+    if variant != "multimap":
+        assert len(used[0]) > 0.8 * tabs[0].n_cells
+    else:
+        assert len(set(map_id.tolist())) == len(maps)
+    # sharding independence: envs [1000, 1500) of a second handle with env_id_base = 1000
+    env2 = make(500, 1000)
+    for k in ("px", "py", "ref_cells", "ref_w"):
+        assert torch.equal(env.state[k][1000:1500], env2.state[k]), k
+    # episodes keep being drawn on the device through the fused auto-reset
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(0)
+    for t in range(10):
+        env.step((torch.rand((E, n, 2), device="cuda", generator=gen) * 2 - 1).contiguous(), autoreset=True)
+    assert env.read_stats()[0] > 0 and int(env.state["ep_index"].max()) >= 2

@@ -150,3 +150,27 @@ def test_episode_stats_allreduce_gloo_world2():
         assert res[r]["bound_crash"] == 4 and res[r]["building_crash"] == 4
         assert abs(res[r]["mean_return"] + 0.3) < 1e-12
     assert res[0]["span"] == (0, 501) and res[1]["span"] == (501, 1001)
+
+
+def test_host_planner_matches_python_restatement_of_the_reference_search():
+    """aac_plan_path (C++, host only) against reset.ref_line_cells (the Python restatement that reproduces the
+    reference's episodes in tests/test_gpu_parity.py::test_ref_compat_env_reproduces_reference_episode)."""
+    from multi_agent_aac_b200.reset import OdTable, ref_line_cells
+    _capi.build()
+    for m in (synthetic_map(seed=0), multimap_set(seed=0)[5]):
+        tab = OdTable(m, w_max=32)
+        P = tab.n_cells
+        assert tab.pool_off[0] == 0 and tab.pool_off[4] == P and (np.diff(tab.pool_off) > 0).all()
+        rng = np.random.default_rng(0)
+        checked = 0
+        while checked < 150:
+            s, t = int(rng.integers(0, P)), int(rng.integers(0, P))
+            if tab.path_len[s * P + t] == 0:
+                qs = np.searchsorted(tab.pool_off, s, side="right") - 1
+                qt = np.searchsorted(tab.pool_off, t, side="right") - 1
+                assert qs == qt                      # only same-quadrant pairs are left out
+                continue
+            want = ref_line_cells(m, m.cell_centre(*divmod(int(tab.cell_code[s]), 256)), m.cell_centre(*divmod(int(tab.cell_code[t]), 256)))
+            got = [divmod(int(c), 256) for c in tab.path(s, t)]
+            assert got == [tuple(c) for c in want], (s, t)
+            checked += 1
