@@ -1242,8 +1242,14 @@ static cudaError_t launch_aux(const KParams &p, int mode, int threads, int sms, 
 cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     if (p.E <= 0) return cudaSuccess;
     switch (variant) {
-        case AAC_VARIANT_ATT: return launch_aux<AAC_VARIANT_ATT, 0, 0>(p, mode, threads, sms, grid_cache, stream);
-        case AAC_VARIANT_MM: return launch_aux<AAC_VARIANT_MM, 0, 0>(p, mode, threads, sms, grid_cache, stream);
+        // the reference's own shapes (3 drones; 18 rays, or the 36 of the batched configuration) are specialised too
+        case AAC_VARIANT_ATT:
+            if (p.N == 3 && p.R == 36) return launch_aux<AAC_VARIANT_ATT, 3, 36>(p, mode, threads, sms, grid_cache, stream);
+            if (p.N == 3 && p.R == 18) return launch_aux<AAC_VARIANT_ATT, 3, 18>(p, mode, threads, sms, grid_cache, stream);
+            return launch_aux<AAC_VARIANT_ATT, 0, 0>(p, mode, threads, sms, grid_cache, stream);
+        case AAC_VARIANT_MM:
+            if (p.N == 3 && p.R == 18) return launch_aux<AAC_VARIANT_MM, 3, 18>(p, mode, threads, sms, grid_cache, stream);
+            return launch_aux<AAC_VARIANT_MM, 0, 0>(p, mode, threads, sms, grid_cache, stream);
         case AAC_VARIANT_V2:
             // the benchmark configurations get kernels specialised on the drone and ray counts (register-resident
             // neighbour sort, constant loop bounds and addressing); everything else runs the generic kernel
