@@ -265,6 +265,16 @@ class BatchedDroneEnv:
     def launch_count(self):
         return int(self.L.aac_launch_count(self.h))
 
+    def state_dict(self):
+        """Everything needed to resume: the per-drone records and episode counters (host copies).  The reference
+        checkpoints actor weights only (ATT/maddpg_agent:131-139); env state is plain tensors here, so it is cheap."""
+        return {k: v.detach().cpu().clone() for k, v in self.state.items()}
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            self.state[k].copy_(v.to(self.device))
+        return self.observe()
+
     def close(self):
         if getattr(self, "h", None):
             self.L.aac_destroy(self.h)

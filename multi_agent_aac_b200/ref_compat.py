@@ -240,6 +240,98 @@ class RefCompatEnvV2(RefCompatEnv):
         return raw, norm
 
 
+class RefCompatEnvMM:
+    """radar_multipleMap drop-in (MM:42): the constructor takes per-map collections, `reset_world / step / ss_reward`
+    take the episode's `random_map_idx` (drawn by the caller, MM/ma_main:464).  States are `[p1, p2, p3]` with
+    p1 = own block (6), p2 = radar; p3 (the reference's ragged, never-cleared legacy neighbour block, which its
+    actors do not read, MM/maddpg_agent:361-399) is returned as one zero row per drone."""
+
+    def __init__(self, world_map_collection, building_polygons, grid_length, bound_collection, allGridPoly_collection=None,
+                 agentConfig=None, cropped_coord_match_actual_coord=None, n_rays=18, device="cuda:0"):
+        keys = sorted(world_map_collection.keys())
+        self._keys = {k: i for i, k in enumerate(keys)}
+        self.world_map_2D_collection = world_map_collection
+        self.bound_collection = bound_collection
+        self.world_map_2D_polyList_collection = allGridPoly_collection
+        self.cropped_coord_match_actual_coord = cropped_coord_match_actual_coord
+        self.buildingPolygons, self.gridlength, self.agentConfig = building_polygons, grid_length, agentConfig
+        self.maps = [GridMap(list(bound_collection[k]), int(grid_length), (np.asarray(world_map_collection[k]) != 0).astype(np.uint8))
+                     for k in keys]
+        self.time_step, self.global_time = 0.5, 0.0
+        self.all_agents, self.normalizer = None, None
+        self._n_rays, self._device, self._env, self._last = n_rays, device, None, None
+
+    def create_world(self, total_agentNum, n_actions, gamma, tau, target_update, largest_Nsigma, smallest_Nsigma, ini_Nsigma,
+                     max_xy, max_spd, acc_range):
+        self._max_spd, self._acc_range = float(max_spd), list(acc_range)
+        self.all_agents = {i: AgentView(i, max_spd) for i in range(total_agentNum)}
+        cfg = preset("multimap", n_envs=1, n_agents=total_agentNum, n_rays=self._n_rays, w_max=32, vmax=float(max_spd),
+                     out_flags=K.OUT_RAW | K.OUT_PARTS)
+        self._env = BatchedDroneEnv(cfg, self.maps, device=self._device)
+        self.target_pool_collection = {k: self.maps[i].target_pools() for k, i in self._keys.items()}
+
+    def reset_world(self, total_agentNum, random_map_idx, show=0):
+        self.global_time = 0.0
+        m = self._keys[random_map_idx]
+        gmap = self.maps[m]
+        b = gmap.bound
+        self.normalizer = _Normalizer([b[0], b[1]], [b[2], b[3]], self._max_spd, self._acc_range)   # rebuilt per episode (MM:257-261)
+        ep = sample_episode_reference_order(random, gmap, total_agentNum)
+        self._episode = ep
+        self._env.set_episode(0, ep.starts, ep.lines, ep.headings, map_id=m)
+        for i, ag in self.all_agents.items():
+            ag.pos = np.array(ep.starts[i], dtype=np.float64)
+            ag.ini_pos, ag.pre_pos = ag.pos.copy(), ag.pos.copy()
+            ag.vel, ag.pre_vel = np.zeros(2), np.zeros(2)
+            ag.heading = ep.headings[i]
+            ag.goal = [list(p) for p in ep.lines[i][1:]]
+            ag.ref_line = ep.lines[i].copy()
+            ag.reach_target, ag.collide_wall_count = False, 0
+        self._env.observe()
+        return self._pack_states()
+
+    def step(self, actions, current_ts, random_map_idx):
+        a = np.asarray([np.asarray(x, dtype=np.float32).reshape(2) for x in actions], dtype=np.float32)
+        for ag in self.all_agents.values():
+            ag.pre_pos, ag.pre_vel = ag.pos.copy(), ag.vel.copy()
+        self._env.step(torch.from_numpy(a[None]).to(self._env.device).contiguous())
+        self.global_time += self.time_step
+        o = {k: v[0].cpu().numpy() for k, v in self._env.out.items()}
+        s = self._env.agent_state()
+        for i, ag in self.all_agents.items():
+            ag.pos, ag.vel = s["pos"][0, i].copy(), s["vel"][0, i].copy()
+            ag.reach_target = bool(s["reach"][0, i])
+            ag.collide_wall_count = int(s["wall_cnt"][0, i])
+            mask = int(s["wp_mask"][0, i])
+            ag.goal = [list(p) for k, p in enumerate(self._episode.lines[i]) if (mask >> k) & 1]
+            ag.observableSpace = o["radar"][i].astype(np.float64)
+        self._last = o
+        st, nst = self._pack_states()
+        return st, nst, [], [], [], [], [], []
+
+    def ss_reward(self, current_ts, step_reward_record, eps_status_holder, step_collision_record, random_map_idx):
+        if self._last is None:
+            raise RuntimeError("ss_reward called before step")
+        o = self._last
+        n = len(self.all_agents)
+        for i in range(n):
+            step_reward_record[i] = [float(o["parts"][i][1]), float(o["parts"][i][0])]   # [dist_to_ref_line, dist_to_goal] (MM:2003)
+            if step_collision_record is not None and step_collision_record[i] is not None and hasattr(step_collision_record[i], "append"):
+                step_collision_record[i].append([0.0, 0, 0, int(o["branch"][i] == 1), 0, 0])
+        reward = [np.array(float(v)) for v in o["reward"]]
+        done = [bool(v) for v in o["done"]]
+        check_goal = [bool(v) for v in o["check_goal"]]
+        bbc = [bool(v) for v in o["bbc"][:2]]
+        return reward, done, check_goal, step_reward_record, eps_status_holder, step_collision_record, bbc
+
+    def _pack_states(self):
+        o = {k: v[0].cpu().numpy().astype(np.float64) for k, v in self._env.out.items() if k in ("raw_own", "norm_own", "radar")}
+        n = len(self.all_agents)
+        radar = [o["radar"][i] for i in range(n)]
+        p3 = [[np.zeros((1, 6))] for _ in range(n)]
+        return [[o["raw_own"][i] for i in range(n)], radar, p3], [[o["norm_own"][i] for i in range(n)], radar, p3]
+
+
 def env_simulator(variant, *a, **kw):
-    """Factory named like the reference class: env_simulator("att" | "v2", world_map, ...)."""
-    return (RefCompatEnv if variant == "att" else RefCompatEnvV2)(*a, **kw)
+    """Factory named like the reference class: env_simulator("att" | "v2" | "mm", world_map, ...)."""
+    return {"att": RefCompatEnv, "v2": RefCompatEnvV2, "mm": RefCompatEnvMM}[variant](*a, **kw)

@@ -298,3 +298,57 @@ def test_device_side_origin_destination_sampling(variant):
     for t in range(10):
         env.step((torch.rand((E, n, 2), device="cuda", generator=gen) * 2 - 1).contiguous(), autoreset=True)
     assert env.read_stats()[0] > 0 and int(env.state["ep_index"].max()) >= 2
+
+
+def test_ref_compat_env_multimap_reproduces_reference_episode():
+    import random
+    import numpy as np
+    from multi_agent_aac_b200.ref_compat import RefCompatEnvMM
+    d, n, rays, ep_len, maps = load_case_mm("mm_n3_seek")
+    seed = int(d["meta"][1])
+    env = RefCompatEnvMM({k: m.occ.astype(float) for k, m in enumerate(maps)}, [], 10, {k: list(m.bound) for k, m in enumerate(maps)},
+                         None, None, None, n_rays=rays)
+    env.create_world(n, 2, 0.95, 0.01, 1, 0.15, 0.05, 0.15, (1800, 1300), 5, [-4, 4])
+    random.seed(seed)
+    map_idx = random.randrange(len(maps))                 # MM/ma_main:464, drawn by the caller
+    assert map_idx == int(d["ep_map"][0])
+    state, norm_state = env.reset_world(n, map_idx, 0)
+    assert np.allclose(np.array([env.all_agents[i].pos for i in range(n)]), d["ep_start"][0])
+    assert np.allclose(np.stack(norm_state[0]), d["ep_norm_own"][0], rtol=1e-4, atol=1e-5)
+    margins = oracle_margins_mm(d, n, rays, maps)
+    T = int(np.sum(d["episode_id"] == 0))
+    for t in range(T):
+        srr, scr = [None] * n, [[] for _ in range(n)]
+        out = env.step(d["actions"][t], t + 1, map_idx)
+        reward, done, check_goal, _, _, _, bbc = env.ss_reward(t + 1, srr, [None] * n, scr, map_idx)
+        assert np.allclose(np.stack(out[0][0])[:, :4], d["raw_own"][t][:, :4], rtol=1e-4, atol=5e-3), t
+        if (margins[t] >= 1e-3).all():
+            assert np.allclose([float(r) for r in reward], d["reward"][t], rtol=1e-3, atol=2e-2), t
+            assert list(done) == [bool(v) for v in d["done"][t]] and list(bbc) == [bool(v) for v in d["bbc"][t]], t
+            assert list(check_goal) == [bool(v) for v in d["check_goal"][t]], t
+
+
+def test_state_dict_roundtrip():
+    import torch
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import synthetic_map
+    from multi_agent_aac_b200.reset import OdTable
+    gmap = synthetic_map(seed=0)
+    tab = OdTable(gmap, w_max=32)
+    envs = []
+    for _ in range(2):
+        env = BatchedDroneEnv(preset("tdcpa_v2", n_envs=64, n_agents=5, n_rays=36, w_max=32, seed=4), gmap)
+        env.set_od_tables([tab])
+        env.reset()
+        envs.append(env)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(2)
+    acts = [(torch.rand((64, 5, 2), device="cuda", generator=gen) * 2 - 1).contiguous() for _ in range(12)]
+    for t in range(6):
+        envs[0].step(acts[t], autoreset=True)
+    envs[1].load_state_dict(envs[0].state_dict())
+    for t in range(6, 12):
+        envs[0].step(acts[t], autoreset=True)
+        envs[1].step(acts[t], autoreset=True)
+        for k in ("norm_own", "norm_nbr", "radar", "reward", "done"):
+            assert torch.equal(envs[0].out[k], envs[1].out[k]), (t, k)

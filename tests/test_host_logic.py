@@ -174,3 +174,17 @@ def test_host_planner_matches_python_restatement_of_the_reference_search():
             got = [divmod(int(c), 256) for c in tab.path(s, t)]
             assert got == [tuple(c) for c in want], (s, t)
             checked += 1
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--cpu-envs", "64"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "agent_steps_per_sec" and line["unit"] == "agent-steps/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"] and line["cpu_baseline"]["cores"] >= 1
