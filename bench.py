@@ -39,6 +39,25 @@ def algorithmic_bytes(variant, n, r):
     return 4 * (26 + 2 * W_REF + obs)
 
 
+def profiled_traffic(kernel_tag):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/), or None when that capture is of another kernel."""
+    p = os.path.join(ROOT, "profiles", "r1_env_kernel_v2_ncu_full_summary.csv")
+    try:
+        import csv
+        rows = {r[0]: (r[1], r[2]) for r in csv.reader(open(p)) if len(r) == 3}
+        if kernel_tag not in rows.get("Kernel Name", ("", ""))[1]:
+            return None
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            unit, val = rows[k]
+            tot += float(val) * scale[unit]
+        return tot
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -317,7 +336,9 @@ def main():
             "gpu_launches": int(launches),
             "kernels": {"env_kernel(step+autoreset)_ms": step_kernel_ms, "host_issue_ms_per_step": host_issue_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "bytes_per_agent_step": bytes_per,
+                         "traffic": profiled_traffic("env_kernel<1, 0, 10, 36>") if args.workload == "c3" else None,
+                         "traffic_note": "bytes per launch, profiles/r1_env_kernel_v2_ncu_full_summary.csv (one ncu --set full capture)",
+                         "peak_kind": peak_kind, "bytes_per_agent_step": bytes_per,
                          "kernel": "env_kernel<%s> step+autoreset" % variant.upper()},
             "clocks": clocks,
             "episode_stats": {k: float(v) for k, v in zip(K.STAT_NAMES, stats)},
