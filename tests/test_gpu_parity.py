@@ -352,3 +352,76 @@ def test_state_dict_roundtrip():
         envs[1].step(acts[t], autoreset=True)
         for k in ("norm_own", "norm_nbr", "radar", "reward", "done"):
             assert torch.equal(envs[0].out[k], envs[1].out[k]), (t, k)
+
+
+def test_full_size_c3_properties_and_oracle_spot_check():
+    """BASELINE config C3 at full size (65 536 envs x 10 drones x 36 rays): size-independent properties on every env,
+    determinism, and an oracle comparison of 384 randomly chosen envs of the big batch."""
+    import numpy as np
+    import torch
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import synthetic_map
+    from multi_agent_aac_b200.reset import OdTable
+    from oracle.oracle import OracleEnv, RADAR_LAST_HIT
+    gmap = synthetic_map(seed=0)
+    tab = OdTable(gmap, w_max=32)
+    E, N, R = 65536, 10, 36
+    cfg = preset("tdcpa_v2", n_envs=E, n_agents=N, n_rays=R, w_max=32, seed=21, out_flags=parity.K.OUT_PARTS)
+    envs = [BatchedDroneEnv(cfg, gmap) for _ in range(2)]
+    for env in envs:
+        env.set_od_tables([tab])
+        env.reset()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    hx, hy = 0.5 * (gmap.bound[1] - gmap.bound[0]), 0.5 * (gmap.bound[3] - gmap.bound[2])
+    for t in range(6):
+        act = (torch.rand((E, N, 2), device="cuda", generator=gen) * 2 - 1).contiguous()
+        if t == 5:   # snapshot a sample of the big batch for the oracle before the last step
+            idx = torch.randperm(E, generator=torch.Generator().manual_seed(1))[:384].numpy()
+            s = envs[0].agent_state()
+            cells = envs[0].state["ref_cells"].cpu().numpy().view(np.uint16)
+            orc = OracleEnv("v2", gmap, len(idx), N, R, w_max=32, radar_mode=RADAR_LAST_HIT)
+            for k in ("pos", "vel", "heading", "reach", "wp_cur", "wall_cnt", "vflags"):
+                orc.state[k][:] = s[k][idx]
+            pn = s["prev_nn"][idx].copy(); pn[pn == 255] = -1
+            orc.state["prev_nn"][:] = pn
+            orc.state["ref_line"][:] = parity.cells_to_lines(gmap, cells[idx], None)
+            orc.state["ref_w"][:] = s["ref_w"][idx]
+        for env in envs:
+            env.step(act, autoreset=(t < 5))
+        o = envs[0].out
+        # determinism: two handles, same seed and inputs, bit-identical
+        for k in ("norm_own", "norm_nbr", "radar", "reward", "done", "terminated"):
+            assert torch.equal(o[k], envs[1].out[k]), (t, k)
+        radar = o["radar"]
+        assert float(radar[~radar.isnan()].max()) <= 15.0 and float(radar[~radar.isnan()].min()) >= 0.0
+        spd = torch.sqrt(envs[0].state["vx"] ** 2 + envs[0].state["vy"] ** 2)
+        assert float(spd.max()) <= 5.0 * (1 + 1e-5)
+        done_env = o["done"].any(dim=1)
+        assert bool((o["bbc"][:, :3].any(dim=1) == done_env).all())            # done <=> a bound / building / drone flag
+        assert bool((((o["terminated"] >> 1) & 1).bool() == done_env).all())
+        assert bool(torch.isfinite(o["reward"]).all())
+        if t == 5:   # no reset in the last step: observations describe the stepped state
+            assert torch.allclose(o["norm_own"][..., 0], envs[0].state["px"] / hx, atol=1e-6)
+            assert torch.allclose(o["norm_own"][..., 1], envs[0].state["py"] / hy, atol=1e-6)
+            nb = o["norm_nbr"].view(E, N, N - 1, 5)
+            d2 = (nb[..., 0] * hx) ** 2 + (nb[..., 1] * hy) ** 2
+            assert bool((d2[..., 1:] >= d2[..., :-1] * (1 - 1e-5) - 1e-4).all())      # neighbour blocks sorted by distance
+    # oracle spot check of the sampled envs (ties masked exactly as in the lock-step tests)
+    want = {k: v.copy() for k, v in orc.step(act.cpu().numpy().astype(np.float64)[idx]).items()}
+    got = {k: v.cpu().numpy()[idx] for k, v in envs[0].out.items()}
+    pos = orc.state["pos"]
+    d = np.linalg.norm(pos[:, :, None, :] - pos[:, None, :, :], axis=-1)
+    ds = np.take_along_axis(d, want["nbr_order"].astype(np.int64), axis=2)
+    gap = np.min(np.diff(ds, axis=2), axis=(1, 2))
+    ok = ((gap >= parity.TIE_EPS) | (gap == 0)) & (want["margin"] >= parity.TIE_EPS).all(axis=1)
+    assert ok.sum() > 300
+    rad_ok = np.abs(got["radar"] - want["radar"]) <= 1e-4 * np.abs(want["radar"]) + 2e-4
+    ok &= (rad_ok | (np.isnan(got["radar"]) & np.isnan(want["radar"]))).all(axis=(1, 2))     # grazing rays are covered by the lock-step tests
+    assert ok.sum() > 280
+    for k, atol in (("norm_own", 2e-6), ("norm_nbr", 2e-6), ("radar", 2e-4), ("reward", 2e-4)):
+        a, b = got[k][ok].astype(np.float64), want[k][ok]
+        both_nan = np.isnan(a) & np.isnan(b)
+        assert np.all((np.abs(a - b) <= 1e-4 * np.abs(b) + atol) | both_nan), k
+    for k in ("done", "check_goal", "bbc", "branch"):
+        assert np.array_equal(got[k][ok].astype(np.int64), want[k][ok].astype(np.int64)), k
