@@ -403,6 +403,14 @@ extern "C" int aac_autoreset(AacEnv *env, const AacOut *out, void *stream) {
     return launch(env, MODE_RESET, out->terminated, nullptr, out, stream);
 }
 
+// one device -> host copy of the env rows [e_lo, e_lo + cnt) of an output array (skipped when the host side is NULL)
+static int copy_rows(void *host, const void *dev, size_t per_env, size_t e_lo, size_t cnt, cudaStream_t s, const char *name) {
+    if (!host) return 0;
+    if (!dev) return fail(AAC_ERR_ARG, "aac_step_host: host buffer without a device buffer: %s", name);
+    CU(cudaMemcpyAsync((char *)host + e_lo * per_env, (const char *)dev + e_lo * per_env, cnt * per_env, cudaMemcpyDeviceToHost, s));
+    return 0;
+}
+
 extern "C" int aac_step_host(AacEnv *env, const float *actions_host, const AacOut *od, const AacOut *oh, int32_t autoreset, void *stream_) {
     if (!env || !actions_host || !od || !oh) return fail(AAC_ERR_ARG, "aac_step_host: null argument");
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -413,39 +421,47 @@ extern "C" int aac_step_host(AacEnv *env, const float *actions_host, const AacOu
         for (auto &s : env->pipe) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         for (auto &e : env->pipe_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    // The envs are cut into chunks that rotate over three streams: while chunk c's outputs cross PCIe, chunk c+1
-    // steps and chunk c+2's actions arrive.  Small batches go as one chunk.  With autoreset the terminal
+    // The envs are cut into chunks that rotate over three streams: while chunk c's observations cross PCIe, chunk
+    // c+1 steps and chunk c+2's actions arrive.  Small batches go as one chunk.  With autoreset the terminal
     // transition's reward / done / flags are kept and the observation rows of the finished envs carry their reset
     // observation (one fused launch per chunk).
     const size_t G = env->group;
     size_t n_chunks = E * N >= 65536 ? 8 : 1;
-    size_t per = ((E + n_chunks - 1) / n_chunks + G - 1) / G * G;
+    const size_t per = ((E + n_chunks - 1) / n_chunks + G - 1) / G * G;
     n_chunks = (E + per - 1) / per;
+#define ROWS(field, per_env, lo, cnt, s)                                                           \
+    do {                                                                                           \
+        const int rc_ = copy_rows(oh->field, od->field, (per_env), (lo), (cnt), (s), #field);      \
+        if (rc_) return rc_;                                                                       \
+    } while (0)
     CU(cudaEventRecord(env->pipe_ev[3], stream));
     for (size_t ch = 0; ch < n_chunks; ++ch) {
-        const size_t e_lo = ch * per, cnt = (e_lo + per <= E ? per : E - e_lo), a_lo = e_lo * N, A = cnt * N;
+        const size_t e_lo = ch * per, cnt = (e_lo + per <= E ? per : E - e_lo), a_lo = e_lo * N;
         cudaStream_t s = env->pipe[ch % 3];
         if (ch < 3) CU(cudaStreamWaitEvent(s, env->pipe_ev[3], 0));
-        CU(cudaMemcpyAsync(env->d_actions + a_lo * 2, actions_host + a_lo * 2, A * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(env->d_actions + a_lo * 2, actions_host + a_lo * 2, cnt * N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
         const int rc = launch(env, MODE_STEP, nullptr, env->d_actions, od, s, autoreset ? 1 : 0, (int)e_lo, (int)cnt, 1 + (int)ch);
         if (rc) return rc;
-#define D2H(field, per_env)                                                                                              \
-        if (oh->field) {                                                                                                 \
-            if (!od->field) return fail(AAC_ERR_ARG, "aac_step_host: host buffer without a device buffer: %s", #field);  \
-            CU(cudaMemcpyAsync((char *)oh->field + e_lo * (per_env), (const char *)od->field + e_lo * (per_env), cnt * (per_env), \
-                               cudaMemcpyDeviceToHost, s));                                                              \
-        }
-        D2H(reward, N * 4) D2H(done, N) D2H(check_goal, N) D2H(bbc, 4) D2H(terminated, 1) D2H(tcpa_min, N * 16)
-        D2H(norm_own, N * D * 4) D2H(norm_nbr, N * 5 * M * 4) D2H(radar, N * R * 4) D2H(norm_nbr6, N * M * 24)
-        D2H(raw_own, N * D * 4) D2H(raw_nbr, N * 5 * M * 4) D2H(raw_nbr6, N * M * 24)
-        D2H(tcpa_pair, N * M * 16) D2H(nbr_order, N * M) D2H(radar_min, N * R * 4) D2H(radar_hit, N * R * 2)
-        D2H(parts, N * 32) D2H(branch, N)
-#undef D2H
+        // the wide observation blocks leave with their chunk ...
+        ROWS(norm_own, N * D * 4, e_lo, cnt, s); ROWS(norm_nbr, N * 5 * M * 4, e_lo, cnt, s); ROWS(radar, N * R * 4, e_lo, cnt, s);
+        ROWS(norm_nbr6, N * M * 24, e_lo, cnt, s); ROWS(raw_own, N * D * 4, e_lo, cnt, s); ROWS(raw_nbr, N * 5 * M * 4, e_lo, cnt, s);
+        ROWS(raw_nbr6, N * M * 24, e_lo, cnt, s); ROWS(tcpa_pair, N * M * 16, e_lo, cnt, s); ROWS(radar_min, N * R * 4, e_lo, cnt, s);
+        ROWS(radar_hit, N * R * 2, e_lo, cnt, s);
     }
+    // ... the narrow arrays (a few bytes per drone) go once for the whole batch, after every chunk has stepped:
+    // fewer, larger transfers
+    cudaStream_t last = env->pipe[(n_chunks - 1) % 3];
     for (int k = 0; k < 3 && (size_t)k < n_chunks; ++k) {
+        if (env->pipe[k] == last) continue;
         CU(cudaEventRecord(env->pipe_ev[k], env->pipe[k]));
-        CU(cudaStreamWaitEvent(stream, env->pipe_ev[k], 0));
+        CU(cudaStreamWaitEvent(last, env->pipe_ev[k], 0));
     }
+    ROWS(reward, N * 4, 0, E, last); ROWS(done, N, 0, E, last); ROWS(check_goal, N, 0, E, last); ROWS(bbc, 4, 0, E, last);
+    ROWS(terminated, 1, 0, E, last); ROWS(tcpa_min, N * 16, 0, E, last); ROWS(nbr_order, N * M, 0, E, last);
+    ROWS(parts, N * 32, 0, E, last); ROWS(branch, N, 0, E, last);
+#undef ROWS
+    CU(cudaEventRecord(env->pipe_ev[0], last));
+    CU(cudaStreamWaitEvent(stream, env->pipe_ev[0], 0));
     CU(cudaStreamSynchronize(stream));
     return 0;
 }
