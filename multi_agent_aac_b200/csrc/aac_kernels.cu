@@ -395,13 +395,13 @@ __device__ __forceinline__ void flush_items(float *dst, int n_valid, const float
 
 // observation pipeline for the drones [a_lo, a_lo + n_ag) of the warp's group (whole envs):
 // neighbour order + window -> { pairs | rays | own block }.  `cells` = the lane's reference-line row.
-template <int VAR, bool AUX, int NT, int RT>
+template <int VAR, bool AUX, bool LEAN, int NT, int RT>
 __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, const int a_lo, const int n_ag, const uint16_t *cells) {
     const int lane = w.lane;
     // NT / RT > 0: drone count / ray count known at compile time
     const int N = NT ? NT : p.N, M = N - 1, R = RT ? RT : p.R, Mp = M | 1;
     const int D = own_dim(VAR, N);
-    const int flags = p.out_flags;
+    const int flags = LEAN ? 0 : p.out_flags;   // LEAN: no optional output was requested, their code is compiled out
     // one map staged in shared memory, or (multipleMap) the env's own map read through L1
     auto map_of = [&](const int aa) -> const MapDev & { return VAR == AAC_VARIANT_MM ? p.maps[w.amap[aa]] : *w.map; };
     const float inv_vmax = 1.0f / p.vmax;
@@ -799,13 +799,13 @@ __device__ __forceinline__ void polyline_nearest(const MapDev &mp, const uint16_
     total = run;
 }
 
-template <int VAR, bool AUX, int NT, int RT>
+template <int VAR, bool AUX, bool LEAN, int NT, int RT>
 __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_constant__ KParams p, const int mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = NT ? NT : p.N, M = N - 1, W = p.W, G = p.G;
     const int Mp = M | 1;
-    const int flags = p.out_flags;
+    const int flags = LEAN ? 0 : p.out_flags;   // LEAN: no optional output was requested, their code is compiled out
     const CtaLayout &CL = p.CL;
     const WarpLayout &WL = p.WL;
 
@@ -911,7 +911,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                 a_lo = g * N; n_ag = N;
                 cl = lane < N ? row : p.st.ref_cells;
             }
-            observe_range<VAR, AUX, NT, RT>(p, w, a_lo, n_ag, cl);
+            observe_range<VAR, AUX, LEAN, NT, RT>(p, w, a_lo, n_ag, cl);
             if (job > 0 || mode != MODE_STEP) continue;
 
             // ---- reward / collision / goal per drone
@@ -1204,11 +1204,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
     }
 }
 
-template <int VAR, bool AUX, int NT, int RT>
+template <int VAR, bool AUX, bool LEAN, int NT, int RT>
 static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     const int wpc = threads / 32;
     const int groups = (p.E + p.G - 1) / p.G;
-    auto fn = env_kernel<VAR, AUX, NT, RT>;
+    auto fn = env_kernel<VAR, AUX, LEAN, NT, RT>;
     static int opted_in[64] = {0};   // dynamic shared memory this instantiation has opted in to, per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1235,8 +1235,9 @@ static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, 
 
 template <int VAR, int NT, int RT>
 static cudaError_t launch_aux(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
-    return (p.out_flags & AAC_OUT_RADAR_AUX) ? launch_one<VAR, true, NT, RT>(p, mode, threads, sms, grid_cache, stream)
-                                             : launch_one<VAR, false, NT, RT>(p, mode, threads, sms, grid_cache, stream);
+    if (p.out_flags == 0) return launch_one<VAR, false, true, NT, RT>(p, mode, threads, sms, grid_cache, stream);
+    return (p.out_flags & AAC_OUT_RADAR_AUX) ? launch_one<VAR, true, false, NT, RT>(p, mode, threads, sms, grid_cache, stream)
+                                             : launch_one<VAR, false, false, NT, RT>(p, mode, threads, sms, grid_cache, stream);
 }
 
 cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
