@@ -46,7 +46,8 @@ def profiled_traffic(kernel_tag):
     try:
         import csv
         rows = {r[0]: (r[1], r[2]) for r in csv.reader(open(p)) if len(r) == 3}
-        if kernel_tag not in rows.get("Kernel Name", ("", ""))[1]:
+        name = rows.get("Kernel Name", ("", ""))[1]
+        if not all(t in name for t in kernel_tag):
             return None
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         tot = 0.0
@@ -336,7 +337,7 @@ def main():
             "gpu_launches": int(launches),
             "kernels": {"env_kernel(step+autoreset)_ms": step_kernel_ms, "host_issue_ms_per_step": host_issue_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": profiled_traffic("env_kernel<1, 0, 10, 36>") if args.workload == "c3" else None,
+                         "traffic": profiled_traffic(("env_kernel<1,", " 10, 36>")) if args.workload == "c3" else None,
                          "traffic_note": "bytes per launch, profiles/r1_env_kernel_v2_ncu_full_summary.csv (one ncu --set full capture)",
                          "peak_kind": peak_kind, "bytes_per_agent_step": bytes_per,
                          "kernel": "env_kernel<%s> step+autoreset" % variant.upper()},

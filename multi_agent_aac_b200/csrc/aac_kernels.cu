@@ -1057,7 +1057,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                     } else if (at_goal) { res |= F_GOAL; meta |= M_REACH; rew = 20.0f; branch = 3; }
                     else {
                         if (wp_flag && (nw - 1 - cur) > 1) meta = (meta & ~0xFFu) | (unsigned)(cur + 1);  // ATT:2565-2566
-                        rew = dist_to_goal - small_step - near_bldg - near_drone;                            // ATT:2576-2578
+                        rew = __fsub_rn(__fsub_rn(__fsub_rn(dist_to_goal, small_step), near_bldg), near_drone);  // ATT:2576-2578
                         branch = 4;
                     }
                     if (flags & AAC_OUT_PARTS) {  // cross-track error is reported, not rewarded (ATT:2368 coefficient 0)
@@ -1093,7 +1093,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                     } else if (at_goal) { res |= F_GOAL; rew = 20.0f; branch = 3; }
                     else {
                         if (wp_flag && (nw - 1 - cur) > 1) meta = (meta & ~0xFFu) | (unsigned)(cur + 1);
-                        rew = dist_to_goal - small_step - near_bldg - near_drone;  // V2:3631-3633
+                        // explicit roundings: the terms are also an output (parts), and a product contracted into
+                        // this sum in one instantiation but not another would make them differ in the last bit
+                        rew = __fsub_rn(__fsub_rn(__fsub_rn(dist_to_goal, small_step), near_bldg), near_drone);  // V2:3631-3633
                         branch = 4;
                     }
                 }

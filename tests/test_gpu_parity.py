@@ -425,3 +425,36 @@ def test_full_size_c3_properties_and_oracle_spot_check():
         assert np.all((np.abs(a - b) <= 1e-4 * np.abs(b) + atol) | both_nan), k
     for k in ("done", "check_goal", "bbc", "branch"):
         assert np.array_equal(got[k][ok].astype(np.int64), want[k][ok].astype(np.int64)), k
+
+
+@pytest.mark.parametrize("variant,n,r", [("tdcpa_v2", 10, 36), ("tdcpa_v2", 7, 24), ("att", 3, 18), ("multimap", 3, 18)])
+def test_lean_kernel_equals_full_kernel(variant, n, r):
+    """With no optional output requested the library runs an instantiation with that code compiled out; it must
+    produce exactly the core outputs and state of the full kernel (which the oracle tests exercise)."""
+    import torch
+    from multi_agent_aac_b200 import _capi as K
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import multimap_set, synthetic_map
+    from multi_agent_aac_b200.reset import OdTable
+    maps = multimap_set(seed=0)[:4] if variant == "multimap" else [synthetic_map(seed=0)]
+    tabs = [OdTable(m, w_max=32) for m in maps]
+    E = 500
+    full_flags = K.OUT_RAW | K.OUT_RADAR_AUX | K.OUT_PARTS | (0 if variant == "multimap" else K.OUT_NBR6 | K.OUT_TCPA_PAIR)
+    envs = []
+    for flags in (0, full_flags):
+        env = BatchedDroneEnv(preset(variant, n_envs=E, n_agents=n, n_rays=r, w_max=32, seed=6, out_flags=flags),
+                              maps if variant == "multimap" else maps[0])
+        env.set_od_tables(tabs)
+        env.reset()
+        envs.append(env)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(9)
+    for t in range(20):
+        act = (torch.rand((E, n, 2), device="cuda", generator=gen) * 2 - 1).contiguous()
+        for env in envs:
+            env.step(act, autoreset=True)
+        for k in envs[0].out:
+            assert torch.equal(envs[0].out[k].view(torch.uint8), envs[1].out[k].view(torch.uint8)), (t, k)
+        for k in envs[0].state:
+            assert torch.equal(envs[0].state[k].view(torch.uint8), envs[1].state[k].view(torch.uint8)), (t, k)
+    assert envs[0].read_stats()[0] == envs[1].read_stats()[0] > 0
