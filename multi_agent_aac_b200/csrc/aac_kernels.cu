@@ -226,42 +226,69 @@ __device__ __forceinline__ unsigned pick_scenario(long long gid, int episode, un
 
 // the boundary lines in the reference's order L, R, B, T (V2:145-152); ray = (dx, dy, 1/dx, 1/dy).  `lines` has
 // one bit per line that can be reached at all from the drone's position.
+struct RadarAcc {
+    float shortest, sensed;
+    int shortest_id, sensed_id;
+};
 template <bool AUX>
-__device__ __forceinline__ void radar_bounds(const MapDev &mp, float px, float py, float4 ray, float len, unsigned lines, float &shortest,
-                                             float &sensed, int &shortest_id, int &sensed_id) {
+__device__ __forceinline__ void bound_line(const int b, const int nb, const float dd, const float pp, const float inv, const float line, const float len,
+                                           float &shortest, float &sensed, int &shortest_id, int &sensed_id) {
+    if (dd != 0.0f) {
+        const float t = (line - pp) * inv;
+        if (t >= 0.0f && t <= 1.0f) {
+            const float d = t * len;
+            sensed = d;
+            if (AUX) sensed_id = nb + b;
+            if (d < shortest) { shortest = d; if (AUX) shortest_id = nb + b; }
+        }
+    } else if (pp == line) {  // ray runs along the boundary: GEOS returns the whole overlap
+        sensed = len;
+        if (AUX) sensed_id = nb + b;
+        if (0.0f < shortest) { shortest = 0.0f; if (AUX) shortest_id = nb + b; }
+    }
+}
+// any set of lines (a map narrower than two ray lengths can have both lines of an axis in reach); off the hot
+// path, so the accumulators travel by value
+template <bool AUX>
+__device__ __noinline__ RadarAcc radar_bounds_any(const MapDev &mp, float px, float py, float4 ray, float len, unsigned lines, RadarAcc acc) {
     const int nb = mp.gx * mp.gy;
 #pragma unroll 1
     while (lines) {
         const int b = __ffs(lines) - 1;
         lines &= lines - 1;
-        const float dd = b < 2 ? ray.x : ray.y, pp = b < 2 ? px : py, inv = b < 2 ? ray.z : ray.w;
-        const float lim = b < 2 ? mp.hx : mp.hy, line = (b & 1) ? lim : -lim;
-        if (dd != 0.0f) {
-            const float t = (line - pp) * inv;
-            if (t >= 0.0f && t <= 1.0f) {
-                const float d = t * len;
-                sensed = d;
-                if (AUX) sensed_id = nb + b;
-                if (d < shortest) { shortest = d; if (AUX) shortest_id = nb + b; }
-            }
-        } else if (pp == line) {  // ray runs along the boundary: GEOS returns the whole overlap
-            sensed = len;
-            if (AUX) sensed_id = nb + b;
-            if (0.0f < shortest) { shortest = 0.0f; if (AUX) shortest_id = nb + b; }
-        }
+        const float lim = b < 2 ? mp.hx : mp.hy;
+        bound_line<AUX>(b, nb, b < 2 ? ray.x : ray.y, b < 2 ? px : py, b < 2 ? ray.z : ray.w, (b & 1) ? lim : -lim, len, acc.shortest, acc.sensed,
+                        acc.shortest_id, acc.sensed_id);
     }
+    return acc;
+}
+template <bool AUX>
+__device__ __forceinline__ void radar_bounds(const MapDev &mp, float px, float py, float4 ray, float len, unsigned lines, float &shortest,
+                                             float &sensed, int &shortest_id, int &sensed_id) {
+    if ((lines & 3u) == 3u || (lines & 12u) == 12u) {
+        const RadarAcc r = radar_bounds_any<AUX>(mp, px, py, ray, len, lines, RadarAcc{shortest, sensed, shortest_id, sensed_id});
+        shortest = r.shortest; sensed = r.sensed; shortest_id = r.shortest_id; sensed_id = r.sensed_id;
+        return;
+    }
+    // usual case: at most one line per axis, x first
+    const int nb = AUX ? mp.gx * mp.gy : 0;
+    if (lines & 3u) bound_line<AUX>((lines & 1u) ? 0 : 1, nb, ray.x, px, ray.z, (lines & 1u) ? -mp.hx : mp.hx, len, shortest, sensed, shortest_id, sensed_id);
+    if (lines & 12u) bound_line<AUX>((lines & 4u) ? 2 : 3, nb, ray.y, py, ray.w, (lines & 4u) ? -mp.hy : mp.hy, len, shortest, sensed, shortest_id, sensed_id);
 }
 
 // Fast path.  One ray against the occupied cells of the drone's 4x4 window (V2:1210-1300): a slab test per
 // set bit of the window mask, lowest bit first = ascending (ix, iy) = ascending cell index, so `sensed`
 // ends as the reference's last hit.  `wrel` = window origin relative to the drone.  The loop
 // is deliberately not unrolled: all lanes of a warp iteration work on the same drone, so the trip count
-// is warp-uniform and the body stays resident in the instruction cache.
+// is warp-uniform and the body stays resident in the instruction cache; the hit update is branch-free and
+// works on the ray parameter (the range is t * len, monotone in t, so the minimum commutes with the scaling).
 // Axis-parallel rays carry 1/d = +inf: the products are +-inf (or NaN exactly on a grid line, which
 // fminf / fmaxf drop), i.e. no constraint from that axis.
 template <bool AUX>
 __device__ __forceinline__ void radar_window(const MapDev &mp, const float2 *lut, float2 wrel, unsigned win, int wix0, int wiy0, float4 ray,
                                              float len, float &shortest, float &sensed, int &shortest_id, int &sensed_id) {
+    float t_min = CUDART_INF_F, t_last = 1.0f;
+    int b_min = -1, b_last = -1;
 #pragma unroll 1
     while (win) {
         const int b = __ffs(win) - 1;
@@ -271,12 +298,16 @@ __device__ __forceinline__ void radar_window(const MapDev &mp, const float2 *lut
         const float tx0 = x0 * ray.z, tx1 = (x0 + mp.cell) * ray.z, ty0 = y0 * ray.w, ty1 = (y0 + mp.cell) * ray.w;
         const float lo = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), 0.0f);
         const float hi = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), 1.0f);
-        if (lo <= hi) {
-            const float d = lo * len;
-            sensed = d;
-            if (AUX) sensed_id = (wix0 + (b >> 2)) * mp.gy + wiy0 + (b & 3);
-            if (d < shortest) { shortest = d; if (AUX) shortest_id = (wix0 + (b >> 2)) * mp.gy + wiy0 + (b & 3); }
-        }
+        const bool hit = lo <= hi;
+        t_last = hit ? lo : t_last;
+        if (AUX) { b_last = hit ? b : b_last; b_min = (hit && lo < t_min) ? b : b_min; }
+        t_min = hit ? fminf(t_min, lo) : t_min;
+    }
+    shortest = t_min * len;
+    sensed = t_last * len;
+    if (AUX) {
+        shortest_id = b_min < 0 ? -1 : (wix0 + (b_min >> 2)) * mp.gy + wiy0 + (b_min & 3);
+        sensed_id = b_last < 0 ? -1 : (wix0 + (b_last >> 2)) * mp.gy + wiy0 + (b_last & 3);
     }
 }
 
