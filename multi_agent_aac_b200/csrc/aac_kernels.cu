@@ -282,22 +282,25 @@ __device__ __forceinline__ void radar_bounds(const MapDev &mp, float px, float p
 // is deliberately not unrolled: all lanes of a warp iteration work on the same drone, so the trip count
 // is warp-uniform and the body stays resident in the instruction cache; the hit update is branch-free and
 // works on the ray parameter (the range is t * len, monotone in t, so the minimum commutes with the scaling).
-// Axis-parallel rays carry 1/d = +inf: the products are +-inf (or NaN exactly on a grid line, which
-// fminf / fmaxf drop), i.e. no constraint from that axis.
+// Axis-parallel rays carry 1/d = +inf: the products are -inf on the entry side and +inf on the exit side of a
+// cell whose slab contains the ray (or NaN exactly on a grid line, which fminf / fmaxf drop: the ray runs along
+// the cell's edge and touches it), i.e. no constraint from that axis.
 template <bool AUX>
 __device__ __forceinline__ void radar_window(const MapDev &mp, const float2 *lut, float2 wrel, unsigned win, int wix0, int wiy0, float4 ray,
-                                             float len, float &shortest, float &sensed, int &shortest_id, int &sensed_id) {
+                                             float2 eo, float len, float &shortest, float &sensed, int &shortest_id, int &sensed_id) {
     float t_min = CUDART_INF_F, t_last = 1.0f;
     int b_min = -1, b_last = -1;
+    // the ray's direction signs say which edge of a cell is the entry side on each axis (`eo` = that edge's
+    // offset from the cell's low corner, a property of the ray alone): shift the window origin once per ray
+    // instead of ordering the two products per cell
+    const float xn = wrel.x + eo.x, xf = wrel.x + (mp.cell - eo.x), yn = wrel.y + eo.y, yf = wrel.y + (mp.cell - eo.y);
 #pragma unroll 1
     while (win) {
         const int b = __ffs(win) - 1;
         win &= win - 1;
         const float2 off = lut[b];   // (row, column) of window cell b times the cell size
-        const float x0 = wrel.x + off.x, y0 = wrel.y + off.y;
-        const float tx0 = x0 * ray.z, tx1 = (x0 + mp.cell) * ray.z, ty0 = y0 * ray.w, ty1 = (y0 + mp.cell) * ray.w;
-        const float lo = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), 0.0f);
-        const float hi = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), 1.0f);
+        const float lo = fmaxf(fmaxf((xn + off.x) * ray.z, (yn + off.y) * ray.w), 0.0f);
+        const float hi = fminf(fminf((xf + off.x) * ray.z, (yf + off.y) * ray.w), 1.0f);
         const bool hit = lo <= hi;
         t_last = hit ? lo : t_last;
         if (AUX) { b_last = hit ? b : b_last; b_min = (hit && lo < t_min) ? b : b_min; }
@@ -579,7 +582,8 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
     //      (min_radar) is one redux.sync per drone and iteration.
     {
         const float len = p.ray_len;
-        auto cast = [&](const int aa, const float4 ray, float &out_min, int &id) -> float {
+        auto entry_off = [&](const float4 ray, const float cell) { return make_float2(ray.z > 0.0f ? 0.0f : cell, ray.w > 0.0f ? 0.0f : cell); };
+        auto cast = [&](const int aa, const float4 ray, const float2 eo, float &out_min, int &id) -> float {
             const MapDev &mr = map_of(aa);
             float out;
             if (VAR == AAC_VARIANT_ATT) {
@@ -591,7 +595,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
                 float shortest = CUDART_INF_F, sensed = len;
                 int shortest_id = -1, sensed_id = -1;
                 if (!(wn.x & W_SLOW))
-                    radar_window<AUX>(mr, w.lut, w.wrel[aa], wn.x & 0xFFFFu, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16), ray, len, shortest,
+                    radar_window<AUX>(mr, w.lut, w.wrel[aa], wn.x & 0xFFFFu, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16), ray, eo, len, shortest,
                                       sensed, shortest_id, sensed_id);
                 else {
                     const GenericHit h = radar_generic<AUX>(mr, w.px[aa], w.py[aa], ray, len);
@@ -611,6 +615,8 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
         // full chunks: lanes = rays 32c .. 32c+31 of drone q
         // a lane casts the same ray(s) for every drone: the table entry of the first chunk stays in registers
         const float4 ray0 = w.ray[lane < R ? lane : 0];
+        const float cell = p.cell;
+        const float2 eo0 = entry_off(ray0, cell);
 #pragma unroll 1
         for (int q = 0; q < n_ag; ++q) {
 #pragma unroll 1
@@ -618,7 +624,8 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
                 const int k = (c << 5) + lane;
                 float out_min;
                 int id = -1;
-                const float out = cast(a_lo + q, c == 0 ? ray0 : w.ray[k], out_min, id);
+                const float4 ray = c == 0 ? ray0 : w.ray[k];
+                const float out = cast(a_lo + q, ray, c == 0 ? eo0 : entry_off(ray, cell), out_min, id);
                 g_out[q * R + k] = out;
                 if (AUX) { p.out.radar_min[rg0 + q * R + k] = out_min; p.out.radar_hit[rg0 + q * R + k] = (int16_t)id; }
                 const unsigned m = __reduce_min_sync(FULL, __float_as_uint(out));
@@ -630,6 +637,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
             const int per = 32 / rem;
             const int sub = lane / rem, k = (full << 5) + lane - sub * rem;
             const float4 rayr = w.ray[k < R ? k : 0];
+            const float2 eor = entry_off(rayr, cell);
 #pragma unroll 1
             for (int q0 = 0; q0 < n_ag; q0 += per) {
                 const int nsub = min(per, n_ag - q0);
@@ -637,7 +645,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
                 const int q = q0 + (ok ? sub : 0);
                 float out_min;
                 int id = -1;
-                const float out = cast(a_lo + q, rayr, out_min, id);
+                const float out = cast(a_lo + q, rayr, eor, out_min, id);
                 if (ok) {
                     g_out[q * R + k] = out;
                     if (AUX) { p.out.radar_min[rg0 + q * R + k] = out_min; p.out.radar_hit[rg0 + q * R + k] = (int16_t)id; }
