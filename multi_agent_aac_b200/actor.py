@@ -1,0 +1,109 @@
+"""Batched actor: the reference's `choose_action` for every drone of every env in one launch.
+
+Mirrors, for the network the tdCPA_forV2 configuration trains (`ActorNetwork_allnei_wRadar`,
+V2/Nnetworks:273-340; selected by use_allNeigh_wRadar=True, one shared model, V2/ma_main:81,95,100),
+
+    maddpg.choose_action(state, ..., noisy=...)        V2/maddpg_agent:1241-1310
+
+which runs N sequential batch-1 forwards per env step on `[obs, obs_full_nei, obs_grid]`.  Here the three
+inputs are the env step's `norm_own`, `norm_nbr`, `radar` tensors as they lie in device memory, and the
+actions come back in the `[E, N, 2]` layout `BatchedDroneEnv.step` takes, so a rollout never leaves HBM:
+
+    actor = BatchedActor.for_env(env); actor.load_state_dict(reference_actor.state_dict())
+    obs = env.reset()
+    for _ in range(T):
+        obs, reward, done, info = env.step(actor(obs, noise_scale=var), autoreset=True)
+
+Compute: bf16 tensor-core GEMM chain with fp32 accumulation inside one fused sm_100a kernel
+(csrc/aac_actor.cu); there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _actor_capi as K
+
+# reference module names (V2/Nnetworks:292-298) -> fields of AacActorParams
+_MODULES = [("own_fc.0", "own"), ("own_full_nei.0", "nbr"), ("own_grid.0", "grid"), ("merge_feature.0", "merge"), ("act_out.0", "hid"),
+            ("act_out.2", "out")]
+
+
+class BatchedActor:
+    def __init__(self, d_own, d_nbr, d_grid, max_rows, device="cuda:0"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise K.AacActorError("BatchedActor runs on a CUDA device only (no CPU path)")
+        self.d_own, self.d_nbr, self.d_grid, self.max_rows = int(d_own), int(d_nbr), int(d_grid), int(max_rows)
+        self._h = C.c_void_p()
+        cfg = K.AacActorConfig(K.ABI_VERSION, self.d_own, self.d_nbr, self.d_grid, self.max_rows)
+        with torch.cuda.device(self.device):
+            K.check(K.lib().aac_actor_create(C.byref(cfg), C.byref(self._h)), "aac_actor_create")
+
+    @classmethod
+    def for_env(cls, env):
+        """Actor sized for a `BatchedDroneEnv` of the tdCPA_forV2 preset (own 7, nbr 5 (N - 1), grid R)."""
+        return cls(env.D, 5 * (env.N - 1), env.R, env.E * env.N, device=env.device)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and K is not None and getattr(K, "_lib", None) is not None:   # module globals may be gone at interpreter exit
+            K._lib.aac_actor_destroy(h)
+
+    def load_state_dict(self, sd):
+        """`sd`: the reference module's state_dict (tensors or arrays keyed 'own_fc.0.weight', ...)."""
+        keep, params = [], K.AacActorParams()
+        shapes = {"own": (K.H1, self.d_own), "nbr": (K.H1, self.d_nbr), "grid": (K.H1, self.d_grid), "merge": (K.H2, 3 * K.H1),
+                  "hid": (K.H3, K.H2), "out": (K.NACT, K.H3)}
+        for mod, field in _MODULES:
+            for kind, pre in (("weight", "w_"), ("bias", "b_")):
+                v = sd[mod + "." + kind]
+                a = np.ascontiguousarray(v.detach().cpu().numpy() if torch.is_tensor(v) else v, dtype=np.float32)
+                want = shapes[field] if kind == "weight" else (shapes[field][0],)
+                if a.shape != want:
+                    raise ValueError("%s.%s has shape %s, expected %s" % (mod, kind, a.shape, want))
+                keep.append(a)
+                setattr(params, pre + field, a.ctypes.data)
+        with torch.cuda.device(self.device):
+            K.check(K.lib().aac_actor_load(self._h, C.byref(params)), "aac_actor_load")
+
+    def _rows(self, own, nbr, grid):
+        for t, d, name in ((own, self.d_own, "own"), (nbr, self.d_nbr, "nbr"), (grid, self.d_grid, "grid")):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device or t.shape[-1] != d:
+                raise ValueError("%s must be a contiguous float32 tensor [..., %d] on %s" % (name, d, self.device))
+        n = own.numel() // self.d_own
+        if nbr.numel() != n * self.d_nbr or grid.numel() != n * self.d_grid:
+            raise ValueError("own / nbr / grid disagree on the number of rows")
+        return n
+
+    def forward(self, own, nbr, grid, noise_scale=0.0, noise_seed=0, out=None):
+        """actions [..., 2] = clamp(actor(own, nbr, grid) + noise_scale * N(0, 1), -1, 1); leading dims follow `own`."""
+        n = self._rows(own, nbr, grid)
+        if out is None:
+            out = torch.empty(tuple(own.shape[:-1]) + (K.NACT,), dtype=torch.float32, device=self.device)
+        elif out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != n * K.NACT or out.device != self.device:
+            raise ValueError("out must be a contiguous float32 tensor with %d elements" % (n * K.NACT))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        K.check(K.lib().aac_actor_forward(self._h, own.data_ptr(), nbr.data_ptr(), grid.data_ptr(), n, float(noise_scale), int(noise_seed),
+                                          out.data_ptr(), stream), "aac_actor_forward")
+        return out
+
+    def __call__(self, obs, noise_scale=0.0, noise_seed=0, out=None):
+        """`obs`: the dict `BatchedDroneEnv.reset/step` returns ([obs, obs_full_nei, obs_grid] of V2/maddpg_agent:1243-1245)."""
+        return self.forward(obs["norm_own"], obs["norm_nbr"], obs["radar"], noise_scale, noise_seed, out)
+
+    def hidden(self, layer, own, nbr, grid):
+        """Post-activation output of hidden layer 1 / 2 / 3 (parity aid)."""
+        n = self._rows(own, nbr, grid)
+        width = {1: 3 * K.H1, 2: K.H2, 3: K.H3}[layer]
+        out = torch.empty((n, width), dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        K.check(K.lib().aac_actor_hidden(self._h, own.data_ptr(), nbr.data_ptr(), grid.data_ptr(), n, layer, out.data_ptr(), stream),
+                "aac_actor_hidden")
+        return out
+
+    @property
+    def launch_count(self):
+        return int(K.lib().aac_actor_launch_count(self._h))

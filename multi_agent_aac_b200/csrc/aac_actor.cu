@@ -1,0 +1,515 @@
+// Batched actor forward (include/aac_actor.h): one persistent, warp-specialised sm_100a kernel that runs the
+// whole ActorNetwork_allnei_wRadar (V2/Nnetworks:273-340) for 128 drones per tile on the 5th-generation
+// tensor cores.
+//
+//   warps 0-3  stage the tile's observations as the bf16 A operand, then act as the epilogue of every layer:
+//              tcgen05.ld the fp32 accumulators out of tensor memory, add the bias, LeakyReLU, round to bf16
+//              and write the result back to shared memory AS THE NEXT LAYER'S A OPERAND (activations never
+//              leave the SM); the last layer (256 -> 2), tanh, exploration noise and clamp run in fp32 here
+//   warp 4     streams the pre-tiled bf16 weights through a 6-slot shared-memory ring with bulk async copies
+//              (cp.async.bulk + mbarrier complete_tx); also owns the tensor-memory allocation
+//   warp 5     one elected thread issues tcgen05.mma (M = 128, N = 128 / 256, K = 16, kind::f16 with bf16
+//              operands, fp32 accumulators in TMEM) and tcgen05.commit's ring slots / layer completion
+//
+// Operand layout: the canonical K-major no-swizzle UMMA layout, 8 x 8 "core matrices" of 128 contiguous bytes;
+// an operand of `rows` rows is stored K-chunk-major: byte = (k / 8) * rows * 16 + row * 16 + (k % 8) * 2, i.e.
+// stride-byte-offset (next 8 rows) = 128 and leading-byte-offset (next 8 k) = rows * 16.  With that layout an
+// epilogue thread (= one row) writes 16 contiguous bytes per K chunk and a warp 512 contiguous bytes:
+// conflict-free 128-bit shared stores; the host tiles the weights into the same form once (aac_actor_load).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/aac_actor.h"
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int H1 = AAC_ACTOR_H1, H1C = 3 * AAC_ACTOR_H1, H2 = AAC_ACTOR_H2, H3 = AAC_ACTOR_H3;
+constexpr int KC_BYTES = TILE_M * 16;           // one 8-wide K chunk of a 128-row A operand
+constexpr int ACT_BYTES = (H2 / 8) * KC_BYTES;  // widest A operand: 128 x 512 bf16 = 128 KB
+constexpr int SLOT_BYTES = 16384;
+constexpr int N_SLOTS = 6;
+constexpr int PRODUCER_WARP = 4, MMA_WARP = 5, THREADS = 192;
+constexpr int MAX_CHUNKS = 64;
+constexpr unsigned TMEM_COLS = 512;
+constexpr unsigned CH_LAYER_BEGIN = 1u, CH_LAYER_END = 2u, CH_FRESH = 4u;
+
+// one ring slot's worth of weights and the MMAs that consume it
+struct Chunk {
+    uint32_t src_off;   // byte offset into the packed weights
+    uint32_t bytes;     // multiple of 16
+    uint32_t n_mma;     // K = 16 steps in this chunk
+    uint32_t n;         // MMA N (rows of the B operand)
+    uint32_t lbo;       // leading byte offset of the B operand = n * 16
+    uint32_t a_kc0;     // first 8-wide K chunk of the A operand
+    uint32_t tmem_col;  // accumulator column
+    uint32_t flags;
+};
+
+struct KArgs {
+    const float *own, *nbr, *grid;
+    float *actions, *dbg;
+    int dbg_layer, n_rows, n_tiles;
+    int d_own, d_nbr, d_grid;
+    int kc_nbr0, kc_grid0, kc_end;  // first K chunk of the nbr / grid block of the input operand, total chunks
+    const uint8_t *wpack;
+    const Chunk *sched;
+    int n_chunks;
+    const float *b1, *b2, *b3, *w4, *b4;
+    float noise_scale;
+    unsigned long long noise_seed;
+};
+
+constexpr int SMEM_BARS = ACT_BYTES + N_SLOTS * SLOT_BYTES;
+constexpr int SMEM_SCHED = SMEM_BARS + 128;
+constexpr int SMEM_TOTAL = SMEM_SCHED + MAX_CHUNKS * (int)sizeof(Chunk);
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned ok;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(unsigned *slot, unsigned cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free(unsigned addr, unsigned cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start >> 4 at bit 0, leading byte
+// offset >> 4 at bit 16, stride byte offset >> 4 at bit 32, version 1 at bit 46, layout type 0 at bit 61)
+__device__ __forceinline__ unsigned long long umma_desc(unsigned addr, unsigned lbo, unsigned sbo) {
+    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | ((unsigned long long)(lbo >> 4) << 16) | ((unsigned long long)(sbo >> 4) << 32) |
+           (1ull << 46);
+}
+// instruction descriptor, kind::f16: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17,
+// M >> 4 at bit 24 (cute::UMMA::InstrDescriptor)
+__device__ __forceinline__ unsigned umma_idesc(unsigned n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((TILE_M >> 4) << 24); }
+__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long a, unsigned long long b, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(a), "l"(b),
+        "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(unsigned long long *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of warp w gets row 32 * (w % 4) + t
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
+    unsigned r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
+    unsigned r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float leaky(float x) { return fmaxf(x, 0.01f * x); }
+
+// counter-based standard normal pair for (seed, row): Box-Muller on two hashed uniforms
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ float2 normal_pair(unsigned long long seed, unsigned row) {
+    const unsigned k = mix32((unsigned)seed ^ mix32((unsigned)(seed >> 32) + 0x9e3779b9u) ^ mix32(row * 2u + 1u));
+    const float u1 = ((mix32(k ^ 0x68bc21ebu) >> 8) + 1) * (1.0f / 16777216.0f), u2 = (mix32(k ^ 0x02e5be93u) >> 8) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    __sincosf(6.283185307f * u2, &s, &c);
+    return make_float2(r * c, r * s);
+}
+
+// ------------------------------------------------------------------------------------ epilogue pieces
+
+// one row of one observation block -> bf16 K chunks kc0.. of the A operand (zero padded to a multiple of 16)
+__device__ __forceinline__ void stage_block(uint8_t *act, const float *src, int d, int kc0, int kc1, int m, bool valid) {
+    for (int kc = kc0; kc < kc1; ++kc) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = (kc - kc0) * 8 + i;
+            v[i] = (valid && k < d) ? __ldg(src + k) : 0.0f;
+        }
+        *reinterpret_cast<uint4 *>(act + kc * KC_BYTES + m * 16) =
+            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    }
+}
+
+// accumulators [row, 0..ncols) -> leaky(acc + bias) -> bf16 A operand of the next layer
+__device__ __forceinline__ void hidden_epilogue(uint8_t *act, unsigned tmem_row, int ncols, const float *bias, int m, float *dbg_row) {
+    for (int cb = 0; cb < ncols; cb += 32) {
+        float v[32];
+        tmem_ld32(tmem_row + cb, v);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + cb + 8 * g)), b1 = __ldg(reinterpret_cast<const float4 *>(bias + cb + 8 * g + 4));
+            float *x = v + 8 * g;
+            x[0] = leaky(x[0] + b0.x); x[1] = leaky(x[1] + b0.y); x[2] = leaky(x[2] + b0.z); x[3] = leaky(x[3] + b0.w);
+            x[4] = leaky(x[4] + b1.x); x[5] = leaky(x[5] + b1.y); x[6] = leaky(x[6] + b1.z); x[7] = leaky(x[7] + b1.w);
+            *reinterpret_cast<uint4 *>(act + ((cb >> 3) + g) * KC_BYTES + m * 16) =
+                make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+        }
+        if (dbg_row)
+            for (int i = 0; i < 32; ++i) dbg_row[cb + i] = v[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------ kernel
+
+__global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant__ KArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *act = smem, *ring = smem + ACT_BYTES;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + SMEM_BARS);
+    unsigned long long *full = bars, *empty = bars + N_SLOTS, *act_ready = bars + 2 * N_SLOTS, *layer_done = act_ready + 1;
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(layer_done + 1);
+    Chunk *sched = reinterpret_cast<Chunk *>(smem + SMEM_SCHED);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int i = tid; i < p.n_chunks * (int)(sizeof(Chunk) / 4); i += THREADS) reinterpret_cast<uint32_t *>(sched)[i] = reinterpret_cast<const uint32_t *>(p.sched)[i];
+    if (tid == 0) {
+        for (int s = 0; s < N_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(act_ready, TILE_M);
+        mbar_init(layer_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == PRODUCER_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_slot;
+
+    if (warp == PRODUCER_WARP) {
+        if (lane == 0) {
+            unsigned c_glob = 0;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+                for (int c = 0; c < p.n_chunks; ++c, ++c_glob) {
+                    const unsigned s = c_glob % N_SLOTS, ph = (c_glob / N_SLOTS) & 1u;
+                    mbar_wait(empty + s, ph ^ 1u);  // slot free (passes at once the first time round)
+                    mbar_expect_tx(full + s, sched[c].bytes);
+                    bulk_g2s(ring + s * SLOT_BYTES, p.wpack + sched[c].src_off, sched[c].bytes, full + s);
+                }
+        }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0) {
+            unsigned c_glob = 0, act_phase = 0;
+            const unsigned act_addr = smem_u32(act), ring_addr = smem_u32(ring);
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+                for (int c = 0; c < p.n_chunks; ++c, ++c_glob) {
+                    const Chunk ch = sched[c];
+                    if (ch.flags & CH_LAYER_BEGIN) {  // A operand written, accumulator columns drained
+                        mbar_wait(act_ready, act_phase & 1u);
+                        ++act_phase;
+                        tc_fence_after();
+                    }
+                    const unsigned s = c_glob % N_SLOTS, ph = (c_glob / N_SLOTS) & 1u;
+                    mbar_wait(full + s, ph);
+                    tc_fence_after();
+                    const unsigned idesc = umma_idesc(ch.n);
+                    for (unsigned j = 0; j < ch.n_mma; ++j) {
+                        const unsigned long long a = umma_desc(act_addr + (ch.a_kc0 + 2 * j) * KC_BYTES, KC_BYTES, 128);
+                        const unsigned long long b = umma_desc(ring_addr + s * SLOT_BYTES + 2 * j * ch.lbo, ch.lbo, 128);
+                        umma_bf16(tmem_base + ch.tmem_col, a, b, idesc, ((ch.flags & CH_FRESH) && j == 0) ? 0u : 1u);
+                    }
+                    umma_commit(empty + s);
+                    if (ch.flags & CH_LAYER_END) umma_commit(layer_done);
+                }
+        }
+    } else {
+        const int m = tid;  // row of the tile = TMEM lane
+        const unsigned tmem_row = tmem_base + ((unsigned)(warp * 32) << 16);
+        unsigned done_phase = 0;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            const long long row = (long long)t * TILE_M + m;
+            const bool valid = row < p.n_rows;
+            // observations -> A operand (own | nbr | grid blocks, each zero padded to a multiple of 16)
+            stage_block(act, p.own + row * p.d_own, p.d_own, 0, p.kc_nbr0, m, valid);
+            stage_block(act, p.nbr + row * p.d_nbr, p.d_nbr, p.kc_nbr0, p.kc_grid0, m, valid);
+            stage_block(act, p.grid + row * p.d_grid, p.d_grid, p.kc_grid0, p.kc_end, m, valid);
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(act_ready);
+            // layer 1 (three branches) and layer 2: hidden epilogues
+            for (int layer = 1; layer <= 2; ++layer) {
+                mbar_wait(layer_done, done_phase & 1u);
+                ++done_phase;
+                tc_fence_after();
+                const int ncols = layer == 1 ? H1C : H2;
+                float *dbg_row = (p.dbg_layer == layer && valid) ? p.dbg + row * ncols : nullptr;
+                hidden_epilogue(act, tmem_row, ncols, layer == 1 ? p.b1 : p.b2, m, dbg_row);
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(act_ready);
+            }
+            // layer 3 epilogue fused with the output layer (256 -> 2), tanh, noise, clamp
+            mbar_wait(layer_done, done_phase & 1u);
+            ++done_phase;
+            tc_fence_after();
+            float a0 = __ldg(p.b4), a1 = __ldg(p.b4 + 1);
+            float *dbg_row = (p.dbg_layer == 3 && valid) ? p.dbg + row * H3 : nullptr;
+            for (int cb = 0; cb < H3; cb += 32) {
+                float v[32];
+                tmem_ld32(tmem_row + cb, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float h = leaky(v[i] + __ldg(p.b3 + cb + i));
+                    a0 = fmaf(h, __ldg(p.w4 + cb + i), a0);
+                    a1 = fmaf(h, __ldg(p.w4 + H3 + cb + i), a1);
+                    if (dbg_row) dbg_row[cb + i] = h;
+                }
+            }
+            if (valid && p.actions) {
+                a0 = tanhf(a0); a1 = tanhf(a1);
+                if (p.noise_scale != 0.0f) {  // choose_action: act + randn(2) * var, clamp (V2/maddpg_agent:1290-1294)
+                    const float2 z = normal_pair(p.noise_seed, (unsigned)row);
+                    a0 = fminf(fmaxf(fmaf(p.noise_scale, z.x, a0), -1.0f), 1.0f);
+                    a1 = fminf(fmaxf(fmaf(p.noise_scale, z.y, a1), -1.0f), 1.0f);
+                }
+                reinterpret_cast<float2 *>(p.actions)[row] = make_float2(a0, a1);
+            }
+            tc_fence_before();  // the next tile's staging arrive tells the MMA thread the accumulators are drained
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == PRODUCER_WARP) {
+        __syncwarp();
+        tmem_free(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+
+thread_local char g_err[512] = "";
+int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return AAC_ACTOR_ERR_CUDA;
+}
+
+uint16_t bf16_rne(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40u);
+    return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct AacActor {
+    AacActorConfig cfg;
+    int device = 0, sms = 0;
+    bool loaded = false;
+    int64_t launches = 0;
+    uint8_t *d_wpack = nullptr;
+    Chunk *d_sched = nullptr;
+    float *d_consts = nullptr;  // b1 [384] | b2 [512] | b3 [256] | w4 [512] | b4 [2]
+    int n_chunks = 0, kc_nbr0 = 0, kc_grid0 = 0, kc_end = 0;
+};
+
+extern "C" const char *aac_actor_last_error(void) { return g_err; }
+
+extern "C" int aac_actor_create(const AacActorConfig *cfg, AacActor **out) {
+    if (!cfg || !out) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_create: null argument");
+    if (cfg->abi_version != AAC_ACTOR_ABI_VERSION) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_create: abi_version mismatch");
+    if (cfg->d_own < 1 || cfg->d_nbr < 1 || cfg->d_grid < 1 || cfg->d_own > 64 || cfg->d_nbr > 256 || cfg->d_grid > 256)
+        return fail(AAC_ACTOR_ERR_ARG, "aac_actor_create: input widths out of range (own 1..64, nbr / grid 1..256)");
+    const int k0 = round_up(cfg->d_own, 16) + round_up(cfg->d_nbr, 16) + round_up(cfg->d_grid, 16);
+    if (k0 > H2) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_create: padded input width exceeds 512");
+    if (cfg->max_rows < 1) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_create: max_rows < 1");
+    AacActor *a = new (std::nothrow) AacActor();
+    if (!a) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_create: out of memory");
+    a->cfg = *cfg;
+    cudaError_t e = cudaGetDevice(&a->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&a->sms, cudaDevAttrMultiProcessorCount, a->device);
+    int cc_major = 0, smem_max = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, a->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, a->device);
+    if (e != cudaSuccess) { delete a; return cuda_fail(e, "aac_actor_create: device query"); }
+    if (cc_major != 10 || smem_max < SMEM_TOTAL) { delete a; return fail(AAC_ACTOR_ERR_STATE, "aac_actor_create: needs an sm_100 device (tcgen05, 227 KB shared memory)"); }
+    e = cudaFuncSetAttribute(actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e != cudaSuccess) { delete a; return cuda_fail(e, "aac_actor_create: cudaFuncSetAttribute"); }
+    *out = a;
+    return 0;
+}
+
+extern "C" void aac_actor_destroy(AacActor *a) {
+    if (!a) return;
+    cudaFree(a->d_wpack);
+    cudaFree(a->d_sched);
+    cudaFree(a->d_consts);
+    delete a;
+}
+
+extern "C" int aac_actor_load(AacActor *a, const AacActorParams *hp) {
+    if (!a || !hp) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_load: null argument");
+    const float *ptrs[12] = {hp->w_own, hp->b_own, hp->w_nbr, hp->b_nbr, hp->w_grid, hp->b_grid, hp->w_merge, hp->b_merge, hp->w_hid, hp->b_hid, hp->w_out, hp->b_out};
+    for (const float *q : ptrs)
+        if (!q) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_load: null parameter pointer");
+    std::vector<uint8_t> pack;
+    std::vector<Chunk> sched;
+    // B operand chunk: rows n0 .. n0 + nc of W [out, in], columns k0 .. k0 + kw (zero beyond `in`), K-chunk-major
+    auto add_chunk = [&](const float *w, int in_dim, int n0, int nc, int k0, int kw, int a_kc0, int col, unsigned flags) {
+        Chunk ch;
+        ch.src_off = (uint32_t)pack.size();
+        ch.bytes = (uint32_t)(nc * kw * 2);
+        ch.n_mma = (uint32_t)(kw / 16);
+        ch.n = (uint32_t)nc;
+        ch.lbo = (uint32_t)(nc * 16);
+        ch.a_kc0 = (uint32_t)a_kc0;
+        ch.tmem_col = (uint32_t)col;
+        ch.flags = flags;
+        pack.resize(pack.size() + ch.bytes);
+        uint16_t *dst = reinterpret_cast<uint16_t *>(pack.data() + ch.src_off);
+        for (int kc = 0; kc < kw / 8; ++kc)
+            for (int n = 0; n < nc; ++n)
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int k = k0 + kc * 8 + kk;
+                    dst[(kc * nc + n) * 8 + kk] = k < in_dim ? bf16_rne(w[(size_t)(n0 + n) * in_dim + k]) : (uint16_t)0;
+                }
+        sched.push_back(ch);
+    };
+    // layer 1: three branches into accumulator columns 0 / 128 / 256; K pieces of at most 64 (= one ring slot)
+    const int dims[3] = {a->cfg.d_own, a->cfg.d_nbr, a->cfg.d_grid};
+    const float *w1[3] = {hp->w_own, hp->w_nbr, hp->w_grid};
+    int kc = 0;
+    for (int b = 0; b < 3; ++b) {
+        const int kpad = round_up(dims[b], 16);
+        if (b == 1) a->kc_nbr0 = kc;
+        if (b == 2) a->kc_grid0 = kc;
+        for (int k0 = 0; k0 < kpad; k0 += 64) add_chunk(w1[b], dims[b], 0, H1, k0, kpad - k0 < 64 ? kpad - k0 : 64, kc + k0 / 8, H1 * b, k0 == 0 ? CH_FRESH : 0u);
+        kc += kpad / 8;
+    }
+    a->kc_end = kc;
+    sched.front().flags |= CH_LAYER_BEGIN;
+    sched.back().flags |= CH_LAYER_END;
+    // layer 2: two halves of 256 output columns, K = 384 in slices of 32
+    size_t first = sched.size();
+    for (int h = 0; h < 2; ++h)
+        for (int k0 = 0; k0 < H1C; k0 += 32) add_chunk(hp->w_merge, H1C, 256 * h, 256, k0, 32, k0 / 8, 256 * h, k0 == 0 ? CH_FRESH : 0u);
+    sched[first].flags |= CH_LAYER_BEGIN;
+    sched.back().flags |= CH_LAYER_END;
+    // layer 3: 256 output columns, K = 512
+    first = sched.size();
+    for (int k0 = 0; k0 < H2; k0 += 32) add_chunk(hp->w_hid, H2, 0, 256, k0, 32, k0 / 8, 0, k0 == 0 ? CH_FRESH : 0u);
+    sched[first].flags |= CH_LAYER_BEGIN;
+    sched.back().flags |= CH_LAYER_END;
+    if ((int)sched.size() > MAX_CHUNKS) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_load: chunk schedule too long");
+    for (const Chunk &c : sched)
+        if (c.bytes > (uint32_t)SLOT_BYTES || c.bytes % 16) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_load: bad chunk size");
+
+    std::vector<float> consts(H1C + H2 + H3 + 2 * H3 + 2);
+    memcpy(consts.data(), hp->b_own, H1 * 4);
+    memcpy(consts.data() + H1, hp->b_nbr, H1 * 4);
+    memcpy(consts.data() + 2 * H1, hp->b_grid, H1 * 4);
+    memcpy(consts.data() + H1C, hp->b_merge, H2 * 4);
+    memcpy(consts.data() + H1C + H2, hp->b_hid, H3 * 4);
+    memcpy(consts.data() + H1C + H2 + H3, hp->w_out, 2 * H3 * 4);
+    memcpy(consts.data() + H1C + H2 + H3 + 2 * H3, hp->b_out, 2 * 4);
+
+    cudaFree(a->d_wpack); cudaFree(a->d_sched); cudaFree(a->d_consts);
+    a->d_wpack = nullptr; a->d_sched = nullptr; a->d_consts = nullptr;
+    a->loaded = false;
+    cudaError_t e = cudaMalloc(&a->d_wpack, pack.size());
+    if (e == cudaSuccess) e = cudaMalloc(&a->d_sched, sched.size() * sizeof(Chunk));
+    if (e == cudaSuccess) e = cudaMalloc(&a->d_consts, consts.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(a->d_wpack, pack.data(), pack.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(a->d_sched, sched.data(), sched.size() * sizeof(Chunk), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(a->d_consts, consts.data(), consts.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "aac_actor_load: upload");
+    a->n_chunks = (int)sched.size();
+    a->loaded = true;
+    return 0;
+}
+
+static int actor_launch(AacActor *a, const float *own, const float *nbr, const float *grid, int n_rows, float noise_scale, uint64_t seed,
+                        float *actions, float *dbg, int dbg_layer, void *stream) {
+    if (!a) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_forward: null handle");
+    if (!a->loaded) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_forward: no parameters loaded (aac_actor_load)");
+    if (!own || !nbr || !grid) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_forward: null observation pointer");
+    if (n_rows < 0 || n_rows > a->cfg.max_rows) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_forward: n_rows outside 0..max_rows");
+    if (n_rows == 0) return 0;
+    KArgs k;
+    k.own = own; k.nbr = nbr; k.grid = grid; k.actions = actions; k.dbg = dbg; k.dbg_layer = dbg_layer;
+    k.n_rows = n_rows; k.n_tiles = (n_rows + TILE_M - 1) / TILE_M;
+    k.d_own = a->cfg.d_own; k.d_nbr = a->cfg.d_nbr; k.d_grid = a->cfg.d_grid;
+    k.kc_nbr0 = a->kc_nbr0; k.kc_grid0 = a->kc_grid0; k.kc_end = a->kc_end;
+    k.wpack = a->d_wpack; k.sched = a->d_sched; k.n_chunks = a->n_chunks;
+    k.b1 = a->d_consts; k.b2 = k.b1 + H1C; k.b3 = k.b2 + H2; k.w4 = k.b3 + H3; k.b4 = k.w4 + 2 * H3;
+    k.noise_scale = noise_scale; k.noise_seed = seed;
+    const int grid_dim = k.n_tiles < a->sms ? k.n_tiles : a->sms;
+    actor_kernel<<<grid_dim, THREADS, SMEM_TOTAL, (cudaStream_t)stream>>>(k);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "aac_actor_forward: launch");
+    ++a->launches;
+    return 0;
+}
+
+extern "C" int aac_actor_forward(AacActor *a, const float *own, const float *nbr, const float *grid, int32_t n_rows, float noise_scale,
+                                 uint64_t noise_seed, float *actions, void *stream) {
+    if (!actions) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_forward: null actions pointer");
+    return actor_launch(a, own, nbr, grid, n_rows, noise_scale, noise_seed, actions, nullptr, 0, stream);
+}
+
+extern "C" int aac_actor_hidden(AacActor *a, const float *own, const float *nbr, const float *grid, int32_t n_rows, int32_t layer, float *hidden,
+                                void *stream) {
+    if (!hidden || layer < 1 || layer > 3) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_hidden: layer must be 1..3 and hidden non-null");
+    return actor_launch(a, own, nbr, grid, n_rows, 0.0f, 0, nullptr, hidden, layer, stream);
+}
+
+extern "C" int64_t aac_actor_launch_count(const AacActor *a) { return a ? a->launches : 0; }

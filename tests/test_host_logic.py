@@ -188,3 +188,34 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["higher_is_better"] is True and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and line["cpu_baseline"]["cores"] >= 1
+
+
+def test_actor_library_exports_every_declared_symbol():
+    from multi_agent_aac_b200 import _actor_capi
+    _actor_capi.build()
+    header = open(os.path.join(ROOT, "include", "aac_actor.h")).read()
+    declared = set(re.findall(r"\b(aac_actor_[a-z_]+)\s*\(", header))
+    assert declared == set(_actor_capi.EXPORTS), declared ^ set(_actor_capi.EXPORTS)
+    lib = ctypes.CDLL(_actor_capi.LIB_PATH)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    lib.aac_actor_last_error.restype = ctypes.c_char_p
+    h = ctypes.c_void_p()
+    cfg = _actor_capi.AacActorConfig(999, 7, 45, 36, 10)
+    lib.aac_actor_create.argtypes = [ctypes.POINTER(_actor_capi.AacActorConfig), ctypes.POINTER(ctypes.c_void_p)]
+    assert lib.aac_actor_create(ctypes.byref(cfg), ctypes.byref(h)) == -1 and b"abi_version" in lib.aac_actor_last_error()
+    assert ctypes.sizeof(_actor_capi.AacActorConfig) == 5 * 4 and ctypes.sizeof(_actor_capi.AacActorParams) == 12 * 8
+
+
+def test_actor_oracle_matches_reference_fixture():
+    """The float64 restatement against the outputs of the unmodified reference class (gen_golden_actor.py)."""
+    import numpy as np
+    from oracle import actor_oracle
+    for name in ("actor_v2", "actor_v2_r18_n4"):
+        d = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        d_own, d_nbr, d_grid, seed = (int(v) for v in d["dims"])
+        sd = actor_oracle.reference_like_params(d_own, d_nbr, d_grid, seed)
+        act = actor_oracle.forward(sd, d["own"], d["nbr"], d["grid"])
+        assert np.abs(act - d["act"]).max() < 1e-12
+    noisy = actor_oracle.explore(np.array([[0.9, -0.2]]), np.array([[1.0, -1.0]]), 0.5)
+    assert np.allclose(noisy, [[1.0, -0.7]])
