@@ -11,15 +11,19 @@
 //   warp 5     one elected thread issues tcgen05.mma (M = 128, N = 128 / 256, K = 16, kind::f16 with bf16
 //              operands, fp32 accumulators in TMEM) and tcgen05.commit's ring slots / layer completion
 //
-// Operand layout: the canonical K-major no-swizzle UMMA layout, 8 x 8 "core matrices" of 128 contiguous bytes;
-// an operand of `rows` rows is stored K-chunk-major: byte = (k / 8) * rows * 16 + row * 16 + (k % 8) * 2, i.e.
-// stride-byte-offset (next 8 rows) = 128 and leading-byte-offset (next 8 k) = rows * 16.  With that layout an
-// epilogue thread (= one row) writes 16 contiguous bytes per K chunk and a warp 512 contiguous bytes:
-// conflict-free 128-bit shared stores; the host tiles the weights into the same form once (aac_actor_load).
+// Operand layout: the canonical K-major 128-byte-swizzled UMMA layout.  An operand of `rows` rows is cut into
+// K blocks of 64 elements; a block is `rows` rows of 128 bytes, and the 16-byte chunk c of row r sits at chunk
+// position c ^ (r % 8):  byte = block * rows * 128 + r * 128 + ((k / 8 % 8) ^ (r % 8)) * 16 + (k % 8) * 2
+// (stride byte offset = 1024 = 8 rows; a K = 16 step advances the descriptor's start address by 32 bytes).
+// An epilogue thread (= one row) writes whole 16-byte chunks, and the swizzle spreads the eight rows of a
+// store phase over all banks: conflict-free 128-bit shared stores; the host tiles the weights into the same
+// form once (aac_actor_load).  (A first version used the no-swizzle interleaved layout: correct, but the
+// tensor core fetched those operands at ~1/3 of the rate: 325 instead of ~130 cycles per 128x256x16 MMA.)
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -31,10 +35,10 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int H1 = AAC_ACTOR_H1, H1C = 3 * AAC_ACTOR_H1, H2 = AAC_ACTOR_H2, H3 = AAC_ACTOR_H3;
-constexpr int KC_BYTES = TILE_M * 16;           // one 8-wide K chunk of a 128-row A operand
-constexpr int ACT_BYTES = (H2 / 8) * KC_BYTES;  // widest A operand: 128 x 512 bf16 = 128 KB
-constexpr int SLOT_BYTES = 16384;
-constexpr int N_SLOTS = 6;
+constexpr int BLK_BYTES = TILE_M * 128;          // one 64-wide K block of a 128-row A operand
+constexpr int ACT_BYTES = (H2 / 64) * BLK_BYTES;  // widest A operand: 128 x 512 bf16 = 128 KB
+constexpr int SLOT_BYTES = 32768;                // one 64-wide K block of a 256-row B operand
+constexpr int N_SLOTS = 3;
 constexpr int PRODUCER_WARP = 4, MMA_WARP = 5, THREADS = 192;
 constexpr int MAX_CHUNKS = 64;
 constexpr unsigned TMEM_COLS = 512;
@@ -46,8 +50,8 @@ struct Chunk {
     uint32_t bytes;     // multiple of 16
     uint32_t n_mma;     // K = 16 steps in this chunk
     uint32_t n;         // MMA N (rows of the B operand)
-    uint32_t lbo;       // leading byte offset of the B operand = n * 16
-    uint32_t a_kc0;     // first 8-wide K chunk of the A operand
+    uint32_t rsvd;
+    uint32_t a_blk;     // K block of the A operand
     uint32_t tmem_col;  // accumulator column
     uint32_t flags;
 };
@@ -57,13 +61,15 @@ struct KArgs {
     float *actions, *dbg;
     int dbg_layer, n_rows, n_tiles;
     int d_own, d_nbr, d_grid;
-    int kc_nbr0, kc_grid0, kc_end;  // first K chunk of the nbr / grid block of the input operand, total chunks
+    int blk_nbr0, blk_grid0, blk_end;  // first K block of the nbr / grid part of the input operand, total blocks
     const uint8_t *wpack;
     const Chunk *sched;
     int n_chunks;
     const float *b1, *b2, *b3, *w4, *b4;
     float noise_scale;
     unsigned long long noise_seed;
+    int dbg_nocopy;   // tuning aid: after the first pass over the ring, signal slots full without copying
+    long long *prof;  // optional [gridDim.x][8] phase clocks of epilogue thread 0 (tuning aid)
 };
 
 constexpr int SMEM_BARS = ACT_BYTES + N_SLOTS * SLOT_BYTES;
@@ -113,11 +119,11 @@ __device__ __forceinline__ void tmem_alloc(unsigned *slot, unsigned cols) {
 __device__ __forceinline__ void tmem_free(unsigned addr, unsigned cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
-// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor: start >> 4 at bit 0, leading byte
-// offset >> 4 at bit 16, stride byte offset >> 4 at bit 32, version 1 at bit 46, layout type 0 at bit 61)
-__device__ __forceinline__ unsigned long long umma_desc(unsigned addr, unsigned lbo, unsigned sbo) {
-    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | ((unsigned long long)(lbo >> 4) << 16) | ((unsigned long long)(sbo >> 4) << 32) |
-           (1ull << 46);
+// shared-memory matrix descriptor, K-major SWIZZLE_128B (cute::UMMA::SmemDescriptor: start >> 4 at bit 0,
+// leading byte offset (unused for this layout, 1) at bit 16, stride byte offset >> 4 = 1024 >> 4 at bit 32,
+// version 1 at bit 46, layout type 2 at bit 61)
+__device__ __forceinline__ unsigned long long umma_desc(unsigned addr) {
+    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((unsigned long long)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor, kind::f16: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17,
 // M >> 4 at bit 24 (cute::UMMA::InstrDescriptor)
@@ -172,16 +178,19 @@ __device__ __forceinline__ float2 normal_pair(unsigned long long seed, unsigned 
 
 // ------------------------------------------------------------------------------------ epilogue pieces
 
-// one row of one observation block -> bf16 K chunks kc0.. of the A operand (zero padded to a multiple of 16)
-__device__ __forceinline__ void stage_block(uint8_t *act, const float *src, int d, int kc0, int kc1, int m, bool valid) {
-    for (int kc = kc0; kc < kc1; ++kc) {
+// byte offset of the 16-byte chunk holding columns 8c .. 8c+7 of row m in a 128-row K-major SWIZZLE_128B operand
+__device__ __forceinline__ int a_chunk(int c, int m) { return (c >> 3) * BLK_BYTES + m * 128 + (((c & 7) ^ (m & 7)) << 4); }
+
+// one row of one observation part -> bf16 chunks of the A operand, K blocks blk0 .. (zero padded to a multiple of 16)
+__device__ __forceinline__ void stage_block(uint8_t *act, const float *src, int d, int blk0, int m, bool valid) {
+    for (int c = 0; c * 8 < d || (c & 1); ++c) {  // chunks come in pairs: an MMA step spans 16 columns
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int k = (kc - kc0) * 8 + i;
+            const int k = c * 8 + i;
             v[i] = (valid && k < d) ? __ldg(src + k) : 0.0f;
         }
-        *reinterpret_cast<uint4 *>(act + kc * KC_BYTES + m * 16) =
+        *reinterpret_cast<uint4 *>(act + a_chunk(blk0 * 8 + c, m)) =
             make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
 }
@@ -197,7 +206,7 @@ __device__ __forceinline__ void hidden_epilogue(uint8_t *act, unsigned tmem_row,
             float *x = v + 8 * g;
             x[0] = leaky(x[0] + b0.x); x[1] = leaky(x[1] + b0.y); x[2] = leaky(x[2] + b0.z); x[3] = leaky(x[3] + b0.w);
             x[4] = leaky(x[4] + b1.x); x[5] = leaky(x[5] + b1.y); x[6] = leaky(x[6] + b1.z); x[7] = leaky(x[7] + b1.w);
-            *reinterpret_cast<uint4 *>(act + ((cb >> 3) + g) * KC_BYTES + m * 16) =
+            *reinterpret_cast<uint4 *>(act + a_chunk((cb >> 3) + g, m)) =
                 make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
         }
         if (dbg_row)
@@ -236,6 +245,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                 for (int c = 0; c < p.n_chunks; ++c, ++c_glob) {
                     const unsigned s = c_glob % N_SLOTS, ph = (c_glob / N_SLOTS) & 1u;
                     mbar_wait(empty + s, ph ^ 1u);  // slot free (passes at once the first time round)
+                    if (p.dbg_nocopy && c_glob >= N_SLOTS) { mbar_arrive(full + s); continue; }
                     mbar_expect_tx(full + s, sched[c].bytes);
                     bulk_g2s(ring + s * SLOT_BYTES, p.wpack + sched[c].src_off, sched[c].bytes, full + s);
                 }
@@ -257,8 +267,8 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                     tc_fence_after();
                     const unsigned idesc = umma_idesc(ch.n);
                     for (unsigned j = 0; j < ch.n_mma; ++j) {
-                        const unsigned long long a = umma_desc(act_addr + (ch.a_kc0 + 2 * j) * KC_BYTES, KC_BYTES, 128);
-                        const unsigned long long b = umma_desc(ring_addr + s * SLOT_BYTES + 2 * j * ch.lbo, ch.lbo, 128);
+                        const unsigned long long a = umma_desc(act_addr + ch.a_blk * BLK_BYTES + j * 32);
+                        const unsigned long long b = umma_desc(ring_addr + s * SLOT_BYTES + j * 32);
                         umma_bf16(tmem_base + ch.tmem_col, a, b, idesc, ((ch.flags & CH_FRESH) && j == 0) ? 0u : 1u);
                     }
                     umma_commit(empty + s);
@@ -269,32 +279,38 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
         const int m = tid;  // row of the tile = TMEM lane
         const unsigned tmem_row = tmem_base + ((unsigned)(warp * 32) << 16);
         unsigned done_phase = 0;
+        long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = clock64();
+        auto lap = [&](int i) { if (p.prof) { const long long now = clock64(); pc[i] += now - tp; tp = now; } };
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
             const long long row = (long long)t * TILE_M + m;
             const bool valid = row < p.n_rows;
             // observations -> A operand (own | nbr | grid blocks, each zero padded to a multiple of 16)
-            stage_block(act, p.own + row * p.d_own, p.d_own, 0, p.kc_nbr0, m, valid);
-            stage_block(act, p.nbr + row * p.d_nbr, p.d_nbr, p.kc_nbr0, p.kc_grid0, m, valid);
-            stage_block(act, p.grid + row * p.d_grid, p.d_grid, p.kc_grid0, p.kc_end, m, valid);
+            stage_block(act, p.own + row * p.d_own, p.d_own, 0, m, valid);
+            stage_block(act, p.nbr + row * p.d_nbr, p.d_nbr, p.blk_nbr0, m, valid);
+            stage_block(act, p.grid + row * p.d_grid, p.d_grid, p.blk_grid0, m, valid);
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(act_ready);
+            lap(0);
             // layer 1 (three branches) and layer 2: hidden epilogues
             for (int layer = 1; layer <= 2; ++layer) {
                 mbar_wait(layer_done, done_phase & 1u);
                 ++done_phase;
                 tc_fence_after();
+                lap(layer == 1 ? 1 : 3);
                 const int ncols = layer == 1 ? H1C : H2;
                 float *dbg_row = (p.dbg_layer == layer && valid) ? p.dbg + row * ncols : nullptr;
                 hidden_epilogue(act, tmem_row, ncols, layer == 1 ? p.b1 : p.b2, m, dbg_row);
                 fence_async_smem();
                 tc_fence_before();
                 mbar_arrive(act_ready);
+                lap(layer == 1 ? 2 : 4);
             }
             // layer 3 epilogue fused with the output layer (256 -> 2), tanh, noise, clamp
             mbar_wait(layer_done, done_phase & 1u);
             ++done_phase;
             tc_fence_after();
+            lap(5);
             float a0 = __ldg(p.b4), a1 = __ldg(p.b4 + 1);
             float *dbg_row = (p.dbg_layer == 3 && valid) ? p.dbg + row * H3 : nullptr;
             for (int cb = 0; cb < H3; cb += 32) {
@@ -318,7 +334,10 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                 reinterpret_cast<float2 *>(p.actions)[row] = make_float2(a0, a1);
             }
             tc_fence_before();  // the next tile's staging arrive tells the MMA thread the accumulators are drained
+            lap(6);
         }
+        if (p.prof && tid == 0)
+            for (int i = 0; i < 8; ++i) p.prof[blockIdx.x * 8 + i] = pc[i];
     }
     tc_fence_before();
     __syncthreads();
@@ -359,7 +378,8 @@ struct AacActor {
     uint8_t *d_wpack = nullptr;
     Chunk *d_sched = nullptr;
     float *d_consts = nullptr;  // b1 [384] | b2 [512] | b3 [256] | w4 [512] | b4 [2]
-    int n_chunks = 0, kc_nbr0 = 0, kc_grid0 = 0, kc_end = 0;
+    int n_chunks = 0, blk_nbr0 = 0, blk_grid0 = 0, blk_end = 0;
+    long long *d_prof = nullptr;  // set by AAC_ACTOR_PROF=1 (tuning aid): per-CTA phase clocks
 };
 
 extern "C" const char *aac_actor_last_error(void) { return g_err; }
@@ -369,8 +389,6 @@ extern "C" int aac_actor_create(const AacActorConfig *cfg, AacActor **out) {
     if (cfg->abi_version != AAC_ACTOR_ABI_VERSION) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_create: abi_version mismatch");
     if (cfg->d_own < 1 || cfg->d_nbr < 1 || cfg->d_grid < 1 || cfg->d_own > 64 || cfg->d_nbr > 256 || cfg->d_grid > 256)
         return fail(AAC_ACTOR_ERR_ARG, "aac_actor_create: input widths out of range (own 1..64, nbr / grid 1..256)");
-    const int k0 = round_up(cfg->d_own, 16) + round_up(cfg->d_nbr, 16) + round_up(cfg->d_grid, 16);
-    if (k0 > H2) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_create: padded input width exceeds 512");
     if (cfg->max_rows < 1) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_create: max_rows < 1");
     AacActor *a = new (std::nothrow) AacActor();
     if (!a) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_create: out of memory");
@@ -384,8 +402,19 @@ extern "C" int aac_actor_create(const AacActorConfig *cfg, AacActor **out) {
     if (cc_major != 10 || smem_max < SMEM_TOTAL) { delete a; return fail(AAC_ACTOR_ERR_STATE, "aac_actor_create: needs an sm_100 device (tcgen05, 227 KB shared memory)"); }
     e = cudaFuncSetAttribute(actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) { delete a; return cuda_fail(e, "aac_actor_create: cudaFuncSetAttribute"); }
+    if (getenv("AAC_ACTOR_PROF")) {
+        cudaMalloc(&a->d_prof, (size_t)a->sms * 8 * sizeof(long long));
+        cudaMemset(a->d_prof, 0, (size_t)a->sms * 8 * sizeof(long long));
+    }
     *out = a;
     return 0;
+}
+
+// tuning aid: copies the [sms][8] phase clocks (stage, wait L1, E1, wait L2, E2, wait L3, E3) to host memory
+extern "C" int aac_actor_prof(AacActor *a, long long *host_out) {
+    if (!a || !a->d_prof || !host_out) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_prof: run with AAC_ACTOR_PROF=1");
+    const cudaError_t e = cudaMemcpy(host_out, a->d_prof, (size_t)a->sms * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? a->sms : cuda_fail(e, "aac_actor_prof");
 }
 
 extern "C" void aac_actor_destroy(AacActor *a) {
@@ -393,6 +422,7 @@ extern "C" void aac_actor_destroy(AacActor *a) {
     cudaFree(a->d_wpack);
     cudaFree(a->d_sched);
     cudaFree(a->d_consts);
+    cudaFree(a->d_prof);
     delete a;
 }
 
@@ -403,50 +433,50 @@ extern "C" int aac_actor_load(AacActor *a, const AacActorParams *hp) {
         if (!q) return fail(AAC_ACTOR_ERR_ARG, "aac_actor_load: null parameter pointer");
     std::vector<uint8_t> pack;
     std::vector<Chunk> sched;
-    // B operand chunk: rows n0 .. n0 + nc of W [out, in], columns k0 .. k0 + kw (zero beyond `in`), K-chunk-major
-    auto add_chunk = [&](const float *w, int in_dim, int n0, int nc, int k0, int kw, int a_kc0, int col, unsigned flags) {
+    // B operand chunk: rows n0 .. n0 + nc of W [out, in], columns k0 .. k0 + kw (kw <= 64; zero beyond `in`), in the
+    // K-major SWIZZLE_128B form: row n = 128 bytes, chunk (k / 8) stored at position (k / 8) ^ (n % 8)
+    auto add_chunk = [&](const float *w, int in_dim, int n0, int nc, int k0, int kw, int a_blk, int col, unsigned flags) {
         Chunk ch;
         ch.src_off = (uint32_t)pack.size();
-        ch.bytes = (uint32_t)(nc * kw * 2);
+        ch.bytes = (uint32_t)(nc * 128);
         ch.n_mma = (uint32_t)(kw / 16);
         ch.n = (uint32_t)nc;
-        ch.lbo = (uint32_t)(nc * 16);
-        ch.a_kc0 = (uint32_t)a_kc0;
+        ch.rsvd = 0;
+        ch.a_blk = (uint32_t)a_blk;
         ch.tmem_col = (uint32_t)col;
         ch.flags = flags;
-        pack.resize(pack.size() + ch.bytes);
+        pack.resize(pack.size() + ch.bytes, 0);
         uint16_t *dst = reinterpret_cast<uint16_t *>(pack.data() + ch.src_off);
-        for (int kc = 0; kc < kw / 8; ++kc)
-            for (int n = 0; n < nc; ++n)
-                for (int kk = 0; kk < 8; ++kk) {
-                    const int k = k0 + kc * 8 + kk;
-                    dst[(kc * nc + n) * 8 + kk] = k < in_dim ? bf16_rne(w[(size_t)(n0 + n) * in_dim + k]) : (uint16_t)0;
-                }
+        for (int n = 0; n < nc; ++n)
+            for (int kk = 0; kk < kw; ++kk) {
+                const int k = k0 + kk;
+                dst[n * 64 + (((kk >> 3) ^ (n & 7)) << 3) + (kk & 7)] = k < in_dim ? bf16_rne(w[(size_t)(n0 + n) * in_dim + k]) : (uint16_t)0;
+            }
         sched.push_back(ch);
     };
-    // layer 1: three branches into accumulator columns 0 / 128 / 256; K pieces of at most 64 (= one ring slot)
+    // layer 1: three branches into accumulator columns 0 / 128 / 256, each input part in its own K block(s)
     const int dims[3] = {a->cfg.d_own, a->cfg.d_nbr, a->cfg.d_grid};
     const float *w1[3] = {hp->w_own, hp->w_nbr, hp->w_grid};
-    int kc = 0;
+    int blk = 0;
     for (int b = 0; b < 3; ++b) {
         const int kpad = round_up(dims[b], 16);
-        if (b == 1) a->kc_nbr0 = kc;
-        if (b == 2) a->kc_grid0 = kc;
-        for (int k0 = 0; k0 < kpad; k0 += 64) add_chunk(w1[b], dims[b], 0, H1, k0, kpad - k0 < 64 ? kpad - k0 : 64, kc + k0 / 8, H1 * b, k0 == 0 ? CH_FRESH : 0u);
-        kc += kpad / 8;
+        if (b == 1) a->blk_nbr0 = blk;
+        if (b == 2) a->blk_grid0 = blk;
+        for (int k0 = 0; k0 < kpad; k0 += 64, ++blk) add_chunk(w1[b], dims[b], 0, H1, k0, kpad - k0 < 64 ? kpad - k0 : 64, blk, H1 * b, k0 == 0 ? CH_FRESH : 0u);
     }
-    a->kc_end = kc;
+    a->blk_end = blk;
+    if (blk * BLK_BYTES > ACT_BYTES) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_load: input operand does not fit");
     sched.front().flags |= CH_LAYER_BEGIN;
     sched.back().flags |= CH_LAYER_END;
-    // layer 2: two halves of 256 output columns, K = 384 in slices of 32
+    // layer 2: two halves of 256 output columns, K = 384 in blocks of 64
     size_t first = sched.size();
     for (int h = 0; h < 2; ++h)
-        for (int k0 = 0; k0 < H1C; k0 += 32) add_chunk(hp->w_merge, H1C, 256 * h, 256, k0, 32, k0 / 8, 256 * h, k0 == 0 ? CH_FRESH : 0u);
+        for (int k0 = 0; k0 < H1C; k0 += 64) add_chunk(hp->w_merge, H1C, 256 * h, 256, k0, 64, k0 / 64, 256 * h, k0 == 0 ? CH_FRESH : 0u);
     sched[first].flags |= CH_LAYER_BEGIN;
     sched.back().flags |= CH_LAYER_END;
     // layer 3: 256 output columns, K = 512
     first = sched.size();
-    for (int k0 = 0; k0 < H2; k0 += 32) add_chunk(hp->w_hid, H2, 0, 256, k0, 32, k0 / 8, 0, k0 == 0 ? CH_FRESH : 0u);
+    for (int k0 = 0; k0 < H2; k0 += 64) add_chunk(hp->w_hid, H2, 0, 256, k0, 64, k0 / 64, 0, k0 == 0 ? CH_FRESH : 0u);
     sched[first].flags |= CH_LAYER_BEGIN;
     sched.back().flags |= CH_LAYER_END;
     if ((int)sched.size() > MAX_CHUNKS) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_load: chunk schedule too long");
@@ -488,10 +518,12 @@ static int actor_launch(AacActor *a, const float *own, const float *nbr, const f
     k.own = own; k.nbr = nbr; k.grid = grid; k.actions = actions; k.dbg = dbg; k.dbg_layer = dbg_layer;
     k.n_rows = n_rows; k.n_tiles = (n_rows + TILE_M - 1) / TILE_M;
     k.d_own = a->cfg.d_own; k.d_nbr = a->cfg.d_nbr; k.d_grid = a->cfg.d_grid;
-    k.kc_nbr0 = a->kc_nbr0; k.kc_grid0 = a->kc_grid0; k.kc_end = a->kc_end;
+    k.blk_nbr0 = a->blk_nbr0; k.blk_grid0 = a->blk_grid0; k.blk_end = a->blk_end;
     k.wpack = a->d_wpack; k.sched = a->d_sched; k.n_chunks = a->n_chunks;
     k.b1 = a->d_consts; k.b2 = k.b1 + H1C; k.b3 = k.b2 + H2; k.w4 = k.b3 + H3; k.b4 = k.w4 + 2 * H3;
     k.noise_scale = noise_scale; k.noise_seed = seed;
+    k.prof = a->d_prof;
+    k.dbg_nocopy = getenv("AAC_ACTOR_NOCOPY") ? 1 : 0;
     const int grid_dim = k.n_tiles < a->sms ? k.n_tiles : a->sms;
     actor_kernel<<<grid_dim, THREADS, SMEM_TOTAL, (cudaStream_t)stream>>>(k);
     const cudaError_t e = cudaGetLastError();
