@@ -2,13 +2,14 @@
 // whole ActorNetwork_allnei_wRadar (V2/Nnetworks:273-340) for 128 drones per tile on the 5th-generation
 // tensor cores.
 //
-//   warps 0-3  stage the tile's observations as the bf16 A operand, then act as the epilogue of every layer:
+//   warps 0-7  stage the tile's observations as the bf16 A operand, then act as the epilogue of every layer
+//              (warp w owns rows 32 (w % 4) .. and column half w / 4):
 //              tcgen05.ld the fp32 accumulators out of tensor memory, add the bias, LeakyReLU, round to bf16
 //              and write the result back to shared memory AS THE NEXT LAYER'S A OPERAND (activations never
 //              leave the SM); the last layer (256 -> 2), tanh, exploration noise and clamp run in fp32 here
-//   warp 4     streams the pre-tiled bf16 weights through a 6-slot shared-memory ring with bulk async copies
+//   warp 8     streams the pre-tiled bf16 weights through a 3-slot shared-memory ring with bulk async copies
 //              (cp.async.bulk + mbarrier complete_tx); also owns the tensor-memory allocation
-//   warp 5     one elected thread issues tcgen05.mma (M = 128, N = 128 / 256, K = 16, kind::f16 with bf16
+//   warp 9     one elected thread issues tcgen05.mma (M = 128, N = 128 / 256, K = 16, kind::f16 with bf16
 //              operands, fp32 accumulators in TMEM) and tcgen05.commit's ring slots / layer completion
 //
 // Operand layout: the canonical K-major 128-byte-swizzled UMMA layout.  An operand of `rows` rows is cut into
@@ -39,7 +40,8 @@ constexpr int BLK_BYTES = TILE_M * 128;          // one 64-wide K block of a 128
 constexpr int ACT_BYTES = (H2 / 64) * BLK_BYTES;  // widest A operand: 128 x 512 bf16 = 128 KB
 constexpr int SLOT_BYTES = 32768;                // one 64-wide K block of a 256-row B operand
 constexpr int N_SLOTS = 3;
-constexpr int PRODUCER_WARP = 4, MMA_WARP = 5, THREADS = 192;
+constexpr int EPI_THREADS = 256, PRODUCER_WARP = 8, MMA_WARP = 9, THREADS = 320;
+constexpr int SCRATCH_OFF = 7 * BLK_BYTES;  // last K block of the A buffer: free between the layer-3 MMAs and the next layer-2 epilogue
 constexpr int MAX_CHUNKS = 64;
 constexpr unsigned TMEM_COLS = 512;
 constexpr unsigned CH_LAYER_BEGIN = 1u, CH_LAYER_END = 2u, CH_FRESH = 4u;
@@ -68,6 +70,7 @@ struct KArgs {
     const float *b1, *b2, *b3, *w4, *b4;
     float noise_scale;
     unsigned long long noise_seed;
+    int raw_off;      // byte offset in the A buffer for bulk-fetched fp32 observations, 0 = fetch rows with plain loads
     int dbg_nocopy;   // tuning aid: after the first pass over the ring, signal slots full without copying
     long long *prof;  // optional [gridDim.x][8] phase clocks of epilogue thread 0 (tuning aid)
 };
@@ -138,9 +141,9 @@ __device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long a,
 __device__ __forceinline__ void umma_commit(unsigned long long *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns: thread t of warp w gets row 32 * (w % 4) + t
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
-    unsigned r[32];
+// 32 lanes x 32 consecutive fp32 columns: thread t of warp w gets row 32 * (w % 4) + t.  Issue only: the
+// registers are valid after tmem_ld_wait(), so the next block's load can fly while this one is processed.
+__device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, unsigned (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
         "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -150,10 +153,9 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
           "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps only
 
 __device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
     unsigned r;
@@ -181,36 +183,56 @@ __device__ __forceinline__ float2 normal_pair(unsigned long long seed, unsigned 
 // byte offset of the 16-byte chunk holding columns 8c .. 8c+7 of row m in a 128-row K-major SWIZZLE_128B operand
 __device__ __forceinline__ int a_chunk(int c, int m) { return (c >> 3) * BLK_BYTES + m * 128 + (((c & 7) ^ (m & 7)) << 4); }
 
-// one row of one observation part -> bf16 chunks of the A operand, K blocks blk0 .. (zero padded to a multiple of 16)
-__device__ __forceinline__ void stage_block(uint8_t *act, const float *src, int d, int blk0, int m, bool valid) {
-    for (int c = 0; c * 8 < d || (c & 1); ++c) {  // chunks come in pairs: an MMA step spans 16 columns
-        float v[8];
+// one row of one observation part -> bf16 chunks of the A operand, K blocks blk0 .. (zero padded to a multiple of
+// 16 columns).  32 columns are fetched per batch so that their global loads are in flight together.
+template <bool FROM_SMEM>
+__device__ __forceinline__ void stage_part(uint8_t *act, const float *src, int d, int blk0, int m, bool valid) {
+    const int n_chunks = ((d + 15) >> 4) << 1;
+    for (int c0 = 0; c0 < n_chunks; c0 += 4) {
+        float v[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int k = c * 8 + i;
-            v[i] = (valid && k < d) ? __ldg(src + k) : 0.0f;
+        for (int i = 0; i < 32; ++i) {
+            const int k = c0 * 8 + i;
+            v[i] = (valid && k < d) ? (FROM_SMEM ? src[k] : __ldg(src + k)) : 0.0f;
         }
-        *reinterpret_cast<uint4 *>(act + a_chunk(blk0 * 8 + c, m)) =
-            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            if (c0 + g < n_chunks)
+                *reinterpret_cast<uint4 *>(act + a_chunk(blk0 * 8 + c0 + g, m)) = make_uint4(
+                    pack_bf16(v[8 * g], v[8 * g + 1]), pack_bf16(v[8 * g + 2], v[8 * g + 3]), pack_bf16(v[8 * g + 4], v[8 * g + 5]), pack_bf16(v[8 * g + 6], v[8 * g + 7]));
     }
 }
+__device__ __forceinline__ void prefetch_row(const float *src, int d) {
+    const char *q = reinterpret_cast<const char *>(src);
+    for (int off = 0; off < d * 4 + 127; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + (off < d * 4 ? off : d * 4 - 1)));
+}
 
-// accumulators [row, 0..ncols) -> leaky(acc + bias) -> bf16 A operand of the next layer
-__device__ __forceinline__ void hidden_epilogue(uint8_t *act, unsigned tmem_row, int ncols, const float *bias, int m, float *dbg_row) {
-    for (int cb = 0; cb < ncols; cb += 32) {
-        float v[32];
-        tmem_ld32(tmem_row + cb, v);
+// accumulators [row, col0 .. col0 + ncols) -> leaky(acc + bias) -> bf16 A operand of the next layer
+__device__ __forceinline__ void hidden_epilogue(uint8_t *act, unsigned tmem_row, int col0, int ncols, const float *bias, int m, float *dbg_row) {
+    unsigned r[2][32];
+    tmem_ld32_issue(tmem_row + col0, r[0]);
+    tmem_ld_wait();
+#pragma unroll 1
+    for (int cb = col0; cb < col0 + ncols; cb += 64) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + cb + 8 * g)), b1 = __ldg(reinterpret_cast<const float4 *>(bias + cb + 8 * g + 4));
-            float *x = v + 8 * g;
-            x[0] = leaky(x[0] + b0.x); x[1] = leaky(x[1] + b0.y); x[2] = leaky(x[2] + b0.z); x[3] = leaky(x[3] + b0.w);
-            x[4] = leaky(x[4] + b1.x); x[5] = leaky(x[5] + b1.y); x[6] = leaky(x[6] + b1.z); x[7] = leaky(x[7] + b1.w);
-            *reinterpret_cast<uint4 *>(act + a_chunk((cb >> 3) + g, m)) =
-                make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+        for (int u = 0; u < 2; ++u) {  // two blocks per trip: the register buffers are indexed statically
+            const int c = cb + 32 * u;
+            if (c + 32 < col0 + ncols) tmem_ld32_issue(tmem_row + c + 32, r[u ^ 1]);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + c + 8 * g)), b1 = __ldg(reinterpret_cast<const float4 *>(bias + c + 8 * g + 4));
+                float x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(r[u][8 * g + i]);
+                x[0] = leaky(x[0] + b0.x); x[1] = leaky(x[1] + b0.y); x[2] = leaky(x[2] + b0.z); x[3] = leaky(x[3] + b0.w);
+                x[4] = leaky(x[4] + b1.x); x[5] = leaky(x[5] + b1.y); x[6] = leaky(x[6] + b1.z); x[7] = leaky(x[7] + b1.w);
+                *reinterpret_cast<uint4 *>(act + a_chunk((c >> 3) + g, m)) =
+                    make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+                if (dbg_row)
+                    for (int i = 0; i < 8; ++i) dbg_row[c + 8 * g + i] = x[i];
+            }
+            tmem_ld_wait();
         }
-        if (dbg_row)
-            for (int i = 0; i < 32; ++i) dbg_row[cb + i] = v[i];
     }
 }
 
@@ -220,16 +242,17 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *act = smem, *ring = smem + ACT_BYTES;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + SMEM_BARS);
-    unsigned long long *full = bars, *empty = bars + N_SLOTS, *act_ready = bars + 2 * N_SLOTS, *layer_done = act_ready + 1;
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(layer_done + 1);
+    unsigned long long *full = bars, *empty = bars + N_SLOTS, *act_ready = bars + 2 * N_SLOTS, *layer_done = act_ready + 1, *in_ready = layer_done + 1;
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(in_ready + 1);
     Chunk *sched = reinterpret_cast<Chunk *>(smem + SMEM_SCHED);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     for (int i = tid; i < p.n_chunks * (int)(sizeof(Chunk) / 4); i += THREADS) reinterpret_cast<uint32_t *>(sched)[i] = reinterpret_cast<const uint32_t *>(p.sched)[i];
     if (tid == 0) {
         for (int s = 0; s < N_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(act_ready, TILE_M);
+        mbar_init(act_ready, EPI_THREADS);
         mbar_init(layer_done, 1);
+        mbar_init(in_ready, 1);
         fence_barrier_init();
     }
     if (warp == PRODUCER_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -276,21 +299,58 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                 }
         }
     } else {
-        const int m = tid;  // row of the tile = TMEM lane
-        const unsigned tmem_row = tmem_base + ((unsigned)(warp * 32) << 16);
-        unsigned done_phase = 0;
+        // 8 epilogue warps: warp w works on TMEM lanes 32 * (w % 4) .. (the hardware's lane window of a warp), i.e.
+        // row m = tid % 128, and on column half tid / 128 of every layer
+        const int m = tid & 127, half = tid >> 7;
+        const unsigned tmem_row = tmem_base + ((unsigned)((warp & 3) * 32) << 16);
+        unsigned done_phase = 0, in_phase = 0;
         long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = clock64();
         auto lap = [&](int i) { if (p.prof) { const long long now = clock64(); pc[i] += now - tp; tp = now; } };
+        // A full tile's observations are three contiguous fp32 blocks in global memory: when they fit beside the
+        // input operand (p.raw_off > 0), one thread pulls them into the idle K blocks of the A buffer with bulk async
+        // copies, issued as soon as the previous tile's last MMA has read that memory, so the fetch hides behind the
+        // layer-3 epilogue; the rows are then converted shared -> shared.  Otherwise: direct global loads.
+        float *raw = reinterpret_cast<float *>(act + p.raw_off);
+        const float *raw_own = raw, *raw_nbr = raw + TILE_M * p.d_own, *raw_grid = raw_nbr + TILE_M * p.d_nbr;
+        auto bulk_tile = [&](int t) -> bool { return p.raw_off > 0 && (long long)(t + 1) * TILE_M <= p.n_rows; };
+        auto fetch_tile = [&](int t) {
+            if (tid == 0 && t < p.n_tiles && bulk_tile(t)) {
+                const long long r0 = (long long)t * TILE_M;
+                mbar_expect_tx(in_ready, (unsigned)(TILE_M * 4 * (p.d_own + p.d_nbr + p.d_grid)));
+                bulk_g2s(raw, p.own + r0 * p.d_own, TILE_M * 4 * p.d_own, in_ready);
+                bulk_g2s(raw + TILE_M * p.d_own, p.nbr + r0 * p.d_nbr, TILE_M * 4 * p.d_nbr, in_ready);
+                bulk_g2s(raw + TILE_M * (p.d_own + p.d_nbr), p.grid + r0 * p.d_grid, TILE_M * 4 * p.d_grid, in_ready);
+            }
+        };
+        fetch_tile(blockIdx.x);
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
             const long long row = (long long)t * TILE_M + m;
             const bool valid = row < p.n_rows;
-            // observations -> A operand (own | nbr | grid blocks, each zero padded to a multiple of 16)
-            stage_block(act, p.own + row * p.d_own, p.d_own, 0, m, valid);
-            stage_block(act, p.nbr + row * p.d_nbr, p.d_nbr, p.blk_nbr0, m, valid);
-            stage_block(act, p.grid + row * p.d_grid, p.d_grid, p.blk_grid0, m, valid);
+            // observations -> A operand (own | nbr | grid parts, each zero padded to a multiple of 16 columns, each
+            // starting a K block); the two halves share the work
+            if (bulk_tile(t)) {
+                mbar_wait(in_ready, in_phase & 1u);
+                ++in_phase;
+                if (half == 0) stage_part<true>(act, raw_nbr + m * p.d_nbr, p.d_nbr, p.blk_nbr0, m, true);
+                else {
+                    stage_part<true>(act, raw_own + m * p.d_own, p.d_own, 0, m, true);
+                    stage_part<true>(act, raw_grid + m * p.d_grid, p.d_grid, p.blk_grid0, m, true);
+                }
+            } else if (half == 0) stage_part<false>(act, p.nbr + row * p.d_nbr, p.d_nbr, p.blk_nbr0, m, valid);
+            else {
+                stage_part<false>(act, p.own + row * p.d_own, p.d_own, 0, m, valid);
+                stage_part<false>(act, p.grid + row * p.d_grid, p.d_grid, p.blk_grid0, m, valid);
+            }
             fence_async_smem();
             tc_fence_before();
             mbar_arrive(act_ready);
+            if (p.raw_off == 0) {  // pull the next tile's rows towards L2 while this tile computes
+                const long long nrow = row + (long long)gridDim.x * TILE_M;
+                if (nrow < p.n_rows) {
+                    if (half == 0) prefetch_row(p.nbr + nrow * p.d_nbr, p.d_nbr);
+                    else { prefetch_row(p.own + nrow * p.d_own, p.d_own); prefetch_row(p.grid + nrow * p.d_grid, p.d_grid); }
+                }
+            }
             lap(0);
             // layer 1 (three branches) and layer 2: hidden epilogues
             for (int layer = 1; layer <= 2; ++layer) {
@@ -300,7 +360,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                 lap(layer == 1 ? 1 : 3);
                 const int ncols = layer == 1 ? H1C : H2;
                 float *dbg_row = (p.dbg_layer == layer && valid) ? p.dbg + row * ncols : nullptr;
-                hidden_epilogue(act, tmem_row, ncols, layer == 1 ? p.b1 : p.b2, m, dbg_row);
+                hidden_epilogue(act, tmem_row, half * (ncols / 2), ncols / 2, layer == 1 ? p.b1 : p.b2, m, dbg_row);
                 fence_async_smem();
                 tc_fence_before();
                 mbar_arrive(act_ready);
@@ -311,21 +371,40 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
             ++done_phase;
             tc_fence_after();
             lap(5);
-            float a0 = __ldg(p.b4), a1 = __ldg(p.b4 + 1);
+            fetch_tile(t + gridDim.x);  // the layer-3 MMAs were the last readers of the A buffer
+            float a0 = 0.0f, a1 = 0.0f;
             float *dbg_row = (p.dbg_layer == 3 && valid) ? p.dbg + row * H3 : nullptr;
-            for (int cb = 0; cb < H3; cb += 32) {
-                float v[32];
-                tmem_ld32(tmem_row + cb, v);
+            {
+                unsigned r[2][32];
+                const int col0 = half * (H3 / 2);
+                tmem_ld32_issue(tmem_row + col0, r[0]);
+                tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float h = leaky(v[i] + __ldg(p.b3 + cb + i));
-                    a0 = fmaf(h, __ldg(p.w4 + cb + i), a0);
-                    a1 = fmaf(h, __ldg(p.w4 + H3 + cb + i), a1);
-                    if (dbg_row) dbg_row[cb + i] = h;
+                for (int u = 0; u < 4; ++u) {
+                    const int c = col0 + 32 * u;
+                    if (u < 3) tmem_ld32_issue(tmem_row + c + 32, r[(u & 1) ^ 1]);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.b3 + c + 4 * g));
+                        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.w4 + c + 4 * g)), w1 = __ldg(reinterpret_cast<const float4 *>(p.w4 + H3 + c + 4 * g));
+                        const float h0 = leaky(__uint_as_float(r[u & 1][4 * g]) + b.x), h1 = leaky(__uint_as_float(r[u & 1][4 * g + 1]) + b.y);
+                        const float h2 = leaky(__uint_as_float(r[u & 1][4 * g + 2]) + b.z), h3 = leaky(__uint_as_float(r[u & 1][4 * g + 3]) + b.w);
+                        a0 = fmaf(h0, w0.x, a0); a0 = fmaf(h1, w0.y, a0); a0 = fmaf(h2, w0.z, a0); a0 = fmaf(h3, w0.w, a0);
+                        a1 = fmaf(h0, w1.x, a1); a1 = fmaf(h1, w1.y, a1); a1 = fmaf(h2, w1.z, a1); a1 = fmaf(h3, w1.w, a1);
+                        if (dbg_row) { dbg_row[c + 4 * g] = h0; dbg_row[c + 4 * g + 1] = h1; dbg_row[c + 4 * g + 2] = h2; dbg_row[c + 4 * g + 3] = h3; }
+                    }
+                    tmem_ld_wait();
                 }
             }
-            if (valid && p.actions) {
-                a0 = tanhf(a0); a1 = tanhf(a1);
+            tc_fence_before();  // the next tile's staging arrive tells the MMA thread the accumulators are drained
+            // the two column halves of a row meet through a scratch line of the (now idle) A buffer
+            float2 *scratch = reinterpret_cast<float2 *>(act + SCRATCH_OFF);
+            if (half == 1) scratch[m] = make_float2(a0, a1);
+            epi_bar();
+            if (half == 0 && valid && p.actions) {
+                const float2 o = scratch[m];
+                a0 = tanhf(a0 + o.x + __ldg(p.b4));
+                a1 = tanhf(a1 + o.y + __ldg(p.b4 + 1));
                 if (p.noise_scale != 0.0f) {  // choose_action: act + randn(2) * var, clamp (V2/maddpg_agent:1290-1294)
                     const float2 z = normal_pair(p.noise_seed, (unsigned)row);
                     a0 = fminf(fmaxf(fmaf(p.noise_scale, z.x, a0), -1.0f), 1.0f);
@@ -333,7 +412,6 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                 }
                 reinterpret_cast<float2 *>(p.actions)[row] = make_float2(a0, a1);
             }
-            tc_fence_before();  // the next tile's staging arrive tells the MMA thread the accumulators are drained
             lap(6);
         }
         if (p.prof && tid == 0)
@@ -465,7 +543,7 @@ extern "C" int aac_actor_load(AacActor *a, const AacActorParams *hp) {
         for (int k0 = 0; k0 < kpad; k0 += 64, ++blk) add_chunk(w1[b], dims[b], 0, H1, k0, kpad - k0 < 64 ? kpad - k0 : 64, blk, H1 * b, k0 == 0 ? CH_FRESH : 0u);
     }
     a->blk_end = blk;
-    if (blk * BLK_BYTES > ACT_BYTES) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_load: input operand does not fit");
+    if (blk * BLK_BYTES > SCRATCH_OFF) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_load: input operand does not fit");
     sched.front().flags |= CH_LAYER_BEGIN;
     sched.back().flags |= CH_LAYER_END;
     // layer 2: two halves of 256 output columns, K = 384 in blocks of 64
@@ -523,6 +601,10 @@ static int actor_launch(AacActor *a, const float *own, const float *nbr, const f
     k.b1 = a->d_consts; k.b2 = k.b1 + H1C; k.b3 = k.b2 + H2; k.w4 = k.b3 + H3; k.b4 = k.w4 + 2 * H3;
     k.noise_scale = noise_scale; k.noise_seed = seed;
     k.prof = a->d_prof;
+    // bulk fetch needs 16-byte aligned blocks and room for the raw tile between the input operand and the scratch line
+    const int raw_bytes = TILE_M * 4 * (k.d_own + k.d_nbr + k.d_grid);
+    const bool aligned = ((uintptr_t)own % 16 == 0) && ((uintptr_t)nbr % 16 == 0) && ((uintptr_t)grid % 16 == 0);
+    k.raw_off = (aligned && a->blk_end * BLK_BYTES + raw_bytes <= SCRATCH_OFF && !getenv("AAC_ACTOR_NOBULK")) ? a->blk_end * BLK_BYTES : 0;
     k.dbg_nocopy = getenv("AAC_ACTOR_NOCOPY") ? 1 : 0;
     const int grid_dim = k.n_tiles < a->sms ? k.n_tiles : a->sms;
     actor_kernel<<<grid_dim, THREADS, SMEM_TOTAL, (cudaStream_t)stream>>>(k);
