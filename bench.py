@@ -189,6 +189,49 @@ def quick_device_rate(wl, dev, steps=300, warmup=10):
     return {"workload": desc, "value": envs * n / (ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms, "steps": steps}
 
 
+def policy_rollout(env, dev, steps=200, warmup=5):
+    """the caller side of the step.  The batched actor (ActorNetwork_allnei_wRadar, random-init
+    parameters of the reference's architecture) reads the env's observation tensors where the env kernel left them and
+    its actions drive the next step, so a rollout never leaves HBM.  Reports the actor kernel against the measured
+    bf16 tensor peak (algorithmic flops = 2 * MACs of the six Linear layers) and the closed-loop rate."""
+    import torch
+    from multi_agent_aac_b200.actor import BatchedActor
+    from oracle import actor_oracle      # parameters only (numpy Generator); nothing of the oracle is timed
+    rows = env.E * env.N
+    actor = BatchedActor.for_env(env)
+    actor.load_state_dict(actor_oracle.reference_like_params(env.D, 5 * (env.N - 1), env.R, seed=0))
+    act = torch.empty((env.E, env.N, 2), dtype=torch.float32, device=dev)
+    obs = env.observe()
+    for k in range(warmup):
+        actor(obs, noise_scale=0.1, noise_seed=k, out=act)
+        obs = env.step(act, autoreset=True)[0]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize(dev)
+    ev[0].record()
+    for k in range(steps):
+        actor(obs, noise_scale=0.1, noise_seed=100 + k, out=act)
+    ev[1].record()
+    for k in range(steps):
+        actor(obs, noise_scale=0.1, noise_seed=k, out=act)
+        obs = env.step(act, autoreset=True)[0]
+    ev[2].record()
+    torch.cuda.synchronize(dev)
+    actor_ms, loop_ms = ev[0].elapsed_time(ev[1]) / steps, ev[1].elapsed_time(ev[2]) / steps
+    flop = 2.0 * rows * (128 * (env.D + 5 * (env.N - 1) + env.R) + 384 * 512 + 512 * 256 + 256 * 2)
+    peak = None
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    tf = flop / (actor_ms * 1e-3) / 1e12
+    return {"what": "actor forward (choose_action for every drone) + env step + auto-reset, closed loop on the device",
+            "actor_ms": actor_ms, "actor_rows_per_s": rows / (actor_ms * 1e-3), "loop_ms_per_step": loop_ms,
+            "agent_steps_per_s": rows / (loop_ms * 1e-3), "steps": steps, "actor_launches": actor.launch_count,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": (tf / peak) if peak else None,
+                         "peak_kind": "measured cuBLAS bf16 burst (MEASURED_PEAKS.json)" if peak else "unavailable",
+                         "flop_per_row": flop / rows, "dtype": "bf16 operands, f32 accumulate", "kernel": "actor_kernel (tcgen05, TMEM accumulators)"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -344,6 +387,8 @@ def main():
             "clocks": clocks,
             "episode_stats": {k: float(v) for k, v in zip(K.STAT_NAMES, stats)},
         }
+        if world == 1 and not args.no_aux and preset_name == "tdcpa_v2":
+            line["policy_rollout"] = policy_rollout(env, dev)
         if world == 1 and not args.no_aux:   # the other single-GPU configurations of BASELINE.json, device-resident
             line["other_workloads"] = {w: quick_device_rate(w, dev) for w in ("c2", "c4") if w != args.workload}
         if not args.no_cpu and world == 1:
