@@ -1,3 +1,4 @@
+"""Tuning aid: a few actor launches for `ncu -k regex:actor_kernel`."""
 import sys, torch
 sys.path.insert(0, ".")
 from multi_agent_aac_b200.actor import BatchedActor

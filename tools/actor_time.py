@@ -1,3 +1,4 @@
+"""Tuning aid: times the actor kernel (CUDA events) and, with AAC_ACTOR_PROF=1, prints its per-tile phase clocks."""
 import sys, os, ctypes, torch, numpy as np
 sys.path.insert(0, ".")
 from multi_agent_aac_b200.actor import BatchedActor
