@@ -44,7 +44,11 @@ constexpr int EPI_THREADS = 256, PRODUCER_WARP = 8, MMA_WARP = 9, THREADS = 320;
 constexpr int SCRATCH_OFF = 7 * BLK_BYTES;  // last K block of the A buffer: free between the layer-3 MMAs and the next layer-2 epilogue
 constexpr int MAX_CHUNKS = 64;
 constexpr unsigned TMEM_COLS = 512;
-constexpr unsigned CH_LAYER_BEGIN = 1u, CH_LAYER_END = 2u, CH_FRESH = 4u;
+constexpr unsigned CH_LAYER_END = 2u, CH_FRESH = 4u;
+// `ready` barriers the MMA thread waits on before a chunk: the A operand blocks it reads are written and the
+// accumulator columns it overwrites are drained (one completion of each per tile)
+constexpr int RDY_STAGE = 0, RDY_E1 = 1 /* .. 3: own | nbr | grid third of layer 1's output */, RDY_E2 = 4 /* .. 5: halves of layer 2's output */, N_READY = 6;
+constexpr int L1_COL0 = 128;  // layer 1 accumulates in TMEM columns 128 .. 511 so that columns 0 .. 255 are free for layer 2's first half as soon as the `own` third is drained
 
 // one ring slot's worth of weights and the MMAs that consume it
 struct Chunk {
@@ -52,7 +56,7 @@ struct Chunk {
     uint32_t bytes;     // multiple of 16
     uint32_t n_mma;     // K = 16 steps in this chunk
     uint32_t n;         // MMA N (rows of the B operand)
-    uint32_t rsvd;
+    uint32_t wait_rdy;  // 1 + index of the ready barrier to pass first, 0 = none
     uint32_t a_blk;     // K block of the A operand
     uint32_t tmem_col;  // accumulator column
     uint32_t flags;
@@ -163,6 +167,21 @@ __device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
     return r;
 }
 __device__ __forceinline__ float leaky(float x) { return fmaxf(x, 0.01f * x); }
+// (x0, x1) <- leaky((x0, x1) + (b0, b1)) with the packed fp32 pair instructions of sm_100 (FADD2 / FMUL2): the same
+// roundings as the scalar form, two thirds of the instructions
+__device__ __forceinline__ void bias_leaky2(unsigned &x0, unsigned &x1, float b0, float b1) {
+    unsigned long long a, b, y, t;
+    const unsigned long long c = 0x3c23d70a3c23d70aull;  // (0.01f, 0.01f)
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(x0), "r"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(y) : "l"(a), "l"(b));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(y), "l"(c));
+    float y0, y1, t0, t1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(y));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
+    x0 = __float_as_uint(fmaxf(y0, t0));
+    x1 = __float_as_uint(fmaxf(y1, t1));
+}
 
 // counter-based standard normal pair for (seed, row): Box-Muller on two hashed uniforms
 __device__ __forceinline__ unsigned mix32(unsigned x) {
@@ -208,41 +227,47 @@ __device__ __forceinline__ void prefetch_row(const float *src, int d) {
 }
 
 // accumulators [row, col0 .. col0 + ncols) -> leaky(acc + bias) -> bf16 A operand of the next layer
-__device__ __forceinline__ void hidden_epilogue(uint8_t *act, unsigned tmem_row, int col0, int ncols, const float *bias, int m, float *dbg_row) {
+// (columns col0 .. of the layer's output; they sit at TMEM column col0 + tshift; ncols = 32 * NBLK).
+// Per 32-column block: the biases are fetched while the block's TMEM load is still in flight, and the next block's
+// load is issued before this block is processed.
+template <int NBLK, bool DBG>
+__device__ __forceinline__ void hidden_epilogue(uint8_t *act, unsigned tmem_row, int tshift, int col0, const float *bias, int m, float *dbg_row) {
     unsigned r[2][32];
+    tmem_row += tshift;
     tmem_ld32_issue(tmem_row + col0, r[0]);
-    tmem_ld_wait();
-#pragma unroll 1
-    for (int cb = col0; cb < col0 + ncols; cb += 64) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {  // two blocks per trip: the register buffers are indexed statically
-            const int c = cb + 32 * u;
-            if (c + 32 < col0 + ncols) tmem_ld32_issue(tmem_row + c + 32, r[u ^ 1]);
+    for (int u = 0; u < NBLK; ++u) {
+        const int c = col0 + 32 * u;
+        float4 bv[8];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + c + 8 * g)), b1 = __ldg(reinterpret_cast<const float4 *>(bias + c + 8 * g + 4));
-                float x[8];
+        for (int g = 0; g < 8; ++g) bv[g] = __ldg(reinterpret_cast<const float4 *>(bias + c + 4 * g));
+        tmem_ld_wait();
+        if (u + 1 < NBLK) tmem_ld32_issue(tmem_row + c + 32, r[(u & 1) ^ 1]);
+        unsigned(&x)[32] = r[u & 1];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(r[u][8 * g + i]);
-                x[0] = leaky(x[0] + b0.x); x[1] = leaky(x[1] + b0.y); x[2] = leaky(x[2] + b0.z); x[3] = leaky(x[3] + b0.w);
-                x[4] = leaky(x[4] + b1.x); x[5] = leaky(x[5] + b1.y); x[6] = leaky(x[6] + b1.z); x[7] = leaky(x[7] + b1.w);
-                *reinterpret_cast<uint4 *>(act + a_chunk((c >> 3) + g, m)) =
-                    make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
-                if (dbg_row)
-                    for (int i = 0; i < 8; ++i) dbg_row[c + 8 * g + i] = x[i];
-            }
-            tmem_ld_wait();
+        for (int g = 0; g < 4; ++g) {
+            const float4 b0 = bv[2 * g], b1 = bv[2 * g + 1];
+            bias_leaky2(x[8 * g], x[8 * g + 1], b0.x, b0.y);
+            bias_leaky2(x[8 * g + 2], x[8 * g + 3], b0.z, b0.w);
+            bias_leaky2(x[8 * g + 4], x[8 * g + 5], b1.x, b1.y);
+            bias_leaky2(x[8 * g + 6], x[8 * g + 7], b1.z, b1.w);
+            auto f = [&](int i) { return __uint_as_float(x[8 * g + i]); };
+            *reinterpret_cast<uint4 *>(act + a_chunk((c >> 3) + g, m)) =
+                make_uint4(pack_bf16(f(0), f(1)), pack_bf16(f(2), f(3)), pack_bf16(f(4), f(5)), pack_bf16(f(6), f(7)));
+            if (DBG && dbg_row)
+                for (int i = 0; i < 8; ++i) dbg_row[c + 8 * g + i] = f(i);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------ kernel
 
+template <bool DBG>
 __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant__ KArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *act = smem, *ring = smem + ACT_BYTES;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + SMEM_BARS);
-    unsigned long long *full = bars, *empty = bars + N_SLOTS, *act_ready = bars + 2 * N_SLOTS, *layer_done = act_ready + 1, *in_ready = layer_done + 1;
+    unsigned long long *full = bars, *empty = bars + N_SLOTS, *ready = bars + 2 * N_SLOTS, *layer_done = ready + N_READY, *in_ready = layer_done + 1;
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(in_ready + 1);
     Chunk *sched = reinterpret_cast<Chunk *>(smem + SMEM_SCHED);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -250,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
     for (int i = tid; i < p.n_chunks * (int)(sizeof(Chunk) / 4); i += THREADS) reinterpret_cast<uint32_t *>(sched)[i] = reinterpret_cast<const uint32_t *>(p.sched)[i];
     if (tid == 0) {
         for (int s = 0; s < N_SLOTS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(act_ready, EPI_THREADS);
+        for (int i = 0; i < N_READY; ++i) mbar_init(ready + i, EPI_THREADS / 32);  // one arrival per epilogue warp
         mbar_init(layer_done, 1);
         mbar_init(in_ready, 1);
         fence_barrier_init();
@@ -275,14 +300,13 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
-            unsigned c_glob = 0, act_phase = 0;
+            unsigned c_glob = 0, tile_par = 0;
             const unsigned act_addr = smem_u32(act), ring_addr = smem_u32(ring);
-            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, tile_par ^= 1u)
                 for (int c = 0; c < p.n_chunks; ++c, ++c_glob) {
                     const Chunk ch = sched[c];
-                    if (ch.flags & CH_LAYER_BEGIN) {  // A operand written, accumulator columns drained
-                        mbar_wait(act_ready, act_phase & 1u);
-                        ++act_phase;
+                    if (ch.wait_rdy) {  // A operand blocks written, accumulator columns drained
+                        mbar_wait(ready + ch.wait_rdy - 1, tile_par);
                         tc_fence_after();
                     }
                     const unsigned s = c_glob % N_SLOTS, ph = (c_glob / N_SLOTS) & 1u;
@@ -322,6 +346,13 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                 bulk_g2s(raw + TILE_M * (p.d_own + p.d_nbr), p.grid + r0 * p.d_grid, TILE_M * 4 * p.d_grid, in_ready);
             }
         };
+        // this warp's writes to the A buffer (generic proxy) and reads of the accumulators are done: tell the MMA thread
+        auto publish = [&](int rdy) {
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ready + rdy);
+        };
         fetch_tile(blockIdx.x);
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
             const long long row = (long long)t * TILE_M + m;
@@ -341,9 +372,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                 stage_part<false>(act, p.own + row * p.d_own, p.d_own, 0, m, valid);
                 stage_part<false>(act, p.grid + row * p.d_grid, p.d_grid, p.blk_grid0, m, valid);
             }
-            fence_async_smem();
-            tc_fence_before();
-            mbar_arrive(act_ready);
+            publish(RDY_STAGE);
             if (p.raw_off == 0) {  // pull the next tile's rows towards L2 while this tile computes
                 const long long nrow = row + (long long)gridDim.x * TILE_M;
                 if (nrow < p.n_rows) {
@@ -352,18 +381,29 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                 }
             }
             lap(0);
-            // layer 1 (three branches) and layer 2: hidden epilogues
+            // hidden epilogues, published piecewise so that the next layer's MMAs start on the finished K blocks while
+            // the rest is still being converted: layer 1 by branch (own | nbr | grid), layer 2 by output half; in each
+            // piece the two warp groups take half of the columns each
             for (int layer = 1; layer <= 2; ++layer) {
                 mbar_wait(layer_done, done_phase & 1u);
                 ++done_phase;
                 tc_fence_after();
                 lap(layer == 1 ? 1 : 3);
                 const int ncols = layer == 1 ? H1C : H2;
-                float *dbg_row = (p.dbg_layer == layer && valid) ? p.dbg + row * ncols : nullptr;
-                hidden_epilogue(act, tmem_row, half * (ncols / 2), ncols / 2, layer == 1 ? p.b1 : p.b2, m, dbg_row);
-                fence_async_smem();
-                tc_fence_before();
-                mbar_arrive(act_ready);
+                float *dbg_row = (DBG && p.dbg_layer == layer && valid) ? p.dbg + row * ncols : nullptr;
+                if (layer == 1) {
+#pragma unroll 1
+                    for (int pc_ = 0; pc_ < 3; ++pc_) {  // 128 columns per branch, 64 per warp group
+                        hidden_epilogue<2, DBG>(act, tmem_row, L1_COL0, pc_ * H1 + half * (H1 / 2), p.b1, m, dbg_row);
+                        publish(RDY_E1 + pc_);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int pc_ = 0; pc_ < 2; ++pc_) {  // 256 columns per half of the output, 128 per warp group
+                        hidden_epilogue<4, DBG>(act, tmem_row, 0, pc_ * (H2 / 2) + half * (H2 / 4), p.b2, m, dbg_row);
+                        publish(RDY_E2 + pc_);
+                    }
+                }
                 lap(layer == 1 ? 2 : 4);
             }
             // layer 3 epilogue fused with the output layer (256 -> 2), tanh, noise, clamp
@@ -373,7 +413,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
             lap(5);
             fetch_tile(t + gridDim.x);  // the layer-3 MMAs were the last readers of the A buffer
             float a0 = 0.0f, a1 = 0.0f;
-            float *dbg_row = (p.dbg_layer == 3 && valid) ? p.dbg + row * H3 : nullptr;
+            float *dbg_row = (DBG && p.dbg_layer == 3 && valid) ? p.dbg + row * H3 : nullptr;
             {
                 unsigned r[2][32];
                 const int col0 = half * (H3 / 2);
@@ -391,7 +431,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                         const float h2 = leaky(__uint_as_float(r[u & 1][4 * g + 2]) + b.z), h3 = leaky(__uint_as_float(r[u & 1][4 * g + 3]) + b.w);
                         a0 = fmaf(h0, w0.x, a0); a0 = fmaf(h1, w0.y, a0); a0 = fmaf(h2, w0.z, a0); a0 = fmaf(h3, w0.w, a0);
                         a1 = fmaf(h0, w1.x, a1); a1 = fmaf(h1, w1.y, a1); a1 = fmaf(h2, w1.z, a1); a1 = fmaf(h3, w1.w, a1);
-                        if (dbg_row) { dbg_row[c + 4 * g] = h0; dbg_row[c + 4 * g + 1] = h1; dbg_row[c + 4 * g + 2] = h2; dbg_row[c + 4 * g + 3] = h3; }
+                        if (DBG && dbg_row) { dbg_row[c + 4 * g] = h0; dbg_row[c + 4 * g + 1] = h1; dbg_row[c + 4 * g + 2] = h2; dbg_row[c + 4 * g + 3] = h3; }
                     }
                     tmem_ld_wait();
                 }
@@ -478,7 +518,8 @@ extern "C" int aac_actor_create(const AacActorConfig *cfg, AacActor **out) {
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, a->device);
     if (e != cudaSuccess) { delete a; return cuda_fail(e, "aac_actor_create: device query"); }
     if (cc_major != 10 || smem_max < SMEM_TOTAL) { delete a; return fail(AAC_ACTOR_ERR_STATE, "aac_actor_create: needs an sm_100 device (tcgen05, 227 KB shared memory)"); }
-    e = cudaFuncSetAttribute(actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    e = cudaFuncSetAttribute(actor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(actor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) { delete a; return cuda_fail(e, "aac_actor_create: cudaFuncSetAttribute"); }
     if (getenv("AAC_ACTOR_PROF")) {
         cudaMalloc(&a->d_prof, (size_t)a->sms * 8 * sizeof(long long));
@@ -519,7 +560,7 @@ extern "C" int aac_actor_load(AacActor *a, const AacActorParams *hp) {
         ch.bytes = (uint32_t)(nc * 128);
         ch.n_mma = (uint32_t)(kw / 16);
         ch.n = (uint32_t)nc;
-        ch.rsvd = 0;
+        ch.wait_rdy = 0;
         ch.a_blk = (uint32_t)a_blk;
         ch.tmem_col = (uint32_t)col;
         ch.flags = flags;
@@ -540,22 +581,25 @@ extern "C" int aac_actor_load(AacActor *a, const AacActorParams *hp) {
         const int kpad = round_up(dims[b], 16);
         if (b == 1) a->blk_nbr0 = blk;
         if (b == 2) a->blk_grid0 = blk;
-        for (int k0 = 0; k0 < kpad; k0 += 64, ++blk) add_chunk(w1[b], dims[b], 0, H1, k0, kpad - k0 < 64 ? kpad - k0 : 64, blk, H1 * b, k0 == 0 ? CH_FRESH : 0u);
+        for (int k0 = 0; k0 < kpad; k0 += 64, ++blk) add_chunk(w1[b], dims[b], 0, H1, k0, kpad - k0 < 64 ? kpad - k0 : 64, blk, L1_COL0 + H1 * b, k0 == 0 ? CH_FRESH : 0u);
     }
     a->blk_end = blk;
     if (blk * BLK_BYTES > SCRATCH_OFF) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_load: input operand does not fit");
-    sched.front().flags |= CH_LAYER_BEGIN;
+    sched.front().wait_rdy = 1 + RDY_STAGE;
     sched.back().flags |= CH_LAYER_END;
     // layer 2: two halves of 256 output columns, K = 384 in blocks of 64
-    size_t first = sched.size();
+    // (its first half may start on the K blocks of a layer-1 branch as soon as that branch's epilogue is published)
     for (int h = 0; h < 2; ++h)
-        for (int k0 = 0; k0 < H1C; k0 += 64) add_chunk(hp->w_merge, H1C, 256 * h, 256, k0, 64, k0 / 64, 256 * h, k0 == 0 ? CH_FRESH : 0u);
-    sched[first].flags |= CH_LAYER_BEGIN;
+        for (int k0 = 0; k0 < H1C; k0 += 64) {
+            add_chunk(hp->w_merge, H1C, 256 * h, 256, k0, 64, k0 / 64, 256 * h, k0 == 0 ? CH_FRESH : 0u);
+            sched.back().wait_rdy = 1 + RDY_E1 + (h == 0 ? k0 / H1 : 2);
+        }
     sched.back().flags |= CH_LAYER_END;
     // layer 3: 256 output columns, K = 512
-    first = sched.size();
-    for (int k0 = 0; k0 < H2; k0 += 64) add_chunk(hp->w_hid, H2, 0, 256, k0, 64, k0 / 64, 0, k0 == 0 ? CH_FRESH : 0u);
-    sched[first].flags |= CH_LAYER_BEGIN;
+    for (int k0 = 0; k0 < H2; k0 += 64) {
+        add_chunk(hp->w_hid, H2, 0, 256, k0, 64, k0 / 64, 0, k0 == 0 ? CH_FRESH : 0u);
+        sched.back().wait_rdy = 1 + RDY_E2 + k0 / 256;
+    }
     sched.back().flags |= CH_LAYER_END;
     if ((int)sched.size() > MAX_CHUNKS) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_load: chunk schedule too long");
     for (const Chunk &c : sched)
@@ -607,7 +651,8 @@ static int actor_launch(AacActor *a, const float *own, const float *nbr, const f
     k.raw_off = (aligned && a->blk_end * BLK_BYTES + raw_bytes <= SCRATCH_OFF && !getenv("AAC_ACTOR_NOBULK")) ? a->blk_end * BLK_BYTES : 0;
     k.dbg_nocopy = getenv("AAC_ACTOR_NOCOPY") ? 1 : 0;
     const int grid_dim = k.n_tiles < a->sms ? k.n_tiles : a->sms;
-    actor_kernel<<<grid_dim, THREADS, SMEM_TOTAL, (cudaStream_t)stream>>>(k);
+    if (dbg) actor_kernel<true><<<grid_dim, THREADS, SMEM_TOTAL, (cudaStream_t)stream>>>(k);
+    else actor_kernel<false><<<grid_dim, THREADS, SMEM_TOTAL, (cudaStream_t)stream>>>(k);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "aac_actor_forward: launch");
     ++a->launches;
