@@ -55,9 +55,9 @@ struct Chunk {
     uint32_t src_off;   // byte offset into the packed weights
     uint32_t bytes;     // multiple of 16
     uint32_t n_mma;     // K = 16 steps in this chunk
-    uint32_t n;         // MMA N (rows of the B operand)
+    uint32_t idesc;     // tcgen05 instruction descriptor (N of this chunk)
     uint32_t wait_rdy;  // 1 + index of the ready barrier to pass first, 0 = none
-    uint32_t a_blk;     // K block of the A operand
+    uint32_t a_off16;   // (byte offset of the A operand's K block in the A buffer) >> 4
     uint32_t tmem_col;  // accumulator column
     uint32_t flags;
 };
@@ -96,18 +96,23 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+__device__ __forceinline__ bool mbar_try(unsigned bar_addr, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(unsigned bar_addr, unsigned parity) {
     const long long t0 = clock64();
-    for (;;) {
-        unsigned ok;
-        asm volatile(
-            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (ok) return;
+    while (!mbar_try(bar_addr, parity))
         if (clock64() - t0 > 4000000000ll) __trap();
-    }
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = smem_u32(bar);
+    if (!mbar_try(a, parity)) mbar_wait_slow(a, parity);
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
@@ -134,7 +139,7 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned addr) {
 }
 // instruction descriptor, kind::f16: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17,
 // M >> 4 at bit 24 (cute::UMMA::InstrDescriptor)
-__device__ __forceinline__ unsigned umma_idesc(unsigned n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((TILE_M >> 4) << 24); }
+__host__ __device__ inline unsigned umma_idesc(unsigned n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((TILE_M >> 4) << 24); }
 __device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long a, unsigned long long b, unsigned idesc, unsigned accumulate) {
     asm volatile(
         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(a), "l"(b),
@@ -288,38 +293,42 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
 
     if (warp == PRODUCER_WARP) {
         if (lane == 0) {
-            unsigned c_glob = 0;
+            unsigned s = 0, ph = 0, first = N_SLOTS;
             for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
-                for (int c = 0; c < p.n_chunks; ++c, ++c_glob) {
-                    const unsigned s = c_glob % N_SLOTS, ph = (c_glob / N_SLOTS) & 1u;
+                for (int c = 0; c < p.n_chunks; ++c) {
                     mbar_wait(empty + s, ph ^ 1u);  // slot free (passes at once the first time round)
-                    if (p.dbg_nocopy && c_glob >= N_SLOTS) { mbar_arrive(full + s); continue; }
-                    mbar_expect_tx(full + s, sched[c].bytes);
-                    bulk_g2s(ring + s * SLOT_BYTES, p.wpack + sched[c].src_off, sched[c].bytes, full + s);
+                    if (p.dbg_nocopy && first == 0) mbar_arrive(full + s);  // tuning aid: reuse what the first pass loaded
+                    else {
+                        mbar_expect_tx(full + s, sched[c].bytes);
+                        bulk_g2s(ring + s * SLOT_BYTES, p.wpack + sched[c].src_off, sched[c].bytes, full + s);
+                    }
+                    if (first) --first;
+                    if (++s == N_SLOTS) { s = 0; ph ^= 1u; }
                 }
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
-            unsigned c_glob = 0, tile_par = 0;
-            const unsigned act_addr = smem_u32(act), ring_addr = smem_u32(ring);
+            // One thread feeds the tensor core, so its instruction stream is kept short: descriptors are a constant
+            // plus (address >> 4), the per-chunk fields come precomputed from the host's schedule, ring slot and
+            // parity are running counters.
+            unsigned s = 0, ph = 0, tile_par = 0;
+            const unsigned long long desc_hi = umma_desc(0) & 0xFFFFFFFF00000000ull;
+            const unsigned desc_lo0 = (unsigned)umma_desc(0);  // leading-byte-offset field; the start address is added below
+            const unsigned a_base = (smem_u32(act) & 0x3FFFFu) >> 4, ring_base = (smem_u32(ring) & 0x3FFFFu) >> 4;
             for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, tile_par ^= 1u)
-                for (int c = 0; c < p.n_chunks; ++c, ++c_glob) {
-                    const Chunk ch = sched[c];
-                    if (ch.wait_rdy) {  // A operand blocks written, accumulator columns drained
-                        mbar_wait(ready + ch.wait_rdy - 1, tile_par);
-                        tc_fence_after();
-                    }
-                    const unsigned s = c_glob % N_SLOTS, ph = (c_glob / N_SLOTS) & 1u;
+                for (int c = 0; c < p.n_chunks; ++c) {
+                    const uint4 c0 = reinterpret_cast<const uint4 *>(sched + c)[0], c1 = reinterpret_cast<const uint4 *>(sched + c)[1];
+                    const unsigned n_mma = c0.z, idesc = c0.w, wait_rdy = c1.x, a_off16 = c1.y, tmem_col = c1.z, flags = c1.w;
+                    if (wait_rdy) mbar_wait(ready + wait_rdy - 1, tile_par);  // A operand blocks written, accumulator columns drained
                     mbar_wait(full + s, ph);
                     tc_fence_after();
-                    const unsigned idesc = umma_idesc(ch.n);
-                    for (unsigned j = 0; j < ch.n_mma; ++j) {
-                        const unsigned long long a = umma_desc(act_addr + ch.a_blk * BLK_BYTES + j * 32);
-                        const unsigned long long b = umma_desc(ring_addr + s * SLOT_BYTES + j * 32);
-                        umma_bf16(tmem_base + ch.tmem_col, a, b, idesc, ((ch.flags & CH_FRESH) && j == 0) ? 0u : 1u);
-                    }
+                    const unsigned a_lo = desc_lo0 + a_base + a_off16, b_lo = desc_lo0 + ring_base + s * (SLOT_BYTES >> 4);
+                    const unsigned d = tmem_base + tmem_col;
+                    umma_bf16(d, desc_hi | a_lo, desc_hi | b_lo, idesc, (flags & CH_FRESH) ? 0u : 1u);
+                    for (unsigned j = 1; j < n_mma; ++j) umma_bf16(d, desc_hi | (a_lo + 2 * j), desc_hi | (b_lo + 2 * j), idesc, 1u);
                     umma_commit(empty + s);
-                    if (ch.flags & CH_LAYER_END) umma_commit(layer_done);
+                    if (flags & CH_LAYER_END) umma_commit(layer_done);
+                    if (++s == N_SLOTS) { s = 0; ph ^= 1u; }
                 }
         }
     } else {
@@ -329,7 +338,14 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
         const unsigned tmem_row = tmem_base + ((unsigned)((warp & 3) * 32) << 16);
         unsigned done_phase = 0, in_phase = 0;
         long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = clock64();
-        auto lap = [&](int i) { if (p.prof) { const long long now = clock64(); pc[i] += now - tp; tp = now; } };
+        auto lap = [&](int i) {
+            if (p.prof) {
+                const long long now = clock64();
+                pc[i] += now - tp;
+                tp = now;
+                if (tid == 0 && blockIdx.x == 0) p.prof[gridDim.x * 8 + i] = now;  // absolute time of the phase boundary (the last tile's survives)
+            }
+        };
         // A full tile's observations are three contiguous fp32 blocks in global memory: when they fit beside the
         // input operand (p.raw_off > 0), one thread pulls them into the idle K blocks of the A buffer with bulk async
         // copies, issued as soon as the previous tile's last MMA has read that memory, so the fetch hides behind the
@@ -522,8 +538,8 @@ extern "C" int aac_actor_create(const AacActorConfig *cfg, AacActor **out) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(actor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) { delete a; return cuda_fail(e, "aac_actor_create: cudaFuncSetAttribute"); }
     if (getenv("AAC_ACTOR_PROF")) {
-        cudaMalloc(&a->d_prof, (size_t)a->sms * 8 * sizeof(long long));
-        cudaMemset(a->d_prof, 0, (size_t)a->sms * 8 * sizeof(long long));
+        cudaMalloc(&a->d_prof, ((size_t)a->sms * 8 + 128) * sizeof(long long));
+        cudaMemset(a->d_prof, 0, ((size_t)a->sms * 8 + 128) * sizeof(long long));
     }
     *out = a;
     return 0;
@@ -532,7 +548,7 @@ extern "C" int aac_actor_create(const AacActorConfig *cfg, AacActor **out) {
 // tuning aid: copies the [sms][8] phase clocks (stage, wait L1, E1, wait L2, E2, wait L3, E3) to host memory
 extern "C" int aac_actor_prof(AacActor *a, long long *host_out) {
     if (!a || !a->d_prof || !host_out) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_prof: run with AAC_ACTOR_PROF=1");
-    const cudaError_t e = cudaMemcpy(host_out, a->d_prof, (size_t)a->sms * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+    const cudaError_t e = cudaMemcpy(host_out, a->d_prof, ((size_t)a->sms * 8 + 128) * sizeof(long long), cudaMemcpyDeviceToHost);
     return e == cudaSuccess ? a->sms : cuda_fail(e, "aac_actor_prof");
 }
 
@@ -559,9 +575,9 @@ extern "C" int aac_actor_load(AacActor *a, const AacActorParams *hp) {
         ch.src_off = (uint32_t)pack.size();
         ch.bytes = (uint32_t)(nc * 128);
         ch.n_mma = (uint32_t)(kw / 16);
-        ch.n = (uint32_t)nc;
+        ch.idesc = umma_idesc((unsigned)nc);
         ch.wait_rdy = 0;
-        ch.a_blk = (uint32_t)a_blk;
+        ch.a_off16 = (uint32_t)(a_blk * BLK_BYTES) >> 4;
         ch.tmem_col = (uint32_t)col;
         ch.flags = flags;
         pack.resize(pack.size() + ch.bytes, 0);
@@ -650,7 +666,8 @@ static int actor_launch(AacActor *a, const float *own, const float *nbr, const f
     const bool aligned = ((uintptr_t)own % 16 == 0) && ((uintptr_t)nbr % 16 == 0) && ((uintptr_t)grid % 16 == 0);
     k.raw_off = (aligned && a->blk_end * BLK_BYTES + raw_bytes <= SCRATCH_OFF && !getenv("AAC_ACTOR_NOBULK")) ? a->blk_end * BLK_BYTES : 0;
     k.dbg_nocopy = getenv("AAC_ACTOR_NOCOPY") ? 1 : 0;
-    const int grid_dim = k.n_tiles < a->sms ? k.n_tiles : a->sms;
+    int grid_dim = k.n_tiles < a->sms ? k.n_tiles : a->sms;
+    if (const char *g = getenv("AAC_ACTOR_GRID")) grid_dim = atoi(g) > 0 && atoi(g) < grid_dim ? atoi(g) : grid_dim;  // tuning aid
     if (dbg) actor_kernel<true><<<grid_dim, THREADS, SMEM_TOTAL, (cudaStream_t)stream>>>(k);
     else actor_kernel<false><<<grid_dim, THREADS, SMEM_TOTAL, (cudaStream_t)stream>>>(k);
     const cudaError_t e = cudaGetLastError();

@@ -25,9 +25,12 @@ print("actor kernel: %.4f ms  %.3e rows/s  %.1f TFLOP/s (algorithmic)" % (ms, ro
 ref = actor_oracle.forward(sd, own[:512].cpu().numpy(), nbr[:512].cpu().numpy(), grid[:512].cpu().numpy())
 print("max |action - float64 oracle| on 512 rows: %.2e" % np.abs(out[:512].cpu().numpy() - ref).max())
 if os.environ.get("AAC_ACTOR_PROF"):
-    buf = (ctypes.c_longlong * (256 * 8))()
+    buf = (ctypes.c_longlong * (256 * 8 + 128))()
     L = K.lib(); L.aac_actor_prof.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     n = L.aac_actor_prof(actor._h, buf)
     a = np.array(buf[: n * 8], dtype=np.float64).reshape(n, 8)
     tiles = (rows + 127) // 128 / n
     print("per-tile cycles (mean over CTAs): stage %.0f | wait L1 %.0f | E1 %.0f | wait L2 %.0f | E2 %.0f | wait L3 %.0f | E3 %.0f | total %.0f" % (*(a[:, :7].mean(0) / tiles), a[:, :7].sum(1).mean() / tiles))
+    tl = np.array(buf[n * 8: n * 8 + 8], dtype=np.int64)
+    names = ["stage end", "L1 done", "E1 end", "L2 done", "E2 end", "L3 done", "E3 end"]
+    print("CTA 0, last tile, cycles after the end of staging:", ", ".join("%s %d" % (names[i], tl[i] - tl[0]) for i in range(7)))
