@@ -2,14 +2,14 @@
 // whole ActorNetwork_allnei_wRadar (V2/Nnetworks:273-340) for 128 drones per tile on the 5th-generation
 // tensor cores.
 //
-//   warps 0-7  stage the tile's observations as the bf16 A operand, then act as the epilogue of every layer
-//              (warp w owns rows 32 (w % 4) .. and column half w / 4):
+//   warps 0-15 stage the tile's observations as the bf16 A operand, then act as the epilogue of every layer
+//              (warp w owns rows 32 (w % 4) .. and column group w / 4; four warps per scheduler hide the latencies):
 //              tcgen05.ld the fp32 accumulators out of tensor memory, add the bias, LeakyReLU, round to bf16
 //              and write the result back to shared memory AS THE NEXT LAYER'S A OPERAND (activations never
 //              leave the SM); the last layer (256 -> 2), tanh, exploration noise and clamp run in fp32 here
-//   warp 8     streams the pre-tiled bf16 weights through a 3-slot shared-memory ring with bulk async copies
+//   warp 16    streams the pre-tiled bf16 weights through a 3-slot shared-memory ring with bulk async copies
 //              (cp.async.bulk + mbarrier complete_tx); also owns the tensor-memory allocation
-//   warp 9     one elected thread issues tcgen05.mma (M = 128, N = 128 / 256, K = 16, kind::f16 with bf16
+//   warp 17    one elected thread issues tcgen05.mma (M = 128, N = 128 / 256, K = 16, kind::f16 with bf16
 //              operands, fp32 accumulators in TMEM) and tcgen05.commit's ring slots / layer completion
 //
 // Operand layout: the canonical K-major 128-byte-swizzled UMMA layout.  An operand of `rows` rows is cut into
@@ -40,7 +40,8 @@ constexpr int BLK_BYTES = TILE_M * 128;          // one 64-wide K block of a 128
 constexpr int ACT_BYTES = (H2 / 64) * BLK_BYTES;  // widest A operand: 128 x 512 bf16 = 128 KB
 constexpr int SLOT_BYTES = 32768;                // one 64-wide K block of a 256-row B operand
 constexpr int N_SLOTS = 3;
-constexpr int EPI_THREADS = 256, PRODUCER_WARP = 8, MMA_WARP = 9, THREADS = 320;
+constexpr int NPART = 4;  // column groups of the epilogue: 4 warps (the four TMEM lane windows) each
+constexpr int EPI_THREADS = 128 * NPART, PRODUCER_WARP = 4 * NPART, MMA_WARP = 4 * NPART + 1, THREADS = EPI_THREADS + 64;
 constexpr int SCRATCH_OFF = 7 * BLK_BYTES;  // last K block of the A buffer: free between the layer-3 MMAs and the next layer-2 epilogue
 constexpr int MAX_CHUNKS = 64;
 constexpr unsigned TMEM_COLS = 512;
@@ -164,7 +165,7 @@ __device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, unsigned (&r)[32
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps only
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }  // the epilogue warps only
 
 __device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
     unsigned r;
@@ -207,23 +208,33 @@ __device__ __forceinline__ float2 normal_pair(unsigned long long seed, unsigned 
 // byte offset of the 16-byte chunk holding columns 8c .. 8c+7 of row m in a 128-row K-major SWIZZLE_128B operand
 __device__ __forceinline__ int a_chunk(int c, int m) { return (c >> 3) * BLK_BYTES + m * 128 + (((c & 7) ^ (m & 7)) << 4); }
 
-// one row of one observation part -> bf16 chunks of the A operand, K blocks blk0 .. (zero padded to a multiple of
-// 16 columns).  32 columns are fetched per batch so that their global loads are in flight together.
+// 32 columns c0 * 8 .. of one row of one observation part -> bf16 chunks of the A operand, K blocks blk0 .. (zero
+// padded to a multiple of 16 columns); the batch's loads are in flight together
 template <bool FROM_SMEM>
-__device__ __forceinline__ void stage_part(uint8_t *act, const float *src, int d, int blk0, int m, bool valid) {
-    const int n_chunks = ((d + 15) >> 4) << 1;
-    for (int c0 = 0; c0 < n_chunks; c0 += 4) {
-        float v[32];
+__device__ __forceinline__ void stage_batch(uint8_t *act, const float *src, int d, int blk0, int c0, int n_chunks, int m, bool valid) {
+    float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int k = c0 * 8 + i;
-            v[i] = (valid && k < d) ? (FROM_SMEM ? src[k] : __ldg(src + k)) : 0.0f;
-        }
+    for (int i = 0; i < 32; ++i) {
+        const int k = c0 * 8 + i;
+        v[i] = (valid && k < d) ? (FROM_SMEM ? src[k] : __ldg(src + k)) : 0.0f;
+    }
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-            if (c0 + g < n_chunks)
-                *reinterpret_cast<uint4 *>(act + a_chunk(blk0 * 8 + c0 + g, m)) = make_uint4(
-                    pack_bf16(v[8 * g], v[8 * g + 1]), pack_bf16(v[8 * g + 2], v[8 * g + 3]), pack_bf16(v[8 * g + 4], v[8 * g + 5]), pack_bf16(v[8 * g + 6], v[8 * g + 7]));
+    for (int g = 0; g < 4; ++g)
+        if (c0 + g < n_chunks)
+            *reinterpret_cast<uint4 *>(act + a_chunk(blk0 * 8 + c0 + g, m)) = make_uint4(
+                pack_bf16(v[8 * g], v[8 * g + 1]), pack_bf16(v[8 * g + 2], v[8 * g + 3]), pack_bf16(v[8 * g + 4], v[8 * g + 5]), pack_bf16(v[8 * g + 6], v[8 * g + 7]));
+}
+// the three parts of a row (own | nbr | grid) as batches of 32 columns, dealt round-robin to the NPART warp groups
+template <bool FROM_SMEM>
+__device__ __forceinline__ void stage_row(uint8_t *act, const float *own, const float *nbr, const float *grid, const KArgs &p, int part, int m, bool valid) {
+    const float *src[3] = {own, nbr, grid};
+    const int d[3] = {p.d_own, p.d_nbr, p.d_grid}, blk0[3] = {0, p.blk_nbr0, p.blk_grid0};
+    int item = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int n_chunks = ((d[q] + 15) >> 4) << 1;
+        for (int c0 = 0; c0 < n_chunks; c0 += 4, ++item)
+            if (item % NPART == part) stage_batch<FROM_SMEM>(act, src[q], d[q], blk0[q], c0, n_chunks, m, valid);
     }
 }
 __device__ __forceinline__ void prefetch_row(const float *src, int d) {
@@ -231,24 +242,21 @@ __device__ __forceinline__ void prefetch_row(const float *src, int d) {
     for (int off = 0; off < d * 4 + 127; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + (off < d * 4 ? off : d * 4 - 1)));
 }
 
-// accumulators [row, col0 .. col0 + ncols) -> leaky(acc + bias) -> bf16 A operand of the next layer
-// (columns col0 .. of the layer's output; they sit at TMEM column col0 + tshift; ncols = 32 * NBLK).
-// Per 32-column block: the biases are fetched while the block's TMEM load is still in flight, and the next block's
-// load is issued before this block is processed.
+// accumulators [row, col0 .. col0 + 32 NBLK) -> leaky(acc + bias) -> bf16 A operand of the next layer (columns of
+// the layer's output; they sit at TMEM column col0 + tshift).  The biases of a 32-column block are fetched while
+// its TMEM load is in flight; latency is otherwise hidden by the four epilogue warps per scheduler.
 template <int NBLK, bool DBG>
 __device__ __forceinline__ void hidden_epilogue(uint8_t *act, unsigned tmem_row, int tshift, int col0, const float *bias, int m, float *dbg_row) {
-    unsigned r[2][32];
     tmem_row += tshift;
-    tmem_ld32_issue(tmem_row + col0, r[0]);
 #pragma unroll
     for (int u = 0; u < NBLK; ++u) {
         const int c = col0 + 32 * u;
+        unsigned x[32];
+        tmem_ld32_issue(tmem_row + c, x);
         float4 bv[8];
 #pragma unroll
         for (int g = 0; g < 8; ++g) bv[g] = __ldg(reinterpret_cast<const float4 *>(bias + c + 4 * g));
         tmem_ld_wait();
-        if (u + 1 < NBLK) tmem_ld32_issue(tmem_row + c + 32, r[(u & 1) ^ 1]);
-        unsigned(&x)[32] = r[u & 1];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const float4 b0 = bv[2 * g], b1 = bv[2 * g + 1];
@@ -332,9 +340,9 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                 }
         }
     } else {
-        // 8 epilogue warps: warp w works on TMEM lanes 32 * (w % 4) .. (the hardware's lane window of a warp), i.e.
-        // row m = tid % 128, and on column half tid / 128 of every layer
-        const int m = tid & 127, half = tid >> 7;
+        // epilogue warps: warp w works on TMEM lanes 32 * (w % 4) .. (the hardware's lane window of a warp), i.e. row
+        // m = tid % 128, and on column group tid / 128 of every piece of every layer
+        const int m = tid & 127, part = tid >> 7;
         const unsigned tmem_row = tmem_base + ((unsigned)((warp & 3) * 32) << 16);
         unsigned done_phase = 0, in_phase = 0;
         long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = clock64();
@@ -378,28 +386,20 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
             if (bulk_tile(t)) {
                 mbar_wait(in_ready, in_phase & 1u);
                 ++in_phase;
-                if (half == 0) stage_part<true>(act, raw_nbr + m * p.d_nbr, p.d_nbr, p.blk_nbr0, m, true);
-                else {
-                    stage_part<true>(act, raw_own + m * p.d_own, p.d_own, 0, m, true);
-                    stage_part<true>(act, raw_grid + m * p.d_grid, p.d_grid, p.blk_grid0, m, true);
-                }
-            } else if (half == 0) stage_part<false>(act, p.nbr + row * p.d_nbr, p.d_nbr, p.blk_nbr0, m, valid);
-            else {
-                stage_part<false>(act, p.own + row * p.d_own, p.d_own, 0, m, valid);
-                stage_part<false>(act, p.grid + row * p.d_grid, p.d_grid, p.blk_grid0, m, valid);
-            }
+                stage_row<true>(act, raw_own + m * p.d_own, raw_nbr + m * p.d_nbr, raw_grid + m * p.d_grid, p, part, m, true);
+            } else stage_row<false>(act, p.own + row * p.d_own, p.nbr + row * p.d_nbr, p.grid + row * p.d_grid, p, part, m, valid);
             publish(RDY_STAGE);
             if (p.raw_off == 0) {  // pull the next tile's rows towards L2 while this tile computes
                 const long long nrow = row + (long long)gridDim.x * TILE_M;
                 if (nrow < p.n_rows) {
-                    if (half == 0) prefetch_row(p.nbr + nrow * p.d_nbr, p.d_nbr);
-                    else { prefetch_row(p.own + nrow * p.d_own, p.d_own); prefetch_row(p.grid + nrow * p.d_grid, p.d_grid); }
+                    if (part == 0) prefetch_row(p.nbr + nrow * p.d_nbr, p.d_nbr);
+                    else if (part == 1) { prefetch_row(p.own + nrow * p.d_own, p.d_own); prefetch_row(p.grid + nrow * p.d_grid, p.d_grid); }
                 }
             }
             lap(0);
             // hidden epilogues, published piecewise so that the next layer's MMAs start on the finished K blocks while
             // the rest is still being converted: layer 1 by branch (own | nbr | grid), layer 2 by output half; in each
-            // piece the two warp groups take half of the columns each
+            // piece the NPART warp groups take an equal share of the columns
             for (int layer = 1; layer <= 2; ++layer) {
                 mbar_wait(layer_done, done_phase & 1u);
                 ++done_phase;
@@ -409,14 +409,14 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                 float *dbg_row = (DBG && p.dbg_layer == layer && valid) ? p.dbg + row * ncols : nullptr;
                 if (layer == 1) {
 #pragma unroll 1
-                    for (int pc_ = 0; pc_ < 3; ++pc_) {  // 128 columns per branch, 64 per warp group
-                        hidden_epilogue<2, DBG>(act, tmem_row, L1_COL0, pc_ * H1 + half * (H1 / 2), p.b1, m, dbg_row);
+                    for (int pc_ = 0; pc_ < 3; ++pc_) {  // 128 columns per branch
+                        hidden_epilogue<H1 / NPART / 32, DBG>(act, tmem_row, L1_COL0, pc_ * H1 + part * (H1 / NPART), p.b1, m, dbg_row);
                         publish(RDY_E1 + pc_);
                     }
                 } else {
 #pragma unroll 1
-                    for (int pc_ = 0; pc_ < 2; ++pc_) {  // 256 columns per half of the output, 128 per warp group
-                        hidden_epilogue<4, DBG>(act, tmem_row, 0, pc_ * (H2 / 2) + half * (H2 / 4), p.b2, m, dbg_row);
+                    for (int pc_ = 0; pc_ < 2; ++pc_) {  // 256 columns per half of the output
+                        hidden_epilogue<H2 / 2 / NPART / 32, DBG>(act, tmem_row, 0, pc_ * (H2 / 2) + part * (H2 / 2 / NPART), p.b2, m, dbg_row);
                         publish(RDY_E2 + pc_);
                     }
                 }
@@ -431,36 +431,45 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
             float a0 = 0.0f, a1 = 0.0f;
             float *dbg_row = (DBG && p.dbg_layer == 3 && valid) ? p.dbg + row * H3 : nullptr;
             {
-                unsigned r[2][32];
-                const int col0 = half * (H3 / 2);
-                tmem_ld32_issue(tmem_row + col0, r[0]);
-                tmem_ld_wait();
+                const int col0 = part * (H3 / NPART);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < H3 / NPART / 32; ++u) {
                     const int c = col0 + 32 * u;
-                    if (u < 3) tmem_ld32_issue(tmem_row + c + 32, r[(u & 1) ^ 1]);
+                    unsigned x[32];
+                    tmem_ld32_issue(tmem_row + c, x);
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.b3 + c + 4 * g));
-                        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.w4 + c + 4 * g)), w1 = __ldg(reinterpret_cast<const float4 *>(p.w4 + H3 + c + 4 * g));
-                        const float h0 = leaky(__uint_as_float(r[u & 1][4 * g]) + b.x), h1 = leaky(__uint_as_float(r[u & 1][4 * g + 1]) + b.y);
-                        const float h2 = leaky(__uint_as_float(r[u & 1][4 * g + 2]) + b.z), h3 = leaky(__uint_as_float(r[u & 1][4 * g + 3]) + b.w);
-                        a0 = fmaf(h0, w0.x, a0); a0 = fmaf(h1, w0.y, a0); a0 = fmaf(h2, w0.z, a0); a0 = fmaf(h3, w0.w, a0);
-                        a1 = fmaf(h0, w1.x, a1); a1 = fmaf(h1, w1.y, a1); a1 = fmaf(h2, w1.z, a1); a1 = fmaf(h3, w1.w, a1);
-                        if (DBG && dbg_row) { dbg_row[c + 4 * g] = h0; dbg_row[c + 4 * g + 1] = h1; dbg_row[c + 4 * g + 2] = h2; dbg_row[c + 4 * g + 3] = h3; }
+                    for (int hb = 0; hb < 2; ++hb) {  // 16 columns at a time: their bias / output weights are fetched first
+                        float4 bq[4], w0[4], w1[4];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            bq[g] = __ldg(reinterpret_cast<const float4 *>(p.b3 + c + 16 * hb + 4 * g));
+                            w0[g] = __ldg(reinterpret_cast<const float4 *>(p.w4 + c + 16 * hb + 4 * g));
+                            w1[g] = __ldg(reinterpret_cast<const float4 *>(p.w4 + H3 + c + 16 * hb + 4 * g));
+                        }
+                        if (hb == 0) tmem_ld_wait();
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            unsigned *y = x + 16 * hb + 4 * g;
+                            bias_leaky2(y[0], y[1], bq[g].x, bq[g].y);
+                            bias_leaky2(y[2], y[3], bq[g].z, bq[g].w);
+                            const float h0 = __uint_as_float(y[0]), h1 = __uint_as_float(y[1]), h2 = __uint_as_float(y[2]), h3 = __uint_as_float(y[3]);
+                            a0 = fmaf(h0, w0[g].x, a0); a0 = fmaf(h1, w0[g].y, a0); a0 = fmaf(h2, w0[g].z, a0); a0 = fmaf(h3, w0[g].w, a0);
+                            a1 = fmaf(h0, w1[g].x, a1); a1 = fmaf(h1, w1[g].y, a1); a1 = fmaf(h2, w1[g].z, a1); a1 = fmaf(h3, w1[g].w, a1);
+                            if (DBG && dbg_row) { float *o = dbg_row + c + 16 * hb + 4 * g; o[0] = h0; o[1] = h1; o[2] = h2; o[3] = h3; }
+                        }
                     }
-                    tmem_ld_wait();
                 }
             }
             tc_fence_before();  // the next tile's staging arrive tells the MMA thread the accumulators are drained
-            // the two column halves of a row meet through a scratch line of the (now idle) A buffer
+            // the column groups of a row meet through scratch lines in the (now idle) A buffer
             float2 *scratch = reinterpret_cast<float2 *>(act + SCRATCH_OFF);
-            if (half == 1) scratch[m] = make_float2(a0, a1);
+            if (part > 0) scratch[(part - 1) * TILE_M + m] = make_float2(a0, a1);
             epi_bar();
-            if (half == 0 && valid && p.actions) {
-                const float2 o = scratch[m];
-                a0 = tanhf(a0 + o.x + __ldg(p.b4));
-                a1 = tanhf(a1 + o.y + __ldg(p.b4 + 1));
+            if (part == 0 && valid && p.actions) {
+#pragma unroll
+                for (int q = 0; q < NPART - 1; ++q) { const float2 o = scratch[q * TILE_M + m]; a0 += o.x; a1 += o.y; }
+                a0 = tanhf(a0 + __ldg(p.b4));
+                a1 = tanhf(a1 + __ldg(p.b4 + 1));
                 if (p.noise_scale != 0.0f) {  // choose_action: act + randn(2) * var, clamp (V2/maddpg_agent:1290-1294)
                     const float2 z = normal_pair(p.noise_seed, (unsigned)row);
                     a0 = fminf(fmaxf(fmaf(p.noise_scale, z.x, a0), -1.0f), 1.0f);
