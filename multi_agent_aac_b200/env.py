@@ -164,6 +164,16 @@ class BatchedDroneEnv:
     def _out_struct(o, only=None):
         return K.AacOut(*[o[n].data_ptr() if n in o and (only is None or n in only) else None for n in K.OUT_FIELDS])
 
+    def bind_outputs(self, tensors):
+        """Make the kernels write the named outputs straight into caller-owned tensors (same shape / dtype / device,
+        contiguous) from the next call on, e.g. a slot of a `replay.DeviceReplay` ring: no copy of the step's results."""
+        for k, t in tensors.items():
+            ref = self.out[k]
+            if t.shape != ref.shape or t.dtype != ref.dtype or t.device != ref.device or not t.is_contiguous():
+                raise ValueError("output %r must be a contiguous %s tensor of shape %s on %s" % (k, ref.dtype, tuple(ref.shape), ref.device))
+            self.out[k] = t
+        self._out_c = self._out_struct(self.out)
+
     def _stream_ptr(self):
         s = self.stream if self.stream is not None else torch.cuda.current_stream(self.device)
         return C.c_void_p(s.cuda_stream)

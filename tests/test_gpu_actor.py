@@ -121,3 +121,50 @@ def test_policy_rollout_through_env():
         assert act.shape == (300, 10, 2) and np.abs(act.reshape(3000, 2).cpu().numpy() - ref).max() <= 2e-2
         obs, reward, done, info = env.step(act, autoreset=True)
     assert torch.isfinite(reward).all()
+
+
+def test_device_replay_ring_is_written_in_place():
+    """Slots of the replay ring are the env's output buffers: a rollout through the ring equals the same rollout of a
+    twin env without it, slot by slot, and sampled transitions chain obs -> next_obs across slots (incl. wrap-around)."""
+    import torch
+    from multi_agent_aac_b200.actor import BatchedActor
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import synthetic_map
+    from multi_agent_aac_b200.replay import DeviceReplay, OBS_KEYS
+    from multi_agent_aac_b200.reset import OdTable
+    gmap = synthetic_map(seed=0)
+    tab = [OdTable(gmap, w_max=32)]
+    envs = []
+    for _ in range(2):
+        env = BatchedDroneEnv(preset("tdcpa_v2", n_envs=200, n_agents=6, n_rays=36, w_max=32, seed=4), gmap)
+        env.set_od_tables(tab)
+        env.reset()
+        envs.append(env)
+    ring_env, twin = envs
+    actor = BatchedActor.for_env(ring_env)
+    actor.load_state_dict(actor_oracle.reference_like_params(7, 25, 36, 2))
+    T = 6
+    ring = DeviceReplay(ring_env, T)
+    obs = ring.begin()
+    twin_obs = twin.observe()
+    log = []
+    for t in range(9):                                   # wraps the 6-slot ring
+        assert all(torch.equal(obs[k], twin_obs[k]) for k in OBS_KEYS)
+        actor(ring.current_obs(), noise_scale=0.2, noise_seed=t, out=ring.action_slot())
+        act = ring.action_slot().clone()
+        obs, reward, done, info = ring.step()
+        twin_obs, r2, d2, i2 = twin.step(act, autoreset=True)
+        assert torch.equal(reward, r2) and torch.equal(done, d2) and torch.equal(info["terminated"], i2["terminated"])
+        log.append((act, reward.clone(), {k: obs[k].clone() for k in OBS_KEYS}))
+    assert ring.filled == T - 1
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(0)
+    b = ring.sample(4096, generator=gen)
+    age = (ring.head - b["step_slot"]) % T               # 1 = newest
+    assert int(age.min()) >= 1 and int(age.max()) <= T - 1
+    for a in range(1, T):
+        sel = age == a
+        act, reward, nobs = log[-a]
+        e = b["env"][sel]
+        assert torch.equal(b["act"][sel], act[e]) and torch.equal(b["reward"][sel], reward[e])
+        assert all(torch.equal(b["next_" + k][sel], nobs[k][e]) for k in OBS_KEYS)
