@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define AAC_ABI_VERSION 1
+#define AAC_ABI_VERSION 2
 
 /* variants */
 #define AAC_VARIANT_ATT 0 /* one_model_att: radar senses other drones' 64-gons, summed reward      */
@@ -81,6 +81,9 @@ typedef struct {
     float prot;             /* 2.5   (ATT/agent:43) */
     float ray_len;          /* 15    (ATT:1066 detectionRange/2) */
     float goal_r;           /* 1     (ATT:2266) */
+    int32_t eval_by_step;   /* V2 only: args.mode == 'eval' with evaluation_by_episode == False: crashed / arrived drones stay
+                               where they are, crashes do not end the episode (V2:3729-3734, :3128-3156, :3551-3587) */
+    int32_t reserved;
 } AacConfig;
 
 /* one 10 m occupancy grid (ATT/grid_env_generation:140-185) */

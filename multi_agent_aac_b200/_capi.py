@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("AAC_LIB") or os.path.join(_HERE, "libaac_env.so")   #
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("aac_kernels.cu", "aac_capi.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "aac_kernels.cuh"), os.path.join(os.path.dirname(_HERE), "include", "aac_env.h")]
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 VARIANT_ATT, VARIANT_V2, VARIANT_MM = 0, 1, 2
 RADAR_MIN, RADAR_LAST_HIT = 0, 1
 OUT_RAW, OUT_NBR6, OUT_TCPA_PAIR, OUT_RADAR_AUX, OUT_PARTS = 0x01, 0x02, 0x04, 0x08, 0x10
@@ -33,7 +33,7 @@ class AacConfig(C.Structure):
                 ("episode_length", C.c_int32), ("out_flags", C.c_int32), ("tile_envs", C.c_int32),
                 ("block_threads", C.c_int32), ("env_id_base", C.c_int64), ("seed", C.c_uint64),
                 ("dt", C.c_float), ("vmax", C.c_float), ("acc_max", C.c_float), ("prot", C.c_float),
-                ("ray_len", C.c_float), ("goal_r", C.c_float)]
+                ("ray_len", C.c_float), ("goal_r", C.c_float), ("eval_by_step", C.c_int32), ("reserved", C.c_int32)]
 
 
 class AacMapDesc(C.Structure):

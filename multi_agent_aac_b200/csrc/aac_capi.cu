@@ -71,6 +71,7 @@ extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
         return fail(AAC_ERR_ARG, "aac_create: unknown variant");
     if (cfg->variant == AAC_VARIANT_MM && (cfg->out_flags & (AAC_OUT_NBR6 | AAC_OUT_TCPA_PAIR)))
         return fail(AAC_ERR_ARG, "aac_create: the multipleMap variant has no neighbour outputs");
+    if (cfg->eval_by_step && cfg->variant != AAC_VARIANT_V2) return fail(AAC_ERR_ARG, "aac_create: eval_by_step is a mode of the tdCPA_forV2 variant");
     if (cfg->n_envs < 1) return fail(AAC_ERR_ARG, "aac_create: n_envs < 1");
     if (cfg->n_agents < 1 || cfg->n_agents > AAC_MAX_AGENTS) return fail(AAC_ERR_ARG, "aac_create: n_agents out of range");
     if (cfg->n_rays < 1 || cfg->n_rays > AAC_MAX_RAYS || 360 % cfg->n_rays) return fail(AAC_ERR_ARG, "aac_create: n_rays must divide 360");
@@ -366,7 +367,7 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     memset(&p, 0, sizeof(p));
     const AacConfig &c = env->cfg;
     p.E = c.n_envs; p.N = c.n_agents; p.R = c.n_rays; p.W = c.w_max; p.G = env->group;
-    p.radar_mode = c.radar_mode; p.sum_reward = c.sum_reward; p.ep_len = c.episode_length; p.out_flags = c.out_flags;
+    p.radar_mode = c.radar_mode; p.sum_reward = c.sum_reward; p.ep_len = c.episode_length; p.out_flags = c.out_flags; p.eval_by_step = c.eval_by_step;
     p.cell = env->cell; p.dt = c.dt; p.vmax = c.vmax; p.acc_max = c.acc_max; p.prot = c.prot; p.ray_len = c.ray_len; p.goal_r = c.goal_r;
     p.env_id_base = c.env_id_base; p.seed = c.seed;
     p.maps = env->d_maps; p.n_maps = env->n_maps; p.ray_tab = env->d_ray; p.autoreset = autoreset;

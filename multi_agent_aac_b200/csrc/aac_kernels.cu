@@ -838,7 +838,43 @@ __device__ __forceinline__ void polyline_nearest(const MapDev &mp, const uint16_
     total = run;
 }
 
-template <int VAR, bool AUX, bool LEAN, int NT, int RT>
+// EVS, per-env lane, drone i of the env in loop order: the collision part of ss_reward_Mar's neighbour scan with the
+// crash flags as they stand at that point of the reference's loop (V2:3143-3158) - previous steps' flags, this step's
+// boundary / building flags of the drones already visited, and the drone_collision flags raised so far in this pass
+// (`dcol`).  A collision overrides the goal / normal outcome computed in the per-drone phase.
+__device__ __noinline__ void evs_collisions(const KParams &p, const Warp &w, int eb, int i, int N, int M, int Mp, unsigned &dcol) {
+    const int a = eb + i;
+    const float px = w.px[a], py = w.py[a], coll2 = 4.0f * p.prot * p.prot;
+    const unsigned old = w.meta[a], crash = M_VBOUND | M_VBLDG | M_VDRONE;
+    const int pn0 = (old >> 16) & 0xFF, pn1 = (old >> 24) & 0xFF;
+    int n_coll = 0;
+    bool prev2 = false;
+    float brg = -1.0f;
+    for (int k = 0; k < M; ++k) {
+        const int j = w.order[a * M + k], b = eb + j;
+        if (w.atgoal[b]) continue;                  // V2:3128-3130
+        if (w.d2[a * Mp + k] > coll2) break;        // neighbours come in ascending distance
+        brg = bearing_deg(px, py, w.px[b], w.py[b]);  // taken before the terminal-state test (V2:3146)
+        const unsigned fj = (j < i ? w.meta2[b] : w.meta[b]) & crash;
+        if (fj || ((dcol >> j) & 1u)) continue;     // V2:3149-3152
+        ++n_coll;
+        dcol |= (1u << i) | (1u << j);              // V2:3157-3158
+        w.meta2[b] |= M_VDRONE;
+        prev2 |= (j == pn0) || (M > 1 && j == pn1);
+    }
+    if ((dcol >> i) & 1u) w.meta2[a] |= M_VDRONE;
+    const unsigned f = w.agf[a], br = (f >> F_BRANCH_SHIFT) & 7u;
+    if (n_coll > 0 && br >= 3) {  // boundary and building come first in the branch chain (V2:3546-3567)
+        w.agf[a] = (2u << F_BRANCH_SHIFT) | ((brg >= 90.0f && brg <= 180.0f) ? F_DOUBLE : 0u) | (prev2 ? F_BBC3 : 0u);
+        w.meta2[a] = (w.meta2[a] & ~0xFFu) | (old & 0xFFu);  // no waypoint pop on the crash branch
+        if (p.out.branch) p.out.branch[w.a0 + a] = 2;
+    }
+}
+
+// EVS: forV2's evaluation "by sorties" (args.mode == 'eval' and evaluation_by_episode == False): terminal drones stay put
+// (V2:3729-3734), neighbours at their goal are invisible and crash flags are live across the drone loop (V2:3128-3158),
+// crashes do not end the episode (V2:3551-3587).  A separate instantiation: the training kernels carry none of it.
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false>
 __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_constant__ KParams p, const int mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -911,7 +947,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
             float px = p.st.px[ga], py = p.st.py[ga], vx = p.st.vx[ga], vy = p.st.vy[ga], hd = p.st.heading[ga];
             const unsigned meta = p.st.meta[ga];
             w.ppx[a] = px; w.ppy[a] = py; w.pvx[a] = vx; w.pvy[a] = vy;
-            if (mode == MODE_STEP) {
+            const bool frozen = EVS && (meta & (M_REACH | M_VBOUND | M_VBLDG | M_VDRONE));  // V2:3729-3734
+            if (mode == MODE_STEP && !frozen) {
                 const float2 act = reinterpret_cast<const float2 *>(p.actions)[ga];
                 const float cvx = fmaf(act.x * p.acc_max, p.dt, vx), cvy = fmaf(act.y * p.acc_max, p.dt, vy);
                 const float sp = sqrtf(cvx * cvx + cvy * cvy);
@@ -981,9 +1018,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                     conf_cur += c1; conf_pre += c2;
                     if (t1 >= 0.0f && t1 < imm_tcpa) { imm_tcpa = t1; imm_d = d1; imm_key = j; }
                     else if (t1 == -10.0f && d1 < imm_tcpa) { imm_tcpa = t1; imm_d = d1; imm_key = j; }
+                    if (EVS && w.atgoal[b]) continue;  // a neighbour touching its goal is invisible (V2:3114-3130)
                     const float d2 = w.d2[a * Mp + k];
                     if (d2 < shortest2) { shortest2 = d2; nearest = j; }
-                    if (d2 <= coll2) {
+                    if (!EVS && d2 <= coll2) {  // EVS: collisions depend on flags set along the drone loop: per-env pass below
                         if (VAR == AAC_VARIANT_V2) {
                             // reach_target of drone j as drone i sees it: set in earlier steps, or earlier in
                             // this step's loop when j < i (V2:3160)
@@ -1122,8 +1160,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                     if (min_radar >= p.prot && min_radar <= 5.0f) near_bldg = 3.0f * fmaf((0.0f - 1.0f) / (5.0f - p.prot), min_radar, 2.0f);  // V2:3522-3539
                     // crash rewards are filled in by the per-env lanes below: the penalty doubles along the
                     // drone loop (V2:3590-3594)
-                    if (hit_bound) { meta |= M_VBOUND; res |= F_DONE; branch = 0; }
-                    else if (collide_building) { res |= F_DONE; branch = 1; }
+                    if (hit_bound) { meta |= M_VBOUND; res |= EVS ? 0u : F_DONE; branch = 0; }
+                    else if (collide_building) { res |= EVS ? 0u : F_DONE; branch = 1; }
                     else if (n_coll > 0) {
                         res |= F_DONE; branch = 2;
                         const float brg = bearing_deg(px, py, w.px[eb + last_coll], w.py[eb + last_coll]);
@@ -1158,9 +1196,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
             if (lane < w.ng) {
                 const int ge = w.e_lo + lane, eb = lane * N;
                 float cp = 20.0f, sum = 0.0f;
-                unsigned bbc = 0, any_done = 0, all_reach = 1, n_reach = 0, any_goal = 0;
+                unsigned bbc = 0, any_done = 0, all_reach = 1, n_reach = 0, any_goal = 0, evs_dcol = 0;
 #pragma unroll 1
                 for (int i = 0; i < N; ++i) {
+                    if (EVS) evs_collisions(p, w, eb, i, N, M, Mp, evs_dcol);
                     const unsigned f = w.agf[eb + i], br = (f >> F_BRANCH_SHIFT) & 7u;
                     if (VAR == AAC_VARIANT_V2 && br <= 2) {
                         if (f & F_DOUBLE) cp *= 2.0f;
@@ -1245,11 +1284,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
     }
 }
 
-template <int VAR, bool AUX, bool LEAN, int NT, int RT>
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false>
 static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     const int wpc = threads / 32;
     const int groups = (p.E + p.G - 1) / p.G;
-    auto fn = env_kernel<VAR, AUX, LEAN, NT, RT>;
+    auto fn = env_kernel<VAR, AUX, LEAN, NT, RT, EVS>;
     static int opted_in[64] = {0};   // dynamic shared memory this instantiation has opted in to, per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1293,6 +1332,9 @@ cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threa
             if (p.N == 3 && p.R == 18) return launch_aux<AAC_VARIANT_MM, 3, 18>(p, mode, threads, sms, grid_cache, stream);
             return launch_aux<AAC_VARIANT_MM, 0, 0>(p, mode, threads, sms, grid_cache, stream);
         case AAC_VARIANT_V2:
+            if (p.eval_by_step)  // evaluation mode: one generic instantiation per output set
+                return (p.out_flags & AAC_OUT_RADAR_AUX) ? launch_one<AAC_VARIANT_V2, true, false, 0, 0, true>(p, mode, threads, sms, grid_cache, stream)
+                                                         : launch_one<AAC_VARIANT_V2, false, false, 0, 0, true>(p, mode, threads, sms, grid_cache, stream);
             // the benchmark configurations get kernels specialised on the drone and ray counts (register-resident
             // neighbour sort, constant loop bounds and addressing); everything else runs the generic kernel
             if (p.N == 10 && p.R == 36) return launch_aux<AAC_VARIANT_V2, 10, 36>(p, mode, threads, sms, grid_cache, stream);

@@ -59,7 +59,7 @@ struct WarpLayout {
 
 struct KParams {
     int E, N, R, W, G;      // G = envs per warp (G * N <= 32)
-    int radar_mode, sum_reward, ep_len, out_flags;
+    int radar_mode, sum_reward, ep_len, out_flags, eval_by_step;
     float dt, vmax, acc_max, prot, ray_len, goal_r;
     float cell;             // cell size shared by every map of the handle
     long long env_id_base;

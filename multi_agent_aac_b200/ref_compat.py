@@ -215,8 +215,14 @@ class RefCompatEnvV2(RefCompatEnv):
     variant = "v2"
 
     def step(self, actions, current_ts, acc_max=None, args=None, evaluation_by_episode=True, full_observable_critic_flag=False):
-        if args is not None and getattr(args, "mode", "train") == "eval" and not evaluation_by_episode:
-            raise NotImplementedError("eval-by-step mode (V2:3729-3734) is not part of the accelerated path")
+        # evaluation "by sorties" (V2:3729-3734): the underlying env is rebuilt once in that mode, keeping its state
+        by_step = args is not None and getattr(args, "mode", "train") == "eval" and not evaluation_by_episode
+        if by_step != bool(self._env.cfg.eval_by_step):
+            import dataclasses
+            sd = self._env.state_dict()
+            self._env.close()
+            self._env = BatchedDroneEnv(dataclasses.replace(self._env.cfg, eval_by_step=by_step), self.gmap, device=self._device)
+            self._env.load_state_dict(sd)
         return super().step(actions, current_ts, acc_max)
 
     def ss_reward_Mar(self, current_ts, step_reward_record, step_collision_record, xy, full_observable_critic_flag, args=None,

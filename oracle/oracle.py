@@ -25,7 +25,7 @@ class OracleCfg(C.Structure):
                 ("radar_mode", C.c_int32), ("sum_reward", C.c_int32), ("gx", C.c_int32), ("gy", C.c_int32),
                 ("dt", C.c_double), ("vmax", C.c_double), ("acc_max", C.c_double), ("prot", C.c_double),
                 ("ray_len", C.c_double), ("goal_r", C.c_double), ("bound", C.c_double * 4),
-                ("x0c", C.c_double), ("y0c", C.c_double), ("cell", C.c_double)]
+                ("x0c", C.c_double), ("y0c", C.c_double), ("cell", C.c_double), ("eval_by_step", C.c_int32), ("pad_", C.c_int32)]
 
 
 _STATE_FIELDS = ["pos", "vel", "heading", "reach", "wp_cur", "wall_cnt", "prev_nn", "vflags", "ref_line", "ref_w", "wp_mask"]
@@ -67,7 +67,7 @@ class OracleEnv:
     multipleMap variant, a list of them (env e lives on maps[env_map[e]])."""
 
     def __init__(self, variant, gmap, n_envs, n_agents, n_rays=18, w_max=32, radar_mode=None, sum_reward=None,
-                 vmax=5.0, acc_max=None):
+                 vmax=5.0, acc_max=None, eval_by_step=False):
         maps = list(gmap) if isinstance(gmap, (list, tuple)) else [gmap]
         self.variant, self.maps, self.gmap = variant, maps, maps[0]
         self.E, self.N, self.R, self.w_max = n_envs, n_agents, n_rays, w_max
@@ -88,6 +88,7 @@ class OracleEnv:
             for q in range(4):
                 cfg.bound[q] = float(m.bound[q])
             cfg.x0c, cfg.y0c, cfg.cell = m.x0c, m.y0c, float(m.grid_length)
+            cfg.eval_by_step = int(bool(eval_by_step))
             self.occ[k, :m.gx * m.gy] = np.ascontiguousarray(m.occ, dtype=np.uint8).reshape(-1)
         self.cfg = self.cfgs[0]
         self.env_map = np.zeros(n_envs, dtype=np.int32)

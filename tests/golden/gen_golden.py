@@ -28,6 +28,10 @@ CASES = {
     "v2_n4_cluster": ("v2", 4, 4, 80, 100, 10.0, 0.0, 18, 0, "random"),
     "v2_n4_near": ("v2", 4, 13, 120, 100, 12.0, 5.5, 18, 0, "seek"),
     "v2_n6_near_r36": ("v2", 6, 5, 70, 100, 16.0, 5.5, 36, 1, "random"),
+    # forV2 evaluation "by sorties" (an 11th field = eval_by_step): crashed / arrived drones stay put, episodes run on
+    "v2_n3_evalstep_seek": ("v2", 3, 35, 160, 80, None, 0.0, 18, 0, "seek", 1),
+    "v2_n4_evalstep_cluster": ("v2", 4, 41, 100, 40, 7.0, 5.2, 18, 0, "random", 1),
+    "v2_n5_evalstep_cluster": ("v2", 5, 31, 90, 30, 9.0, 0.0, 18, 0, "random", 1),
 }
 
 
@@ -92,15 +96,18 @@ def main_mm(names=None):
 
 
 def main(names=None):
-    for name, (variant, n, seed, steps, ep_len, cl, sep, rays, mseed, policy) in CASES.items():
+    for name, case in CASES.items():
+        variant, n, seed, steps, ep_len, cl, sep, rays, mseed, policy = case[:10]
+        evs = int(case[10]) if len(case) > 10 else 0
         if names and name not in names:
             continue
         t = time.time()
         gmap = synthetic_map(seed=mseed)
-        r = H.rollout(variant, gmap, n, seed, steps, ep_len, cluster_radius=cl, n_rays=rays, cluster_min_sep=sep, policy=policy)
+        r = H.rollout(variant, gmap, n, seed, steps, ep_len, cluster_radius=cl, n_rays=rays, cluster_min_sep=sep, policy=policy,
+                      eval_by_step=bool(evs))
         d = pack(r)
         d["meta_variant"] = np.array(variant)
-        d["meta"] = np.array([n, seed, steps, ep_len, rays, mseed])
+        d["meta"] = np.array([n, seed, steps, ep_len, rays, mseed] + ([evs] if evs else []))
         d["occ"] = gmap.occ
         d["bound"] = np.array(gmap.bound, dtype=np.float64)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)

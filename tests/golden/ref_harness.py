@@ -143,7 +143,7 @@ def pack_state_v2(state, n):
 
 
 def rollout(variant, gmap, n_agents, seed, n_steps, episode_length, action_scale=1.0, max_spd=5, acc_max=8,
-            quiet=True, cluster_radius=None, n_rays=18, cluster_min_sep=0.0, policy="random"):
+            quiet=True, cluster_radius=None, n_rays=18, cluster_min_sep=0.0, policy="random", eval_by_step=False):
     """Seeded rollout of the reference env with auto-reset on (any done | all goal | step cap).
 
     Returns a dict of stacked per-step arrays plus the per-episode reset data."""
@@ -157,7 +157,10 @@ def rollout(variant, gmap, n_agents, seed, n_steps, episode_length, action_scale
     rng = np.random.default_rng(seed)
     crng = np.random.default_rng(seed + 7919)
     random.seed(seed)
-    args = SimpleNamespace(mode="train")
+    # eval_by_step: the forV2 evaluation mode "by sorties" (args.mode == 'eval', evaluation_by_episode == False):
+    # terminal drones stay where they are, crashes do not end the episode (V2:3729-3734, :3128-3156, :3551-3587)
+    args = SimpleNamespace(mode="eval" if eval_by_step else "train")
+    by_episode = not eval_by_step
     rec = {k: [] for k in ("actions", "reward", "done", "check_goal", "bbc", "pos", "vel", "reach", "n_wp",
                            "heading", "episode_id", "step_in_ep", "srr")}
     obs_keys = ("own", "radar", "nbr6") if variant == "att" else ("own", "nbr", "radar", "nbr6")
@@ -221,8 +224,8 @@ def rollout(variant, gmap, n_agents, seed, n_steps, episode_length, action_scale
                 esh = [None] * n_agents
                 rw = env.ss_reward(ep_step, srr, esh, scr, (None, None), True, args)
             else:
-                out = env.step(act, ep_step, acc_max, args, True, False)
-                rw = env.ss_reward_Mar(ep_step, srr, scr, (None, None), False, args, True)
+                out = env.step(act, ep_step, acc_max, args, by_episode, False)
+                rw = env.ss_reward_Mar(ep_step, srr, scr, (None, None), False, args, by_episode)
             st, nst = out[0], out[1]
             reward, done, check_goal, srr_out, _, _, bbc = rw
             pk = pack_state_att if variant == "att" else pack_state_v2

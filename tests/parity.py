@@ -43,8 +43,9 @@ def np_out(env):
 class GpuGoldenAdapter:
     """OracleEnv surface (set_episode / observe / step / .state) over a 1-env BatchedDroneEnv."""
 
-    def __init__(self, variant, gmap, n_agents, n_rays, device="cuda:0"):
-        cfg = preset("att" if variant == "att" else "tdcpa_v2", n_envs=1, n_agents=n_agents, n_rays=n_rays, w_max=32, out_flags=ALL_OUT)
+    def __init__(self, variant, gmap, n_agents, n_rays, device="cuda:0", eval_by_step=False):
+        cfg = preset("att" if variant == "att" else "tdcpa_v2", n_envs=1, n_agents=n_agents, n_rays=n_rays, w_max=32, out_flags=ALL_OUT,
+                     eval_by_step=eval_by_step)
         self.env = BatchedDroneEnv(cfg, gmap, device=device)
         self.variant = variant
         self.state = {}
@@ -242,7 +243,7 @@ def compare_obs(T, variant, g, o, where, env_ok, s_gpu, orc, rows=None):
 
 
 def lockstep(variant, n_envs, n_agents, n_rays, steps, seed=0, radar_mode=None, n_scen=128, cluster=None, map_seed=0,
-             device="cuda:0", autoreset=True, tile_envs=0, block_threads=0, action_scale=1.0):
+             device="cuda:0", autoreset=True, tile_envs=0, block_threads=0, action_scale=1.0, eval_by_step=False):
     """Returns a Tally.  `cluster` = radius (m): after every reset drones 1.. are moved next to drone 0 so
     that drone-radar / near-drone / collision branches fire."""
     E, N, R, M = n_envs, n_agents, n_rays, n_agents - 1
@@ -257,11 +258,11 @@ def lockstep(variant, n_envs, n_agents, n_rays, steps, seed=0, radar_mode=None, 
     else:
         gmap = synthetic_map(seed=map_seed)
         cfg = preset("att" if variant == "att" else "tdcpa_v2", n_envs=E, n_agents=N, n_rays=R, w_max=32, out_flags=ALL_OUT,
-                     radar_mode=radar_mode, seed=seed, tile_envs=tile_envs, block_threads=block_threads)
+                     radar_mode=radar_mode, seed=seed, tile_envs=tile_envs, block_threads=block_threads, eval_by_step=eval_by_step)
         bank = ScenarioBank(gmap, N, n_scen, w_max=32, seed=seed)
     env = BatchedDroneEnv(cfg, gmap, device=device)
     env.set_bank(bank)
-    orc = OracleEnv(variant, gmap, E, N, R, w_max=32, radar_mode=radar_mode)
+    orc = OracleEnv(variant, gmap, E, N, R, w_max=32, radar_mode=radar_mode, eval_by_step=eval_by_step)
     rng = np.random.default_rng(seed + 1)
     T = Tally()
 

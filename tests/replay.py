@@ -15,7 +15,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def load_case(name):
     d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     variant = str(d["meta_variant"])
-    n, seed, steps, ep_len, rays, mseed = [int(v) for v in d["meta"]]
+    n, seed, steps, ep_len, rays, mseed = [int(v) for v in d["meta"][:6]]   # a 7th entry = eval_by_step (forV2 "by sorties")
     gmap = GridMap([int(v) for v in d["bound"]], 10, d["occ"].astype(np.uint8))
     return d, variant, n, rays, ep_len, gmap
 

@@ -24,7 +24,7 @@ def _built():
 def test_golden_replay(name):
     """The unmodified reference's recorded rollouts, replayed through the CUDA env (teacher forced)."""
     d, variant, n, rays, ep_len, gmap = load_case(name)
-    ad = parity.GpuGoldenAdapter(variant, gmap, n, rays)
+    ad = parity.GpuGoldenAdapter(variant, gmap, n, rays, eval_by_step=len(d["meta"]) > 6 and bool(d["meta"][6]))
     diff = replay(ad, d, variant, rtol=1e-4, atol=2e-4, resync=ad.resync)
     assert not diff.fail, "\n".join(diff.fail[:10])
 
@@ -175,12 +175,13 @@ def test_partial_reset_leaves_other_envs_untouched():
     assert (env.state["vx"][mask != 0] == 0).all()
 
 
-@pytest.mark.parametrize("name", ["att_n3_plain", "v2_n3_plain"])
+@pytest.mark.parametrize("name", ["att_n3_plain", "v2_n3_plain", "v2_n3_evalstep_seek"])
 def test_ref_compat_env_reproduces_reference_episode(name):
     """The drop-in class (reference method names / nested-list tuples, E = 1): with `random.seed(k)` it draws
     the reference's first episode, and free-running on the recorded actions it tracks the reference's
     float64 rollout for that episode."""
     import random
+    from types import SimpleNamespace
     import numpy as np
     from multi_agent_aac_b200.ref_compat import RefCompatEnv, RefCompatEnvV2
     d, variant, n, rays, ep_len, gmap = load_case(name)
@@ -203,8 +204,10 @@ def test_ref_compat_env_reproduces_reference_episode(name):
             out = env.step(d["actions"][t], t + 1, 8, None)
             rw = env.ss_reward(t + 1, srr, [None] * n, scr, (None, None), True, None)
         else:
-            out = env.step(d["actions"][t], t + 1, 8, None, True, False)
-            rw = env.ss_reward_Mar(t + 1, srr, scr, (None, None), False, None, True)
+            by_step = len(d["meta"]) > 6 and bool(d["meta"][6])   # forV2 evaluation "by sorties"
+            args = SimpleNamespace(mode="eval" if by_step else "train")
+            out = env.step(d["actions"][t], t + 1, 8, args, not by_step, False)
+            rw = env.ss_reward_Mar(t + 1, srr, scr, (None, None), False, args, not by_step)
         assert len(out) == 8 and len(rw) == 7
         reward, done, check_goal, _, _, _, bbc = rw
         assert np.allclose(np.stack(out[0][0])[:, :4], d["raw_own"][t][:, :4], rtol=1e-4, atol=2e-3), t
@@ -458,3 +461,12 @@ def test_lean_kernel_equals_full_kernel(variant, n, r):
         for k in envs[0].state:
             assert torch.equal(envs[0].state[k].view(torch.uint8), envs[1].state[k].view(torch.uint8)), (t, k)
     assert envs[0].read_stats()[0] == envs[1].read_stats()[0] > 0
+
+
+def test_lockstep_v2_eval_by_step():
+    """forV2's evaluation "by sorties": terminal drones stay put, crash flags are live along the drone loop, crashes do not
+    end the episode - clustered starts so that drone collisions, frozen neighbours and goal contacts all occur."""
+    T = parity.lockstep(variant="v2", n_envs=96, n_agents=6, n_rays=36, steps=40, seed=21, cluster=9.0, eval_by_step=True)
+    assert not T.fail, "\n".join(T.fail[:10])
+    T = parity.lockstep(variant="v2", n_envs=64, n_agents=10, n_rays=18, steps=30, seed=22, eval_by_step=True)
+    assert not T.fail, "\n".join(T.fail[:10])
