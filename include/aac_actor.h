@@ -75,6 +75,10 @@ int aac_actor_forward(AacActor *actor, const float *own, const float *nbr, const
 int aac_actor_hidden(AacActor *actor, const float *own, const float *nbr, const float *grid, int32_t n_rows, int32_t layer, float *hidden,
                      void *stream);
 
+/* Tuning aid: with AAC_ACTOR_PROF=1 in the environment at aac_actor_create, the kernel accumulates per-CTA phase clocks
+ * (staging, wait / epilogue of layers 1-3); copies [n_ctas][8] + 128 int64 to host_out and returns n_ctas. */
+int aac_actor_prof(AacActor *actor, long long *host_out);
+
 int64_t aac_actor_launch_count(const AacActor *actor); /* kernels launched by this handle so far */
 const char *aac_actor_last_error(void);
 

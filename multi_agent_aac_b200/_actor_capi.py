@@ -15,7 +15,7 @@ HEADERS = [os.path.join(os.path.dirname(_HERE), "include", "aac_actor.h")]
 
 ABI_VERSION = 1
 H1, H2, H3, NACT = 128, 512, 256, 2
-EXPORTS = ["aac_actor_create", "aac_actor_destroy", "aac_actor_load", "aac_actor_forward", "aac_actor_hidden", "aac_actor_launch_count",
+EXPORTS = ["aac_actor_create", "aac_actor_destroy", "aac_actor_load", "aac_actor_forward", "aac_actor_hidden", "aac_actor_prof", "aac_actor_launch_count",
            "aac_actor_last_error"]
 PARAM_FIELDS = ["w_own", "b_own", "w_nbr", "b_nbr", "w_grid", "b_grid", "w_merge", "b_merge", "w_hid", "b_hid", "w_out", "b_out"]
 
@@ -66,6 +66,7 @@ def lib():
     L.aac_actor_load.argtypes = [P, C.POINTER(AacActorParams)]
     L.aac_actor_forward.argtypes = [P, P, P, P, C.c_int32, C.c_float, C.c_uint64, P, P]
     L.aac_actor_hidden.argtypes = [P, P, P, P, C.c_int32, C.c_int32, P, P]
+    L.aac_actor_prof.argtypes = [P, P]
     L.aac_actor_launch_count.argtypes = [P]
     L.aac_actor_launch_count.restype = C.c_int64
     L.aac_actor_last_error.restype = C.c_char_p

@@ -76,7 +76,6 @@ struct KArgs {
     float noise_scale;
     unsigned long long noise_seed;
     int raw_off;      // byte offset in the A buffer for bulk-fetched fp32 observations, 0 = fetch rows with plain loads
-    int dbg_nocopy;   // tuning aid: after the first pass over the ring, signal slots full without copying
     long long *prof;  // optional [gridDim.x][8] phase clocks of epilogue thread 0 (tuning aid)
 };
 
@@ -172,7 +171,6 @@ __device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
-__device__ __forceinline__ float leaky(float x) { return fmaxf(x, 0.01f * x); }
 // (x0, x1) <- leaky((x0, x1) + (b0, b1)) with the packed fp32 pair instructions of sm_100 (FADD2 / FMUL2): the same
 // roundings as the scalar form, two thirds of the instructions
 __device__ __forceinline__ void bias_leaky2(unsigned &x0, unsigned &x1, float b0, float b1) {
@@ -301,16 +299,12 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
 
     if (warp == PRODUCER_WARP) {
         if (lane == 0) {
-            unsigned s = 0, ph = 0, first = N_SLOTS;
+            unsigned s = 0, ph = 0;
             for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
                 for (int c = 0; c < p.n_chunks; ++c) {
                     mbar_wait(empty + s, ph ^ 1u);  // slot free (passes at once the first time round)
-                    if (p.dbg_nocopy && first == 0) mbar_arrive(full + s);  // tuning aid: reuse what the first pass loaded
-                    else {
-                        mbar_expect_tx(full + s, sched[c].bytes);
-                        bulk_g2s(ring + s * SLOT_BYTES, p.wpack + sched[c].src_off, sched[c].bytes, full + s);
-                    }
-                    if (first) --first;
+                    mbar_expect_tx(full + s, sched[c].bytes);
+                    bulk_g2s(ring + s * SLOT_BYTES, p.wpack + sched[c].src_off, sched[c].bytes, full + s);
                     if (++s == N_SLOTS) { s = 0; ph ^= 1u; }
                 }
         }
@@ -673,10 +667,8 @@ static int actor_launch(AacActor *a, const float *own, const float *nbr, const f
     // bulk fetch needs 16-byte aligned blocks and room for the raw tile between the input operand and the scratch line
     const int raw_bytes = TILE_M * 4 * (k.d_own + k.d_nbr + k.d_grid);
     const bool aligned = ((uintptr_t)own % 16 == 0) && ((uintptr_t)nbr % 16 == 0) && ((uintptr_t)grid % 16 == 0);
-    k.raw_off = (aligned && a->blk_end * BLK_BYTES + raw_bytes <= SCRATCH_OFF && !getenv("AAC_ACTOR_NOBULK")) ? a->blk_end * BLK_BYTES : 0;
-    k.dbg_nocopy = getenv("AAC_ACTOR_NOCOPY") ? 1 : 0;
-    int grid_dim = k.n_tiles < a->sms ? k.n_tiles : a->sms;
-    if (const char *g = getenv("AAC_ACTOR_GRID")) grid_dim = atoi(g) > 0 && atoi(g) < grid_dim ? atoi(g) : grid_dim;  // tuning aid
+    k.raw_off = (aligned && a->blk_end * BLK_BYTES + raw_bytes <= SCRATCH_OFF) ? a->blk_end * BLK_BYTES : 0;
+    const int grid_dim = k.n_tiles < a->sms ? k.n_tiles : a->sms;
     if (dbg) actor_kernel<true><<<grid_dim, THREADS, SMEM_TOTAL, (cudaStream_t)stream>>>(k);
     else actor_kernel<false><<<grid_dim, THREADS, SMEM_TOTAL, (cudaStream_t)stream>>>(k);
     const cudaError_t e = cudaGetLastError();
