@@ -82,6 +82,45 @@ int aac_actor_prof(AacActor *actor, long long *host_out);
 int64_t aac_actor_launch_count(const AacActor *actor); /* kernels launched by this handle so far */
 const char *aac_actor_last_error(void);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * The attention actor of the one_model_att variant: ActorNetwork_ATT_TwoPortion (ATT/Nnetworks:177-213), called one drone
+ * at a time by choose_action (ATT/maddpg_agent:455-503) on [obs, obs_grid, obs_nei] = the env step's norm_own / radar /
+ * norm_nbr6 outputs:
+ *   own [d_own] -> Linear(64) + ReLU = own_obs;  grid [d_grid] -> Linear(64) + ReLU;  nei [n_nei, d_nei] -> Linear(64) + ReLU = x_e
+ *   score_m = k(x_e[m]) . q(own_obs) / 8, softmax over the neighbours whose row does not average to zero, v_att = sum alpha_m v(x_e[m])
+ *   concat [192] -> Linear(256) + ReLU -> Linear(2) -> tanh
+ * fp32 on the CUDA cores (66 k multiply-adds per drone; this variant's batches are small), same calling conventions as
+ * above; actions get the same exploration noise + clamp (ATT/maddpg_agent:497-501). */
+typedef struct AacActorAttConfig {
+    int32_t abi_version; /* AAC_ACTOR_ABI_VERSION */
+    int32_t d_own;       /* 6 + 4 (n_agents - 1): what the env emits */
+    int32_t d_grid;      /* radar rays */
+    int32_t d_nei;       /* 6 */
+    int32_t n_nei;       /* n_agents - 1 neighbour rows per drone */
+} AacActorAttConfig;
+
+/* torch layout ([out, in] row-major), float32, HOST memory: own_fc.0, own_grid.0, neigh_fc.0, q, k, v (no bias),
+ * merge_feature.0, act_out.0 (ATT/Nnetworks:181-190) */
+typedef struct AacActorAttParams {
+    const float *w_own, *b_own;     /* [64, d_own],  [64] */
+    const float *w_grid, *b_grid;   /* [64, d_grid], [64] */
+    const float *w_nei, *b_nei;     /* [64, d_nei],  [64] */
+    const float *w_q, *w_k, *w_v;   /* [64, 64] each */
+    const float *w_merge, *b_merge; /* [256, 192],   [256] */
+    const float *w_out, *b_out;     /* [2, 256],     [2] */
+} AacActorAttParams;
+
+typedef struct AacActorAtt AacActorAtt;
+
+int aac_actor_att_create(const AacActorAttConfig *cfg, AacActorAtt **out);
+void aac_actor_att_destroy(AacActorAtt *actor);
+int aac_actor_att_load(AacActorAtt *actor, const AacActorAttParams *host_params);
+/* own [n_rows, d_own], grid [n_rows, d_grid], nei [n_rows, n_nei, d_nei], actions [n_rows, 2]: device pointers */
+int aac_actor_att_forward(AacActorAtt *actor, const float *own, const float *grid, const float *nei, int32_t n_rows, float noise_scale,
+                          uint64_t noise_seed, float *actions, void *stream);
+int64_t aac_actor_att_launch_count(const AacActorAtt *actor);
+const char *aac_actor_att_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

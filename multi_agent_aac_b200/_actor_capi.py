@@ -10,13 +10,15 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AAC_ACTOR_LIB") or os.path.join(_HERE, "libaac_actor.so")
-SOURCES = [os.path.join(_HERE, "csrc", "aac_actor.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("aac_actor.cu", "aac_actor_att.cu")]
 HEADERS = [os.path.join(os.path.dirname(_HERE), "include", "aac_actor.h")]
 
 ABI_VERSION = 1
 H1, H2, H3, NACT = 128, 512, 256, 2
 EXPORTS = ["aac_actor_create", "aac_actor_destroy", "aac_actor_load", "aac_actor_forward", "aac_actor_hidden", "aac_actor_prof", "aac_actor_launch_count",
-           "aac_actor_last_error"]
+           "aac_actor_last_error", "aac_actor_att_create", "aac_actor_att_destroy", "aac_actor_att_load", "aac_actor_att_forward",
+           "aac_actor_att_launch_count", "aac_actor_att_last_error"]
+ATT_PARAM_FIELDS = ["w_own", "b_own", "w_grid", "b_grid", "w_nei", "b_nei", "w_q", "w_k", "w_v", "w_merge", "b_merge", "w_out", "b_out"]
 PARAM_FIELDS = ["w_own", "b_own", "w_nbr", "b_nbr", "w_grid", "b_grid", "w_merge", "b_merge", "w_hid", "b_hid", "w_out", "b_out"]
 
 
@@ -26,6 +28,14 @@ class AacActorConfig(C.Structure):
 
 class AacActorParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
+
+
+class AacActorAttConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("d_own", C.c_int32), ("d_grid", C.c_int32), ("d_nei", C.c_int32), ("n_nei", C.c_int32)]
+
+
+class AacActorAttParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ATT_PARAM_FIELDS]
 
 
 class AacActorError(RuntimeError):
@@ -70,6 +80,16 @@ def lib():
     L.aac_actor_launch_count.argtypes = [P]
     L.aac_actor_launch_count.restype = C.c_int64
     L.aac_actor_last_error.restype = C.c_char_p
+    L.aac_actor_att_create.argtypes = [C.POINTER(AacActorAttConfig), C.POINTER(P)]
+    L.aac_actor_att_destroy.argtypes = [P]
+    L.aac_actor_att_destroy.restype = None
+    L.aac_actor_att_load.argtypes = [P, C.POINTER(AacActorAttParams)]
+    L.aac_actor_att_forward.argtypes = [P, P, P, P, C.c_int32, C.c_float, C.c_uint64, P, P]
+    L.aac_actor_att_launch_count.argtypes = [P]
+    L.aac_actor_att_launch_count.restype = C.c_int64
+    L.aac_actor_att_last_error.restype = C.c_char_p
+    for name in ("aac_actor_att_create", "aac_actor_att_load", "aac_actor_att_forward"):
+        getattr(L, name).restype = C.c_int
     for name in ("aac_actor_create", "aac_actor_load", "aac_actor_forward", "aac_actor_hidden"):
         getattr(L, name).restype = C.c_int
     _lib = L

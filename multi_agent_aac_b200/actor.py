@@ -107,3 +107,78 @@ class BatchedActor:
     @property
     def launch_count(self):
         return int(K.lib().aac_actor_launch_count(self._h))
+
+
+class BatchedAttActor:
+    """The attention actor of the one_model_att variant (`ActorNetwork_ATT_TwoPortion`, ATT/Nnetworks:177-213) for every
+    drone of every env in one launch: `choose_action` (ATT/maddpg_agent:455-503) on `[obs, obs_grid, obs_nei]` = the env's
+    `norm_own`, `radar`, `norm_nbr6` tensors.  fp32 on the CUDA cores (csrc/aac_actor_att.cu); no fallback path."""
+
+    _MODULES = [("own_fc.0", "own", True), ("own_grid.0", "grid", True), ("neigh_fc.0", "nei", True), ("q", "q", False), ("k", "k", False),
+                ("v", "v", False), ("merge_feature.0", "merge", True), ("act_out.0", "out", True)]
+
+    def __init__(self, d_own, d_grid, n_nei, d_nei=6, device="cuda:0"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise K.AacActorError("BatchedAttActor runs on a CUDA device only (no CPU path)")
+        self.d_own, self.d_grid, self.n_nei, self.d_nei = int(d_own), int(d_grid), int(n_nei), int(d_nei)
+        self._h = C.c_void_p()
+        cfg = K.AacActorAttConfig(K.ABI_VERSION, self.d_own, self.d_grid, self.d_nei, self.n_nei)
+        with torch.cuda.device(self.device):
+            rc = K.lib().aac_actor_att_create(C.byref(cfg), C.byref(self._h))
+        self._check(rc, "aac_actor_att_create")
+
+    @staticmethod
+    def _check(rc, what):
+        if rc != 0:
+            raise K.AacActorError("%s failed (%d): %s" % (what, rc, K.lib().aac_actor_att_last_error().decode()))
+
+    @classmethod
+    def for_env(cls, env):
+        """Actor sized for a `BatchedDroneEnv` of the att preset (own 6 + 4 (N - 1), grid R, N - 1 neighbour rows of 6)."""
+        return cls(env.D, env.R, env.N - 1, device=env.device)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and K is not None and getattr(K, "_lib", None) is not None:
+            K._lib.aac_actor_att_destroy(h)
+
+    def load_state_dict(self, sd):
+        """`sd`: the reference module's state_dict ('own_fc.0.weight', ..., 'q.weight', 'k.weight', 'v.weight')."""
+        keep, params = [], K.AacActorAttParams()
+        shapes = {"own": (64, self.d_own), "grid": (64, self.d_grid), "nei": (64, self.d_nei), "q": (64, 64), "k": (64, 64), "v": (64, 64),
+                  "merge": (256, 192), "out": (2, 256)}
+        for mod, field, has_bias in self._MODULES:
+            for kind, pre in (("weight", "w_"), ("bias", "b_")) if has_bias else (("weight", "w_"),):
+                v = sd[mod + "." + kind]
+                a = np.ascontiguousarray(v.detach().cpu().numpy() if torch.is_tensor(v) else v, dtype=np.float32)
+                want = shapes[field] if kind == "weight" else (shapes[field][0],)
+                if a.shape != want:
+                    raise ValueError("%s.%s has shape %s, expected %s" % (mod, kind, a.shape, want))
+                keep.append(a)
+                setattr(params, pre + field, a.ctypes.data)
+        with torch.cuda.device(self.device):
+            self._check(K.lib().aac_actor_att_load(self._h, C.byref(params)), "aac_actor_att_load")
+
+    def forward(self, own, grid, nei, noise_scale=0.0, noise_seed=0, out=None):
+        """actions [..., 2]; own [..., d_own], grid [..., d_grid], nei [..., n_nei, d_nei] (leading dims follow `own`)."""
+        for t, tail, name in ((own, (self.d_own,), "own"), (grid, (self.d_grid,), "grid"), (nei, (self.n_nei, self.d_nei), "nei")):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device or tuple(t.shape[-len(tail):]) != tail:
+                raise ValueError("%s must be a contiguous float32 tensor [..., %s] on %s" % (name, ", ".join(map(str, tail)), self.device))
+        n = own.numel() // self.d_own
+        if grid.numel() != n * self.d_grid or nei.numel() != n * self.n_nei * self.d_nei:
+            raise ValueError("own / grid / nei disagree on the number of rows")
+        if out is None:
+            out = torch.empty(tuple(own.shape[:-1]) + (K.NACT,), dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(K.lib().aac_actor_att_forward(self._h, own.data_ptr(), grid.data_ptr(), nei.data_ptr(), n, float(noise_scale),
+                                                  int(noise_seed), out.data_ptr(), stream), "aac_actor_att_forward")
+        return out
+
+    def __call__(self, obs, noise_scale=0.0, noise_seed=0, out=None):
+        """`obs`: the dict an att-preset `BatchedDroneEnv` returns ([obs, obs_grid, obs_nei] of ATT/maddpg_agent:457-459)."""
+        return self.forward(obs["norm_own"], obs["radar"], obs["norm_nbr6"], noise_scale, noise_seed, out)
+
+    @property
+    def launch_count(self):
+        return int(K.lib().aac_actor_att_launch_count(self._h))

@@ -51,3 +51,52 @@ def forward(sd, own, nbr, grid, hidden=False):
 def explore(act, noise, scale):
     """choose_action's exploration (V2/maddpg_agent:1290-1294)."""
     return np.clip(act + scale * noise, -1.0, 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ActorNetwork_ATT_TwoPortion (ATT/Nnetworks:177-213): the attention actor of the one_model_att variant
+#   own_fc / own_grid / neigh_fc = Linear(d, 64) + ReLU                         ATT/Nnetworks:181-183
+#   q, k, v = Linear(64, 64, bias=False)                                         ATT/Nnetworks:188-190
+#   score = k(x_e) . q(own) / sqrt(64), masked softmax over the neighbours, v_att = sum alpha v   ATT/Nnetworks:197-208
+#   merge_feature = Linear(192, 256) + ReLU; act_out = Linear(256, 2) + Tanh     ATT/Nnetworks:184-185, :210-212
+# Parity pinned: tests/golden/actor_att*.npz (outputs of the unmodified reference class in float64).
+
+ATT_KEYS = ["own_fc.0", "own_grid.0", "neigh_fc.0", "merge_feature.0", "act_out.0"]
+
+
+def reference_like_params_att(d_own, d_grid, seed=0, d_nei=6):
+    rng = np.random.default_rng(seed)
+    shapes = {"own_fc.0": (64, d_own), "own_grid.0": (64, d_grid), "neigh_fc.0": (64, d_nei), "merge_feature.0": (256, 192),
+              "act_out.0": (2, 256)}
+    sd = {}
+    for k in ATT_KEYS:
+        out_f, in_f = shapes[k]
+        lim = 1.0 / np.sqrt(in_f)
+        sd[k + ".weight"] = rng.uniform(-lim, lim, (out_f, in_f)).astype(np.float32)
+        sd[k + ".bias"] = rng.uniform(-lim, lim, (out_f,)).astype(np.float32)
+    for k in ("k", "q", "v"):
+        sd[k + ".weight"] = rng.uniform(-0.125, 0.125, (64, 64)).astype(np.float32)
+    return sd
+
+
+def forward_att(sd, own, grid, nei):
+    """float64 forward; own [B, d_own], grid [B, R], nei [B, M, 6] -> actions [B, 2]."""
+    p = {k: np.asarray(v, dtype=np.float64) for k, v in sd.items()}
+    relu = lambda x: np.maximum(x, 0.0)
+    own, grid, nei = (np.asarray(a, np.float64) for a in (own, grid, nei))
+    own_obs = relu(own @ p["own_fc.0.weight"].T + p["own_fc.0.bias"])
+    own_grid = relu(grid @ p["own_grid.0.weight"].T + p["own_grid.0.bias"])
+    x_e = relu(nei @ p["neigh_fc.0.weight"].T + p["neigh_fc.0.bias"])              # [B, M, 64]
+    q = own_obs @ p["q.weight"].T
+    k = x_e @ p["k.weight"].T
+    v = x_e @ p["v.weight"].T
+    mask = nei.mean(axis=2) != 0.0                                                   # [B, M]
+    score = np.einsum("bmc,bc->bm", k, q) / np.sqrt(64.0)
+    score = np.where(mask, score, -np.inf)
+    with np.errstate(invalid="ignore"):
+        e = np.exp(score - score.max(axis=1, keepdims=True))
+        alpha = e / e.sum(axis=1, keepdims=True)                                     # all-masked rows: nan, zeroed below
+    alpha = np.where(mask, alpha, 0.0)
+    v_att = np.einsum("bm,bmc->bc", alpha, v)
+    h = relu(np.concatenate([own_obs, own_grid, v_att], axis=1) @ p["merge_feature.0.weight"].T + p["merge_feature.0.bias"])
+    return np.tanh(h @ p["act_out.0.weight"].T + p["act_out.0.bias"])

@@ -168,3 +168,42 @@ def test_device_replay_ring_is_written_in_place():
         e = b["env"][sel]
         assert torch.equal(b["act"][sel], act[e]) and torch.equal(b["reward"][sel], reward[e])
         assert all(torch.equal(b["next_" + k][sel], nobs[k][e]) for k in OBS_KEYS)
+
+
+@pytest.mark.parametrize("name", ["actor_att", "actor_att_n5_r18"])
+def test_att_actor_matches_reference_fixture(name):
+    """ActorNetwork_ATT_TwoPortion in fp32 against the float64 outputs of the unmodified reference class: 2e-5 absolute
+    (fp32 accumulation over <= 192 terms, folded attention algebra); rows with masked and all-masked neighbours included."""
+    from multi_agent_aac_b200.actor import BatchedAttActor
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d_own, d_grid, n_nei, seed = (int(v) for v in d["dims"])
+    actor = BatchedAttActor(d_own, d_grid, n_nei)
+    actor.load_state_dict(actor_oracle.reference_like_params_att(d_own, d_grid, seed))
+    own, grid, nei = to_dev(d["own"], d["grid"], d["nei"])
+    act = actor.forward(own, grid, nei).cpu().numpy().astype(np.float64)
+    assert np.isfinite(act).all()
+    assert np.abs(act - d["act"]).max() <= 2e-5, np.abs(act - d["act"]).max()
+    assert actor.launch_count == 1
+
+
+def test_att_actor_rollout_through_env():
+    """The att-preset env's observation tensors feed the attention actor in place; ragged last block; oracle agreement."""
+    import torch
+    from multi_agent_aac_b200.actor import BatchedAttActor
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import synthetic_map
+    from multi_agent_aac_b200.reset import OdTable
+    gmap = synthetic_map(seed=0)
+    env = BatchedDroneEnv(preset("att", n_envs=1111, n_agents=3, n_rays=36, w_max=32, seed=3), gmap)
+    env.set_od_tables([OdTable(gmap, w_max=32)])
+    actor = BatchedAttActor.for_env(env)
+    sd = actor_oracle.reference_like_params_att(14, 36, 5)
+    actor.load_state_dict(sd)
+    obs = env.reset()
+    for t in range(4):
+        act = actor(obs)
+        ref = actor_oracle.forward_att(sd, obs["norm_own"].reshape(3333, 14).cpu().numpy(), obs["radar"].reshape(3333, 36).cpu().numpy(),
+                                       obs["norm_nbr6"].reshape(3333, 2, 6).cpu().numpy())
+        assert act.shape == (1111, 3, 2) and np.abs(act.reshape(3333, 2).cpu().numpy() - ref).max() <= 2e-5
+        obs, reward, done, info = env.step(actor(obs, noise_scale=0.3, noise_seed=t), autoreset=True)
+    assert torch.isfinite(reward).all()

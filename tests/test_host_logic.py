@@ -219,3 +219,13 @@ def test_actor_oracle_matches_reference_fixture():
         assert np.abs(act - d["act"]).max() < 1e-12
     noisy = actor_oracle.explore(np.array([[0.9, -0.2]]), np.array([[1.0, -1.0]]), 0.5)
     assert np.allclose(noisy, [[1.0, -0.7]])
+
+
+def test_att_actor_oracle_matches_reference_fixture():
+    import numpy as np
+    from oracle import actor_oracle
+    for name in ("actor_att", "actor_att_n5_r18"):
+        d = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        d_own, d_grid, n_nei, seed = (int(v) for v in d["dims"])
+        act = actor_oracle.forward_att(actor_oracle.reference_like_params_att(d_own, d_grid, seed), d["own"], d["grid"], d["nei"])
+        assert np.abs(act - d["act"]).max() < 1e-12
