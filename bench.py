@@ -232,6 +232,38 @@ def policy_rollout(env, dev, steps=200, warmup=5):
                          "flop_per_row": flop / rows, "dtype": "bf16 operands, f32 accumulate", "kernel": "actor_kernel (tcgen05, TMEM accumulators)"}}
 
 
+def policy_rollout_att(env, dev, steps=200, warmup=5):
+    """The canonical variant's caller side: the attention actor (ActorNetwork_ATT_TwoPortion, fp32 CUDA-core kernel) on the
+    att-preset env's observation tensors, closed loop with the step."""
+    import torch
+    from multi_agent_aac_b200.actor import BatchedAttActor
+    from oracle import actor_oracle      # parameters only (numpy Generator); nothing of the oracle is timed
+    rows = env.E * env.N
+    actor = BatchedAttActor.for_env(env)
+    actor.load_state_dict(actor_oracle.reference_like_params_att(env.D, env.R, seed=0))
+    act = torch.empty((env.E, env.N, 2), dtype=torch.float32, device=dev)
+    obs = env.observe()
+    for k in range(warmup):
+        obs = env.step(actor(obs, noise_scale=0.1, noise_seed=k, out=act), autoreset=True)[0]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize(dev)
+    ev[0].record()
+    for k in range(steps):
+        actor(obs, noise_scale=0.1, noise_seed=100 + k, out=act)
+    ev[1].record()
+    for k in range(steps):
+        obs = env.step(actor(obs, noise_scale=0.1, noise_seed=k, out=act), autoreset=True)[0]
+    ev[2].record()
+    torch.cuda.synchronize(dev)
+    actor_ms, loop_ms = ev[0].elapsed_time(ev[1]) / steps, ev[1].elapsed_time(ev[2]) / steps
+    M = env.N - 1
+    flop = 2.0 * rows * (64 * (env.D + env.R) + 3 * 64 * 64 + 2 * M * (64 * 6 + 64) + 192 * 256 + 256 * 2)
+    return {"what": "attention actor forward + env step + auto-reset, closed loop on the device", "actor_ms": actor_ms,
+            "actor_rows_per_s": rows / (actor_ms * 1e-3), "actor_tflops_fp32": flop / (actor_ms * 1e-3) / 1e12, "loop_ms_per_step": loop_ms,
+            "agent_steps_per_s": rows / (loop_ms * 1e-3), "steps": steps, "actor_launches": actor.launch_count,
+            "kernel": "actor_att_kernel (fp32 GEMM chain on the CUDA cores)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -389,6 +421,8 @@ def main():
         }
         if world == 1 and not args.no_aux and preset_name == "tdcpa_v2":
             line["policy_rollout"] = policy_rollout(env, dev)
+        if world == 1 and not args.no_aux and preset_name == "att":
+            line["policy_rollout"] = policy_rollout_att(env, dev)
         if world == 1 and not args.no_aux:   # the other single-GPU configurations of BASELINE.json, device-resident
             line["other_workloads"] = {w: quick_device_rate(w, dev) for w in ("c2", "c4") if w != args.workload}
         if not args.no_cpu and world == 1:
