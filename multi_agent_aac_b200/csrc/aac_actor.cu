@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                     tc_fence_after();
                     const unsigned a_lo = desc_lo0 + a_base + a_off16, b_lo = desc_lo0 + ring_base + s * (SLOT_BYTES >> 4);
                     const unsigned d = tmem_base + tmem_col;
+                    if (p.prof && blockIdx.x == 0) p.prof[gridDim.x * 8 + 64 + c] = clock64();  // issue time of chunk c (the last tile's survives)
                     umma_bf16(d, desc_hi | a_lo, desc_hi | b_lo, idesc, (flags & CH_FRESH) ? 0u : 1u);
                     for (unsigned j = 1; j < n_mma; ++j) umma_bf16(d, desc_hi | (a_lo + 2 * j), desc_hi | (b_lo + 2 * j), idesc, 1u);
                     umma_commit(empty + s);

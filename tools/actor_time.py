@@ -31,6 +31,7 @@ if os.environ.get("AAC_ACTOR_PROF"):
     a = np.array(buf[: n * 8], dtype=np.float64).reshape(n, 8)
     tiles = (rows + 127) // 128 / n
     print("per-tile cycles (mean over CTAs): stage %.0f | wait L1 %.0f | E1 %.0f | wait L2 %.0f | E2 %.0f | wait L3 %.0f | E3 %.0f | total %.0f" % (*(a[:, :7].mean(0) / tiles), a[:, :7].sum(1).mean() / tiles))
-    tl = np.array(buf[n * 8: n * 8 + 8], dtype=np.int64)
+    tl = np.array(buf[n * 8: n * 8 + 128], dtype=np.int64)
     names = ["stage end", "L1 done", "E1 end", "L2 done", "E2 end", "L3 done", "E3 end"]
     print("CTA 0, last tile, cycles after the end of staging:", ", ".join("%s %d" % (names[i], tl[i] - tl[0]) for i in range(7)))
+    print("MMA thread issues chunk c at:", " ".join("%d:%d" % (c, tl[64 + c] - tl[0]) for c in range(32) if tl[64 + c]))
