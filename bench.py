@@ -196,10 +196,10 @@ def policy_rollout(env, dev, steps=200, warmup=5):
     bf16 tensor peak (algorithmic flops = 2 * MACs of the six Linear layers) and the closed-loop rate."""
     import torch
     from multi_agent_aac_b200.actor import BatchedActor
-    from oracle import actor_oracle      # parameters only (numpy Generator); nothing of the oracle is timed
+    from multi_agent_aac_b200 import actor_params
     rows = env.E * env.N
     actor = BatchedActor.for_env(env)
-    actor.load_state_dict(actor_oracle.reference_like_params(env.D, 5 * (env.N - 1), env.R, seed=0))
+    actor.load_state_dict(actor_params.reference_like_params(env.D, 5 * (env.N - 1), env.R, seed=0))
     act = torch.empty((env.E, env.N, 2), dtype=torch.float32, device=dev)
     obs = env.observe()
     for k in range(warmup):
@@ -237,10 +237,10 @@ def policy_rollout_att(env, dev, steps=200, warmup=5):
     att-preset env's observation tensors, closed loop with the step."""
     import torch
     from multi_agent_aac_b200.actor import BatchedAttActor
-    from oracle import actor_oracle      # parameters only (numpy Generator); nothing of the oracle is timed
+    from multi_agent_aac_b200 import actor_params
     rows = env.E * env.N
     actor = BatchedAttActor.for_env(env)
-    actor.load_state_dict(actor_oracle.reference_like_params_att(env.D, env.R, seed=0))
+    actor.load_state_dict(actor_params.reference_like_params_att(env.D, env.R, seed=0))
     act = torch.empty((env.E, env.N, 2), dtype=torch.float32, device=dev)
     obs = env.observe()
     for k in range(warmup):
