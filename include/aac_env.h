@@ -168,6 +168,15 @@ int aac_create(const AacConfig *cfg, AacEnv **out);
 void aac_destroy(AacEnv *env);
 /* world_map / bound / allGridPoly constructor arguments (ATT:41; MM:42 takes collections) */
 int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *occ /* [M,AAC_MAP_STRIDE] */, int32_t n_maps);
+
+/* Optional (V2 / multipleMap): the radar of a drone standing on a cell centre, for every cell of every map - device arrays
+ * [n_maps][AAC_MAP_STRIDE][n_rays], cell index ix * gy + iy: `radar` as aac_observe writes it for this handle's radar_mode,
+ * `radar_min` / `radar_hit` likewise (required with AAC_OUT_RADAR_AUX), `min_bits` [n_maps][AAC_MAP_STRIDE] = the smallest
+ * IEEE bit pattern of a cell's `radar` row.  reset_world puts every drone on a cell centre (ATT:301-372), so the observation
+ * of a freshly reset env reads its ranges here instead of casting the rays again; build it with THIS library (observe on
+ * drones placed at the cell centres, as `BatchedDroneEnv.build_radar_table` does) so that the values are the ones the
+ * kernel itself computes.  The arrays stay caller-owned; all NULL removes the table; aac_set_maps removes it too. */
+int aac_set_radar_table(AacEnv *env, const float *radar, const float *radar_min, const int16_t *radar_hit, const uint32_t *min_bits);
 int aac_set_bank(AacEnv *env, const AacBank *bank);
 /* one table per map (host pointers, copied); resets draw from the tables instead of the scenario bank */
 int aac_set_od_tables(AacEnv *env, const AacOdTable *tables, int32_t n_maps);

@@ -22,7 +22,7 @@ N_STATS = 16
 STAT_NAMES = ["episodes", "steps", "return_sum", "bound_crash", "building_crash", "drone_crash", "drone_crash_nearest",
               "all_reached", "drones_reached", "step_cap"]
 
-EXPORTS = ["aac_create", "aac_destroy", "aac_set_maps", "aac_set_bank", "aac_set_od_tables", "aac_plan_path", "aac_bind_state", "aac_reset", "aac_observe",
+EXPORTS = ["aac_create", "aac_destroy", "aac_set_maps", "aac_set_radar_table", "aac_set_bank", "aac_set_od_tables", "aac_plan_path", "aac_bind_state", "aac_reset", "aac_observe",
            "aac_step", "aac_step_autoreset", "aac_autoreset", "aac_step_host", "aac_read_stats", "aac_launch_count", "aac_own_dim",
            "aac_last_error"]
 
@@ -102,6 +102,7 @@ def lib():
     L.aac_destroy.argtypes = [P]
     L.aac_destroy.restype = None
     L.aac_set_maps.argtypes = [P, C.POINTER(AacMapDesc), P, C.c_int32]
+    L.aac_set_radar_table.argtypes = [P, P, P, P, P]
     L.aac_set_bank.argtypes = [P, C.POINTER(AacBank)]
     L.aac_set_od_tables.argtypes = [P, C.POINTER(AacOdTable), C.c_int32]
     L.aac_plan_path.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, C.c_int32]

@@ -26,6 +26,9 @@ struct AacEnv {
     uint8_t *d_bank_w = nullptr;
     int32_t *d_bank_map = nullptr;
     int n_scen = 0;
+    const float *rtab = nullptr, *rtab_min = nullptr;   // caller-owned radar table (aac_set_radar_table)
+    const int16_t *rtab_hit = nullptr;
+    const uint32_t *rtab_minr = nullptr;
     OdDev *d_od = nullptr;       // origin / destination tables (one per map) and the buffers they point into
     std::vector<void *> od_bufs;
     float *d_actions = nullptr;  // staging for aac_step_host
@@ -158,6 +161,7 @@ extern "C" void aac_destroy(AacEnv *env) {
 }
 
 extern "C" int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *occ, int32_t n_maps) {
+    if (env) { env->rtab = env->rtab_min = nullptr; env->rtab_hit = nullptr; env->rtab_minr = nullptr; }   // a radar table belongs to the maps it was built for
     if (!env || !maps || !occ || n_maps < 1) return fail(AAC_ERR_ARG, "aac_set_maps: bad argument");
     if (env->cfg.variant != AAC_VARIANT_MM && n_maps != 1) return fail(AAC_ERR_ARG, "aac_set_maps: this variant uses exactly one map");
     if (n_maps > 255) return fail(AAC_ERR_ARG, "aac_set_maps: at most 255 maps");
@@ -373,6 +377,7 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     p.maps = env->d_maps; p.n_maps = env->n_maps; p.ray_tab = env->d_ray; p.autoreset = autoreset;
     p.bank_cells = env->d_bank_cells; p.bank_w = env->d_bank_w; p.bank_map = env->d_bank_map; p.n_scen = env->n_scen; p.od = env->d_od;
     p.mask = mask; p.actions = actions; p.stats = env->d_stats;
+    p.rtab = env->rtab; p.rtab_min = env->rtab_min; p.rtab_hit = env->rtab_hit; p.rtab_minr = env->rtab_minr;
     p.work = env->d_work + 2 * pair; p.parity = (int)(env->pair_launches[pair] & 1);
     p.st = env->st; p.out = *out; p.CL = env->cl; p.WL = env->wl;
     if (e_cnt > 0) {
@@ -386,6 +391,20 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     if (e != cudaSuccess) return cuda_fail(e, "env_kernel launch");
     env->launches += 1;
     env->pair_launches[pair] += 1;
+    return 0;
+}
+
+extern "C" int aac_set_radar_table(AacEnv *env, const float *radar, const float *radar_min, const int16_t *radar_hit, const uint32_t *min_bits) {
+    if (!env) return fail(AAC_ERR_ARG, "null handle");
+    if (!radar && !radar_min && !radar_hit && !min_bits) {   // remove the table
+        env->rtab = env->rtab_min = nullptr; env->rtab_hit = nullptr; env->rtab_minr = nullptr;
+        return 0;
+    }
+    if (env->cfg.variant == AAC_VARIANT_ATT) return fail(AAC_ERR_ARG, "aac_set_radar_table: the one_model_att radar senses the other drones, not the map");
+    if (!radar || !min_bits) return fail(AAC_ERR_ARG, "aac_set_radar_table: radar and min_bits are required");
+    if ((env->cfg.out_flags & AAC_OUT_RADAR_AUX) && (!radar_min || !radar_hit))
+        return fail(AAC_ERR_ARG, "aac_set_radar_table: radar_min and radar_hit are required with AAC_OUT_RADAR_AUX");
+    env->rtab = radar; env->rtab_min = radar_min; env->rtab_hit = radar_hit; env->rtab_minr = min_bits;
     return 0;
 }
 

@@ -430,7 +430,9 @@ __device__ __forceinline__ void flush_items(float *dst, int n_valid, const float
 // observation pipeline for the drones [a_lo, a_lo + n_ag) of the warp's group (whole envs):
 // neighbour order + window -> { pairs | rays | own block }.  `cells` = the lane's reference-line row.
 template <int VAR, bool AUX, bool LEAN, int NT, int RT>
-__device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, const int a_lo, const int n_ag, const uint16_t *cells) {
+__device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, const int a_lo, const int n_ag, const uint16_t *cells, const bool tab) {
+    // tab: the drones of the range have just been reset, i.e. stand on cell centres, and the handle has a radar table:
+    // their ranges are looked up (they are what this very code computes for that cell, see aac_set_radar_table)
     const int lane = w.lane;
     // NT / RT > 0: drone count / ray count known at compile time
     const int N = NT ? NT : p.N, M = N - 1, R = RT ? RT : p.R, Mp = M | 1;
@@ -490,6 +492,12 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
                 ++m;
             }
         }
+        if (VAR != AAC_VARIANT_ATT && tab) {
+            const int row = VAR == AAC_VARIANT_MM ? w.amap[a] : 0;
+            const int idx = row * MAP_STRIDE_CELLS + (int)floorf((px - mp.ex0) * mp.inv_cell) * mp.gy + (int)floorf((py - mp.ey0) * mp.inv_cell);
+            w.win[a] = make_uint2(0u, (unsigned)idx);
+            w.minr[a] = p.rtab_minr[idx];
+        } else {
         // 4x4 occupancy window covering the square the rays can reach
         const float fx = (px - p.ray_len - mp.ex0) * mp.inv_cell, fy = (py - p.ray_len - mp.ey0) * mp.inv_cell;
         const int rx0 = (int)floorf(fx), ry0 = (int)floorf(fy);
@@ -524,6 +532,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
         w.win[a] = make_uint2(mask | (lines << W_LINE_SHIFT) | slow, (unsigned)(ix0 & 0xFFFF) | ((unsigned)iy0 << 16));
         w.wrel[a] = make_float2(wx, wy);
         w.minr[a] = 0x7F800000u;
+        }
     }
     __syncwarp();
 
@@ -580,7 +589,15 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
     //      are packed into shared iterations.  Ranges are >= 0, so their bit patterns order like unsigned
     //      integers and nan (0x7FC00000) sorts above every number: the per-drone minimum the reward needs
     //      (min_radar) is one redux.sync per drone and iteration.
-    {
+    if (VAR != AAC_VARIANT_ATT && tab) {
+        const size_t rg0 = (size_t)(w.a0 + a_lo) * R;
+        for (int f = lane; f < n_ag * R; f += 32) {
+            const int q = f / R, k = f - q * R;
+            const size_t src = (size_t)w.win[a_lo + q].y * R + k;
+            p.out.radar[rg0 + f] = p.rtab[src];
+            if (AUX) { p.out.radar_min[rg0 + f] = p.rtab_min[src]; p.out.radar_hit[rg0 + f] = p.rtab_hit[src]; }
+        }
+    } else {
         const float len = p.ray_len;
         auto entry_off = [&](const float4 ray, const float cell) { return make_float2(ray.z > 0.0f ? 0.0f : cell, ray.w > 0.0f ? 0.0f : cell); };
         auto cast = [&](const int aa, const float4 ray, const float2 eo, float &out_min, int &id) -> float {
@@ -987,7 +1004,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                 a_lo = g * N; n_ag = N;
                 cl = lane < N ? row : p.st.ref_cells;
             }
-            observe_range<VAR, AUX, LEAN, NT, RT>(p, w, a_lo, n_ag, cl);
+            observe_range<VAR, AUX, LEAN, NT, RT>(p, w, a_lo, n_ag, cl, job > 0 && p.rtab != nullptr);
             if (job > 0 || mode != MODE_STEP) continue;
 
             // ---- reward / collision / goal per drone

@@ -7,6 +7,7 @@
 
 namespace aac {
 
+constexpr int MAP_STRIDE_CELLS = 1024;   // rows per map in the radar table (= AAC_MAP_STRIDE: gx * gy <= 1024)
 constexpr int MAP_PAD = 4;      // free cells added on every side of the occupancy bitmap
 constexpr int MAP_WORDS = 64;   // 2048 bits: (gx + 8) * (gy + 8) + 32 must fit
 constexpr int MAX_THREADS = 256;
@@ -60,6 +61,10 @@ struct WarpLayout {
 struct KParams {
     int E, N, R, W, G;      // G = envs per warp (G * N <= 32)
     int radar_mode, sum_reward, ep_len, out_flags, eval_by_step;
+    // radar of a drone standing on a cell centre, per (map, cell, ray): what every freshly reset drone observes (aac_set_radar_table)
+    const float *rtab, *rtab_min;
+    const int16_t *rtab_hit;
+    const unsigned *rtab_minr;
     float dt, vmax, acc_max, prot, ray_len, goal_r;
     float cell;             // cell size shared by every map of the handle
     long long env_id_base;

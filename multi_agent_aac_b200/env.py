@@ -191,6 +191,7 @@ class BatchedDroneEnv:
         with torch.cuda.device(self.device):
             K.check(self.L.aac_set_bank(self.h, C.byref(b)), "aac_set_bank")
         self._bank = bank
+        self.build_radar_table()
 
     def set_od_tables(self, tables):
         """Install one OdTable per map: resets then draw origins / destinations on the device (ATT:254-276)."""
@@ -208,6 +209,57 @@ class BatchedDroneEnv:
         with torch.cuda.device(self.device):
             K.check(self.L.aac_set_od_tables(self.h, arr, len(tables)), "aac_set_od_tables")
         self._od = tables
+        self.build_radar_table()
+
+    def build_radar_table(self, enable=True):
+        """reset_world puts every drone on a cell centre (ATT:301-372), so the radar a freshly reset drone sees depends on
+        (map, cell) only: it is computed once here - by this library's own observe kernel on drones placed at the centre of
+        every cell, so the values are exactly the ones a reset would compute - and installed with aac_set_radar_table; the
+        observation of a reset env then looks its ranges up.  Not for the att variant (its radar senses the other drones)."""
+        self._rtab = None
+        with torch.cuda.device(self.device):
+            K.check(self.L.aac_set_radar_table(self.h, None, None, None, None), "aac_set_radar_table")
+        if not enable or self.cfg.variant == "att":
+            return
+        import dataclasses
+        N, R, n_maps, S = self.N, self.R, len(self.maps), K.MAP_STRIDE
+        per_map = -(-S // N)                                   # probe envs per map, N cell slots each
+        cfg = dataclasses.replace(self.cfg, n_envs=n_maps * per_map, tile_envs=0, block_threads=0)
+        probe = BatchedDroneEnv(cfg, self.maps if self.cfg.variant == "mm" else self.maps[0], device=self.device, stream=self.stream)
+        px = np.zeros((n_maps, per_map * N), dtype=np.float32)
+        py = np.zeros_like(px)
+        code = np.zeros((n_maps, per_map * N), dtype=np.int64)
+        for k, m in enumerate(self.maps):
+            # the kernel's own arithmetic for a cell centre (float32; the products are exact): ex0 + (ix + 0.5) * cell
+            cell, ox, oy = np.float32(m.grid_length), np.float32(m.origin[0]), np.float32(m.origin[1])
+            ex0 = (np.float32(m.x0c) - np.float32(0.5) * cell) - ox
+            ey0 = (np.float32(m.y0c) - np.float32(0.5) * cell) - oy
+            idx = np.minimum(np.arange(per_map * N), m.gx * m.gy - 1)    # slots past the last cell repeat it
+            ix, iy = idx // m.gy, idx % m.gy
+            px[k] = ex0 + (ix.astype(np.float32) + np.float32(0.5)) * cell
+            py[k] = ey0 + (iy.astype(np.float32) + np.float32(0.5)) * cell
+            code[k] = (ix << 8) | iy
+        st, dev = probe.state, self.device
+        st["px"].copy_(torch.from_numpy(px.reshape(-1, N)).to(dev))
+        st["py"].copy_(torch.from_numpy(py.reshape(-1, N)).to(dev))
+        cells = torch.from_numpy(code.reshape(-1, N).astype(np.int16)).to(dev)
+        st["ref_cells"].zero_()
+        st["ref_cells"][:, :, 0] = cells
+        st["ref_cells"][:, :, 1] = cells
+        st["ref_w"].fill_(2)
+        if "map_id" in st:
+            st["map_id"].copy_(torch.arange(n_maps, device=dev, dtype=torch.int32).repeat_interleave(per_map))
+        probe.observe()
+        grab = lambda key: probe.out[key].reshape(n_maps, per_map * N, R)[:, :S].contiguous().clone()
+        tab = grab("radar")
+        self._rtab = {"radar": tab, "min_bits": tab.view(torch.int32).min(dim=2).values.contiguous()}   # ranges are >= 0 (nan sorts last): bit patterns order like the values
+        if "radar_min" in probe.out:
+            self._rtab["radar_min"], self._rtab["radar_hit"] = grab("radar_min"), grab("radar_hit")
+        torch.cuda.synchronize(dev)
+        probe.close()
+        ptr = lambda key: C.c_void_p(self._rtab[key].data_ptr()) if key in self._rtab else None
+        with torch.cuda.device(self.device):
+            K.check(self.L.aac_set_radar_table(self.h, ptr("radar"), ptr("radar_min"), ptr("radar_hit"), ptr("min_bits")), "aac_set_radar_table")
 
     # ------------------------------------------------------------------ the env surface
     def reset(self, mask=None):

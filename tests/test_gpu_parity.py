@@ -470,3 +470,42 @@ def test_lockstep_v2_eval_by_step():
     assert not T.fail, "\n".join(T.fail[:10])
     T = parity.lockstep(variant="v2", n_envs=64, n_agents=10, n_rays=18, steps=30, seed=22, eval_by_step=True)
     assert not T.fail, "\n".join(T.fail[:10])
+
+
+@pytest.mark.parametrize("variant,n,r,flags", [("tdcpa_v2", 10, 36, 0), ("tdcpa_v2", 6, 24, "all"), ("multimap", 3, 18, "all")])
+def test_radar_table_equals_direct_cast(variant, n, r, flags):
+    """A freshly reset drone stands on a cell centre, so its radar is looked up in the per-(map, cell) table the library builds
+    with its own observe kernel: the looked-up observation must equal, bit for bit, what the direct ray casting computes for
+    the same state (observe), and a rollout with the table must equal one without it."""
+    import torch
+    from multi_agent_aac_b200 import _capi as K
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import multimap_set, synthetic_map
+    from multi_agent_aac_b200.reset import OdTable
+    maps = multimap_set(seed=0)[:5] if variant == "multimap" else [synthetic_map(seed=0)]
+    tabs = [OdTable(m, w_max=32) for m in maps]
+    of = 0 if flags == 0 else (K.OUT_RAW | K.OUT_RADAR_AUX | K.OUT_PARTS)
+    envs = []
+    for use_table in (True, False):
+        env = BatchedDroneEnv(preset(variant, n_envs=700, n_agents=n, n_rays=r, w_max=32, seed=8, out_flags=of), maps if variant == "multimap" else maps[0])
+        env.set_od_tables(tabs)
+        if not use_table:
+            env.build_radar_table(enable=False)
+        envs.append(env)
+    with_tab, without = envs
+    assert with_tab._rtab is not None and without._rtab is None
+    with_tab.reset()
+    looked_up = {k: with_tab.out[k].clone() for k in ("radar", "radar_min", "radar_hit") if k in with_tab.out}
+    with_tab.observe()                                    # job 0 of the observe mode always casts the rays
+    for k, v in looked_up.items():
+        assert torch.equal(v.view(torch.uint8), with_tab.out[k].view(torch.uint8)), k
+    without.reset()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(3)
+    for t in range(25):
+        act = (torch.rand((700, n, 2), device="cuda", generator=gen) * 2 - 1).contiguous()
+        for env in envs:
+            env.step(act, autoreset=True)
+        for k in with_tab.out:
+            assert torch.equal(with_tab.out[k].view(torch.uint8), without.out[k].view(torch.uint8)), (t, k)
+    assert with_tab.read_stats()[0] == without.read_stats()[0] > 0
