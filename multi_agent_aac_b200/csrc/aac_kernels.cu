@@ -591,11 +591,24 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
     //      (min_radar) is one redux.sync per drone and iteration.
     if (VAR != AAC_VARIANT_ATT && tab) {
         const size_t rg0 = (size_t)(w.a0 + a_lo) * R;
-        for (int f = lane; f < n_ag * R; f += 32) {
-            const int q = f / R, k = f - q * R;
-            const size_t src = (size_t)w.win[a_lo + q].y * R + k;
-            p.out.radar[rg0 + f] = p.rtab[src];
-            if (AUX) { p.out.radar_min[rg0 + f] = p.rtab_min[src]; p.out.radar_hit[rg0 + f] = p.rtab_hit[src]; }
+        // four table reads in flight per lane (they come from L2)
+        for (int f0 = lane; f0 < n_ag * R; f0 += 128) {
+            float v[4];
+            size_t src[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int f = f0 + 32 * u, q = f / R, k = f - q * R;
+                src[u] = f < n_ag * R ? (size_t)w.win[a_lo + q].y * R + k : 0;
+                v[u] = __ldg(p.rtab + src[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int f = f0 + 32 * u;
+                if (f < n_ag * R) {
+                    p.out.radar[rg0 + f] = v[u];
+                    if (AUX) { p.out.radar_min[rg0 + f] = p.rtab_min[src[u]]; p.out.radar_hit[rg0 + f] = p.rtab_hit[src[u]]; }
+                }
+            }
         }
     } else {
         const float len = p.ray_len;
