@@ -35,6 +35,8 @@ namespace aac {
 __constant__ float2 c_n16[16];  // edge normals of the 64-gon at (i + 0.5) * 5.625 deg, i = 0..15
 __constant__ float2 c_n64[64];  // all 64 edge normals
 __constant__ float c_apo;       // cos(pi / 64): apothem of the unit 64-gon
+__device__ float2 g_n64[64];    // the same 64 normals in global memory: read with one edge per lane (a constant-bank read
+                                // with 32 different addresses would be serialised)
 
 cudaError_t upload_constants() {
     float2 n16[16], n64[64];
@@ -51,6 +53,8 @@ cudaError_t upload_constants() {
     cudaError_t e = cudaMemcpyToSymbol(c_n16, n16, sizeof(n16));
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_n64, n64, sizeof(n64));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(g_n64, n64, sizeof(n64));
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_apo, &apo, sizeof(apo));
 }
@@ -355,33 +359,74 @@ __device__ __noinline__ GenericHit radar_generic(const MapDev &mp, float px, flo
     return GenericHit{shortest, sensed, shortest_id, sensed_id};
 }
 
-// one ray against the other drones' protective 64-gons (ATT:1052-1170): entry distance, 0 inside
+// order-preserving map float <-> unsigned (for redux.sync min / max over float values)
+__device__ __forceinline__ unsigned f2ord(float f) {
+    const unsigned b = __float_as_uint(f);
+    return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned k) { return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xFFFFFFFFu)); }
+
+// one ray against the other drones' protective 64-gons (ATT:1052-1170): entry distance, 0 inside.  Called by all 32
+// lanes together (one ray each).  Few rays pass near another drone, so when at most 12 lanes need the 64 half-plane
+// clip of a neighbour the warp does them one after the other with the edges spread over the lanes (two per lane, the
+// running max / min by redux.sync - max and min do not depend on the order, the result is the serial loop's); with more
+// lanes in need every lane clips its own ray against the 64 edges in turn.
 __device__ __forceinline__ void radar_drones_ray(const float *s_px, const float *s_py, int env_base, int N, int i, float4 ray, float len,
                                                  float r, int id_base, float &out, int &out_id) {
+    constexpr unsigned ALL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
     const float dx = ray.x, dy = ray.y;
     const float px = s_px[env_base + i], py = s_py[env_base + i];
     const float apo = r * c_apo, inv_l2 = 1.0f / (len * len);
     float best = len, shortest = CUDART_INF_F;
     int best_id = -1;
     for (int j = 0; j < N; ++j) {
-        if (j == i) continue;
         const float qx = px - s_px[env_base + j], qy = py - s_py[env_base + j];
         // distance from the polygon centre to the segment; beyond r the ray cannot touch it
         float tt = -(qx * dx + qy * dy) * inv_l2;
         tt = fminf(fmaxf(tt, 0.0f), 1.0f);
         const float cx = fmaf(tt, dx, qx), cy = fmaf(tt, dy, qy);
-        if (cx * cx + cy * cy > r * r * 1.00001f) continue;
+        const bool near = j != i && !(cx * cx + cy * cy > r * r * 1.00001f);
+        const unsigned need = __ballot_sync(ALL, near);
+        if (!need) continue;
         float lo = 0.0f, hi = 1.0f;
         bool ok = true;
-        for (int e = 0; e < 64; ++e) {  // clip q + t*d to every half-plane n_e . x <= apothem
-            const float f0 = apo - fmaf(c_n64[e].x, qx, c_n64[e].y * qy);
-            const float f1 = -fmaf(c_n64[e].x, dx, c_n64[e].y * dy);
-            if (f1 == 0.0f) { if (f0 < 0.0f) { ok = false; break; } continue; }
-            const float t = -f0 / f1;
-            if (f1 > 0.0f) lo = fmaxf(lo, t); else hi = fminf(hi, t);
-            if (lo > hi) { ok = false; break; }
+        if (__popc(need) > 12) {
+            if (near)
+                for (int e = 0; e < 64; ++e) {  // clip q + t*d to every half-plane n_e . x <= apothem
+                    const float f0 = apo - fmaf(c_n64[e].x, qx, c_n64[e].y * qy);
+                    const float f1 = -fmaf(c_n64[e].x, dx, c_n64[e].y * dy);
+                    if (f1 == 0.0f) { if (f0 < 0.0f) { ok = false; break; } continue; }
+                    const float t = -f0 / f1;
+                    if (f1 > 0.0f) lo = fmaxf(lo, t); else hi = fminf(hi, t);
+                    if (lo > hi) { ok = false; break; }
+                }
+        } else {
+            const float2 n0 = g_n64[lane], n1 = g_n64[lane + 32];
+#pragma unroll 1
+            for (unsigned rest = need; rest; rest &= rest - 1) {
+                const int src = __ffs(rest) - 1;
+                const float bqx = __shfl_sync(ALL, qx, src), bqy = __shfl_sync(ALL, qy, src);
+                const float bdx = __shfl_sync(ALL, dx, src), bdy = __shfl_sync(ALL, dy, src);
+                float l_lo = 0.0f, l_hi = 1.0f;
+                bool bad = false;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float2 n = h ? n1 : n0;
+                    const float f0 = apo - fmaf(n.x, bqx, n.y * bqy);
+                    const float f1 = -fmaf(n.x, bdx, n.y * bdy);
+                    if (f1 == 0.0f) bad |= f0 < 0.0f;
+                    else {
+                        const float t = -f0 / f1;
+                        if (f1 > 0.0f) l_lo = fmaxf(l_lo, t); else l_hi = fminf(l_hi, t);
+                    }
+                }
+                const float w_lo = ord2f(__reduce_max_sync(ALL, f2ord(l_lo))), w_hi = ord2f(__reduce_min_sync(ALL, f2ord(l_hi)));
+                const bool w_bad = __ballot_sync(ALL, bad) != 0u;
+                if (lane == src) { lo = w_lo; hi = w_hi; ok = !w_bad && !(w_lo > w_hi); }
+            }
         }
-        if (!ok) continue;
+        if (!near || !ok) continue;
         const float d = lo * len;
         if (d < shortest) { shortest = d; best = d; best_id = id_base + j; }
     }
