@@ -542,6 +542,8 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
             const int idx = row * MAP_STRIDE_CELLS + (int)floorf((px - mp.ex0) * mp.inv_cell) * mp.gy + (int)floorf((py - mp.ey0) * mp.inv_cell);
             w.win[a] = make_uint2(0u, (unsigned)idx);
             w.minr[a] = p.rtab_minr[idx];
+        } else if (VAR == AAC_VARIANT_ATT) {
+            w.minr[a] = 0x7F800000u;   // the one_model_att radar senses the other drones only: no occupancy window
         } else {
         // 4x4 occupancy window covering the square the rays can reach
         const float fx = (px - p.ray_len - mp.ex0) * mp.inv_cell, fy = (py - p.ray_len - mp.ey0) * mp.inv_cell;
