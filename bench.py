@@ -59,6 +59,19 @@ def profiled_traffic(kernel_tag):
         return None
 
 
+def profiled_metric(name, kernel_tag):
+    """One counter of the committed ncu capture of the dominant kernel (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_env_kernel_v2_ncu_full_summary.csv")
+    try:
+        import csv
+        rows = {r[0]: (r[1], r[2]) for r in csv.reader(open(p)) if len(r) == 3}
+        if not all(t in rows.get("Kernel Name", ("", ""))[1] for t in kernel_tag):
+            return None
+        return float(rows[name][1])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -417,8 +430,18 @@ def main():
                          "peak_kind": peak_kind, "bytes_per_agent_step": bytes_per,
                          "kernel": "env_kernel<%s> step+autoreset" % variant.upper()},
             "clocks": clocks,
+            "roofline_issue": None,
             "episode_stats": {k: float(v) for k, v in zip(K.STAT_NAMES, stats)},
         }
+        # what actually bounds the kernel (it is not HBM): warp-instruction issue.  Instructions per launch come from the
+        # committed ncu capture, the launch time and SM clock are this run's; peak = 4 schedulers x SMs x clock.
+        inst = profiled_metric("smsp__inst_executed.sum", ("env_kernel<1,", " 10, 36")) if args.workload == "c3" else None
+        if inst and clocks and clocks.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak_issue = 4.0 * sms * clocks["sm_mhz"] * 1e6
+            line["roofline_issue"] = {"bound": "issue", "achieved": inst / (step_kernel_ms * 1e-3), "peak": peak_issue, "unit": "warp-inst/s",
+                                      "frac": inst / (step_kernel_ms * 1e-3) / peak_issue, "warp_inst_per_agent_step": inst / (envs * n),
+                                      "note": "instructions per launch from profiles/r1_env_kernel_v2_ncu_full_summary.csv; ncu itself reports smsp__issue_active and the pipe shares (profiles/README.md)"}
         if world == 1 and not args.no_aux and preset_name == "tdcpa_v2":
             line["policy_rollout"] = policy_rollout(env, dev)
         if world == 1 and not args.no_aux and preset_name == "att":
