@@ -140,3 +140,79 @@ def synthetic_map(bound=None, seed=0, grid_length=10, fill=0.25):
 def multimap_set(seed=0, grid_length=10):
     """14 synthetic maps on the multipleMap variant's bound table (MM/parameters:52-55)."""
     return [synthetic_map(b, seed=seed * 100 + k, grid_length=grid_length) for k, b in enumerate(MULTIMAP_BOUNDS)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Map ingestion (SURVEY 8f rank 4): building footprints -> occupancy grid, as ATT/grid_env_generation:108-185 does it.
+
+def _polygon_touches_squares(poly, cx, cy, h):
+    """Closed-set test `not polygon.disjoint(square)` (ATT/grid_env_generation:83,90) of one simple polygon (vertex array
+    [V, 2], closed or open ring) against the axis-aligned squares centred at (cx[k], cy[k]) with half side h: a polygon
+    vertex in a square, a square corner in the polygon, or a polygon edge crossing a square edge."""
+    p = np.asarray(poly, dtype=np.float64)
+    if np.allclose(p[0], p[-1]):
+        p = p[:-1]
+    a, b = p, np.roll(p, -1, axis=0)                                    # edges a -> b
+    cx, cy = np.asarray(cx, np.float64)[:, None], np.asarray(cy, np.float64)[:, None]
+    hit = ((np.abs(p[None, :, 0] - cx) <= h) & (np.abs(p[None, :, 1] - cy) <= h)).any(1)
+
+    def inside(x, y):                                                    # even-odd rule, boundary counts
+        x, y = x[:, None], y[:, None]
+        ax, ay, bx, by = a[None, :, 0], a[None, :, 1], b[None, :, 0], b[None, :, 1]
+        cross = (bx - ax) * (y - ay) - (by - ay) * (x - ax)
+        on = (cross == 0) & (x >= np.minimum(ax, bx)) & (x <= np.maximum(ax, bx)) & (y >= np.minimum(ay, by)) & (y <= np.maximum(ay, by))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            xi = ax + (y - ay) * (bx - ax) / (by - ay)
+        crossing = ((ay > y) != (by > y)) & (x < xi)
+        return (crossing.sum(1) % 2 == 1) | on.any(1)
+
+    def seg_hits(x0, y0, x1, y1):                                        # closed segments (x0,y0)-(x1,y1) vs every polygon edge
+        x0, y0, x1, y1 = (v[:, None] for v in (x0, y0, x1, y1))
+        ax, ay, bx, by = a[None, :, 0], a[None, :, 1], b[None, :, 0], b[None, :, 1]
+        o = lambda px, py, qx, qy, rx, ry: np.sign((qx - px) * (ry - py) - (qy - py) * (rx - px))
+        d1, d2 = o(x0, y0, x1, y1, ax, ay), o(x0, y0, x1, y1, bx, by)
+        d3, d4 = o(ax, ay, bx, by, x0, y0), o(ax, ay, bx, by, x1, y1)
+        proper = (d1 * d2 < 0) & (d3 * d4 < 0)
+        between = lambda px, py, qx, qy, rx, ry: (np.minimum(px, qx) <= rx) & (rx <= np.maximum(px, qx)) & (np.minimum(py, qy) <= ry) & (ry <= np.maximum(py, qy))
+        touch = ((d1 == 0) & between(x0, y0, x1, y1, ax, ay)) | ((d2 == 0) & between(x0, y0, x1, y1, bx, by)) | \
+                ((d3 == 0) & between(ax, ay, bx, by, x0, y0)) | ((d4 == 0) & between(ax, ay, bx, by, x1, y1))
+        return (proper | touch).any(1)
+
+    cxf, cyf = cx[:, 0], cy[:, 0]
+    for sx, sy in ((-h, -h), (h, -h), (h, h), (-h, h)):
+        hit |= inside(cxf + sx, cyf + sy)
+    corners = [(-h, -h), (h, -h), (h, h), (-h, h), (-h, -h)]
+    for (x0, y0), (x1, y1) in zip(corners[:-1], corners[1:]):
+        hit |= seg_hits(cxf + x0, cyf + y0, cxf + x1, cyf + y1)
+    return hit
+
+
+def gridmap_from_polygons(polygons, bound, grid_length=10, extent=(1800, 1300)):
+    """Building footprints (vertex lists in metres) -> GridMap, the way the reference builds `world_map_2D`
+    (ATT/grid_env_generation:140-171): grid points at multiples of `grid_length` over `extent`, a cell (the square of
+    half side grid_length / 2 around its grid point) is occupied when it is not disjoint from some footprint, holes
+    enclosed by occupied cells are filled (`ndimage.binary_fill_holes`), and the bounded map is the cells whose
+    grid point lies inside the closed bound."""
+    from scipy import ndimage
+    g, h = grid_length, grid_length / 2.0
+    nx, ny = int(math.ceil(extent[0] / g)), int(math.ceil(extent[1] / g))   # initialize_3d_array_environment's x / y extents
+    env = np.zeros((nx, ny), dtype=bool)
+    for poly in polygons:
+        p = np.asarray(poly, dtype=np.float64)
+        ix0, ix1 = max(int(math.floor((p[:, 0].min() - h) / g)), 0), min(int(math.ceil((p[:, 0].max() + h) / g)), nx - 1)
+        iy0, iy1 = max(int(math.floor((p[:, 1].min() - h) / g)), 0), min(int(math.ceil((p[:, 1].max() + h) / g)), ny - 1)
+        if ix1 < ix0 or iy1 < iy0:
+            continue
+        ix, iy = np.meshgrid(np.arange(ix0, ix1 + 1), np.arange(iy0, iy1 + 1), indexing="ij")
+        hit = _polygon_touches_squares(p, ix.ravel() * g, iy.ravel() * g, h)
+        env[ix.ravel()[hit], iy.ravel()[hit]] = True
+    env = ndimage.binary_fill_holes(env)
+    # the cells of the bounded map: grid points inside the closed bound, as the reference lists them for its occupied /
+    # free polygons (ATT/grid_env_generation:166-176; its `env_map_bounded` slice stops one index short of a bound that
+    # falls on a grid point, the polygon lists do not)
+    xl, yl = math.ceil(bound[0] / g), math.ceil(bound[2] / g)
+    gx, gy = grid_shape(bound, g)
+    occ = np.zeros((gx, gy), dtype=np.uint8)
+    sub = env[xl:xl + gx, yl:yl + gy]
+    occ[:sub.shape[0], :sub.shape[1]] = sub
+    return GridMap(list(bound), g, occ)

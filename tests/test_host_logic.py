@@ -229,3 +229,38 @@ def test_att_actor_oracle_matches_reference_fixture():
         d_own, d_grid, n_nei, seed = (int(v) for v in d["dims"])
         act = actor_oracle.forward_att(actor_oracle.reference_like_params_att(d_own, d_grid, seed), d["own"], d["grid"], d["nei"])
         assert np.abs(act - d["act"]).max() < 1e-12
+
+
+def test_gridmap_from_polygons_matches_geometry_restatement():
+    """Map ingestion (ATT/grid_env_generation:140-171): the vectorised polygon-vs-cell test against the GEOS restatement's
+    Polygon.intersects on random star-shaped (non-convex) footprints, including cells that are only touched; holes fill."""
+    import math
+    import numpy as np
+    from scipy import ndimage
+    from multi_agent_aac_b200.maps import gridmap_from_polygons, grid_shape
+    from oracle import geos_lite as G
+    rng = np.random.default_rng(5)
+    bound = [455, 680, 255, 385]
+    polys = []
+    for _ in range(12):
+        cx, cy = rng.uniform(470, 670), rng.uniform(265, 375)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, rng.integers(3, 9)))
+        rad = rng.uniform(4, 28, len(ang))
+        polys.append([(cx + r * math.cos(a), cy + r * math.sin(a)) for a, r in zip(ang, rad)])
+    polys.append([(500, 300), (520, 300), (520, 305), (500, 305)])          # edges exactly on cell borders: touching cells count
+    m = gridmap_from_polygons(polys, bound)
+    gx, gy = grid_shape(bound, 10)
+    brute = np.zeros((180, 130), dtype=bool)
+    for ix in range(180):
+        for iy in range(130):
+            if not (440 <= ix * 10 <= 700 and 240 <= iy * 10 <= 400):
+                continue
+            sq = G.Point(ix * 10, iy * 10).buffer(5, cap_style=3)
+            brute[ix, iy] = any(G.Polygon(p).intersects(sq) for p in polys)
+    brute = ndimage.binary_fill_holes(brute)
+    want = brute[46:46 + gx, 26:26 + gy]                                      # grid points 460..680 x 260..380
+    assert m.occ.shape == (gx, gy) and np.array_equal(m.occ.astype(bool), want)
+    assert m.occ[(500 - 460) // 10, (310 - 260) // 10] == 1                  # the cell above the strip touches its top edge
+    ring = [[(560, 330), (620, 330), (620, 340), (560, 340)], [(560, 370), (620, 370), (620, 380), (560, 380)],
+            [(560, 330), (570, 330), (570, 380), (560, 380)], [(610, 330), (620, 330), (620, 380), (610, 380)]]
+    assert gridmap_from_polygons(ring, bound).occ[(590 - 460) // 10, (355 - 260) // 10] == 1   # enclosed courtyard is filled
