@@ -119,6 +119,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp
+    unsigned pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -309,10 +314,12 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                 }
         }
     } else if (warp == MMA_WARP) {
-        if (lane == 0) {
+        {
             // One thread feeds the tensor core, so its instruction stream is kept short: descriptors are a constant
             // plus (address >> 4), the per-chunk fields come precomputed from the host's schedule, ring slot and
-            // parity are running counters.
+            // parity are running counters.  The whole warp walks the loop (warp-uniform values live in uniform
+            // registers, which is where tcgen05.mma takes its operands from); one elected lane issues.
+            const bool issuer = elect_one();
             unsigned s = 0, ph = 0, tile_par = 0;
             const unsigned long long desc_hi = umma_desc(0) & 0xFFFFFFFF00000000ull;
             const unsigned desc_lo0 = (unsigned)umma_desc(0);  // leading-byte-offset field; the start address is added below
@@ -326,11 +333,14 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                     tc_fence_after();
                     const unsigned a_lo = desc_lo0 + a_base + a_off16, b_lo = desc_lo0 + ring_base + s * (SLOT_BYTES >> 4);
                     const unsigned d = tmem_base + tmem_col;
-                    if (p.prof && blockIdx.x == 0) p.prof[gridDim.x * 8 + 64 + c] = clock64();  // issue time of chunk c (the last tile's survives)
-                    umma_bf16(d, desc_hi | a_lo, desc_hi | b_lo, idesc, (flags & CH_FRESH) ? 0u : 1u);
-                    for (unsigned j = 1; j < n_mma; ++j) umma_bf16(d, desc_hi | (a_lo + 2 * j), desc_hi | (b_lo + 2 * j), idesc, 1u);
-                    umma_commit(empty + s);
-                    if (flags & CH_LAYER_END) umma_commit(layer_done);
+                    if (issuer) {
+                        if (p.prof && blockIdx.x == 0) p.prof[gridDim.x * 8 + 64 + c] = clock64();  // issue time of chunk c (the last tile's survives)
+                        umma_bf16(d, desc_hi | a_lo, desc_hi | b_lo, idesc, (flags & CH_FRESH) ? 0u : 1u);
+                        for (unsigned j = 1; j < n_mma; ++j) umma_bf16(d, desc_hi | (a_lo + 2 * j), desc_hi | (b_lo + 2 * j), idesc, 1u);
+                        umma_commit(empty + s);
+                        if (flags & CH_LAYER_END) umma_commit(layer_done);
+                    }
+                    __syncwarp();
                     if (++s == N_SLOTS) { s = 0; ph ^= 1u; }
                 }
         }
