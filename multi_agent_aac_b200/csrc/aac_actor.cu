@@ -45,10 +45,10 @@ constexpr int EPI_THREADS = 128 * NPART, PRODUCER_WARP = 4 * NPART, MMA_WARP = 4
 constexpr int SCRATCH_OFF = 7 * BLK_BYTES;  // last K block of the A buffer: free between the layer-3 MMAs and the next layer-2 epilogue
 constexpr int MAX_CHUNKS = 64;
 constexpr unsigned TMEM_COLS = 512;
-constexpr unsigned CH_LAYER_END = 2u, CH_FRESH = 4u;
+constexpr unsigned CH_LAYER_END = 2u, CH_FRESH = 4u, CH_HALF_END = 8u;
 // `ready` barriers the MMA thread waits on before a chunk: the A operand blocks it reads are written and the
 // accumulator columns it overwrites are drained (one completion of each per tile)
-constexpr int RDY_STAGE = 0, RDY_E1 = 1 /* .. 3: own | nbr | grid third of layer 1's output */, RDY_E2 = 4 /* .. 5: halves of layer 2's output */, N_READY = 6;
+constexpr int RDY_STAGE = 0, RDY_E1 = 1 /* .. 3: own | nbr | grid third of layer 1's output */, RDY_E2 = 4 /* first half of layer 2's output, 5 .. 6: the two quarters of its second half */, N_READY = 7;
 constexpr int L1_COL0 = 128;  // layer 1 accumulates in TMEM columns 128 .. 511 so that columns 0 .. 255 are free for layer 2's first half as soon as the `own` third is drained
 
 // one ring slot's worth of weights and the MMAs that consume it
@@ -276,6 +276,39 @@ __device__ __forceinline__ void hidden_epilogue(uint8_t *act, unsigned tmem_row,
     }
 }
 
+// The same, in two steps: the accumulators are converted into registers (`held`) while the MMAs of the layer's other
+// half still read the A buffer, and stored once they are done.
+template <int NBLK, bool DBG>
+__device__ __forceinline__ void hidden_epilogue_hold(unsigned tmem_row, int col0, const float *bias, uint4 (&held)[4 * NBLK], float *dbg_row) {
+#pragma unroll
+    for (int u = 0; u < NBLK; ++u) {
+        const int c = col0 + 32 * u;
+        unsigned x[32];
+        tmem_ld32_issue(tmem_row + c, x);
+        float4 bv[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) bv[g] = __ldg(reinterpret_cast<const float4 *>(bias + c + 4 * g));
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float4 b0 = bv[2 * g], b1 = bv[2 * g + 1];
+            bias_leaky2(x[8 * g], x[8 * g + 1], b0.x, b0.y);
+            bias_leaky2(x[8 * g + 2], x[8 * g + 3], b0.z, b0.w);
+            bias_leaky2(x[8 * g + 4], x[8 * g + 5], b1.x, b1.y);
+            bias_leaky2(x[8 * g + 6], x[8 * g + 7], b1.z, b1.w);
+            auto f = [&](int i) { return __uint_as_float(x[8 * g + i]); };
+            held[4 * u + g] = make_uint4(pack_bf16(f(0), f(1)), pack_bf16(f(2), f(3)), pack_bf16(f(4), f(5)), pack_bf16(f(6), f(7)));
+            if (DBG && dbg_row)
+                for (int i = 0; i < 8; ++i) dbg_row[c + 8 * g + i] = f(i);
+        }
+    }
+}
+template <int NBLK>
+__device__ __forceinline__ void hidden_epilogue_store(uint8_t *act, int col0, int m, const uint4 (&held)[4 * NBLK]) {
+#pragma unroll
+    for (int q = 0; q < 4 * NBLK; ++q) *reinterpret_cast<uint4 *>(act + a_chunk((col0 >> 3) + q, m)) = held[q];
+}
+
 // ------------------------------------------------------------------------------------ kernel
 
 template <bool DBG>
@@ -283,8 +316,9 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *act = smem, *ring = smem + ACT_BYTES;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + SMEM_BARS);
-    unsigned long long *full = bars, *empty = bars + N_SLOTS, *ready = bars + 2 * N_SLOTS, *layer_done = ready + N_READY, *in_ready = layer_done + 1;
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(in_ready + 1);
+    unsigned long long *full = bars, *empty = bars + N_SLOTS, *ready = bars + 2 * N_SLOTS, *layer_done = ready + N_READY, *in_ready = layer_done + 1,
+                       *half_done = in_ready + 1;
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(half_done + 1);
     Chunk *sched = reinterpret_cast<Chunk *>(smem + SMEM_SCHED);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -294,6 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
         for (int i = 0; i < N_READY; ++i) mbar_init(ready + i, EPI_THREADS / 32);  // one arrival per epilogue warp
         mbar_init(layer_done, 1);
         mbar_init(in_ready, 1);
+        mbar_init(half_done, 1);
         fence_barrier_init();
     }
     if (warp == PRODUCER_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -339,6 +374,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                         for (unsigned j = 1; j < n_mma; ++j) umma_bf16(d, desc_hi | (a_lo + 2 * j), desc_hi | (b_lo + 2 * j), idesc, 1u);
                         umma_commit(empty + s);
                         if (flags & CH_LAYER_END) umma_commit(layer_done);
+                        if (flags & CH_HALF_END) umma_commit(half_done);   // layer 2's first output half is complete
                     }
                     __syncwarp();
                     if (++s == N_SLOTS) { s = 0; ph ^= 1u; }
@@ -349,7 +385,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
         // m = tid % 128, and on column group tid / 128 of every piece of every layer
         const int m = tid & 127, part = tid >> 7;
         const unsigned tmem_row = tmem_base + ((unsigned)((warp & 3) * 32) << 16);
-        unsigned done_phase = 0, in_phase = 0;
+        unsigned done_phase = 0, in_phase = 0, tile_par = 0;
         long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = clock64();
         auto lap = [&](int i) {
             if (p.prof) {
@@ -406,6 +442,16 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
             // the rest is still being converted: layer 1 by branch (own | nbr | grid), layer 2 by output half; in each
             // piece the NPART warp groups take an equal share of the columns
             for (int layer = 1; layer <= 2; ++layer) {
+                constexpr int NB2 = H2 / 2 / NPART / 32;
+                uint4 held[4 * NB2];
+                float *dbg2 = (DBG && p.dbg_layer == 2 && valid) ? p.dbg + row * H2 : nullptr;
+                if (layer == 2) {
+                    // layer 2's first output half is finished while the MMAs of its second half still read the A buffer:
+                    // convert it into registers now, store it when they are done
+                    mbar_wait(half_done, tile_par);
+                    tc_fence_after();
+                    hidden_epilogue_hold<NB2, DBG>(tmem_row, part * (H2 / 2 / NPART), p.b2, held, dbg2);
+                }
                 mbar_wait(layer_done, done_phase & 1u);
                 ++done_phase;
                 tc_fence_after();
@@ -419,10 +465,13 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                         publish(RDY_E1 + pc_);
                     }
                 } else {
+                    hidden_epilogue_store<NB2>(act, part * (H2 / 2 / NPART), m, held);
+                    publish(RDY_E2);
+                    // second half in two pieces of 128 columns (two K blocks of layer 3 each), 32 columns per warp group
 #pragma unroll 1
-                    for (int pc_ = 0; pc_ < 2; ++pc_) {  // 256 columns per half of the output
-                        hidden_epilogue<H2 / 2 / NPART / 32, DBG>(act, tmem_row, 0, pc_ * (H2 / 2) + part * (H2 / 2 / NPART), p.b2, m, dbg_row);
-                        publish(RDY_E2 + pc_);
+                    for (int u = 0; u < 2; ++u) {
+                        hidden_epilogue<1, DBG>(act, tmem_row, 0, H2 / 2 + 128 * u + 32 * part, p.b2, m, dbg_row);
+                        publish(RDY_E2 + 1 + u);
                     }
                 }
                 lap(layer == 1 ? 2 : 4);
@@ -483,6 +532,7 @@ __global__ void __launch_bounds__(THREADS, 1) actor_kernel(const __grid_constant
                 reinterpret_cast<float2 *>(p.actions)[row] = make_float2(a0, a1);
             }
             lap(6);
+            tile_par ^= 1u;
         }
         if (p.prof && tid == 0)
             for (int i = 0; i < 8; ++i) p.prof[blockIdx.x * 8 + i] = pc[i];
@@ -623,12 +673,13 @@ extern "C" int aac_actor_load(AacActor *a, const AacActorParams *hp) {
         for (int k0 = 0; k0 < H1C; k0 += 64) {
             add_chunk(hp->w_merge, H1C, 256 * h, 256, k0, 64, k0 / 64, 256 * h, k0 == 0 ? CH_FRESH : 0u);
             sched.back().wait_rdy = 1 + RDY_E1 + (h == 0 ? k0 / H1 : 2);
+            if (h == 0 && k0 + 64 >= H1C) sched.back().flags |= CH_HALF_END;
         }
     sched.back().flags |= CH_LAYER_END;
     // layer 3: 256 output columns, K = 512
     for (int k0 = 0; k0 < H2; k0 += 64) {
         add_chunk(hp->w_hid, H2, 0, 256, k0, 64, k0 / 64, 0, k0 == 0 ? CH_FRESH : 0u);
-        sched.back().wait_rdy = 1 + RDY_E2 + k0 / 256;
+        sched.back().wait_rdy = 1 + RDY_E2 + (k0 < 256 ? 0 : 1 + (k0 - 256) / 128);
     }
     sched.back().flags |= CH_LAYER_END;
     if ((int)sched.size() > MAX_CHUNKS) return fail(AAC_ACTOR_ERR_STATE, "aac_actor_load: chunk schedule too long");
