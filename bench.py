@@ -425,7 +425,7 @@ def main():
             "gpu_launches": int(launches),
             "kernels": {"env_kernel(step+autoreset)_ms": step_kernel_ms, "host_issue_ms_per_step": host_issue_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": profiled_traffic(("env_kernel<1,", " 10, 36>")) if args.workload == "c3" else None,
+                         "traffic": profiled_traffic(("env_kernel<1,", " 10, 36,")) if args.workload == "c3" else None,
                          "traffic_note": "bytes per launch, profiles/r1_env_kernel_v2_ncu_full_summary.csv (one ncu --set full capture)",
                          "peak_kind": peak_kind, "bytes_per_agent_step": bytes_per,
                          "kernel": "env_kernel<%s> step+autoreset" % variant.upper()},
