@@ -186,6 +186,13 @@ int aac_set_od_tables(AacEnv *env, const AacOdTable *tables, int32_t n_maps);
  * ix<<8|iy and returns the vertex count, 0 if the goal is unreachable, -1 if the path needs more than max_cells. */
 int aac_plan_path(const uint8_t *occ, int32_t gx, int32_t gy, int32_t sx, int32_t sy, int32_t tx, int32_t ty, uint16_t *out_cells,
                   int32_t max_cells);
+/* The same search and pruning for many origin / destination pairs at once ON THE DEVICE (one warp per pair; used to
+ * build a map's origin / destination table).  Host buffers: occ uint8[gx*gy] ix-major; pairs
+ * uint16[n_pairs][2] = (start, goal) cell codes ix<<8|iy; out_cells uint16[n_pairs][max_cells] (zero padded);
+ * out_len int32[n_pairs] with aac_plan_path's return convention per pair (vertex count, 0 unreachable, -1 more than
+ * max_cells vertices).  Results equal aac_plan_path's exactly.  Synchronises the stream. */
+int aac_plan_paths_device(const uint8_t *occ, int32_t gx, int32_t gy, const uint16_t *pairs, int64_t n_pairs, uint16_t *out_cells,
+                          int32_t *out_len, int32_t max_cells, void *cuda_stream);
 int aac_bind_state(AacEnv *env, const AacState *state);
 /* reset_world (ATT:199-511): re-initialise the envs whose mask byte is non-zero (NULL = all) from
  * the scenario bank and emit their first observation */

@@ -22,7 +22,7 @@ N_STATS = 16
 STAT_NAMES = ["episodes", "steps", "return_sum", "bound_crash", "building_crash", "drone_crash", "drone_crash_nearest",
               "all_reached", "drones_reached", "step_cap"]
 
-EXPORTS = ["aac_create", "aac_destroy", "aac_set_maps", "aac_set_radar_table", "aac_set_bank", "aac_set_od_tables", "aac_plan_path", "aac_bind_state", "aac_reset", "aac_observe",
+EXPORTS = ["aac_create", "aac_destroy", "aac_set_maps", "aac_set_radar_table", "aac_set_bank", "aac_set_od_tables", "aac_plan_path", "aac_plan_paths_device", "aac_bind_state", "aac_reset", "aac_observe",
            "aac_step", "aac_step_autoreset", "aac_autoreset", "aac_step_host", "aac_read_stats", "aac_launch_count", "aac_own_dim",
            "aac_last_error"]
 
@@ -106,6 +106,7 @@ def lib():
     L.aac_set_bank.argtypes = [P, C.POINTER(AacBank)]
     L.aac_set_od_tables.argtypes = [P, C.POINTER(AacOdTable), C.c_int32]
     L.aac_plan_path.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, C.c_int32]
+    L.aac_plan_paths_device.argtypes = [P, C.c_int32, C.c_int32, P, C.c_int64, P, P, C.c_int32, P]
     L.aac_bind_state.argtypes = [P, C.POINTER(AacState)]
     L.aac_reset.argtypes = [P, P, C.POINTER(AacOut), P]
     L.aac_observe.argtypes = [P, C.POINTER(AacOut), P]

@@ -318,6 +318,155 @@ extern "C" int aac_plan_path(const uint8_t *occ, int32_t gx, int32_t gy, int32_t
     return (int)keep.size();
 }
 
+// ---- the same search on the device: one warp per origin / destination pair ----------------------------------------
+// The frontier keeps discovery order; a popped entry is tombstoned in place (f = 0xFFFF) instead of erased, so "the
+// first minimum in discovery order" is the minimum of (f << 16 | position) over the live entries: the lanes scan the
+// list in strides and meet in one redux.  A cell is queued at most once, so every array is bounded by the cell count.
+// Scratch per warp (global memory, L1 / L2 resident for the reference's 23 x 13 .. 31 x 21 grids): status u8[n],
+// g u16[n], parent u16[n], frontier cell u16[n], frontier f u16[n].
+constexpr int PLAN_SCRATCH_PER_CELL = 9;
+constexpr unsigned PLAN_DEAD = 0xFFFFu;
+
+__global__ void __launch_bounds__(256) plan_paths_kernel(const uint8_t *__restrict__ occ, const int gx, const int gy, const uint16_t *__restrict__ pairs,
+                                                         const long long n_pairs, uint16_t *__restrict__ out_cells, int *__restrict__ out_len,
+                                                         const int max_cells, uint8_t *__restrict__ scratch) {
+    const unsigned FULLM = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int n = gx * gy;
+    const size_t n_al = ((size_t)n + 7) & ~(size_t)7;
+    uint8_t *status = scratch + (size_t)warp * n_al * PLAN_SCRATCH_PER_CELL;
+    uint16_t *gcost = reinterpret_cast<uint16_t *>(status + n_al), *parent = gcost + n_al, *fcell = parent + n_al, *ff = fcell + n_al;
+    for (long long pi = warp; pi < n_pairs; pi += n_warps) {
+        const int sc = pairs[2 * pi], tc = pairs[2 * pi + 1];
+        const int tx = tc >> 8, ty = tc & 255;
+        const int s = (sc >> 8) * gy + (sc & 255), t = tx * gy + ty;
+        for (int c = lane; c < n; c += 32) status[c] = 0;
+        __syncwarp();
+        if (lane == 0) { status[s] = 1; gcost[s] = 0; parent[s] = PLAN_DEAD; fcell[0] = (uint16_t)s; ff[0] = 0; }
+        __syncwarp();
+        int head = 0, tail = 1, live = 1;   // live entries lie in [head, tail)
+        bool found = false;
+        for (;;) {
+            unsigned key = 0xFFFFFFFFu;
+            for (int k = head + lane; k < tail; k += 32) {
+                const unsigned f = ff[k];
+                if (f != PLAN_DEAD) key = min(key, (f << 16) | (unsigned)k);
+            }
+            key = __reduce_min_sync(FULLM, key);
+            if (key == 0xFFFFFFFFu) break;   // frontier empty: the goal is unreachable
+            const int kb = (int)(key & 0xFFFFu), cur = fcell[kb];
+            if (cur == t) { found = true; break; }
+            const int cx = cur / gy, cy = cur - cx * gy, g1 = gcost[cur] + 1;
+            __syncwarp();
+            if (lane == 0) ff[kb] = (uint16_t)PLAN_DEAD;
+            while (head < tail && (head == kb || ff[head] == PLAN_DEAD)) ++head;   // warp-uniform: every lane reads the same entries
+            // neighbours in the reference's order (0,-1), (0,1), (-1,0), (1,0): lane d takes the d-th
+            const int nx = cx + (lane == 2 ? -1 : lane == 3 ? 1 : 0), ny = cy + (lane == 0 ? -1 : lane == 1 ? 1 : 0);
+            bool push = lane < 4 && nx >= 0 && ny >= 0 && nx < gx && ny < gy;
+            const int c = nx * gy + ny;
+            if (push) push = !occ[c] && !status[c];
+            const unsigned m = __ballot_sync(FULLM, push);
+            if (push) {
+                const int k = tail + __popc(m & ((1u << lane) - 1u));
+                status[c] = 1;
+                gcost[c] = (uint16_t)g1;
+                parent[c] = (uint16_t)cur;
+                fcell[k] = (uint16_t)c;
+                ff[k] = (uint16_t)(g1 + abs(nx - tx) + abs(ny - ty));
+            }
+            tail += __popc(m);
+            live += __popc(m) - 1;
+            __syncwarp();
+            // a long search leaves tombstones between the live entries: squeeze them out, order kept, once they outnumber
+            // the live ones (write position <= read position, a chunk is read before it is written)
+            if (tail - head > 64 && 2 * live < tail - head) {
+                int wpos = 0;
+                for (int k0 = head; k0 < tail; k0 += 32) {
+                    const int k = k0 + lane;
+                    const unsigned f = k < tail ? ff[k] : PLAN_DEAD;
+                    const unsigned cc = k < tail ? fcell[k] : 0u;
+                    const unsigned keep = __ballot_sync(FULLM, f != PLAN_DEAD);
+                    __syncwarp();
+                    if (f != PLAN_DEAD) {
+                        const int dst = wpos + __popc(keep & ((1u << lane) - 1u));
+                        ff[dst] = (uint16_t)f;
+                        fcell[dst] = (uint16_t)cc;
+                    }
+                    wpos += __popc(keep);
+                    __syncwarp();
+                }
+                head = 0;
+                tail = wpos;
+            }
+        }
+        // walk back from the goal; the cells where the direction changes are the same in either direction (ATT:321-331)
+        if (lane == 0) {
+            int cnt = 0;
+            if (found) {
+                for (int pass = 0; pass < 2; ++pass) {   // count, then write from the back
+                    int k = 0, c = t, pc = parent[c];
+                    auto emit = [&](int cell) {
+                        if (pass == 1 && cnt <= max_cells) out_cells[pi * max_cells + (cnt - 1 - k)] = (uint16_t)(((cell / gy) << 8) | (cell % gy));
+                        ++k;
+                    };
+                    emit(c);
+                    if (pc != (int)PLAN_DEAD) {
+                        int d = pc - c;   // steps are +-1 or +-gy: the index difference names the direction
+                        for (;;) {
+                            const int nc = parent[pc];
+                            if (nc == (int)PLAN_DEAD) break;
+                            const int e = nc - pc;
+                            if (e != d) { emit(pc); d = e; }
+                            pc = nc;
+                        }
+                        emit(pc);
+                    }
+                    if (pass == 0) cnt = k;
+                }
+            }
+            out_len[pi] = !found ? 0 : (cnt > max_cells ? -1 : cnt);
+        }
+        __syncwarp();
+    }
+}
+
+extern "C" int aac_plan_paths_device(const uint8_t *occ, int32_t gx, int32_t gy, const uint16_t *pairs, int64_t n_pairs, uint16_t *out_cells,
+                                     int32_t *out_len, int32_t max_cells, void *stream_) {
+    if (!occ || !pairs || !out_cells || !out_len || gx < 1 || gy < 1 || gx > 255 || gy > 255 || max_cells < 1 || n_pairs < 0)
+        return fail(AAC_ERR_ARG, "aac_plan_paths_device: bad argument");
+    if (n_pairs == 0) return 0;
+    for (int64_t k = 0; k < 2 * n_pairs; ++k)
+        if ((pairs[k] >> 8) >= gx || (pairs[k] & 255) >= gy) return fail(AAC_ERR_ARG, "aac_plan_paths_device: cell outside the grid");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int threads = 256, wpc = threads / 32;
+    int64_t grid = (n_pairs + wpc - 1) / wpc;
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;   // 8 resident CTAs of 256 threads per SM: persistent warps
+    const size_t n = (size_t)gx * gy, n_al = (n + 7) & ~(size_t)7, n_warps = (size_t)grid * wpc;
+    uint8_t *d_occ = nullptr, *d_scratch = nullptr;
+    uint16_t *d_pairs = nullptr, *d_cells = nullptr;
+    int *d_len = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+    if (ok(cudaMalloc(&d_occ, n)) && ok(cudaMalloc(&d_pairs, (size_t)n_pairs * 4)) && ok(cudaMalloc(&d_cells, (size_t)n_pairs * max_cells * 2)) &&
+        ok(cudaMalloc(&d_len, (size_t)n_pairs * 4)) && ok(cudaMalloc(&d_scratch, n_warps * n_al * PLAN_SCRATCH_PER_CELL)) &&
+        ok(cudaMemcpyAsync(d_occ, occ, n, cudaMemcpyHostToDevice, stream)) &&
+        ok(cudaMemcpyAsync(d_pairs, pairs, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, stream)) &&
+        ok(cudaMemsetAsync(d_cells, 0, (size_t)n_pairs * max_cells * 2, stream))) {
+        plan_paths_kernel<<<(unsigned)grid, threads, 0, stream>>>(d_occ, gx, gy, d_pairs, n_pairs, d_cells, d_len, max_cells, d_scratch);
+        ok(cudaGetLastError());
+        ok(cudaMemcpyAsync(out_cells, d_cells, (size_t)n_pairs * max_cells * 2, cudaMemcpyDeviceToHost, stream));
+        ok(cudaMemcpyAsync(out_len, d_len, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, stream));
+        ok(cudaStreamSynchronize(stream));
+    }
+    cudaFree(d_occ); cudaFree(d_pairs); cudaFree(d_cells); cudaFree(d_len); cudaFree(d_scratch);
+    if (e != cudaSuccess) return cuda_fail(e, "aac_plan_paths_device");
+    return 0;
+}
+
 extern "C" int aac_bind_state(AacEnv *env, const AacState *s) {
     if (!env || !s) return fail(AAC_ERR_ARG, "aac_bind_state: null argument");
     if (!s->px || !s->py || !s->vx || !s->vy || !s->heading || !s->meta || !s->ref_cells || !s->ref_w || !s->ep_step || !s->ep_index || !s->ep_return)

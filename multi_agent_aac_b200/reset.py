@@ -204,17 +204,34 @@ class MultiMapBank:
         return self.cells.shape[0]
 
 
+def plan_paths_device(gmap: GridMap, pairs, w_max=32):
+    """Reference lines for many (start cell, goal cell) pairs in one launch of the library's device planner
+    (`aac_plan_paths_device`: the reference's search and pruning, ATT/jps_straight.py:17-70 + ATT:321-331, one warp per
+    pair).  pairs: int array [n, 4] = (sx, sy, tx, ty).  Returns (cells uint16[n, w_max] codes ix<<8|iy, length int32[n])."""
+    import ctypes as C
+    from . import _capi as K
+    pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 4)
+    code = np.ascontiguousarray(np.stack([pairs[:, 0] * 256 + pairs[:, 1], pairs[:, 2] * 256 + pairs[:, 3]], axis=1).astype(np.uint16))
+    occ = np.ascontiguousarray(gmap.occ, dtype=np.uint8)
+    cells = np.zeros((len(pairs), w_max), dtype=np.uint16)
+    length = np.zeros(len(pairs), dtype=np.int32)
+    K.check(K.lib().aac_plan_paths_device(occ.ctypes.data, gmap.gx, gmap.gy, code.ctypes.data, len(pairs), cells.ctypes.data,
+                                          length.ctypes.data, w_max, None), "aac_plan_paths_device")
+    return cells, length
+
+
 class OdTable:
     """Origin / destination table of one map (include/aac_env.h AacOdTable): the four quadrant pools of free cells
     (ATT:154-197) and the pruned grid path between every start / goal pair in different quadrants, planned by the
-    library's host planner `aac_plan_path` (the reference's search and tie-breaking, ATT/jps_straight.py:17-70).
-    With a table installed the device draws origins and destinations itself at every reset (ATT:254-276)."""
+    library's planner (the reference's search and tie-breaking, ATT/jps_straight.py:17-70): `planner="host"` calls
+    `aac_plan_path` pair by pair, `planner="device"` plans every pair in one launch (`aac_plan_paths_device`, identical
+    results).  With a table installed the device draws origins and destinations itself at every reset (ATT:254-276)."""
 
-    def __init__(self, gmap: GridMap, w_max=32):
-        import ctypes as C
+    def __init__(self, gmap: GridMap, w_max=32, planner="host"):
         from . import _capi as K
         lib = K.lib()
-        self.gmap, self.w_max = gmap, w_max
+        assert planner in ("host", "device")
+        self.gmap, self.w_max, self.planner = gmap, w_max, planner
         pools = gmap.target_pools()
         cells, pool_off, quad = [], [0], []
         for q in range(4):
@@ -227,25 +244,29 @@ class OdTable:
         self.cell_code = np.array([ix * 256 + iy for ix, iy in cells], dtype=np.uint16)
         self.path_off = np.zeros(P * P, dtype=np.uint32)
         self.path_len = np.zeros(P * P, dtype=np.uint8)
-        occ = np.ascontiguousarray(gmap.occ, dtype=np.uint8)
-        buf = np.zeros(w_max, dtype=np.uint16)
-        chunks, total = [], 0
-        for s in range(P):
-            for t in range(P):
-                if quad[s] == quad[t]:
-                    continue
-                n = lib.aac_plan_path(occ.ctypes.data, gmap.gx, gmap.gy, cells[s][0], cells[s][1], cells[t][0], cells[t][1],
-                                      buf.ctypes.data, w_max)
-                if n == 0:
-                    raise ValueError("cell %s is unreachable from %s" % (cells[t], cells[s]))
-                if n < 0:
-                    raise ValueError("a reference line needs more than w_max=%d vertices" % w_max)
-                self.path_off[s * P + t] = total
-                self.path_len[s * P + t] = n
-                pad = (n + 7) // 8 * 8                      # the device copies paths in 16-byte chunks
-                chunks.append(np.concatenate([buf[:n], np.zeros(pad - n, dtype=np.uint16)]))
-                total += pad
-        self.path_cells = np.concatenate(chunks) if chunks else np.zeros(1, dtype=np.uint16)
+        quad = np.array(quad)
+        ss, tt = np.nonzero(quad[:, None] != quad[None, :])          # row-major: s outer, t inner
+        ca = np.array(cells, dtype=np.int64).reshape(-1, 2)
+        if planner == "device":
+            found, n_of = plan_paths_device(gmap, np.concatenate([ca[ss], ca[tt]], axis=1), w_max)
+        else:
+            occ = np.ascontiguousarray(gmap.occ, dtype=np.uint8)
+            found, n_of = np.zeros((len(ss), w_max), dtype=np.uint16), np.zeros(len(ss), dtype=np.int32)
+            for k, (s, t) in enumerate(zip(ss, tt)):
+                n_of[k] = lib.aac_plan_path(occ.ctypes.data, gmap.gx, gmap.gy, cells[s][0], cells[s][1], cells[t][0], cells[t][1],
+                                            found[k].ctypes.data, w_max)
+        for k in np.nonzero(n_of <= 0)[0]:
+            if n_of[k] == 0:
+                raise ValueError("cell %s is unreachable from %s" % (cells[tt[k]], cells[ss[k]]))
+            raise ValueError("a reference line needs more than w_max=%d vertices" % w_max)
+        pad = (n_of.astype(np.int64) + 7) // 8 * 8                   # the device copies paths in 16-byte chunks
+        off = np.concatenate([[0], np.cumsum(pad)])
+        self.path_off[ss * P + tt] = off[:-1]
+        self.path_len[ss * P + tt] = n_of
+        self.path_cells = np.zeros(max(int(off[-1]), 1), dtype=np.uint16)
+        col = np.arange(w_max)
+        keep = col[None, :] < n_of[:, None]
+        self.path_cells[(off[:-1, None] + col[None, :])[keep]] = found[keep]
 
     def path(self, s, t):
         k = s * self.n_cells + t
