@@ -357,9 +357,28 @@ def test_state_dict_roundtrip():
             assert torch.equal(envs[0].out[k], envs[1].out[k]), (t, k)
 
 
-def test_full_size_c3_properties_and_oracle_spot_check():
-    """BASELINE config C3 at full size (65 536 envs x 10 drones x 36 rays): size-independent properties on every env,
-    determinism, and an oracle comparison of 384 randomly chosen envs of the big batch."""
+def test_full_size_c2_lockstep():
+    """BASELINE config C2 at full size (one_model_att, 4096 envs x 3 drones x 36 rays): EVERY env of the batch against
+    the oracle in lock step, auto-reset included."""
+    _run(variant="att", n_envs=4096, n_agents=3, n_rays=36, steps=12, seed=31)
+
+
+def test_full_size_c4_lockstep():
+    """BASELINE config C4 at full size (radar_multipleMap, 65 536 envs x 3 drones x 18 rays, 14 heterogeneous maps drawn
+    per episode): every env of the batch against the oracle in lock step."""
+    T = parity.lockstep(variant="mm", n_envs=65536, n_agents=3, n_rays=18, steps=4, seed=32)
+    print(T.summary())
+    assert not T.fail, "\n".join(T.fail[:12])
+    # every episode is young here: the exact cross-track == protectiveBound tie of a full-speed first step (see
+    # test_golden_replay_multimap) masks a larger share of drone-steps than in the long small-batch runs
+    assert T.n.get("done", 0) >= 0.7 * 65536 * 3 * 4, T.summary()
+
+
+@pytest.mark.parametrize("E,N,R", [(65536, 10, 36), (131072, 20, 72)])
+def test_full_size_c3_properties_and_oracle_spot_check(E, N, R):
+    """BASELINE config C3 at full size (65 536 envs x 10 drones x 36 rays) and one GPU's shard of C5 (1M envs x 20 drones x
+    72 rays over 8 GPUs): size-independent properties on every env, determinism, and an oracle comparison of 384 randomly
+    chosen envs of the big batch."""
     import numpy as np
     import torch
     from multi_agent_aac_b200.env import BatchedDroneEnv, preset
@@ -368,7 +387,6 @@ def test_full_size_c3_properties_and_oracle_spot_check():
     from oracle.oracle import OracleEnv, RADAR_LAST_HIT
     gmap = synthetic_map(seed=0)
     tab = OdTable(gmap, w_max=32)
-    E, N, R = 65536, 10, 36
     cfg = preset("tdcpa_v2", n_envs=E, n_agents=N, n_rays=R, w_max=32, seed=21, out_flags=parity.K.OUT_PARTS)
     envs = [BatchedDroneEnv(cfg, gmap) for _ in range(2)]
     for env in envs:
@@ -418,10 +436,10 @@ def test_full_size_c3_properties_and_oracle_spot_check():
     ds = np.take_along_axis(d, want["nbr_order"].astype(np.int64), axis=2)
     gap = np.min(np.diff(ds, axis=2), axis=(1, 2))
     ok = ((gap >= parity.TIE_EPS) | (gap == 0)) & (want["margin"] >= parity.TIE_EPS).all(axis=1)
-    assert ok.sum() > 300
+    assert ok.sum() > (300 if N <= 10 else 200)
     rad_ok = np.abs(got["radar"] - want["radar"]) <= 1e-4 * np.abs(want["radar"]) + 2e-4
     ok &= (rad_ok | (np.isnan(got["radar"]) & np.isnan(want["radar"]))).all(axis=(1, 2))     # grazing rays are covered by the lock-step tests
-    assert ok.sum() > 280
+    assert ok.sum() > (280 if N <= 10 else 180)
     for k, atol in (("norm_own", 2e-6), ("norm_nbr", 2e-6), ("radar", 2e-4), ("reward", 2e-4)):
         a, b = got[k][ok].astype(np.float64), want[k][ok]
         both_nan = np.isnan(a) & np.isnan(b)
