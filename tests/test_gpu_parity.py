@@ -527,3 +527,14 @@ def test_radar_table_equals_direct_cast(variant, n, r, flags):
         for k in with_tab.out:
             assert torch.equal(with_tab.out[k].view(torch.uint8), without.out[k].view(torch.uint8)), (t, k)
     assert with_tab.read_stats()[0] == without.read_stats()[0] > 0
+
+
+def test_every_instantiation_runs():
+    """tests/tools/sanitize.py: a short rollout through every kernel instantiation and entry point (no launch error, no
+    barrier-wait trap, finite outputs)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "sanitize.py")], cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-800:] + out.stderr[-1500:]
+    assert out.stdout.strip().endswith("done")
