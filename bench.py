@@ -183,7 +183,7 @@ def quick_device_rate(wl, dev, steps=300, warmup=10):
     gmap, bank = build_world(wl, 256, seed=1000)
     env = BatchedDroneEnv(preset(preset_name, n_envs=envs, n_agents=n, n_rays=r, w_max=32, seed=1000), gmap, device=dev)
     from multi_agent_aac_b200.reset import OdTable
-    env.set_od_tables([OdTable(m, w_max=32) for m in (gmap if isinstance(gmap, list) else [gmap])])
+    env.set_od_tables([OdTable(m, w_max=32, planner="device") for m in (gmap if isinstance(gmap, list) else [gmap])])
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(7)
@@ -340,7 +340,7 @@ def main():
         env.set_bank(bank)
     else:   # origins / destinations drawn on the device at every reset from the maps' OD tables
         from multi_agent_aac_b200.reset import OdTable
-        env.set_od_tables([OdTable(m, w_max=32) for m in (gmap if isinstance(gmap, list) else [gmap])])
+        env.set_od_tables([OdTable(m, w_max=32, planner="device") for m in (gmap if isinstance(gmap, list) else [gmap])])
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(1 + rank)
