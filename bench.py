@@ -83,13 +83,24 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """One `nvidia-smi -lms 100` process streaming clocks / throttle reasons while the timed region runs."""
+    """SM clock, power and throttle reasons sampled through NVML every 10 ms while the timed region runs (the same counters
+    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; an `nvidia-smi -lms 25` stream is the fallback when
+    the NVML binding cannot be loaded)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nv, self.h, self.stop_flag = [], None, None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -97,15 +108,34 @@ class ClockSampler(threading.Thread):
             self.proc = None
 
     def run(self):
+        if self.nv:
+            nv = self.nv
+            bits = [getattr(nv, n, 0) for n in ("nvmlClocksEventReasonHwSlowdown", "nvmlClocksEventReasonHwThermalSlowdown",
+                                                "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksEventReasonSwPowerCap")]
+            fallback = [getattr(nv, n, 0) for n in ("nvmlClocksThrottleReasonHwSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown",
+                                                    "nvmlClocksThrottleReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwPowerCap")]
+            bits = [b or f for b, f in zip(bits, fallback)]
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self.stop_flag:
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                    rs = int(reasons_fn(self.h))
+                    self.rows.append((time.perf_counter(), [str(sm), str(self.max_sm), "%.2f" % pw] + ["Active" if (b and rs & b) else "Not Active" for b in bits]))
+                except Exception:
+                    pass
+                time.sleep(0.01)
+            return
         if not self.proc:
             return
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def summary(self, t0, t1):
+        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
-            self.join(timeout=3)
+        self.join(timeout=3)
         rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
 
         def num(x):
@@ -116,10 +146,11 @@ class ClockSampler(threading.Thread):
         sm = [num(r[0]) for r in rows if r and num(r[0]) is not None]
         mx = [num(r[1]) for r in rows if len(r) > 1 and num(r[1]) is not None]
         pw = [num(r[2]) for r in rows if len(r) > 2 and num(r[2]) is not None]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        names = self.NAMES
         reasons = sorted({names[k] for r in rows for k in range(4) if len(r) > 3 + k and r[3 + k].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows),
+                "source": "nvml" if self.nv else "nvidia-smi"}
 
 
 def variant_of(preset_name):
