@@ -339,7 +339,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sample = args.cpu_envs or max(64, min(4096, 20000 // n))
+        sample = args.cpu_envs or max(64, min(8192, 80000 // n))
         steps = max(1, min(args.steps, 20))
         base, sec_per_step = cpu_reference_run(args.workload, steps, max(1, min(args.warmup, 2)), sample)
         line = {"impl": "reference", "metric": "agent_steps_per_sec", "value": base["value"], "unit": "agent-steps/s",
@@ -480,8 +480,8 @@ def main():
         if world == 1 and not args.no_aux:   # the other single-GPU configurations of BASELINE.json, device-resident
             line["other_workloads"] = {w: quick_device_rate(w, dev) for w in ("c2", "c4") if w != args.workload}
         if not args.no_cpu and world == 1:
-            sample = args.cpu_envs or max(64, min(4096, 20000 // n))
-            base, _ = cpu_reference_run(args.workload, 10, 1, sample)
+            sample = args.cpu_envs or max(64, min(8192, 80000 // n))
+            base, _ = cpu_reference_run(args.workload, 30, 1, sample)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if world > 1:
