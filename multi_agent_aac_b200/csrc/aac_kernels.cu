@@ -26,6 +26,7 @@
 // because all of them share vertex angles, polygon-polygon and polygon-square emptiness tests reduce
 // to a support-function test over the 16 first-quadrant edge normals (Minkowski sum of two such
 // polygons is again one, with the radii added).
+#include <type_traits>
 #include <math_constants.h>
 
 #include "aac_kernels.cuh"
@@ -289,7 +290,8 @@ __device__ __forceinline__ void radar_bounds(const MapDev &mp, float px, float p
 // Axis-parallel rays carry 1/d = +inf: the products are -inf on the entry side and +inf on the exit side of a
 // cell whose slab contains the ray (or NaN exactly on a grid line, which fminf / fmaxf drop: the ray runs along
 // the cell's edge and touches it), i.e. no constraint from that axis.
-template <bool AUX>
+// WANT: 1 = the nearest hit only, 2 = the last hit only, 3 = both (the caller's radar mode; optional outputs need both)
+template <bool AUX, int WANT>
 __device__ __forceinline__ void radar_window(const MapDev &mp, const float2 *lut, float2 wrel, unsigned win, int wix0, int wiy0, float4 ray,
                                              float2 eo, float len, float &shortest, float &sensed, int &shortest_id, int &sensed_id) {
     float t_min = CUDART_INF_F, t_last = 1.0f;
@@ -306,12 +308,12 @@ __device__ __forceinline__ void radar_window(const MapDev &mp, const float2 *lut
         const float lo = fmaxf(fmaxf((xn + off.x) * ray.z, (yn + off.y) * ray.w), 0.0f);
         const float hi = fminf(fminf((xf + off.x) * ray.z, (yf + off.y) * ray.w), 1.0f);
         const bool hit = lo <= hi;
-        t_last = hit ? lo : t_last;
+        if (WANT & 2) t_last = hit ? lo : t_last;
         if (AUX) { b_last = hit ? b : b_last; b_min = (hit && lo < t_min) ? b : b_min; }
-        t_min = hit ? fminf(t_min, lo) : t_min;
+        if (WANT & 1) t_min = hit ? fminf(t_min, lo) : t_min;
     }
-    shortest = t_min * len;
-    sensed = t_last * len;
+    if (WANT & 1) shortest = t_min * len;
+    if (WANT & 2) sensed = t_last * len;
     if (AUX) {
         shortest_id = b_min < 0 ? -1 : (wix0 + (b_min >> 2)) * mp.gy + wiy0 + (b_min & 3);
         sensed_id = b_last < 0 ? -1 : (wix0 + (b_last >> 2)) * mp.gy + wiy0 + (b_last & 3);
@@ -660,31 +662,40 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
     } else {
         const float len = p.ray_len;
         auto entry_off = [&](const float4 ray, const float cell) { return make_float2(ray.z > 0.0f ? 0.0f : cell, ray.w > 0.0f ? 0.0f : cell); };
-        auto cast = [&](const int aa, const float4 ray, const float2 eo, float &out_min, int &id) -> float {
+        // the grid radar of one ray; WANT (radar_window) is the part of the result the caller's radar mode reads
+        auto cast_grid = [&](auto want_c, const int aa, const float4 ray, const float2 eo, float &out_min, int &id) -> float {
+            constexpr int WANT = decltype(want_c)::value;
             const MapDev &mr = map_of(aa);
-            float out;
+            const uint2 wn = w.win[aa];
+            float shortest = CUDART_INF_F, sensed = len;
+            int shortest_id = -1, sensed_id = -1;
+            if (!(wn.x & W_SLOW))
+                radar_window<AUX, WANT>(mr, w.lut, w.wrel[aa], wn.x & 0xFFFFu, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16), ray, eo, len, shortest,
+                                        sensed, shortest_id, sensed_id);
+            else {
+                const GenericHit h = radar_generic<AUX>(mr, w.px[aa], w.py[aa], ray, len);
+                shortest = h.shortest; sensed = h.sensed; shortest_id = h.shortest_id; sensed_id = h.sensed_id;
+            }
+            if (wn.x & W_NEAR_BOUND) radar_bounds<AUX>(mr, w.px[aa], w.py[aa], ray, len, (wn.x >> W_LINE_SHIFT) & 0xFu, shortest, sensed, shortest_id, sensed_id);
+            if (WANT == 2) { out_min = sensed; return sensed; }
+            out_min = shortest == CUDART_INF_F ? len : shortest;
+            if (WANT == 1) return out_min;
+            const bool last_hit = VAR == AAC_VARIANT_V2 && p.radar_mode == AAC_RADAR_LAST_HIT;
+            if (AUX) id = last_hit ? sensed_id : shortest_id;
+            return last_hit ? sensed : out_min;
+        };
+        auto cast = [&](const int aa, const float4 ray, const float2 eo, float &out_min, int &id) -> float {
             if (VAR == AAC_VARIANT_ATT) {
+                const MapDev &mr = map_of(aa);
                 const int ebb = (aa / N) * N;
+                float out;
                 radar_drones_ray(w.px, w.py, ebb, N, aa - ebb, ray, len, p.prot, mr.gx * mr.gy + 4, out, id);
                 out_min = out;
-            } else {
-                const uint2 wn = w.win[aa];
-                float shortest = CUDART_INF_F, sensed = len;
-                int shortest_id = -1, sensed_id = -1;
-                if (!(wn.x & W_SLOW))
-                    radar_window<AUX>(mr, w.lut, w.wrel[aa], wn.x & 0xFFFFu, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16), ray, eo, len, shortest,
-                                      sensed, shortest_id, sensed_id);
-                else {
-                    const GenericHit h = radar_generic<AUX>(mr, w.px[aa], w.py[aa], ray, len);
-                    shortest = h.shortest; sensed = h.sensed; shortest_id = h.shortest_id; sensed_id = h.sensed_id;
-                }
-                if (wn.x & W_NEAR_BOUND) radar_bounds<AUX>(mr, w.px[aa], w.py[aa], ray, len, (wn.x >> W_LINE_SHIFT) & 0xFu, shortest, sensed, shortest_id, sensed_id);
-                out_min = shortest == CUDART_INF_F ? len : shortest;
-                const bool last_hit = VAR == AAC_VARIANT_V2 && p.radar_mode == AAC_RADAR_LAST_HIT;
-                out = last_hit ? sensed : out_min;
-                if (AUX) id = last_hit ? sensed_id : shortest_id;
+                return out;
             }
-            return out;
+            if (AUX) return cast_grid(std::integral_constant<int, 3>{}, aa, ray, eo, out_min, id);
+            if (VAR == AAC_VARIANT_V2 && p.radar_mode == AAC_RADAR_LAST_HIT) return cast_grid(std::integral_constant<int, 2>{}, aa, ray, eo, out_min, id);
+            return cast_grid(std::integral_constant<int, 1>{}, aa, ray, eo, out_min, id);
         };
         const int full = R >> 5, rem = R & 31;
         const size_t rg0 = (size_t)(w.a0 + a_lo) * R;
@@ -728,10 +739,16 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
                     if (AUX) { p.out.radar_min[rg0 + q * R + k] = out_min; p.out.radar_hit[rg0 + q * R + k] = (int16_t)id; }
                 }
                 const unsigned key = ok ? __float_as_uint(out) : 0xFFFFFFFFu;
+                if ((rem & (rem - 1)) == 0) {   // aligned power-of-two lane groups: butterfly inside each drone's group
+                    unsigned m = key;
+                    for (int d = 1; d < rem; d <<= 1) m = min(m, __shfl_xor_sync(FULL, m, d));
+                    if (ok && lane == sub * rem) w.minr[a_lo + q] = min(w.minr[a_lo + q], m);
+                } else {
 #pragma unroll 1
-                for (int s2 = 0; s2 < nsub; ++s2) {
-                    const unsigned m = __reduce_min_sync(FULL, sub == s2 ? key : 0xFFFFFFFFu);
-                    if (lane == s2) w.minr[a_lo + q0 + s2] = min(w.minr[a_lo + q0 + s2], m);
+                    for (int s2 = 0; s2 < nsub; ++s2) {
+                        const unsigned m = __reduce_min_sync(FULL, sub == s2 ? key : 0xFFFFFFFFu);
+                        if (lane == s2) w.minr[a_lo + q0 + s2] = min(w.minr[a_lo + q0 + s2], m);
+                    }
                 }
             }
         }
