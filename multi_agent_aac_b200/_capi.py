@@ -23,7 +23,7 @@ STAT_NAMES = ["episodes", "steps", "return_sum", "bound_crash", "building_crash"
               "all_reached", "drones_reached", "step_cap"]
 
 EXPORTS = ["aac_create", "aac_destroy", "aac_set_maps", "aac_set_radar_table", "aac_set_bank", "aac_set_od_tables", "aac_plan_path", "aac_plan_paths_device", "aac_bind_state", "aac_reset", "aac_observe",
-           "aac_step", "aac_step_autoreset", "aac_autoreset", "aac_step_host", "aac_read_stats", "aac_launch_count", "aac_own_dim",
+           "aac_step", "aac_step_autoreset", "aac_step_fused", "aac_autoreset", "aac_step_host", "aac_read_stats", "aac_launch_count", "aac_own_dim",
            "aac_last_error"]
 
 
@@ -112,6 +112,7 @@ def lib():
     L.aac_observe.argtypes = [P, C.POINTER(AacOut), P]
     L.aac_step.argtypes = [P, P, C.POINTER(AacOut), P]
     L.aac_step_autoreset.argtypes = [P, P, C.POINTER(AacOut), P]
+    L.aac_step_fused.argtypes = [P, P, C.POINTER(AacOut), P]
     L.aac_autoreset.argtypes = [P, C.POINTER(AacOut), P]
     L.aac_step_host.argtypes = [P, P, C.POINTER(AacOut), C.POINTER(AacOut), C.c_int32, P]
     L.aac_read_stats.argtypes = [P, P, C.c_int32, P]

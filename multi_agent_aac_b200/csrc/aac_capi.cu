@@ -565,7 +565,20 @@ extern "C" int aac_observe(AacEnv *env, const AacOut *out, void *stream) { retur
 extern "C" int aac_step(AacEnv *env, const float *actions_dev, const AacOut *out, void *stream) {
     return launch(env, MODE_STEP, nullptr, actions_dev, out, stream);
 }
+// Two launches on the stream - the step, then the re-initialisation of the envs it terminated - leave exactly the
+// state and outputs of the single fused launch (tests/test_gpu_parity.py::test_fused_autoreset_equals_step_then_autoreset)
+// and are faster: each launch's executed code is a smaller part of the kernel, which is bound by instruction issue and
+// instruction-cache misses (C3: 0.330 ms against 0.362 ms fused).
+static int step_then_reset(AacEnv *env, const float *actions_dev, const AacOut *out, void *stream, int e_lo = 0, int e_cnt = 0, int pair = 0) {
+    if (out && !out->terminated) return fail(AAC_ERR_ARG, "reward / done / check_goal / bbc / terminated / tcpa_min must be provided");
+    const int rc = launch(env, MODE_STEP, nullptr, actions_dev, out, stream, 0, e_lo, e_cnt, pair);
+    if (rc) return rc;
+    return launch(env, MODE_RESET, out->terminated, nullptr, out, stream, 0, e_lo, e_cnt, pair);
+}
 extern "C" int aac_step_autoreset(AacEnv *env, const float *actions_dev, const AacOut *out, void *stream) {
+    return step_then_reset(env, actions_dev, out, stream);
+}
+extern "C" int aac_step_fused(AacEnv *env, const float *actions_dev, const AacOut *out, void *stream) {
     return launch(env, MODE_STEP, nullptr, actions_dev, out, stream, 1);
 }
 extern "C" int aac_autoreset(AacEnv *env, const AacOut *out, void *stream) {
@@ -610,7 +623,8 @@ extern "C" int aac_step_host(AacEnv *env, const float *actions_host, const AacOu
         cudaStream_t s = env->pipe[ch % 3];
         if (ch < 3) CU(cudaStreamWaitEvent(s, env->pipe_ev[3], 0));
         CU(cudaMemcpyAsync(env->d_actions + a_lo * 2, actions_host + a_lo * 2, cnt * N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
-        const int rc = launch(env, MODE_STEP, nullptr, env->d_actions, od, s, autoreset ? 1 : 0, (int)e_lo, (int)cnt, 1 + (int)ch);
+        const int rc = autoreset ? step_then_reset(env, env->d_actions, od, s, (int)e_lo, (int)cnt, 1 + (int)ch)
+                                 : launch(env, MODE_STEP, nullptr, env->d_actions, od, s, 0, (int)e_lo, (int)cnt, 1 + (int)ch);
         if (rc) return rc;
         // the wide observation blocks leave with their chunk ...
         ROWS(norm_own, N * D * 4, e_lo, cnt, s); ROWS(norm_nbr, N * 5 * M * 4, e_lo, cnt, s); ROWS(radar, N * R * 4, e_lo, cnt, s);

@@ -277,13 +277,15 @@ class BatchedDroneEnv:
             K.check(self.L.aac_observe(self.h, C.byref(self._out_c), self._stream_ptr()), "aac_observe")
         return self.obs()
 
-    def step(self, actions: torch.Tensor, autoreset=False):
-        """actions [E, N, 2] float32 on the device, in [-1, 1] -> (obs, reward, done, info)."""
+    def step(self, actions: torch.Tensor, autoreset=False, fused=False):
+        """actions [E, N, 2] float32 on the device, in [-1, 1] -> (obs, reward, done, info).  autoreset: the envs that
+        terminate are re-initialised and their observation rows carry the reset observation (aac_step_autoreset: step
+        launch + reset launch; fused=True: the single-launch variant aac_step_fused, bit-identical results)."""
         if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous() \
                 or tuple(actions.shape) != (self.E, self.N, 2):
             raise ValueError("actions must be a contiguous float32 [E, N, 2] tensor on %s" % self.device)
         with torch.cuda.device(self.device):
-            fn = self.L.aac_step_autoreset if autoreset else self.L.aac_step
+            fn = (self.L.aac_step_fused if fused else self.L.aac_step_autoreset) if autoreset else self.L.aac_step
             K.check(fn(self.h, C.c_void_p(actions.data_ptr()), C.byref(self._out_c), self._stream_ptr()), "aac_step")
         o = self.out
         info = {k: o[k] for k in ("check_goal", "bbc", "terminated", "tcpa_min", "tcpa_pair", "nbr_order", "radar_min",

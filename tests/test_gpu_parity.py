@@ -102,8 +102,8 @@ def test_lockstep_r72_n20():
 
 
 def test_fused_autoreset_equals_step_then_autoreset():
-    """aac_step_autoreset (one launch) must leave exactly the state and outputs of aac_step followed by
-    aac_autoreset (two launches), bit for bit."""
+    """aac_step_fused (one launch) and aac_step_autoreset must leave exactly the state and outputs of aac_step followed
+    by aac_autoreset, bit for bit."""
     import numpy as np
     import torch
     from multi_agent_aac_b200.env import BatchedDroneEnv, preset
@@ -115,7 +115,7 @@ def test_fused_autoreset_equals_step_then_autoreset():
     from multi_agent_aac_b200 import _capi as K
     for variant, n, r, E in (("tdcpa_v2", 10, 36, 300), ("att", 3, 18, 257), ("multimap", 3, 18, 203)):
         envs = []
-        for _ in range(2):
+        for _ in range(3):
             if variant == "multimap":
                 maps = multimap_set(seed=0)
                 cfg = preset(variant, n_envs=E, n_agents=n, n_rays=r, w_max=32, seed=5, out_flags=K.OUT_RAW | K.OUT_RADAR_AUX | K.OUT_PARTS)
@@ -135,17 +135,21 @@ def test_fused_autoreset_equals_step_then_autoreset():
             envs[0].step(act, autoreset=False)
             term = envs[0].out["terminated"].clone()
             envs[0].autoreset()
-            envs[1].step(act, autoreset=True)
+            envs[1].step(act, autoreset=True, fused=True)
+            envs[2].step(act, autoreset=True)
             n_term += int((term != 0).sum())
-            for k in envs[0].out:
-                a, b = envs[0].out[k], envs[1].out[k]
-                assert torch.equal(a.view(torch.uint8), b.view(torch.uint8)), (variant, t, k)
-            for k in envs[0].state:
-                assert torch.equal(envs[0].state[k].view(torch.uint8), envs[1].state[k].view(torch.uint8)), (variant, t, k)
+            for other in envs[1:]:
+                for k in envs[0].out:
+                    a, b = envs[0].out[k], other.out[k]
+                    assert torch.equal(a.view(torch.uint8), b.view(torch.uint8)), (variant, t, k)
+                for k in envs[0].state:
+                    assert torch.equal(envs[0].state[k].view(torch.uint8), other.state[k].view(torch.uint8)), (variant, t, k)
         assert n_term > 0
-        s0, s1 = envs[0].read_stats(), envs[1].read_stats()
-        assert np.array_equal(s0[[0, 1, 3, 4, 5, 6, 7, 8, 9]], s1[[0, 1, 3, 4, 5, 6, 7, 8, 9]]) and s0[0] == n_term
-        assert abs(s0[2] - s1[2]) <= 1e-3 * max(1.0, abs(s0[2]))
+        s0 = envs[0].read_stats()
+        for other in envs[1:]:
+            s1 = other.read_stats()
+            assert np.array_equal(s0[[0, 1, 3, 4, 5, 6, 7, 8, 9]], s1[[0, 1, 3, 4, 5, 6, 7, 8, 9]]) and s0[0] == n_term
+            assert abs(s0[2] - s1[2]) <= 1e-3 * max(1.0, abs(s0[2]))
 
 
 def test_partial_reset_leaves_other_envs_untouched():
