@@ -3,8 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl reference]
 
-One "step" = env.step + ss_reward for every env of the shard, fused with the auto-reset of the episodes
-that finish: ONE kernel launch through the C ABI (aac_step_autoreset).  Prints ONE JSON line.
+One "step" = env.step + ss_reward for every env of the shard, followed by the auto-reset of the episodes that
+finish: ONE call through the C ABI (aac_step_autoreset) = two launches of the env kernel (step, reset).  Prints ONE JSON line.
 Workloads: c2 = one_model_att 4096 envs x 3 drones x 36 rays; c3 (default, the
 configuration the 1/2/4/8-GPU metric and the north-star target are quoted on) = tdCPA_forV2 65536 envs x
 10 drones x 36 rays per GPU; c5 = 131072 envs x 20 drones x 72 rays per GPU (the 8-GPU 1M-env sweep).
@@ -39,35 +39,41 @@ def algorithmic_bytes(variant, n, r):
     return 4 * (26 + 2 * W_REF + obs)
 
 
-def profiled_traffic(kernel_tag):
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
-    `ncu --set full` capture (profiles/), or None when that capture is of another kernel."""
-    p = os.path.join(ROOT, "profiles", "r1_env_kernel_v2_ncu_full_summary.csv")
-    try:
-        import csv
-        rows = {r[0]: (r[1], r[2]) for r in csv.reader(open(p)) if len(r) == 3}
-        name = rows.get("Kernel Name", ("", ""))[1]
-        if not all(t in name for t in kernel_tag):
+PROFILED = ("r1_env_kernel_v2_ncu_full_summary.csv", "r1_env_kernel_v2_reset_ncu_full_summary.csv")   # step launch, reset launch
+
+
+def _profiled_rows(kernel_tag):
+    """The committed `ncu --set full` captures of the two launches of one step (profiles/), or None when they are of
+    another kernel."""
+    import csv
+    out = []
+    for name in PROFILED:
+        rows = {r[0]: (r[1], r[2]) for r in csv.reader(open(os.path.join(ROOT, "profiles", name))) if len(r) == 3}
+        if not all(t in rows.get("Kernel Name", ("", ""))[1] for t in kernel_tag):
             return None
+        out.append(rows)
+    return out
+
+
+def profiled_traffic(kernel_tag):
+    """DRAM bytes per step (dram__bytes_read.sum + dram__bytes_write.sum, summed over the step launch and the reset
+    launch) from the committed captures, or None."""
+    try:
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         tot = 0.0
-        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            unit, val = rows[k]
-            tot += float(val) * scale[unit]
+        for rows in _profiled_rows(kernel_tag):
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                unit, val = rows[k]
+                tot += float(val) * scale[unit]
         return tot
     except Exception:
         return None
 
 
 def profiled_metric(name, kernel_tag):
-    """One counter of the committed ncu capture of the dominant kernel (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "r1_env_kernel_v2_ncu_full_summary.csv")
+    """One counter of the committed captures, summed over the two launches of a step, or None."""
     try:
-        import csv
-        rows = {r[0]: (r[1], r[2]) for r in csv.reader(open(p)) if len(r) == 3}
-        if not all(t in rows.get("Kernel Name", ("", ""))[1] for t in kernel_tag):
-            return None
-        return float(rows[name][1])
+        return sum(float(rows[name][1]) for rows in _profiled_rows(kernel_tag))
     except Exception:
         return None
 
@@ -401,7 +407,7 @@ def main():
     host_t0 = time.perf_counter()
     for k in range(K_):
         ev[k][0].record(stream)
-        env.step(acts[k % n_act], autoreset=True)     # ONE launch: step + reward + fused auto-reset
+        env.step(acts[k % n_act], autoreset=True)     # step + reward launch, then the reset launch for the envs that terminated
         ev[k][1].record(stream)
     t_end.record(stream)
     host_issue_ms = (time.perf_counter() - host_t0) * 1e3 / K_
@@ -457,14 +463,14 @@ def main():
             "kernels": {"env_kernel(step+autoreset)_ms": step_kernel_ms, "host_issue_ms_per_step": host_issue_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": profiled_traffic(("env_kernel<1,", " 10, 36,")) if args.workload == "c3" else None,
-                         "traffic_note": "bytes per launch, profiles/r1_env_kernel_v2_ncu_full_summary.csv (one ncu --set full capture)",
+                         "traffic_note": "bytes per step = step launch + reset launch, profiles/r1_env_kernel_v2*_ncu_full_summary.csv (one ncu --set full capture of each)",
                          "peak_kind": peak_kind, "bytes_per_agent_step": bytes_per,
-                         "kernel": "env_kernel<%s> step+autoreset" % variant.upper()},
+                         "kernel": "env_kernel<%s>: the step launch and the reset launch of one step, timed together" % variant.upper()},
             "clocks": clocks,
             "roofline_issue": None,
             "episode_stats": {k: float(v) for k, v in zip(K.STAT_NAMES, stats)},
         }
-        # what actually bounds the kernel (it is not HBM): warp-instruction issue.  Instructions per launch come from the
+        # what actually bounds the kernel (it is not HBM): warp-instruction issue.  Instructions per step (both launches) come from the
         # committed ncu capture, the launch time and SM clock are this run's; peak = 4 schedulers x SMs x clock.
         inst = profiled_metric("smsp__inst_executed.sum", ("env_kernel<1,", " 10, 36")) if args.workload == "c3" else None
         if inst and clocks and clocks.get("sm_mhz"):
@@ -472,7 +478,7 @@ def main():
             peak_issue = 4.0 * sms * clocks["sm_mhz"] * 1e6
             line["roofline_issue"] = {"bound": "issue", "achieved": inst / (step_kernel_ms * 1e-3), "peak": peak_issue, "unit": "warp-inst/s",
                                       "frac": inst / (step_kernel_ms * 1e-3) / peak_issue, "warp_inst_per_agent_step": inst / (envs * n),
-                                      "note": "instructions per launch from profiles/r1_env_kernel_v2_ncu_full_summary.csv; ncu itself reports smsp__issue_active and the pipe shares (profiles/README.md)"}
+                                      "note": "instructions per step (step launch + reset launch) from profiles/r1_env_kernel_v2*_ncu_full_summary.csv; ncu itself reports smsp__issue_active and the pipe shares (profiles/README.md)"}
         if world == 1 and not args.no_aux and preset_name == "tdcpa_v2":
             line["policy_rollout"] = policy_rollout(env, dev)
         if world == 1 and not args.no_aux and preset_name == "att":

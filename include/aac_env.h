@@ -83,7 +83,8 @@ typedef struct {
     float goal_r;           /* 1     (ATT:2266) */
     int32_t eval_by_step;   /* V2 only: args.mode == 'eval' with evaluation_by_episode == False: crashed / arrived drones stay
                                where they are, crashes do not end the episode (V2:3729-3734, :3128-3156, :3551-3587) */
-    int32_t reserved;
+    int32_t autoreset_launches; /* aac_step_autoreset / aac_step_host: 1 = one fused launch, 2 = step launch + reset launch,
+                               0 = choose by batch size (two launches pay off on large tdCPA_forV2 batches) */
 } AacConfig;
 
 /* one 10 m occupancy grid (ATT/grid_env_generation:140-185) */

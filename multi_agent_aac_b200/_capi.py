@@ -33,7 +33,7 @@ class AacConfig(C.Structure):
                 ("episode_length", C.c_int32), ("out_flags", C.c_int32), ("tile_envs", C.c_int32),
                 ("block_threads", C.c_int32), ("env_id_base", C.c_int64), ("seed", C.c_uint64),
                 ("dt", C.c_float), ("vmax", C.c_float), ("acc_max", C.c_float), ("prot", C.c_float),
-                ("ray_len", C.c_float), ("goal_r", C.c_float), ("eval_by_step", C.c_int32), ("reserved", C.c_int32)]
+                ("ray_len", C.c_float), ("goal_r", C.c_float), ("eval_by_step", C.c_int32), ("autoreset_launches", C.c_int32)]
 
 
 class AacMapDesc(C.Structure):

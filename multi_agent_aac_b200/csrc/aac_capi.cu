@@ -75,6 +75,7 @@ extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
     if (cfg->variant == AAC_VARIANT_MM && (cfg->out_flags & (AAC_OUT_NBR6 | AAC_OUT_TCPA_PAIR)))
         return fail(AAC_ERR_ARG, "aac_create: the multipleMap variant has no neighbour outputs");
     if (cfg->eval_by_step && cfg->variant != AAC_VARIANT_V2) return fail(AAC_ERR_ARG, "aac_create: eval_by_step is a mode of the tdCPA_forV2 variant");
+    if (cfg->autoreset_launches < 0 || cfg->autoreset_launches > 2) return fail(AAC_ERR_ARG, "aac_create: autoreset_launches must be 0, 1 or 2");
     if (cfg->n_envs < 1) return fail(AAC_ERR_ARG, "aac_create: n_envs < 1");
     if (cfg->n_agents < 1 || cfg->n_agents > AAC_MAX_AGENTS) return fail(AAC_ERR_ARG, "aac_create: n_agents out of range");
     if (cfg->n_rays < 1 || cfg->n_rays > AAC_MAX_RAYS || 360 % cfg->n_rays) return fail(AAC_ERR_ARG, "aac_create: n_rays must divide 360");
@@ -575,8 +576,22 @@ static int step_then_reset(AacEnv *env, const float *actions_dev, const AacOut *
     if (rc) return rc;
     return launch(env, MODE_RESET, out->terminated, nullptr, out, stream, 0, e_lo, e_cnt, pair);
 }
+// One fused launch or two?  Measured on B200 (tests/tools/unfused_time.py): the second launch costs about 0.011 ms,
+// the smaller executed code per launch saves 9-12 % of a tdCPA_forV2 step: C3 (65 536 x 10 x 36) 0.362 -> 0.330 ms,
+// C5 (131 072 x 20 x 72) 2.88 -> 2.52 ms, but C2 (one_model_att 4096 x 3) 0.031 -> 0.041 and C4 (multipleMap 65 536 x 3)
+// 0.088 -> 0.100.  Two launches for tdCPA_forV2 batches of at least 8M (ray + pair) items, one otherwise, unless the
+// configuration says which.
+static bool split_autoreset(const AacEnv *env, int e_cnt = 0) {
+    const AacConfig &c = env->cfg;
+    if (c.autoreset_launches == 1) return false;
+    if (c.autoreset_launches == 2) return true;
+    const double items = (double)(e_cnt > 0 ? e_cnt : c.n_envs) * c.n_agents * (c.n_agents - 1 + c.n_rays);
+    return c.variant == AAC_VARIANT_V2 && items >= 8e6;
+}
 extern "C" int aac_step_autoreset(AacEnv *env, const float *actions_dev, const AacOut *out, void *stream) {
-    return step_then_reset(env, actions_dev, out, stream);
+    if (!env) return fail(AAC_ERR_ARG, "null handle");
+    if (split_autoreset(env)) return step_then_reset(env, actions_dev, out, stream);
+    return launch(env, MODE_STEP, nullptr, actions_dev, out, stream, 1);
 }
 extern "C" int aac_step_fused(AacEnv *env, const float *actions_dev, const AacOut *out, void *stream) {
     return launch(env, MODE_STEP, nullptr, actions_dev, out, stream, 1);
@@ -623,8 +638,8 @@ extern "C" int aac_step_host(AacEnv *env, const float *actions_host, const AacOu
         cudaStream_t s = env->pipe[ch % 3];
         if (ch < 3) CU(cudaStreamWaitEvent(s, env->pipe_ev[3], 0));
         CU(cudaMemcpyAsync(env->d_actions + a_lo * 2, actions_host + a_lo * 2, cnt * N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
-        const int rc = autoreset ? step_then_reset(env, env->d_actions, od, s, (int)e_lo, (int)cnt, 1 + (int)ch)
-                                 : launch(env, MODE_STEP, nullptr, env->d_actions, od, s, 0, (int)e_lo, (int)cnt, 1 + (int)ch);
+        const int rc = (autoreset && split_autoreset(env, (int)cnt)) ? step_then_reset(env, env->d_actions, od, s, (int)e_lo, (int)cnt, 1 + (int)ch)
+                                                                     : launch(env, MODE_STEP, nullptr, env->d_actions, od, s, autoreset ? 1 : 0, (int)e_lo, (int)cnt, 1 + (int)ch);
         if (rc) return rc;
         // the wide observation blocks leave with their chunk ...
         ROWS(norm_own, N * D * 4, e_lo, cnt, s); ROWS(norm_nbr, N * 5 * M * 4, e_lo, cnt, s); ROWS(radar, N * R * 4, e_lo, cnt, s);

@@ -1028,6 +1028,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
         if (gi >= n_groups) break;
         w.e_lo = gi * G;
         w.ng = max(0, min(G, p.E - w.e_lo));
+        // reset launch: a group none of whose envs is masked has nothing to do (with a trained policy most groups)
+        if (mode == MODE_RESET && p.mask && !__ballot_sync(FULL, lane < w.ng && p.mask[w.e_lo + lane])) continue;
         w.a0 = w.e_lo * N;
         w.nA = w.ng * N;
         const int nA = w.nA, a0 = w.a0;

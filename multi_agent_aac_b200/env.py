@@ -47,6 +47,7 @@ class EnvConfig:
     tile_envs: int = 0
     block_threads: int = 0
     eval_by_step: bool = False    # V2 only: evaluation "by sorties" (args.mode == 'eval', evaluation_by_episode == False)
+    autoreset_launches: int = 0   # step(autoreset=True): 1 = fused launch, 2 = step launch + reset launch, 0 = by batch size
 
 
 def preset(name, **kw) -> EnvConfig:
@@ -90,7 +91,7 @@ class BatchedDroneEnv:
         with torch.cuda.device(self.device):
             c = K.AacConfig(K.ABI_VERSION, VARIANTS[cfg.variant], E, N, R, W, cfg.radar_mode, int(cfg.sum_reward),
                             cfg.episode_length, cfg.out_flags, cfg.tile_envs, cfg.block_threads, cfg.env_id_base, cfg.seed,
-                            cfg.dt, cfg.vmax, cfg.acc_max, cfg.prot, cfg.ray_len, cfg.goal_r, int(cfg.eval_by_step), 0)
+                            cfg.dt, cfg.vmax, cfg.acc_max, cfg.prot, cfg.ray_len, cfg.goal_r, int(cfg.eval_by_step), int(cfg.autoreset_launches))
             h = C.c_void_p()
             K.check(self.L.aac_create(C.byref(c), C.byref(h)), "aac_create")
             self.h = h

@@ -115,14 +115,15 @@ def test_fused_autoreset_equals_step_then_autoreset():
     from multi_agent_aac_b200 import _capi as K
     for variant, n, r, E in (("tdcpa_v2", 10, 36, 300), ("att", 3, 18, 257), ("multimap", 3, 18, 203)):
         envs = []
-        for _ in range(3):
+        for idx in range(3):   # env 2: aac_step_autoreset as two launches whatever the batch size
             if variant == "multimap":
                 maps = multimap_set(seed=0)
-                cfg = preset(variant, n_envs=E, n_agents=n, n_rays=r, w_max=32, seed=5, out_flags=K.OUT_RAW | K.OUT_RADAR_AUX | K.OUT_PARTS)
+                cfg = preset(variant, n_envs=E, n_agents=n, n_rays=r, w_max=32, seed=5, out_flags=K.OUT_RAW | K.OUT_RADAR_AUX | K.OUT_PARTS,
+                             autoreset_launches=2 if idx == 2 else 0)
                 env = BatchedDroneEnv(cfg, maps)
                 env.set_bank(MultiMapBank(maps, n, 64, w_max=32, seed=5))
             else:
-                cfg = preset(variant, n_envs=E, n_agents=n, n_rays=r, w_max=32, seed=5, out_flags=parity.ALL_OUT)
+                cfg = preset(variant, n_envs=E, n_agents=n, n_rays=r, w_max=32, seed=5, out_flags=parity.ALL_OUT, autoreset_launches=2 if idx == 2 else 0)
                 env = BatchedDroneEnv(cfg, gmap)
                 env.set_bank(ScenarioBank(gmap, n, 64, w_max=32, seed=5))
             env.reset()
@@ -220,8 +221,8 @@ def test_ref_compat_env_reproduces_reference_episode(name):
         assert isinstance(reward[0], np.ndarray) and reward[0].ndim == 0 and isinstance(done[0], bool)
 
 
-@pytest.mark.parametrize("n_envs", [100, 7001])
-def test_step_host_pipeline_equals_device_step(n_envs):
+@pytest.mark.parametrize("n_envs,launches", [(100, 0), (7001, 0), (7001, 2)])
+def test_step_host_pipeline_equals_device_step(n_envs, launches):
     """aac_step_host (pinned host buffers, chunks pipelined over three streams for large batches) must return
     exactly what aac_step_autoreset leaves on the device."""
     import torch
@@ -232,7 +233,7 @@ def test_step_host_pipeline_equals_device_step(n_envs):
     n, r = 10, 36
     envs = []
     for _ in range(2):
-        env = BatchedDroneEnv(preset("tdcpa_v2", n_envs=n_envs, n_agents=n, n_rays=r, w_max=32, seed=3), gmap)
+        env = BatchedDroneEnv(preset("tdcpa_v2", n_envs=n_envs, n_agents=n, n_rays=r, w_max=32, seed=3, autoreset_launches=launches), gmap)
         env.set_bank(ScenarioBank(gmap, n, 64, w_max=32, seed=3))
         env.reset()
         envs.append(env)
