@@ -314,7 +314,26 @@ def policy_rollout_att(env, dev, steps=200, warmup=5):
             "kernel": "actor_att_kernel (fp32 GEMM chain on the CUDA cores)"}
 
 
+_JSON_OUT = None
+
+
+def keep_stdout_for_the_json_line():
+    """Libraries print to file descriptor 1 (NCCL's version banner at the first collective, for one): send everything
+    written there to stderr and keep the original stdout for the ONE JSON line the contract asks for."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    keep_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -354,7 +373,7 @@ def main():
                 "config": {"workload": desc, "sample_envs": sample, "drones": n, "rays": r},
                 "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": base["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -489,7 +508,7 @@ def main():
             sample = args.cpu_envs or max(64, min(8192, 80000 // n))
             base, _ = cpu_reference_run(args.workload, 30, 1, sample)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
