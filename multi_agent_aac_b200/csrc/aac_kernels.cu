@@ -968,8 +968,14 @@ __device__ __noinline__ void evs_collisions(const KParams &p, const Warp &w, int
 // EVS: forV2's evaluation "by sorties" (args.mode == 'eval' and evaluation_by_episode == False): terminal drones stay put
 // (V2:3729-3734), neighbours at their goal are invisible and crash flags are live across the drone loop (V2:3128-3158),
 // crashes do not end the episode (V2:3551-3587).  A separate instantiation: the training kernels carry none of it.
-template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false>
-__global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_constant__ KParams p, const int mode) {
+// MT: the mode as a compile-time constant for the launches of the benchmark shapes (-1 = the `mode` argument decides;
+// MT_STEP_ONLY = MODE_STEP without the fused auto-reset; MODE_RESET): the step launch then carries no reset code and the
+// reset launch no reward code - less code per launch is what the instruction cache rewards.
+constexpr int MT_STEP_ONLY = 3;
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1>
+__global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_constant__ KParams p, const int mode_arg) {
+    constexpr bool STEP_ONLY = MT == MT_STEP_ONLY;
+    const int mode = MT < 0 ? mode_arg : (STEP_ONLY ? (int)MODE_STEP : MT);
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = NT ? NT : p.N, M = N - 1, W = p.W, G = p.G;
@@ -1073,7 +1079,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
             reset_mask = __ballot_sync(FULL, m);
             store_mask = reset_mask;
         }
-        for (int job = (mode == MODE_RESET ? 1 : 0); job <= w.ng; ++job) {
+        for (int job = (mode == MODE_RESET ? 1 : 0); job <= (STEP_ONLY ? 0 : w.ng); ++job) {
             int a_lo = 0, n_ag = nA;
             const uint16_t *cl = cells;
             if (job > 0) {
@@ -1326,10 +1332,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                     st_bits[4] += all_reach; st_bits[5] += n_reach; st_bits[6] += term == 1u;
                 }
                 w.rs[lane] = any_goal ? 1 : 0;
-                reset_me = term && p.autoreset;
+                reset_me = !STEP_ONLY && term && p.autoreset;
                 if (!reset_me) { p.st.ep_step[ge] = step; p.st.ep_return[ge] = ret; }
             }
-            reset_mask = __ballot_sync(FULL, reset_me);
+            reset_mask = STEP_ONLY ? 0u : __ballot_sync(FULL, reset_me);
             __syncwarp();
             // the terminal transition leaves before the reset touches the records
             if (mine) {
@@ -1380,11 +1386,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
     }
 }
 
-template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false>
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1>
 static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     const int wpc = threads / 32;
     const int groups = (p.E + p.G - 1) / p.G;
-    auto fn = env_kernel<VAR, AUX, LEAN, NT, RT, EVS>;
+    auto fn = env_kernel<VAR, AUX, LEAN, NT, RT, EVS, MT>;
     static int opted_in[64] = {0};   // dynamic shared memory this instantiation has opted in to, per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1411,7 +1417,13 @@ static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, 
 
 template <int VAR, int NT, int RT>
 static cudaError_t launch_aux(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
-    if (p.out_flags == 0) return launch_one<VAR, false, true, NT, RT>(p, mode, threads, sms, grid_cache, stream);
+    if (p.out_flags == 0) {
+        if (VAR == AAC_VARIANT_V2 && NT > 0 && RT > 0) {   // the two launches of a large batch's step: one kernel per mode
+            if (mode == MODE_STEP && !p.autoreset) return launch_one<VAR, false, true, NT, RT, false, MT_STEP_ONLY>(p, mode, threads, sms, grid_cache, stream);
+            if (mode == MODE_RESET) return launch_one<VAR, false, true, NT, RT, false, MODE_RESET>(p, mode, threads, sms, grid_cache, stream);
+        }
+        return launch_one<VAR, false, true, NT, RT>(p, mode, threads, sms, grid_cache, stream);
+    }
     return (p.out_flags & AAC_OUT_RADAR_AUX) ? launch_one<VAR, true, false, NT, RT>(p, mode, threads, sms, grid_cache, stream)
                                              : launch_one<VAR, false, false, NT, RT>(p, mode, threads, sms, grid_cache, stream);
 }

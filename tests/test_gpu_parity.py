@@ -543,3 +543,39 @@ def test_every_instantiation_runs():
     out = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "sanitize.py")], cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-800:] + out.stderr[-1500:]
     assert out.stdout.strip().endswith("done")
+
+
+@pytest.mark.parametrize("n,r,E", [(10, 36, 3001), (20, 72, 700)])
+def test_mode_specialised_launches_equal_fused_launch(n, r, E):
+    """The benchmark shapes without optional outputs run their two-launch auto-reset through kernels specialised on the
+    mode (step without reset code, reset without reward code): state, outputs and counters must equal the fused launch's
+    and the generic-mode path's (step, then autoreset through the runtime-mode kernel of a non-lean handle is covered by
+    test_fused_autoreset_equals_step_then_autoreset), bit for bit."""
+    import numpy as np
+    import torch
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import synthetic_map
+    from multi_agent_aac_b200.reset import OdTable
+    gmap = synthetic_map(seed=0)
+    tab = OdTable(gmap, w_max=32, planner="device")
+    envs = []
+    for launches in (1, 2):
+        env = BatchedDroneEnv(preset("tdcpa_v2", n_envs=E, n_agents=n, n_rays=r, w_max=32, seed=9, autoreset_launches=launches), gmap)
+        env.set_od_tables([tab])
+        env.reset()          # MODE_RESET through the specialised kernel on both handles
+        envs.append(env)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(4)
+    n_term = 0
+    for t in range(20):
+        act = (torch.rand((E, n, 2), device="cuda", generator=gen) * 2 - 1).contiguous()
+        for env in envs:
+            env.step(act, autoreset=True)
+        n_term += int((envs[0].out["terminated"] != 0).sum())
+        for k in envs[0].out:
+            assert torch.equal(envs[0].out[k].view(torch.uint8), envs[1].out[k].view(torch.uint8)), (t, k)
+        for k in envs[0].state:
+            assert torch.equal(envs[0].state[k].view(torch.uint8), envs[1].state[k].view(torch.uint8)), (t, k)
+    assert n_term > 0
+    s0, s1 = envs[0].read_stats(), envs[1].read_stats()
+    assert np.array_equal(s0[[0, 1, 3, 4, 5, 6, 7, 8, 9]], s1[[0, 1, 3, 4, 5, 6, 7, 8, 9]]) and s0[0] == n_term
