@@ -22,6 +22,9 @@ struct AacEnv {
     MapDev *d_maps = nullptr;
     int n_maps = 0;
     float4 *d_ray = nullptr;
+    std::vector<float4> h_ray;   // host copy: the walk constants are derived from it once the cell size is known (aac_set_maps)
+    DdaRay *d_dda = nullptr;
+    uint4 *d_walk = nullptr;     // the walk table of the grid radar (aac_radar.cuh)
     uint16_t *d_bank_cells = nullptr;
     uint8_t *d_bank_w = nullptr;
     int32_t *d_bank_map = nullptr;
@@ -137,6 +140,13 @@ extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
         }
     CU(cudaMalloc(&env->d_ray, sizeof(float4) * cfg->n_rays));
     CU(cudaMemcpy(env->d_ray, rays.data(), sizeof(float4) * cfg->n_rays, cudaMemcpyHostToDevice));
+    env->h_ray = rays;
+    CU(cudaMalloc(&env->d_dda, sizeof(DdaRay) * cfg->n_rays));
+    CU(cudaMemset(env->d_dda, 0, sizeof(DdaRay) * cfg->n_rays));
+    std::vector<uint4> walk(WALK_BYTES / 16);
+    make_walk_table(walk.data());
+    CU(cudaMalloc(&env->d_walk, WALK_BYTES));
+    CU(cudaMemcpy(env->d_walk, walk.data(), WALK_BYTES, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&env->d_work, 2 * 17 * sizeof(int)));   // one ping-pong pair for whole-range launches, 16 for pipeline chunks
     CU(cudaMemset(env->d_work, 0, 2 * 17 * sizeof(int)));
     CU(cudaMalloc(&env->d_stats, sizeof(double) * AAC_N_STATS));
@@ -149,6 +159,8 @@ extern "C" void aac_destroy(AacEnv *env) {
     if (!env) return;
     cudaFree(env->d_maps);
     cudaFree(env->d_ray);
+    cudaFree(env->d_dda);
+    cudaFree(env->d_walk);
     cudaFree(env->d_bank_cells);
     cudaFree(env->d_bank_w);
     cudaFree(env->d_bank_map);
@@ -197,6 +209,10 @@ extern "C" int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *
     CU(cudaMemcpy(env->d_maps, host.data(), sizeof(MapDev) * n_maps, cudaMemcpyHostToDevice));
     env->n_maps = n_maps;
     env->cell = maps[0].cell;
+    // the rays as constants of the cell walk (aac_radar.cuh): they depend on the cell size
+    std::vector<DdaRay> dda(env->h_ray.size());
+    for (size_t k = 0; k < dda.size(); ++k) dda[k] = make_dda_ray(env->h_ray[k].x, env->h_ray[k].y, env->cell);
+    CU(cudaMemcpy(env->d_dda, dda.data(), sizeof(DdaRay) * dda.size(), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -525,7 +541,7 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     p.radar_mode = c.radar_mode; p.sum_reward = c.sum_reward; p.ep_len = c.episode_length; p.out_flags = c.out_flags; p.eval_by_step = c.eval_by_step;
     p.cell = env->cell; p.dt = c.dt; p.vmax = c.vmax; p.acc_max = c.acc_max; p.prot = c.prot; p.ray_len = c.ray_len; p.goal_r = c.goal_r;
     p.env_id_base = c.env_id_base; p.seed = c.seed;
-    p.maps = env->d_maps; p.n_maps = env->n_maps; p.ray_tab = env->d_ray; p.autoreset = autoreset;
+    p.maps = env->d_maps; p.n_maps = env->n_maps; p.ray_tab = env->d_ray; p.dda_tab = env->d_dda; p.walk_tab = env->d_walk; p.autoreset = autoreset;
     p.bank_cells = env->d_bank_cells; p.bank_w = env->d_bank_w; p.bank_map = env->d_bank_map; p.n_scen = env->n_scen; p.od = env->d_od;
     p.mask = mask; p.actions = actions; p.stats = env->d_stats;
     p.rtab = env->rtab; p.rtab_min = env->rtab_min; p.rtab_hit = env->rtab_hit; p.rtab_minr = env->rtab_minr;

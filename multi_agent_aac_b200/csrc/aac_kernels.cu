@@ -109,11 +109,6 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 constexpr unsigned F_DONE = 1u, F_GOAL = 2u, F_BRANCH_SHIFT = 2u, F_BBC3 = 32u, F_DOUBLE = 64u;
 constexpr unsigned M_REACH = 1u << 8, M_VBOUND = 1u << 9, M_VBLDG = 1u << 10, M_VDRONE = 1u << 11;
-// occupancy-window flags (upper half of the window word)
-constexpr unsigned W_SLOW = 1u << 17;        // drone centre inside an occupied cell / window clamped: generic path
-constexpr unsigned W_LINE_SHIFT = 20;        // bits 20..23: boundary line L, R, B, T is within ray reach
-constexpr unsigned W_NEAR_BOUND = 0xFu << W_LINE_SHIFT;
-
 // (hi, lo) = divmod(index, n) advanced by a fixed stride without dividing again
 struct Walk {
     int hi, lo, dhi, dlo, n;
@@ -129,13 +124,6 @@ struct Walk {
 
 __device__ __forceinline__ float cell_cx(const MapDev &m, int ix) { return m.ex0 + (ix + 0.5f) * m.cell; }
 __device__ __forceinline__ float cell_cy(const MapDev &m, int iy) { return m.ey0 + (iy + 0.5f) * m.cell; }
-
-__device__ __forceinline__ bool occupied(const MapDev &m, int ix, int iy) {
-    const int px = ix + MAP_PAD, py = iy + MAP_PAD;
-    if (px < 0 || py < 0 || px >= m.pgx || py >= m.pgy) return false;
-    const int b = px * m.pgy + py;
-    return (m.bits[b >> 5] >> (b & 31)) & 1u;
-}
 
 // max over the 64 edge normals of n . (ax, ay) for ax, ay >= 0 (attained in the first quadrant)
 __device__ __forceinline__ float support64_q1(float ax, float ay) {
@@ -166,11 +154,14 @@ __device__ __forceinline__ bool gon_square_touch(float dxc, float dyc, float h, 
 __device__ __forceinline__ float cap_extent(float t0) {
     const float two_pi = 6.283185307179586f, pi = 3.14159265358979f, q = 0.09817477042468103f;
     float u = t0 - two_pi * floorf(t0 * (1.0f / two_pi));
+    // (the library cosf carries a large-argument reduction of several hundred instructions per call site: both
+    // arguments here are small, a short series / the hardware cosine are exact to a few 1e-7)
     if (u <= pi) {
         const float rem = u - q * floorf(u * (1.0f / q));
-        return cosf(fminf(rem, q - rem));
+        const float x = fminf(rem, q - rem), x2 = x * x;   // |x| <= pi / 64
+        return fmaf(x2, fmaf(x2, 1.0f / 24.0f, -0.5f), 1.0f);
     }
-    return fabsf(cosf(u));
+    return fabsf(__cosf(u - pi));
 }
 
 // LineString([p0, p1]).buffer(r) vertex bounding box against the 4 boundary lines (ATT:2172-2173,
@@ -228,138 +219,6 @@ __device__ __forceinline__ unsigned pick_scenario(long long gid, int episode, un
 }
 
 // ------------------------------------------------------------------------------------ radar
-
-// the boundary lines in the reference's order L, R, B, T (V2:145-152); ray = (dx, dy, 1/dx, 1/dy).  `lines` has
-// one bit per line that can be reached at all from the drone's position.
-struct RadarAcc {
-    float shortest, sensed;
-    int shortest_id, sensed_id;
-};
-template <bool AUX>
-__device__ __forceinline__ void bound_line(const int b, const int nb, const float dd, const float pp, const float inv, const float line, const float len,
-                                           float &shortest, float &sensed, int &shortest_id, int &sensed_id) {
-    if (dd != 0.0f) {
-        const float t = (line - pp) * inv;
-        if (t >= 0.0f && t <= 1.0f) {
-            const float d = t * len;
-            sensed = d;
-            if (AUX) sensed_id = nb + b;
-            if (d < shortest) { shortest = d; if (AUX) shortest_id = nb + b; }
-        }
-    } else if (pp == line) {  // ray runs along the boundary: GEOS returns the whole overlap
-        sensed = len;
-        if (AUX) sensed_id = nb + b;
-        if (0.0f < shortest) { shortest = 0.0f; if (AUX) shortest_id = nb + b; }
-    }
-}
-// any set of lines (a map narrower than two ray lengths can have both lines of an axis in reach); off the hot
-// path, so the accumulators travel by value
-template <bool AUX>
-__device__ __noinline__ RadarAcc radar_bounds_any(const MapDev &mp, float px, float py, float4 ray, float len, unsigned lines, RadarAcc acc) {
-    const int nb = mp.gx * mp.gy;
-#pragma unroll 1
-    while (lines) {
-        const int b = __ffs(lines) - 1;
-        lines &= lines - 1;
-        const float lim = b < 2 ? mp.hx : mp.hy;
-        bound_line<AUX>(b, nb, b < 2 ? ray.x : ray.y, b < 2 ? px : py, b < 2 ? ray.z : ray.w, (b & 1) ? lim : -lim, len, acc.shortest, acc.sensed,
-                        acc.shortest_id, acc.sensed_id);
-    }
-    return acc;
-}
-template <bool AUX>
-__device__ __forceinline__ void radar_bounds(const MapDev &mp, float px, float py, float4 ray, float len, unsigned lines, float &shortest,
-                                             float &sensed, int &shortest_id, int &sensed_id) {
-    if ((lines & 3u) == 3u || (lines & 12u) == 12u) {
-        const RadarAcc r = radar_bounds_any<AUX>(mp, px, py, ray, len, lines, RadarAcc{shortest, sensed, shortest_id, sensed_id});
-        shortest = r.shortest; sensed = r.sensed; shortest_id = r.shortest_id; sensed_id = r.sensed_id;
-        return;
-    }
-    // usual case: at most one line per axis, x first
-    const int nb = AUX ? mp.gx * mp.gy : 0;
-    if (lines & 3u) bound_line<AUX>((lines & 1u) ? 0 : 1, nb, ray.x, px, ray.z, (lines & 1u) ? -mp.hx : mp.hx, len, shortest, sensed, shortest_id, sensed_id);
-    if (lines & 12u) bound_line<AUX>((lines & 4u) ? 2 : 3, nb, ray.y, py, ray.w, (lines & 4u) ? -mp.hy : mp.hy, len, shortest, sensed, shortest_id, sensed_id);
-}
-
-// Fast path.  One ray against the occupied cells of the drone's 4x4 window (V2:1210-1300): a slab test per
-// set bit of the window mask, lowest bit first = ascending (ix, iy) = ascending cell index, so `sensed`
-// ends as the reference's last hit.  `wrel` = window origin relative to the drone.  The loop
-// is deliberately not unrolled: all lanes of a warp iteration work on the same drone, so the trip count
-// is warp-uniform and the body stays resident in the instruction cache; the hit update is branch-free and
-// works on the ray parameter (the range is t * len, monotone in t, so the minimum commutes with the scaling).
-// Axis-parallel rays carry 1/d = +inf: the products are -inf on the entry side and +inf on the exit side of a
-// cell whose slab contains the ray (or NaN exactly on a grid line, which fminf / fmaxf drop: the ray runs along
-// the cell's edge and touches it), i.e. no constraint from that axis.
-// WANT: 1 = the nearest hit only, 2 = the last hit only, 3 = both (the caller's radar mode; optional outputs need both)
-template <bool AUX, int WANT>
-__device__ __forceinline__ void radar_window(const MapDev &mp, const float2 *lut, float2 wrel, unsigned win, int wix0, int wiy0, float4 ray,
-                                             float2 eo, float len, float &shortest, float &sensed, int &shortest_id, int &sensed_id) {
-    float t_min = CUDART_INF_F, t_last = 1.0f;
-    int b_min = -1, b_last = -1;
-    // the ray's direction signs say which edge of a cell is the entry side on each axis (`eo` = that edge's
-    // offset from the cell's low corner, a property of the ray alone): shift the window origin once per ray
-    // instead of ordering the two products per cell
-    const float xn = wrel.x + eo.x, xf = wrel.x + (mp.cell - eo.x), yn = wrel.y + eo.y, yf = wrel.y + (mp.cell - eo.y);
-#pragma unroll 1
-    while (win) {
-        const int b = __ffs(win) - 1;
-        win &= win - 1;
-        const float2 off = lut[b];   // (row, column) of window cell b times the cell size
-        const float lo = fmaxf(fmaxf((xn + off.x) * ray.z, (yn + off.y) * ray.w), 0.0f);
-        const float hi = fminf(fminf((xf + off.x) * ray.z, (yf + off.y) * ray.w), 1.0f);
-        const bool hit = lo <= hi;
-        if (WANT & 2) t_last = hit ? lo : t_last;
-        if (AUX) { b_last = hit ? b : b_last; b_min = (hit && lo < t_min) ? b : b_min; }
-        if (WANT & 1) t_min = hit ? fminf(t_min, lo) : t_min;
-    }
-    if (WANT & 1) shortest = t_min * len;
-    if (WANT & 2) sensed = t_last * len;
-    if (AUX) {
-        shortest_id = b_min < 0 ? -1 : (wix0 + (b_min >> 2)) * mp.gy + wiy0 + (b_min & 3);
-        sensed_id = b_last < 0 ? -1 : (wix0 + (b_last >> 2)) * mp.gy + wiy0 + (b_last & 3);
-    }
-}
-
-// Generic path (drone centre inside an occupied cell, or outside the padded grid): tests every occupied
-// cell whose box overlaps the ray's box, with the reference's inside-the-cell semantics: the nearest
-// point of segment n cell BOUNDARY is the exit point, or nothing (nan) when the whole ray is inside
-// (V2:1258-1265).
-struct GenericHit {
-    float shortest, sensed;
-    int shortest_id, sensed_id;
-};
-template <bool AUX>
-__device__ __noinline__ GenericHit radar_generic(const MapDev &mp, float px, float py, float4 ray, float len) {
-    // results travel by value: reference parameters of a non-inlined function would pin the caller's
-    // accumulators in local memory on the hot path
-    float shortest = CUDART_INF_F, sensed = len;
-    int shortest_id = -1, sensed_id = -1;
-    const float ex = px + ray.x, ey = py + ray.y;
-    const int ixa = (int)floorf((fminf(px, ex) - mp.ex0) * mp.inv_cell), ixb = (int)floorf((fmaxf(px, ex) - mp.ex0) * mp.inv_cell);
-    const int iya = (int)floorf((fminf(py, ey) - mp.ey0) * mp.inv_cell), iyb = (int)floorf((fmaxf(py, ey) - mp.ey0) * mp.inv_cell);
-    for (int ix = max(ixa, 0); ix <= min(ixb, mp.gx - 1); ++ix)
-        for (int iy = max(iya, 0); iy <= min(iyb, mp.gy - 1); ++iy) {
-            if (!occupied(mp, ix, iy)) continue;
-            const float x0 = mp.ex0 + ix * mp.cell, x1 = x0 + mp.cell, y0 = mp.ey0 + iy * mp.cell, y1 = y0 + mp.cell;
-            float ent = -CUDART_INF_F, ext = CUDART_INF_F;
-            if (ray.x != 0.0f) {
-                const float t0 = (x0 - px) * ray.z, t1 = (x1 - px) * ray.z;
-                ent = fminf(t0, t1); ext = fmaxf(t0, t1);
-            } else if (px < x0 || px > x1) continue;
-            if (ray.y != 0.0f) {
-                const float t0 = (y0 - py) * ray.w, t1 = (y1 - py) * ray.w;
-                ent = fmaxf(ent, fminf(t0, t1)); ext = fminf(ext, fmaxf(t0, t1));
-            } else if (py < y0 || py > y1) continue;
-            const float lo = fmaxf(ent, 0.0f), hi = fminf(ext, 1.0f);
-            if (lo > hi) continue;
-            const bool inside = px > x0 && px < x1 && py > y0 && py < y1;
-            const float d = !inside ? lo * len : (ext <= 1.0f ? ext * len : CUDART_NAN_F);
-            sensed = d;
-            if (AUX) sensed_id = ix * mp.gy + iy;
-            if (d < shortest) { shortest = d; if (AUX) shortest_id = ix * mp.gy + iy; }
-        }
-    return GenericHit{shortest, sensed, shortest_id, sensed_id};
-}
 
 // order-preserving map float <-> unsigned (for redux.sync min / max over float values)
 __device__ __forceinline__ unsigned f2ord(float f) {
@@ -444,7 +303,8 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 struct Warp {
     const MapDev *map;
     const float4 *ray;
-    const float2 *lut;  // [16] window cell (row, column) * cell size
+    const DdaRay *dda;  // [R] walk constants of the rays (aac_radar.cuh)
+    WalkRef walk;       // the walk table
     int lane;
     int e_lo, ng, a0, nA;   // first env of the group, envs / drones in it, global index of its first drone
     float *px, *py, *vx, *vy, *hd, *ppx, *ppy, *pvx, *pvy;
@@ -452,8 +312,8 @@ struct Warp {
     float *agr, *d2, *stg, *own, *raw_own;
     uint8_t *order, *atgoal, *refw, *rs, *amap;   // amap: map row per drone (multipleMap)
     uint2 *win;
-    float2 *wrel;
-    const uint16_t *cells[1];  // unused placeholder (cells are read from global rows, see cells_of)
+    float4 *wrel;
+    uint16_t *c8;       // [32][8] first vertices of the reference lines
 };
 
 // lanes hold PI floats each for the items [0, n_valid) of one warp iteration; the block leaves as
@@ -476,8 +336,9 @@ __device__ __forceinline__ void flush_items(float *dst, int n_valid, const float
 
 // observation pipeline for the drones [a_lo, a_lo + n_ag) of the warp's group (whole envs):
 // neighbour order + window -> { pairs | rays | own block }.  `cells` = the lane's reference-line row.
-template <int VAR, bool AUX, bool LEAN, int NT, int RT>
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, int RM>
 __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, const int a_lo, const int n_ag, const uint16_t *cells, const bool tab) {
+    const int radar_mode = RM < 0 ? p.radar_mode : RM;   // RM >= 0: the radar mode is a compile-time constant of the instantiation
     // tab: the drones of the range have just been reset, i.e. stand on cell centres, and the handle has a radar table:
     // their ranges are looked up (they are what this very code computes for that cell, see aac_set_radar_table)
     const int lane = w.lane;
@@ -544,43 +405,13 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
             const int idx = row * MAP_STRIDE_CELLS + (int)floorf((px - mp.ex0) * mp.inv_cell) * mp.gy + (int)floorf((py - mp.ey0) * mp.inv_cell);
             w.win[a] = make_uint2(0u, (unsigned)idx);
             w.minr[a] = p.rtab_minr[idx];
-        } else if (VAR == AAC_VARIANT_ATT) {
-            w.minr[a] = 0x7F800000u;   // the one_model_att radar senses the other drones only: no occupancy window
-        } else {
-        // 4x4 occupancy window covering the square the rays can reach
-        const float fx = (px - p.ray_len - mp.ex0) * mp.inv_cell, fy = (py - p.ray_len - mp.ey0) * mp.inv_cell;
-        const int rx0 = (int)floorf(fx), ry0 = (int)floorf(fy);
-        const int ix0 = min(max(rx0, -MAP_PAD), mp.gx + MAP_PAD - 4), iy0 = min(max(ry0, -MAP_PAD), mp.gy + MAP_PAD - 4);
-        unsigned mask = 0;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int b = (ix0 + r + MAP_PAD) * mp.pgy + iy0 + MAP_PAD;
-            const unsigned lo = mp.bits[b >> 5], hi = mp.bits[min((b >> 5) + 1, MAP_WORDS - 1)];
-            mask |= (__funnelshift_r(lo, hi, b & 31) & 0xFu) << (4 * r);
-        }
-        const float wx = mp.ex0 + ix0 * mp.cell - px, wy = mp.ey0 + iy0 * mp.cell - py;
-        // drop the corner cells no ray of length ray_len can reach; flag the rare geometries
-        unsigned keep = 0, slow = (ix0 != rx0 || iy0 != ry0) ? W_SLOW : 0u;
-#pragma unroll 1
-        for (int r = 0; r < 4; ++r) {
-            const float nx = fmaxf(fmaxf(wx + r * mp.cell, -(wx + (r + 1) * mp.cell)), 0.0f);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float ny = fmaxf(fmaxf(wy + c * mp.cell, -(wy + (c + 1) * mp.cell)), 0.0f);
-                if (nx * nx + ny * ny <= p.ray_len * p.ray_len * 1.0001f) keep |= 1u << (4 * r + c);
-                if (nx == 0.0f && ny == 0.0f && ((mask >> (4 * r + c)) & 1u)) slow = W_SLOW;  // centre inside (or on) an occupied cell
-            }
-        }
-        mask &= keep;
-        // a line can only be crossed if it lies within ray reach along its axis
-        unsigned lines = 0;
-        if (fabsf(px + mp.hx) <= p.ray_len) lines |= 1u;
-        if (fabsf(px - mp.hx) <= p.ray_len) lines |= 2u;
-        if (fabsf(py + mp.hy) <= p.ray_len) lines |= 4u;
-        if (fabsf(py - mp.hy) <= p.ray_len) lines |= 8u;
-        w.win[a] = make_uint2(mask | (lines << W_LINE_SHIFT) | slow, (unsigned)(ix0 & 0xFFFF) | ((unsigned)iy0 << 16));
-        w.wrel[a] = make_float2(wx, wy);
-        w.minr[a] = 0x7F800000u;
+        } else if (VAR != AAC_VARIANT_ATT) {   // (the one_model_att radar senses the other drones only: no occupancy window)
+        // 5x5 occupancy window around the drone's own cell: every cell a ray of length ray_len can enter
+        float ax, ay, dlx, dly;
+        int ixc, iyc;
+        const unsigned win = build_window5(mp, px, py, p.ray_len, ax, ay, dlx, dly, ixc, iyc);
+        w.win[a] = make_uint2(win, (unsigned)(ixc & 0xFFFF) | ((unsigned)iyc << 16));
+        w.wrel[a] = make_float4(ax, ay, dlx, dly);
         }
     }
     __syncwarp();
@@ -661,97 +492,97 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
         }
     } else {
         const float len = p.ray_len;
-        auto entry_off = [&](const float4 ray, const float cell) { return make_float2(ray.z > 0.0f ? 0.0f : cell, ray.w > 0.0f ? 0.0f : cell); };
-        // the grid radar of one ray; WANT (radar_window) is the part of the result the caller's radar mode reads
-        auto cast_grid = [&](auto want_c, const int aa, const float4 ray, const float2 eo, float &out_min, int &id) -> float {
-            constexpr int WANT = decltype(want_c)::value;
-            const MapDev &mr = map_of(aa);
-            const uint2 wn = w.win[aa];
-            float shortest = CUDART_INF_F, sensed = len;
-            int shortest_id = -1, sensed_id = -1;
-            if (!(wn.x & W_SLOW))
-                radar_window<AUX, WANT>(mr, w.lut, w.wrel[aa], wn.x & 0xFFFFu, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16), ray, eo, len, shortest,
-                                        sensed, shortest_id, sensed_id);
-            else {
-                const GenericHit h = radar_generic<AUX>(mr, w.px[aa], w.py[aa], ray, len);
-                shortest = h.shortest; sensed = h.sensed; shortest_id = h.shortest_id; sensed_id = h.sensed_id;
-            }
-            if (wn.x & W_NEAR_BOUND) radar_bounds<AUX>(mr, w.px[aa], w.py[aa], ray, len, (wn.x >> W_LINE_SHIFT) & 0xFu, shortest, sensed, shortest_id, sensed_id);
-            if (WANT == 2) { out_min = sensed; return sensed; }
-            out_min = shortest == CUDART_INF_F ? len : shortest;
-            if (WANT == 1) return out_min;
-            const bool last_hit = VAR == AAC_VARIANT_V2 && p.radar_mode == AAC_RADAR_LAST_HIT;
-            if (AUX) id = last_hit ? sensed_id : shortest_id;
-            return last_hit ? sensed : out_min;
-        };
-        auto cast = [&](const int aa, const float4 ray, const float2 eo, float &out_min, int &id) -> float {
-            if (VAR == AAC_VARIANT_ATT) {
-                const MapDev &mr = map_of(aa);
-                const int ebb = (aa / N) * N;
-                float out;
-                radar_drones_ray(w.px, w.py, ebb, N, aa - ebb, ray, len, p.prot, mr.gx * mr.gy + 4, out, id);
-                out_min = out;
-                return out;
-            }
-            if (AUX) return cast_grid(std::integral_constant<int, 3>{}, aa, ray, eo, out_min, id);
-            if (VAR == AAC_VARIANT_V2 && p.radar_mode == AAC_RADAR_LAST_HIT) return cast_grid(std::integral_constant<int, 2>{}, aa, ray, eo, out_min, id);
-            return cast_grid(std::integral_constant<int, 1>{}, aa, ray, eo, out_min, id);
-        };
-        const int full = R >> 5, rem = R & 31;
+        // One pass over the rays of the range for one radar flavour (WANT: aac_radar.cuh).  A warp iteration covers 32 rays
+        // of ONE drone (full chunks) or `rem` leftover rays of 32 / rem drones; a lane casts the same ray for every drone,
+        // so the ray's walk constants stay in registers across the drone loop.  Ranges are >= 0: their bit patterns order
+        // like unsigned integers and nan (0x7FC00000) sorts above every number, so the per-drone minimum the reward needs
+        // (min_radar) is a redux per iteration, kept by the lane whose index is the drone's and stored once at the end.
         const size_t rg0 = (size_t)(w.a0 + a_lo) * R;
-        float *g_out = p.out.radar + rg0;
-        // full chunks: lanes = rays 32c .. 32c+31 of drone q
-        // a lane casts the same ray(s) for every drone: the table entry of the first chunk stays in registers
-        const float4 ray0 = w.ray[lane < R ? lane : 0];
-        const float cell = p.cell;
-        const float2 eo0 = entry_off(ray0, cell);
-#pragma unroll 1
-        for (int q = 0; q < n_ag; ++q) {
+        auto radar_pass = [&](auto want_c) {
+            constexpr int WANT = decltype(want_c)::value;
+            const bool last_hit = VAR == AAC_VARIANT_V2 && radar_mode == AAC_RADAR_LAST_HIT;
+            auto cast = [&](const int aa, const int k, const DdaRay &dr, float &out_min, int &id) -> float {
+                float out;
+                if (VAR == AAC_VARIANT_ATT) {
+                    const MapDev &mr = map_of(aa);
+                    const int ebb = (aa / N) * N;
+                    radar_drones_ray(w.px, w.py, ebb, N, aa - ebb, w.ray[k], len, p.prot, mr.gx * mr.gy + 4, out, id);
+                    out_min = out;
+                    return out;
+                }
+                const uint2 wn = w.win[aa];
+                bool done = false;
+                if (!(wn.x & WIN5_SLOW)) {
+                    int gx = 0, gy = 0;
+                    if (AUX) { const MapDev &mr = map_of(aa); gx = mr.gx; gy = mr.gy; }
+                    done = cast_grid_fast<WANT, AUX>(dr, WalkRef{0u, nullptr}, p.cell, w.wrel[aa], wn.x, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16), gx, gy, len, last_hit, out, out_min, id);
+                }
+                if (!done) {
+                    const SlowCast sc = cast_grid_slow<AUX>(map_of(aa), w.ray[k], w.px[aa], w.py[aa], wn.x, len, WANT == 3 ? (int)last_hit : (WANT == 2));
+                    out = sc.out; out_min = sc.out_min; id = sc.id;
+                }
+                return out;
+            };
+            const int full = R >> 5, rem = R & 31;
+            unsigned my_min = 0x7F800000u;   // lane q: the minimum of drone a_lo + q so far
 #pragma unroll 1
             for (int c = 0; c < full; ++c) {
                 const int k = (c << 5) + lane;
-                float out_min;
-                int id = -1;
-                const float4 ray = c == 0 ? ray0 : w.ray[k];
-                const float out = cast(a_lo + q, ray, c == 0 ? eo0 : entry_off(ray, cell), out_min, id);
-                g_out[q * R + k] = out;
-                if (AUX) { p.out.radar_min[rg0 + q * R + k] = out_min; p.out.radar_hit[rg0 + q * R + k] = (int16_t)id; }
-                const unsigned m = __reduce_min_sync(FULL, __float_as_uint(out));
-                if (lane == 0) w.minr[a_lo + q] = min(w.minr[a_lo + q], m);
-            }
-        }
-        // leftover rays: `per` drones share an iteration, `rem` lanes each
-        if (rem) {
-            const int per = 32 / rem;
-            const int sub = lane / rem, k = (full << 5) + lane - sub * rem;
-            const float4 rayr = w.ray[k < R ? k : 0];
-            const float2 eor = entry_off(rayr, cell);
+                DdaRay dr = w.dda[k];
+                dr.quad += w.walk.s;   // the walk table's shared-memory address rides in the ray's quadrant offset
+                float *g_row = p.out.radar + rg0 + k;
 #pragma unroll 1
-            for (int q0 = 0; q0 < n_ag; q0 += per) {
-                const int nsub = min(per, n_ag - q0);
-                const bool ok = sub < nsub;
-                const int q = q0 + (ok ? sub : 0);
-                float out_min;
-                int id = -1;
-                const float out = cast(a_lo + q, rayr, eor, out_min, id);
-                if (ok) {
-                    g_out[q * R + k] = out;
+                for (int q = 0; q < n_ag; ++q, g_row += R) {
+                    float out_min;
+                    int id = -1;
+                    const float out = cast(a_lo + q, k, dr, out_min, id);
+                    *g_row = out;
                     if (AUX) { p.out.radar_min[rg0 + q * R + k] = out_min; p.out.radar_hit[rg0 + q * R + k] = (int16_t)id; }
+                    const unsigned m = __reduce_min_sync(FULL, __float_as_uint(out));
+                    if (lane == q) my_min = min(my_min, m);
                 }
-                const unsigned key = ok ? __float_as_uint(out) : 0xFFFFFFFFu;
-                if ((rem & (rem - 1)) == 0) {   // aligned power-of-two lane groups: butterfly inside each drone's group
-                    unsigned m = key;
-                    for (int d = 1; d < rem; d <<= 1) m = min(m, __shfl_xor_sync(FULL, m, d));
-                    if (ok && lane == sub * rem) w.minr[a_lo + q] = min(w.minr[a_lo + q], m);
-                } else {
+            }
+            // leftover rays: `per` drones share an iteration, `rem` lanes each
+            if (rem) {
+                const int per = 32 / rem;
+                const int sub = lane / rem, k = (full << 5) + lane - sub * rem;
+                const int kr = k < R ? k : 0;
+                DdaRay drr = w.dda[kr];
+                drr.quad += w.walk.s;
 #pragma unroll 1
-                    for (int s2 = 0; s2 < nsub; ++s2) {
-                        const unsigned m = __reduce_min_sync(FULL, sub == s2 ? key : 0xFFFFFFFFu);
-                        if (lane == s2) w.minr[a_lo + q0 + s2] = min(w.minr[a_lo + q0 + s2], m);
+                for (int q0 = 0; q0 < n_ag; q0 += per) {
+                    const int nsub = min(per, n_ag - q0);
+                    const bool ok = sub < nsub;
+                    const int q = q0 + (ok ? sub : 0);
+                    float out_min;
+                    int id = -1;
+                    const float out = cast(a_lo + q, kr, drr, out_min, id);
+                    if (ok) {
+                        p.out.radar[rg0 + q * R + k] = out;
+                        if (AUX) { p.out.radar_min[rg0 + q * R + k] = out_min; p.out.radar_hit[rg0 + q * R + k] = (int16_t)id; }
+                    }
+                    const unsigned key = ok ? __float_as_uint(out) : 0xFFFFFFFFu;
+                    if ((rem & (rem - 1)) == 0) {   // aligned power-of-two lane groups: butterfly inside each drone's group
+                        unsigned m = key;
+                        for (int d = 1; d < rem; d <<= 1) m = min(m, __shfl_xor_sync(FULL, m, d));
+                        // lane q0 + s fetches the minimum of sub-group s
+                        const int s_of = lane - q0;
+                        const unsigned mine_m = __shfl_sync(FULL, m, (s_of >= 0 && s_of < per ? s_of : 0) * rem);
+                        if (s_of >= 0 && s_of < nsub) my_min = min(my_min, mine_m);
+                    } else {
+#pragma unroll 1
+                        for (int s2 = 0; s2 < nsub; ++s2) {
+                            const unsigned m = __reduce_min_sync(FULL, sub == s2 ? key : 0xFFFFFFFFu);
+                            if (lane == q0 + s2) my_min = min(my_min, m);
+                        }
                     }
                 }
             }
-        }
+            if (lane < n_ag) w.minr[a_lo + lane] = my_min;
+        };
+        if (AUX) radar_pass(std::integral_constant<int, 3>{});
+        else if (VAR == AAC_VARIANT_V2 && radar_mode == AAC_RADAR_LAST_HIT) radar_pass(std::integral_constant<int, 2>{});
+        else radar_pass(std::integral_constant<int, 1>{});
     }
     __syncwarp();
 
@@ -761,7 +592,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
         // agent.goal[-1]: the last vertex, or (multipleMap, where waypoints are popped from anywhere in the list,
         // MM:1757) the highest vertex still in the list
         const int glast = VAR == AAC_VARIANT_MM ? 31 - __clz(w.wpm[a] | 1u) : nw - 1;
-        const uint16_t cg = cells[glast];
+        const unsigned cg = glast < 8 ? w.c8[a * 8 + glast] : cells[glast];
         const float gx = cell_cx(mp, cg >> 8), gy = cell_cy(mp, cg & 255);
         const float px = w.px[a], py = w.py[a];
         float nvx = w.vx[a] * inv_vmax, nvy = w.vy[a] * inv_vmax;
@@ -894,7 +725,9 @@ __device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp
         const int a = g * N + lane;
         w.refw[a] = (uint8_t)nw;
         p.st.ref_w[(size_t)ge * N + lane] = (uint8_t)nw;
-        const uint16_t c0 = row[0], c1 = row[1];
+        const uint4 head = *reinterpret_cast<const uint4 *>(row);   // table paths and bank rows start on 16-byte boundaries
+        reinterpret_cast<uint4 *>(w.c8)[a] = head;
+        const unsigned c0 = head.x & 0xFFFFu, c1 = head.x >> 16;
         const float px = cell_cx(mp, c0 >> 8), py = cell_cy(mp, c0 & 255);
         w.px[a] = px; w.py[a] = py; w.vx[a] = 0.0f; w.vy[a] = 0.0f;
         w.hd[a] = atan2f(cell_cy(mp, c1 & 255) - py, cell_cx(mp, c1 >> 8) - px);  // ATT:359
@@ -907,9 +740,15 @@ __device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp
     return row;
 }
 
+// vertex k of a drone's reference line: the first 8 sit in shared memory (w.c8), longer lines continue in the global row
+struct CellRow {
+    const uint16_t *s, *g;
+    __device__ __forceinline__ unsigned operator[](int k) const { return k < 8 ? s[k] : g[k]; }
+};
+
 // distance to the reference polyline and arc length of the nearest point: first segment attaining the
 // minimum wins (ATT:3203-3214, V2:4286-4297, UV2:413-441).  Vertices come 8 per 16-byte load.
-__device__ __forceinline__ void polyline_nearest(const MapDev &mp, const uint16_t *cells, int nw, float px, float py, float &best2, float &arc,
+__device__ __forceinline__ void polyline_nearest(const MapDev &mp, const CellRow cells, int nw, float px, float py, float &best2, float &arc,
                                                  float &total) {
     best2 = CUDART_INF_F; arc = 0.0f;
     float run = 0.0f;
@@ -972,8 +811,11 @@ __device__ __noinline__ void evs_collisions(const KParams &p, const Warp &w, int
 // MT_STEP_ONLY = MODE_STEP without the fused auto-reset; MODE_RESET): the step launch then carries no reset code and the
 // reset launch no reward code - less code per launch is what the instruction cache rewards.
 constexpr int MT_STEP_ONLY = 3;
-template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1>
-__global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_constant__ KParams p, const int mode_arg) {
+#ifndef AAC_MIN_BLOCKS
+#define AAC_MIN_BLOCKS 4   // resident CTAs of 256 threads per SM the register allocation aims at (64 registers)
+#endif
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1, int RM = -1>
+__global__ void __launch_bounds__(MAX_THREADS, AAC_MIN_BLOCKS) env_kernel(const __grid_constant__ KParams p, const int mode_arg) {
     constexpr bool STEP_ONLY = MT == MT_STEP_ONLY;
     const int mode = MT < 0 ? mode_arg : (STEP_ONLY ? (int)MODE_STEP : MT);
     extern __shared__ __align__(16) unsigned char smem[];
@@ -998,22 +840,25 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
         if (blockIdx.x == 0) p.work[p.parity ^ 1] = 0;   // the next launch's group counter
     }
     for (int k = tid; k < p.R; k += blockDim.x) s_ray[k] = p.ray_tab[k];
-    float2 *s_lut = reinterpret_cast<float2 *>(smem + CL.lut);
-    if (tid < 16) s_lut[tid] = make_float2((float)(tid >> 2) * p.cell, (float)(tid & 3) * p.cell);
+    DdaRay *s_dda = reinterpret_cast<DdaRay *>(smem + CL.dda);
+    for (int k = tid; k < p.R; k += blockDim.x) s_dda[k] = p.dda_tab[k];
+    uint4 *s_walk = reinterpret_cast<uint4 *>(smem + CL.walk);
+    for (int k = tid; k < (int)(WALK_BYTES / 16); k += blockDim.x) s_walk[k] = p.walk_tab[k];
     __syncthreads();
     mbar_wait(s_bar, 0);
 
     unsigned char *ws = smem + CL.warps + (size_t)warp * WL.total;
     Warp w;
-    w.map = s_map; w.ray = s_ray; w.lut = s_lut; w.lane = lane;
+    w.map = s_map; w.ray = s_ray; w.dda = s_dda; w.walk.s = smem_u32(s_walk); w.walk.p = nullptr; w.lane = lane;
     w.px = reinterpret_cast<float *>(ws + WS_CUR); w.py = w.px + 32; w.vx = w.py + 32; w.vy = w.vx + 32; w.hd = w.vy + 32;
     w.ppx = reinterpret_cast<float *>(ws + WS_PRE); w.ppy = w.ppx + 32; w.pvx = w.ppy + 32; w.pvy = w.pvx + 32;
     w.meta = reinterpret_cast<unsigned *>(ws + WS_META); w.meta2 = w.meta + 32; w.minr = w.meta2 + 32; w.agf = w.minr + 32; w.wpm = w.agf + 32;
     w.agr = reinterpret_cast<float *>(ws + WS_AGR);
     w.atgoal = ws + WS_BYTES; w.refw = w.atgoal + 32; w.rs = w.refw + 32; w.amap = w.rs + 32;
     w.win = reinterpret_cast<uint2 *>(ws + WS_WIN);
-    w.wrel = reinterpret_cast<float2 *>(ws + WS_WREL);
+    w.wrel = reinterpret_cast<float4 *>(ws + WS_WREL);
     w.stg = reinterpret_cast<float *>(ws + WS_STG);
+    w.c8 = reinterpret_cast<uint16_t *>(ws + WS_C8);
     // the variable part: compile-time offsets too when the drone count is a template parameter
     const WarpLayout VL = NT ? make_warp_layout(VAR, NT, 0) : WL;
     w.d2 = reinterpret_cast<float *>(ws + VL.d2);
@@ -1022,8 +867,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
     w.raw_own = reinterpret_cast<float *>(ws + (NT ? WL.raw_own : VL.raw_own));
 
     // episode counters of this lane's envs (ATT/ma_main:581-637), flushed once per warp
-    int st_ep = 0, st_steps = 0, st_bits[7] = {0, 0, 0, 0, 0, 0, 0};
-    float st_ret = 0.0f;
+    // lane j of the warp carries statistic j (aac_read_stats order; lane 2 = the sum of returns, a float): two registers
+    // per lane instead of ten
+    int st_i = 0;
+    float st_f = 0.0f;
 
     // ---- persistent warp: fetch a group of G whole envs, run the pipeline, fetch the next
     const int n_groups = (p.E + G - 1) / G;
@@ -1066,6 +913,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
             w.px[a] = px; w.py[a] = py; w.vx[a] = vx; w.vy[a] = vy; w.hd[a] = hd;
             w.meta[a] = meta;
             w.refw[a] = p.st.ref_w[ga];
+            reinterpret_cast<uint4 *>(w.c8)[a] = *reinterpret_cast<const uint4 *>(cells);   // rows are 16-byte aligned (w_max % 8 == 0)
             if (VAR == AAC_VARIANT_MM) { w.amap[a] = (uint8_t)p.st.map_id[w.e_lo + my_env]; w.wpm[a] = p.st.wp_mask[ga]; }
         }
         __syncwarp();
@@ -1089,7 +937,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                 a_lo = g * N; n_ag = N;
                 cl = lane < N ? row : p.st.ref_cells;
             }
-            observe_range<VAR, AUX, LEAN, NT, RT>(p, w, a_lo, n_ag, cl, job > 0 && p.rtab != nullptr);
+            observe_range<VAR, AUX, LEAN, NT, RT, RM>(p, w, a_lo, n_ag, cl, job > 0 && p.rtab != nullptr);
             if (job > 0 || mode != MODE_STEP) continue;
 
             // ---- reward / collision / goal per drone
@@ -1150,7 +998,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                 if (collide_building && VAR == AAC_VARIANT_V2) meta |= M_VBLDG;
                 // waypoint (ATT:2297-2303)
                 const int cur = meta & 0xFF;
-                const uint16_t cw = cells[1 + cur], cg = cells[nw - 1];
+                const CellRow crow{w.c8 + a * 8, cells};
+                const unsigned cw = crow[1 + cur], cg = crow[nw - 1];
                 const float gx = cell_cx(mp, cg >> 8), gy = cell_cy(mp, cg & 255);
                 const float wdx = px - cell_cx(mp, cw >> 8), wdy = py - cell_cy(mp, cw & 255);
                 const bool wp_flag = wdx * wdx + wdy * wdy < 25.0f;
@@ -1164,7 +1013,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                 if (VAR == AAC_VARIANT_MM) {
                     // ss_reward of the multipleMap variant (MM:1674-2007): no drone-collision branch
                     unsigned mask = w.wpm[a];
-                    const uint16_t cl = cells[31 - __clz(mask | 1u)];   // goal[-1] before this step's pop (MM:1735)
+                    const unsigned cl = crow[31 - __clz(mask | 1u)];   // goal[-1] before this step's pop (MM:1735)
                     const float glx = cell_cx(mp, cl >> 8), gly = cell_cy(mp, cl & 255);
                     after_hg = sqrtf((px - glx) * (px - glx) + (py - gly) * (py - gly));
                     // waypoint scan (MM:1742-1762): walk the remaining waypoints in order; every new running minimum
@@ -1178,7 +1027,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                     while (scan) {
                         const int k = __ffs(scan) - 1;
                         scan &= scan - 1;
-                        const uint16_t c = cells[k];
+                        const unsigned c = crow[k];
                         const float wx = cell_cx(mp, c >> 8), wy = cell_cy(mp, c & 255);
                         const float d2 = (px - wx) * (px - wx) + (py - wy) * (py - wy);
                         if (d2 < smallest2) {
@@ -1193,7 +1042,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                                     while (s2) {
                                         const int q = __ffs(s2) - 1;
                                         s2 &= s2 - 1;
-                                        const uint16_t cq = cells[q];
+                                        const unsigned cq = crow[q];
                                         const float qx = cell_cx(mp, cq >> 8), qy = cell_cy(mp, cq & 255);
                                         const float dq = (px - qx) * (px - qx) + (py - qy) * (py - qy);
                                         if (dq < best) { best = dq; nwx = qx; nwy = qy; }
@@ -1210,7 +1059,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                     const float den = sqrtf(bx * bx + by * by) + sqrtf(cx * cx + cy * cy);
                     dist_to_goal = den > 0.0f ? ((bx - cx) * (bx + cx) + (by - cy) * (by + cy)) / den : 0.0f;
                     float best2, arc, total;
-                    polyline_nearest(mp, cells, nw, px, py, best2, arc, total);
+                    polyline_nearest(mp, crow, nw, px, py, best2, arc, total);
                     cross_err = sqrtf(best2);
                     const float dist_to_ref = cross_err <= p.prot ? 3.0f * (1.0f - cross_err / p.prot) : -3.0f;   // MM:1812-1817
                     near_drone = dist_to_ref;   // reported in the `near_drone` slot of the parts record
@@ -1241,12 +1090,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
                     }
                     if (flags & AAC_OUT_PARTS) {  // cross-track error is reported, not rewarded (ATT:2368 coefficient 0)
                         float best2, arc, total;
-                        polyline_nearest(mp, cells, nw, px, py, best2, arc, total);
+                        polyline_nearest(mp, crow, nw, px, py, best2, arc, total);
                         cross_err = sqrtf(best2);
                     }
                 } else {
                     float best2, arc, total;
-                    polyline_nearest(mp, cells, nw, px, py, best2, arc, total);
+                    polyline_nearest(mp, crow, nw, px, py, best2, arc, total);
                     cross_err = sqrtf(best2);
                     const float dist_left = cross_err + (total - arc);  // UV2:413-441
                     dist_to_goal = 6.0f * (1.0f - dist_left / total);    // V2:3257-3268
@@ -1295,45 +1144,82 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
 
             // ---- per env: crash penalties, summed reward, bound_building_check, episode end
             bool reset_me = false;
+            unsigned bbc = 0, any_done = 0, all_reach = 1, n_reach = 0, any_goal = 0, term = 0;
+            int step = 0;
+            float ret = 0.0f;
+            if (!EVS) {
+                // every drone's outcome flags meet in a handful of ballots; an env lane reads its env's bits out of them
+                const unsigned f = mine ? w.agf[a] : (4u << F_BRANCH_SHIFT), br = (f >> F_BRANCH_SHIFT) & 7u;
+                const unsigned b_dbl = __ballot_sync(FULL, br <= 2 && (f & F_DOUBLE));
+                if (VAR == AAC_VARIANT_V2 && br <= 2) {
+                    // the crash penalty doubles along the drone loop with every doubled crash up to and including this one
+                    // (V2:3590-3594): 20 * 2^count, exact
+                    const unsigned upto = b_dbl & (((N >= 32 ? FULL : ((1u << N) - 1u)) << (my_env * N)) & (0xFFFFFFFFu >> (31 - lane)));
+                    w.agr[a] = -__int_as_float(__float_as_int(20.0f) + (__popc(upto) << 23));
+                }
+                const unsigned b0 = __ballot_sync(FULL, br == 0), b1 = __ballot_sync(FULL, br == 1), b2 = __ballot_sync(FULL, br == 2);
+                const unsigned b3 = __ballot_sync(FULL, (f & F_BBC3) != 0), bd = __ballot_sync(FULL, (f & F_DONE) != 0);
+                const unsigned bg = __ballot_sync(FULL, (f & F_GOAL) != 0), brc = __ballot_sync(FULL, mine && (w.meta2[a] & M_REACH));
+                __syncwarp();
+                if (lane < w.ng) {
+                    const unsigned m = (N >= 32 ? FULL : ((1u << N) - 1u)) << (lane * N);
+                    bbc = ((b0 & m) ? 1u : 0u) | ((b1 & m) ? 2u : 0u) | ((b2 & m) ? 4u : 0u) | ((b3 & m) ? 8u : 0u);
+                    any_done = bd & m; any_goal = bg & m;
+                    all_reach = (brc & m) == m; n_reach = __popc(brc & m);
+                }
+            }
             if (lane < w.ng) {
                 const int ge = w.e_lo + lane, eb = lane * N;
-                float cp = 20.0f, sum = 0.0f;
-                unsigned bbc = 0, any_done = 0, all_reach = 1, n_reach = 0, any_goal = 0, evs_dcol = 0;
+                float sum = 0.0f;
+                if (EVS) {   // crash flags are live along the drone loop (V2:3128-3158): serial
+                    float cp = 20.0f;
+                    unsigned evs_dcol = 0;
 #pragma unroll 1
-                for (int i = 0; i < N; ++i) {
-                    if (EVS) evs_collisions(p, w, eb, i, N, M, Mp, evs_dcol);
-                    const unsigned f = w.agf[eb + i], br = (f >> F_BRANCH_SHIFT) & 7u;
-                    if (VAR == AAC_VARIANT_V2 && br <= 2) {
-                        if (f & F_DOUBLE) cp *= 2.0f;
-                        w.agr[eb + i] = -cp;
+                    for (int i = 0; i < N; ++i) {
+                        evs_collisions(p, w, eb, i, N, M, Mp, evs_dcol);
+                        const unsigned f = w.agf[eb + i], br = (f >> F_BRANCH_SHIFT) & 7u;
+                        if (br <= 2) {
+                            if (f & F_DOUBLE) cp *= 2.0f;
+                            w.agr[eb + i] = -cp;
+                            bbc |= 1u << br;
+                        }
+                        if (f & F_BBC3) bbc |= 8u;
+                        any_done |= f & F_DONE;
+                        any_goal |= f & F_GOAL;
+                        const unsigned reached = (w.meta2[eb + i] & M_REACH) ? 1u : 0u;
+                        all_reach &= reached;
+                        n_reach += reached;
                     }
-                    if (br <= 2) bbc |= 1u << br;
-                    if (f & F_BBC3) bbc |= 8u;
-                    any_done |= f & F_DONE;
-                    any_goal |= f & F_GOAL;
-                    const unsigned reached = (w.meta2[eb + i] & M_REACH) ? 1u : 0u;
-                    all_reach &= reached;
-                    n_reach += reached;
-                    sum += w.agr[eb + i];
                 }
+#pragma unroll 1
+                for (int i = 0; i < N; ++i) sum += w.agr[eb + i];
                 if (p.sum_reward) {  // reward = [sum(reward)] * N (ATT:2602-2603)
 #pragma unroll 1
                     for (int i = 0; i < N; ++i) w.agr[eb + i] = sum;
                     sum *= (float)N;
                 }
-                const int step = p.st.ep_step[ge] + 1;
-                const float ret = p.st.ep_return[ge] + sum;
-                const unsigned term = (step > p.ep_len ? 1u : 0u) | (any_done ? 2u : 0u) | (all_reach ? 4u : 0u);
+                step = p.st.ep_step[ge] + 1;
+                ret = p.st.ep_return[ge] + sum;
+                term = (step > p.ep_len ? 1u : 0u) | (any_done ? 2u : 0u) | (all_reach ? 4u : 0u);
                 reinterpret_cast<uchar4 *>(p.out.bbc)[ge] = make_uchar4(bbc & 1, (bbc >> 1) & 1, (bbc >> 2) & 1, (bbc >> 3) & 1);
                 p.out.terminated[ge] = (uint8_t)term;
-                if (term) {
-                    st_ep += 1; st_steps += step; st_ret += ret;
-                    st_bits[0] += bbc & 1; st_bits[1] += (bbc >> 1) & 1; st_bits[2] += (bbc >> 2) & 1; st_bits[3] += (bbc >> 3) & 1;
-                    st_bits[4] += all_reach; st_bits[5] += n_reach; st_bits[6] += term == 1u;
-                }
                 w.rs[lane] = any_goal ? 1 : 0;
                 reset_me = !STEP_ONLY && term && p.autoreset;
                 if (!reset_me) { p.st.ep_step[ge] = step; p.st.ep_return[ge] = ret; }
+            }
+            // episode counters (ATT/ma_main:581-637) of the envs that finished, summed over the group
+            const unsigned tb = __ballot_sync(FULL, term != 0);
+            if (tb && p.stats) {
+                const int steps_sum = __reduce_add_sync(FULL, term ? step : 0), reach_sum = __reduce_add_sync(FULL, term ? (int)n_reach : 0);
+                float r = term ? ret : 0.0f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
+                const int c0 = __popc(__ballot_sync(FULL, term && (bbc & 1u))), c1 = __popc(__ballot_sync(FULL, term && (bbc & 2u)));
+                const int c2 = __popc(__ballot_sync(FULL, term && (bbc & 4u))), c3 = __popc(__ballot_sync(FULL, term && (bbc & 8u)));
+                const int c4 = __popc(__ballot_sync(FULL, term && all_reach)), c6 = __popc(__ballot_sync(FULL, term == 1u));
+                st_i += lane == 0 ? __popc(tb) : lane == 1 ? steps_sum : lane == 3 ? c0 : lane == 4 ? c1 : lane == 5 ? c2 : lane == 6 ? c3 : lane == 7 ? c4
+                        : lane == 8 ? reach_sum : lane == 9 ? c6 : 0;
+                st_f += r;
             }
             reset_mask = STEP_ONLY ? 0u : __ballot_sync(FULL, reset_me);
             __syncwarp();
@@ -1363,34 +1249,18 @@ __global__ void __launch_bounds__(MAX_THREADS, 4) env_kernel(const __grid_consta
         __syncwarp();
     }
 
-    // ---- warp epilogue: episode counters (ATT/ma_main:581-637), one set of atomics per warp
-    if (mode == MODE_STEP && p.stats) {
-        const int ep = __reduce_add_sync(FULL, st_ep);
-        if (ep) {
-            const int steps = __reduce_add_sync(FULL, st_steps);
-            float ret = st_ret;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ret += __shfl_xor_sync(FULL, ret, o);
-            int b[7];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) b[k] = __reduce_add_sync(FULL, st_bits[k]);
-            if (lane == 0) {
-                atomicAdd(p.stats + 0, (double)ep);
-                atomicAdd(p.stats + 1, (double)steps);
-                atomicAdd(p.stats + 2, (double)ret);
-#pragma unroll
-                for (int k = 0; k < 7; ++k)
-                    if (b[k]) atomicAdd(p.stats + 3 + k, (double)b[k]);
-            }
-        }
+    // ---- warp epilogue: the counters leave, one atomic per statistic and warp
+    if (mode == MODE_STEP && p.stats && lane < 10) {
+        const double v = lane == 2 ? (double)st_f : (double)st_i;
+        if (v != 0.0) atomicAdd(p.stats + lane, v);
     }
 }
 
-template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1>
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1, int RM = -1>
 static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     const int wpc = threads / 32;
     const int groups = (p.E + p.G - 1) / p.G;
-    auto fn = env_kernel<VAR, AUX, LEAN, NT, RT, EVS, MT>;
+    auto fn = env_kernel<VAR, AUX, LEAN, NT, RT, EVS, MT, RM>;
     static int opted_in[64] = {0};   // dynamic shared memory this instantiation has opted in to, per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1418,9 +1288,14 @@ static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, 
 template <int VAR, int NT, int RT>
 static cudaError_t launch_aux(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     if (p.out_flags == 0) {
-        if (VAR == AAC_VARIANT_V2 && NT > 0 && RT > 0) {   // the two launches of a large batch's step: one kernel per mode
-            if (mode == MODE_STEP && !p.autoreset) return launch_one<VAR, false, true, NT, RT, false, MT_STEP_ONLY>(p, mode, threads, sms, grid_cache, stream);
-            if (mode == MODE_RESET) return launch_one<VAR, false, true, NT, RT, false, MODE_RESET>(p, mode, threads, sms, grid_cache, stream);
+        if (VAR == AAC_VARIANT_V2 && NT > 0 && RT > 0) {   // the two launches of a large batch's step: one kernel per mode and radar mode
+            const bool lh = p.radar_mode == AAC_RADAR_LAST_HIT;
+            if (mode == MODE_STEP && !p.autoreset)
+                return lh ? launch_one<VAR, false, true, NT, RT, false, MT_STEP_ONLY, AAC_RADAR_LAST_HIT>(p, mode, threads, sms, grid_cache, stream)
+                          : launch_one<VAR, false, true, NT, RT, false, MT_STEP_ONLY, AAC_RADAR_MIN>(p, mode, threads, sms, grid_cache, stream);
+            if (mode == MODE_RESET)
+                return lh ? launch_one<VAR, false, true, NT, RT, false, MODE_RESET, AAC_RADAR_LAST_HIT>(p, mode, threads, sms, grid_cache, stream)
+                          : launch_one<VAR, false, true, NT, RT, false, MODE_RESET, AAC_RADAR_MIN>(p, mode, threads, sms, grid_cache, stream);
         }
         return launch_one<VAR, false, true, NT, RT>(p, mode, threads, sms, grid_cache, stream);
     }

@@ -4,28 +4,12 @@
 #include <stdint.h>
 
 #include "../../include/aac_env.h"
+#include "aac_radar.cuh"
 
 namespace aac {
 
 constexpr int MAP_STRIDE_CELLS = 1024;   // rows per map in the radar table (= AAC_MAP_STRIDE: gx * gy <= 1024)
-constexpr int MAP_PAD = 4;      // free cells added on every side of the occupancy bitmap
-constexpr int MAP_WORDS = 64;   // 2048 bits: (gx + 8) * (gy + 8) + 32 must fit
 constexpr int MAX_THREADS = 256;
-
-// one map in the LOCAL frame (origin = bound centre): the bound is x in [-hx, hx], y in [-hy, hy].
-// Cell (ix, iy) covers [ex0 + ix*cell, ex0 + (ix+1)*cell] x [ey0 + iy*cell, ...]; occupancy is the
-// padded bitmap bit (ix + MAP_PAD) * pgy + (iy + MAP_PAD).  320 bytes, staged per CTA by one bulk copy.
-struct __align__(16) MapDev {
-    int gx, gy, pgx, pgy;
-    float hx, hy;          // half spans of the bound
-    float ex0, ey0;        // local lower edge of cell (0,0)
-    float ox, oy;          // global coordinates of the local origin
-    float xmin_g, ymin_g;  // global bound minima (ATT applies scale_pos to a delta)
-    float cell, inv_cell;
-    float ihx, ihy;        // 1 / hx, 1 / hy
-    uint32_t bits[MAP_WORDS];
-};
-static_assert(sizeof(MapDev) % 16 == 0, "MapDev is moved with 16-byte bulk copies");
 
 // origin / destination table of one map on the device (AacOdTable with device pointers)
 struct OdDev {
@@ -41,7 +25,7 @@ enum Mode : int { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_RESET = 2 };
 
 // shared-memory carve-up (byte offsets), computed once on the host: CTA-wide data, then one slice per warp
 struct CtaLayout {
-    unsigned map, ray, lut, bar, warps, total;
+    unsigned map, ray, dda, walk, bar, warps, total;
 };
 // Per-warp slice (32 drone slots).  The fixed-size arrays sit at compile-time offsets so the kernel addresses them
 // as `slice + immediate`; the arrays whose size depends on the drone count follow at WS_VAR.
@@ -50,10 +34,11 @@ constexpr unsigned WS_PRE = WS_CUR + 5 * 128;       // pre_pos, pre_vel         
 constexpr unsigned WS_META = WS_PRE + 4 * 128;      // meta, meta2, min radar bits, result flags, waypoint mask
 constexpr unsigned WS_AGR = WS_META + 5 * 128;      // reward
 constexpr unsigned WS_BYTES = WS_AGR + 128;         // at-goal flag, ref-line vertex count, per-env scratch, map row
-constexpr unsigned WS_WIN = WS_BYTES + 4 * 32;      // 4x4 occupancy window: mask | flags, ix0 | iy0 << 16
-constexpr unsigned WS_WREL = WS_WIN + 256;          // window origin relative to the drone
-constexpr unsigned WS_STG = WS_WREL + 256;          // transient staging of one warp iteration's pair blocks
-constexpr unsigned WS_VAR = WS_STG + 32 * 6 * 4;    // d2 [32][M|1] floats, order [32][M] bytes, own rows, raw own rows
+constexpr unsigned WS_WIN = WS_BYTES + 4 * 32;      // 5x5 occupancy window | line / slow flags (aac_radar.cuh), own cell ix | iy << 16
+constexpr unsigned WS_WREL = WS_WIN + 256;          // float4: low corner of the drone's cell and the boundary lines in reach, relative to the drone
+constexpr unsigned WS_STG = WS_WREL + 512;          // transient staging of one warp iteration's pair blocks
+constexpr unsigned WS_C8 = WS_STG + 32 * 6 * 4;     // the first 8 vertices of every drone's reference line (one 16-byte load per drone)
+constexpr unsigned WS_VAR = WS_C8 + 512;            // d2 [32][M|1] floats, order [32][M] bytes, own rows, raw own rows
 struct WarpLayout {
     unsigned d2, order, own, raw_own, total;        // byte offsets of the variable part inside the slice
 };
@@ -72,6 +57,8 @@ struct KParams {
     const MapDev *maps;
     int n_maps;
     const float4 *ray_tab;  // [R] (dx, dy, 1/dx, 1/dy) of the ray at k*360/R degrees; exact zeros on the axes, 1/0 = +inf
+    const DdaRay *dda_tab;  // [R] the same rays as the constants of the cell walk (aac_radar.cuh)
+    const uint4 *walk_tab;  // [WALK_BYTES / 16] the walk table
     int autoreset;          // MODE_STEP: re-initialise the envs that terminate and emit their reset observation
     const uint16_t *bank_cells;
     const uint8_t *bank_w;
@@ -114,7 +101,8 @@ inline CtaLayout make_cta_layout(const WarpLayout &WL, int R, int warps) {
     auto take = [&](unsigned bytes) { unsigned r = o; o = align16(o + bytes); return r; };
     L.map = take(sizeof(MapDev));
     L.ray = take(R * 16);
-    L.lut = take(16 * 8);
+    L.dda = take(R * sizeof(DdaRay));
+    L.walk = take(WALK_BYTES);
     L.bar = take(16);
     L.warps = take(0);
     L.total = L.warps + warps * WL.total;
