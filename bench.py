@@ -350,6 +350,7 @@ def main():
     ap.add_argument("--no-aux", action="store_true", help="skip the short runs of the other single-GPU workloads")
     ap.add_argument("--tile-envs", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--launches", type=int, default=0, help="auto-reset as 1 fused launch or 2 launches (0: the library's rule)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -390,7 +391,7 @@ def main():
     K.lib()
     gmap, bank = build_world(args.workload, args.scenarios, seed=1000)
     cfg = preset(preset_name, n_envs=envs, n_agents=n, n_rays=r, w_max=32, seed=1000, env_id_base=rank * envs,
-                 tile_envs=args.tile_envs, block_threads=args.threads)
+                 tile_envs=args.tile_envs, block_threads=args.threads, autoreset_launches=args.launches)
     env = BatchedDroneEnv(cfg, gmap, device=dev)
     if args.reset_source == "bank":
         env.set_bank(bank)

@@ -1,7 +1,7 @@
 // Grid radar (V2:1210-1300, MM:877-971; V2 = MADDPG_ownENV_randomOD_radar_N_model_use_tdCPA_forV2/env_simulator_...,
 // MM = ..._multipleMap/env_simulator_...): occupancy window, the cell walk of one ray, the generic closed-interval
-// routine and the boundary lines.  Everything here compiles for the host as well (tests/tools/radar_host.cpp runs the
-// same code against the float64 oracle without a GPU).
+// routine and the boundary lines.  Everything here compiles for the host as well (the CPU-side checks under tests/
+// run the same code without a GPU).
 //
 // The reference asks, per ray, every occupied 10 m cell whose box overlaps the ray's box whether the 15 m segment
 // intersects it, and keeps the distance to the nearest point of segment n cell boundary.  A 15 m ray from inside a

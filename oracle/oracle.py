@@ -147,6 +147,14 @@ class OracleEnv:
                                a.ctypes.data_as(C.c_void_p), C.byref(self._o))
         return self.out
 
+    def radar_candidate(self, xy, k, cand_id, map_id=0):
+        """Distance at which ray `k` of a drone at `xy` meets radar candidate `cand_id` (a cell index or gx*gy + line), or
+        None when the reference's `intersects` is false for it (nan: the ray lies strictly inside the cell)."""
+        d = C.c_double(0.0)
+        ok = lib().oracle_radar_candidate(C.byref(self.cfgs[map_id]), self.occ[map_id].ctypes.data_as(C.c_void_p), C.c_double(float(xy[0])),
+                                          C.c_double(float(xy[1])), C.c_int(int(k)), C.c_int(int(cand_id)), C.byref(d))
+        return d.value if ok else None
+
     def radar_probe(self, pos, i, map_id=0):
         """Radar of drone `i` for the position set pos[N,2] -> (stored value[R], true min[R], hit id[R])."""
         pos = np.ascontiguousarray(pos, dtype=np.float64)

@@ -1,9 +1,13 @@
 """Run the UNMODIFIED reference env_simulator classes from /root/reference (build container only).
 
 Test infrastructure: used by gen_golden.py to produce the committed fixtures under tests/golden/.
-Nothing here runs on the GPU box (no /root/reference there).  shapely is replaced by
-oracle/geos_lite.py; matplotlib / rtree / openpyxl / geopandas are inert stubs (the hot path never
-calls them; SURVEY.md section 8c "upgrade path").
+Nothing here runs on the GPU box (no /root/reference there).  Geometry: the REAL shapely when it can be
+imported (SURVEY.md section 8c "upgrade path": the rollouts are then pinned to GEOS itself), else
+oracle/geos_lite.py, the restatement of the GEOS operations the path uses - `GEOMETRY` says which one
+is active.  Neither this container nor the GPU boxes of rounds 1-2 have shapely (probed through gpurun,
+DESIGN.md section 5), so the committed fixtures were produced on geos_lite; tests/test_geos_conformance.py
+compares the two whenever shapely is present.  matplotlib / rtree / openpyxl / geopandas are inert stubs
+(the hot path never calls them).
 """
 import importlib
 import os
@@ -21,6 +25,16 @@ sys.path.insert(0, REPO)
 
 from oracle import geos_lite  # noqa: E402
 
+try:   # the real thing first (AAC_FORCE_GEOS_LITE=1 keeps the restatement, e.g. to regenerate the committed fixtures)
+    if os.environ.get("AAC_FORCE_GEOS_LITE"):
+        raise ImportError("geos_lite forced")
+    import shapely as _shapely
+    import shapely.geometry as _geom
+    GEOMETRY = "shapely " + _shapely.__version__
+except ImportError:
+    _shapely, _geom = None, geos_lite
+    GEOMETRY = "geos_lite (oracle/geos_lite.py)"
+
 VARIANTS = {
     "att": ("MADDPG_ownENV_randomOD_radar_one_model_att",
             "env_simulator_randomOD_radar_sur_drones_oneModel_att"),
@@ -32,7 +46,8 @@ VARIANTS = {
 
 
 def _install_stubs():
-    geos_lite.install_as_shapely()
+    if _shapely is None:
+        geos_lite.install_as_shapely()
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.markers", "matplotlib.transforms",
                  "matplotlib.patches", "matplotlib.colors", "matplotlib.animation", "rtree", "openpyxl",
                  "geopandas", "jps"):
@@ -65,7 +80,7 @@ def grid_polys(gmap):
     for ix in range(gmap.gx):
         for iy in range(gmap.gy):
             cx, cy = gmap.cell_centre(ix, iy)
-            sq = geos_lite.Point(cx, cy).buffer(h, cap_style=3)
+            sq = _geom.Point(cx, cy).buffer(h, cap_style=3)
             (ones if gmap.occ[ix, iy] else zeros).append(sq)
     return [[ones, zeros]]
 
@@ -83,7 +98,7 @@ def make_reference_env_mm(maps, n_agents, max_spd=5, acc_range=(-4, 4)):
         for ix in range(gmap.gx):
             for iy in range(gmap.gy):
                 cx, cy = gmap.cell_centre(ix, iy)
-                c = geos_lite.Point(cx, cy).buffer(gmap.grid_length / 2, cap_style=3).centroid
+                c = _geom.Point(cx, cy).buffer(gmap.grid_length / 2, cap_style=3).centroid
                 cropped[k][(ix, iy)] = [c.x, c.y]
     env = mod.env_simulator(world, [], maps[0].grid_length, bounds, polys, None, cropped)
     env.current_observable_space = lambda agent: []

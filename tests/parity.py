@@ -233,12 +233,38 @@ def compare_obs(T, variant, g, o, where, env_ok, s_gpu, orc, rows=None):
                 T.fail.append("%s %s env=%d drone=%d ray=%d got=%r want=%r pos=%r" % (k, where, e, i, r, g[k][e, i, r], o[k][e, i, r],
                                                                                       orc.state["pos"][e, i].tolist()))
         T.count(k, int(rows.sum()) * g[k].shape[1] * g[k].shape[2])
+    # Hit ids (bit-exact except counted boundary-epsilon ties).  A mismatch whose range agrees is a tie only if the oracle
+    # itself says so: either the candidate the CUDA env names is, for the oracle, at the same distance as its own hit (a ray
+    # through a corner or an edge shared by two cells, a cell face lying on a boundary line), or the oracle names that very
+    # candidate when the drone is displaced by +-RADAR_EPS (a grazing candidate: hit on one side, missed on the other).
+    # Anything else fails.
     hit_ok = (np.abs(g["radar"].astype(np.float64) - o["radar"]) <= 1e-3) & _bcast(rows & ~radar_tie_env, g["radar"].shape)
     badh = (g["radar_hit"].astype(np.int64) != o["radar_hit"]) & hit_ok
-    # equal-distance hits (a ray through a corner shared by two cells) may name either cell
     T.count("radar_hit", int(hit_ok.sum()))
-    if badh.any():
-        T.tie("radar_hit", int(badh.sum()))
+    for e, i, r in zip(*np.nonzero(badh)):
+        e, i, r = int(e), int(i), int(r)
+        gh, oh = int(g["radar_hit"][e, i, r]), int(o["radar_hit"][e, i, r])
+        mid = int(orc.env_map[e])
+        pos = orc.state["pos"][e]
+        want = float(o["radar"][e, i, r])
+        tie = False
+        if variant != "att":
+            d_g = float(orc.cfg.ray_len) if gh < 0 else orc.radar_candidate(pos[i], r, gh, mid)
+            d_o = float(orc.cfg.ray_len) if oh < 0 else orc.radar_candidate(pos[i], r, oh, mid)
+            if d_g is not None and d_o is not None and abs(d_g - d_o) <= RTOL * abs(d_o) + ATOL["radar"] and abs(d_g - want) <= RTOL * abs(want) + ATOL["radar"]:
+                tie = True
+        if not tie:
+            for dx, dy in ((RADAR_EPS, 0), (-RADAR_EPS, 0), (0, RADAR_EPS), (0, -RADAR_EPS), (RADAR_EPS, RADAR_EPS),
+                           (-RADAR_EPS, -RADAR_EPS), (RADAR_EPS, -RADAR_EPS), (-RADAR_EPS, RADAR_EPS)):
+                pp = pos.copy()
+                pp[i] += (dx, dy)
+                if int(orc.radar_probe(pp, i, map_id=mid)[2][r]) == gh:
+                    tie = True
+                    break
+        if tie:
+            T.tie("radar_hit", 1)
+        elif len(T.fail) < 50:
+            T.fail.append("radar_hit %s env=%d drone=%d ray=%d got=%d want=%d range=%r pos=%r" % (where, e, i, r, gh, oh, want, pos[i].tolist()))
     return radar_tie_env
 
 
