@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (preset, envs per GPU, drones, rays, description)
+    "c1": ("att", 1, 3, 18, "one_model_att reference scenario: 1 env x 3 drones, 18-ray radar, seeded random actions, 1000 steps on ONE CPU core (BASELINE config 1)"),
     "c2": ("att", 4096, 3, 36, "one_model_att 4096 envs x 3 drones, 36-ray radar, single grid map"),
     "c2r18": ("att", 4096, 3, 18, "one_model_att 4096 envs x 3 drones, 18-ray radar, single grid map"),
     "c3": ("tdcpa_v2", 65536, 10, 36, "tdCPA_forV2 65536 envs x 10 drones per GPU, 36-ray radar, single grid map"),
@@ -39,29 +40,41 @@ def algorithmic_bytes(variant, n, r):
     return 4 * (26 + 2 * W_REF + obs)
 
 
-PROFILED = ("r1_env_kernel_v2_ncu_full_summary.csv", "r1_env_kernel_v2_reset_ncu_full_summary.csv")   # step launch, reset launch
+PROFILED = ("r2_env_kernel_v2_step_ncu_full_summary.csv", "r2_env_kernel_v2_reset_ncu_full_summary.csv")   # step launch, reset launch
 
 
-def _profiled_rows(kernel_tag):
-    """The committed `ncu --set full` captures of the two launches of one step (profiles/), or None when they are of
-    another kernel."""
+def source_hash():
+    """sha256 over the kernel sources: a committed ncu capture belongs to the build that is being timed only if it
+    carries the same hash (tests/tools/ncu_summary.py writes it into the summary's `Source Hash` row)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("aac_kernels.cu", "aac_kernels.cuh", "aac_radar.cuh", "aac_capi.cu"):
+        h.update(open(os.path.join(ROOT, "multi_agent_aac_b200", "csrc", f), "rb").read())
+    h.update(open(os.path.join(ROOT, "include", "aac_env.h"), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def _profiled_rows(kernel_names):
+    """The committed `ncu --set full` captures of the two launches of one step (profiles/), or None unless each names
+    exactly the kernel instantiation this run launches AND was taken from this very source."""
     import csv
     out = []
-    for name in PROFILED:
+    for name, want in zip(PROFILED, kernel_names):
         rows = {r[0]: (r[1], r[2]) for r in csv.reader(open(os.path.join(ROOT, "profiles", name))) if len(r) == 3}
-        if not all(t in rows.get("Kernel Name", ("", ""))[1] for t in kernel_tag):
+        got = rows.get("Kernel Name", ("", ""))[1].replace("aac::", "").replace("(int)", "").replace("(bool)", "").replace(" ", "")
+        if want.replace(" ", "") not in got or rows.get("Source Hash", ("", ""))[1] != source_hash():
             return None
         out.append(rows)
     return out
 
 
-def profiled_traffic(kernel_tag):
+def profiled_traffic(kernel_names):
     """DRAM bytes per step (dram__bytes_read.sum + dram__bytes_write.sum, summed over the step launch and the reset
     launch) from the committed captures, or None."""
     try:
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         tot = 0.0
-        for rows in _profiled_rows(kernel_tag):
+        for rows in _profiled_rows(kernel_names):
             for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 unit, val = rows[k]
                 tot += float(val) * scale[unit]
@@ -70,12 +83,20 @@ def profiled_traffic(kernel_tag):
         return None
 
 
-def profiled_metric(name, kernel_tag):
+def profiled_metric(name, kernel_names):
     """One counter of the committed captures, summed over the two launches of a step, or None."""
     try:
-        return sum(float(rows[name][1]) for rows in _profiled_rows(kernel_tag))
+        return sum(float(rows[name][1]) for rows in _profiled_rows(kernel_names))
     except Exception:
         return None
+
+
+def launched_kernels(variant, n, r, radar_mode):
+    """The two instantiations one aac_step_autoreset call launches for the specialised tdCPA_forV2 shapes (aac_kernels.cu
+    launch_aux): env_kernel<VAR, AUX, LEAN, N, R, EVS, MT, RM>, MT = 3 step-only / 2 reset-only."""
+    if variant != "v2" or (n, r) not in ((10, 36), (20, 72)):
+        return None
+    return ["env_kernel<1,0,1,%d,%d,0,3,%d>" % (n, r, radar_mode), "env_kernel<1,0,1,%d,%d,0,2,%d>" % (n, r, radar_mode)]
 
 
 def measured_peak():
@@ -89,7 +110,7 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock, power and throttle reasons sampled through NVML every 10 ms while the timed region runs (the same counters
+    """SM clock, power and throttle reasons sampled through NVML every 4 ms while the timed region runs (the same counters
     `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; an `nvidia-smi -lms 25` stream is the fallback when
     the NVML binding cannot be loaded)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -130,7 +151,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append((time.perf_counter(), [str(sm), str(self.max_sm), "%.2f" % pw] + ["Active" if (b and rs & b) else "Not Active" for b in bits]))
                 except Exception:
                     pass
-                time.sleep(0.01)
+                time.sleep(0.004)
             return
         if not self.proc:
             return
@@ -314,6 +335,84 @@ def policy_rollout_att(env, dev, steps=200, warmup=5):
             "kernel": "actor_att_kernel (fp32 GEMM chain on the CUDA cores)"}
 
 
+def cpu_c1_run(steps=1000, seed=0):
+    """BASELINE config 1: the reference's own CPU-runnable case - ONE env of the one_model_att scenario (3 drones, 18 rays),
+    seeded random actions, `steps` steps with the caller's episode rule (reset on any done / all reached / 50-step cap,
+    ATT/ma_main:448-462), on ONE core: the float64 C port, single-threaded as the reference's loop is."""
+    from oracle.oracle import OracleEnv, RADAR_MIN
+    os.environ["OMP_NUM_THREADS"] = "1"
+    gmap, bank = build_world("c1", 64, seed=123)
+    n, r = 3, 18
+    orc = OracleEnv("att", gmap, 1, n, r, w_max=32, radar_mode=RADAR_MIN)
+    g = gmap.grid_length
+
+    def install(s):
+        lines = []
+        for i in range(n):
+            w = int(bank.w[s, i])
+            c = bank.cells[s, i, :w].astype(np.int64)
+            lines.append(np.stack([gmap.x0c + (c >> 8) * g, gmap.y0c + (c & 255) * g], -1).astype(np.float64))
+        heads = [float(np.arctan2(l[1][1] - l[0][1], l[1][0] - l[0][0])) for l in lines]
+        orc.set_episode(0, [l[0] for l in lines], lines, heads)
+        orc.observe()
+    rng = np.random.default_rng(seed)
+    acts = rng.uniform(-1, 1, size=(steps, 1, n, 2))
+    install(0)
+    episodes, ep_step = 0, 0
+    t0 = time.perf_counter()
+    for k in range(steps):
+        o = orc.step(acts[k])
+        ep_step += 1
+        if o["done"].any() or orc.state["reach"].all() or ep_step > 50:
+            episodes += 1
+            ep_step = 0
+            install(episodes % bank.n_scenarios)
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": "agent-steps/s", "cores": 1, "kind": "port",
+            "sample": "1 env x %d drones x %d rays, %d steps of the float64 C oracle on one core, %d episodes (reset on done / all reached / 50-step cap)" % (n, r, steps, episodes),
+            "seconds": dt}, dt / steps
+
+
+def seek_actions(env, noise):
+    """The goal-seeking scripted policy of tests/golden/ref_harness.py (steer at the next waypoint at 0.9 vmax, plus
+    noise) as torch ops on the device state: episodes last tens of steps instead of the 2-3 of uniform random actions."""
+    import torch
+    st, gm, cfg = env.state, env.gmap, env.cfg
+    cur = (st["meta"] & 0xFF).long()
+    idx = torch.minimum(cur + 1, st["ref_w"].long() - 1)
+    code = torch.gather(st["ref_cells"].long() & 0xFFFF, 2, idx[..., None])[..., 0]
+    cell = float(gm.grid_length)
+    wx = (gm.x0c - gm.origin[0]) + (code >> 8).float() * cell
+    wy = (gm.y0c - gm.origin[1]) + (code & 255).float() * cell
+    to = torch.stack([wx - st["px"], wy - st["py"]], -1)
+    want = to / to.norm(dim=-1, keepdim=True).clamp_min(1e-9) * (0.9 * cfg.vmax)
+    vel = torch.stack([st["vx"], st["vy"]], -1)
+    return ((want - vel) / (0.5 * cfg.acc_max) + 0.25 * noise).clamp_(-1.0, 1.0).contiguous()
+
+
+def low_reset_regime(env, dev, acts, steps=200, warmup=100):
+    """The same step with a goal-seeking policy driving the drones: few envs finish per step, so the reset launch has
+    little to do - the regime a trained policy produces.  Only the env calls are timed (CUDA events around each)."""
+    import torch
+    E, N = env.E, env.N
+    for k in range(warmup):
+        env.step(seek_actions(env, acts[k % len(acts)]), autoreset=True)
+    env.read_stats(reset=True)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+    stream = torch.cuda.current_stream(dev)
+    for k in range(steps):
+        a = seek_actions(env, acts[k % len(acts)])
+        ev[k][0].record(stream)
+        env.step(a, autoreset=True)
+        ev[k][1].record(stream)
+    torch.cuda.synchronize(dev)
+    ms = float(np.median([e[0].elapsed_time(e[1]) for e in ev]))
+    st = env.read_stats(reset=True)
+    return {"what": "scripted goal-seeking policy (steer at the next waypoint at 0.9 vmax + noise) instead of uniform random actions; env calls timed alone",
+            "ms_per_step": ms, "agent_steps_per_s": E * N / (ms * 1e-3), "steps": steps,
+            "envs_finishing_per_step": float(st[0]) / (E * steps), "mean_episode_steps": float(st[1]) / max(float(st[0]), 1.0)}
+
+
 _JSON_OUT = None
 
 
@@ -332,8 +431,18 @@ def emit(line):
     out.flush()
 
 
+def self_launch(args):
+    """`python bench.py --gpus N` outside torchrun: start the N ranks the way the driver does."""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    return subprocess.call(cmd)
+
+
 def main():
-    keep_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -351,7 +460,12 @@ def main():
     ap.add_argument("--tile-envs", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--launches", type=int, default=0, help="auto-reset as 1 fused launch or 2 launches (0: the library's rule)")
+    ap.add_argument("--blocks", type=int, default=0, help="timed blocks of --steps steps each (0: at least 10, enough for 0.3 s)")
     args = ap.parse_args()
+
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl != "reference" and args.workload != "c1":
+        return self_launch(args)   # one line: python bench.py --gpus 8 --workload c5
+    keep_stdout_for_the_json_line()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -362,14 +476,19 @@ def main():
     variant = variant_of(preset_name)
     bytes_per = algorithmic_bytes(variant, n, r)
 
-    if args.impl == "reference":
+    if args.impl == "reference" or args.workload == "c1":
         if rank != 0:
             return 0
-        sample = args.cpu_envs or max(64, min(8192, 80000 // n))
-        steps = max(1, min(args.steps, 20))
-        base, sec_per_step = cpu_reference_run(args.workload, steps, max(1, min(args.warmup, 2)), sample)
+        if args.workload == "c1":   # BASELINE config 1 is a CPU case whatever the arm: one env, one core
+            steps, warm = max(1, args.steps), 0
+            base, sec_per_step = cpu_c1_run(steps)
+            sample = 1
+        else:
+            sample = args.cpu_envs or max(64, min(8192, 80000 // n))
+            steps, warm = max(1, min(args.steps, 20)), max(1, min(args.warmup, 2))
+            base, sec_per_step = cpu_reference_run(args.workload, steps, warm, sample)
         line = {"impl": "reference", "metric": "agent_steps_per_sec", "value": base["value"], "unit": "agent-steps/s",
-                "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": sec_per_step * 1e3,
+                "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec_per_step * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": desc, "sample_envs": sample, "drones": n, "rays": r},
                 "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -411,35 +530,50 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    K_ = args.steps
+    step_no = [0]
+
+    def timed_block():
+        """EXACTLY K steps between two events, a barrier + synchronize on both sides; device time, max over ranks."""
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        h0 = time.perf_counter()
+        t0.record(stream)
+        for _ in range(K_):
+            env.step(acts[step_no[0] % n_act], autoreset=True)   # step + reward launch, then the reset launch for the envs that terminated
+            step_no[0] += 1
+        t1.record(stream)
+        host_ms = (time.perf_counter() - h0) * 1e3 / K_
+        barrier()
+        return max_over_ranks(t0.elapsed_time(t1)), host_ms
+
     for k in range(max(args.warmup, 3)):
         env.step(acts[k % n_act], autoreset=True)
-    barrier()
+    # The driver's K may be small (20 steps = 6 ms): the block is repeated - every block is exactly K steps, timed as the
+    # contract says - and the line carries the MEDIAN block with the spread; enough blocks for >= 0.3 s and >= 10 clock samples
+    probe_ms, _ = timed_block()
+    n_blocks = args.blocks or int(min(400, max(10, np.ceil(300.0 / max(probe_ms, 1e-3)))))
     launches0 = env.launch_count
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.3)   # let the first samples arrive
+        time.sleep(0.05)   # let the first samples arrive
     wall_t0 = time.perf_counter()
-    K_ = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K_)]
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record(stream)
-    host_t0 = time.perf_counter()
-    for k in range(K_):
-        ev[k][0].record(stream)
-        env.step(acts[k % n_act], autoreset=True)     # step + reward launch, then the reset launch for the envs that terminated
-        ev[k][1].record(stream)
-    t_end.record(stream)
-    host_issue_ms = (time.perf_counter() - host_t0) * 1e3 / K_
-    barrier()
-    elapsed_ms = t_start.elapsed_time(t_end)
-    step_kernel_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    launches = env.launch_count - launches0
-    clocks = sampler.summary(wall_t0, time.perf_counter()) if sampler else None
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+    blocks = [timed_block() for _ in range(n_blocks)]
+    wall_t1 = time.perf_counter()
+    launches = (env.launch_count - launches0) // n_blocks
+    clocks = sampler.summary(wall_t0, wall_t1) if sampler else None
+    block_ms = np.array([b[0] for b in blocks])
+    elapsed_ms = float(np.median(block_ms))
+    host_issue_ms = float(np.median([b[1] for b in blocks]))
+    step_kernel_ms = elapsed_ms / K_   # launches are issued back to back: the block IS the kernels (plus launch gaps on tiny batches)
     stats = torch.tensor(env.read_stats(), device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)  # episode statistics: the only collective of the path
@@ -455,19 +589,31 @@ def main():
     for k in range(args.e2e_steps):
         env.step_host(h_act[k % 2], autoreset=True)
     torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     h2d = int(h_act[0].numel() * 4)
     d2h = int(sum(v.numel() * v.element_size() for v in host.values()))
+    # the ceiling of that number: the bare copies of one step (same pinned buffers, same bytes, every rank at once, no kernel)
+    def bare_copies(reps):
+        barrier()
+        c0 = time.perf_counter()
+        for _ in range(reps):
+            env.d_actions_probe.copy_(h_act[0], non_blocking=True)
+            for k_, v in host.items():
+                v.copy_(env.out[k_], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return max_over_ranks(time.perf_counter() - c0) / reps
+    env.d_actions_probe = torch.empty_like(acts[0])
+    bare_copies(2)
+    copy_s = bare_copies(max(3, args.e2e_steps // 2))
 
     if rank == 0:
         agents_total = envs * n * world
         value = agents_total * K_ / (elapsed_ms * 1e-3)
         peak, peak_kind = measured_peak()
         achieved = envs * n * bytes_per / (step_kernel_ms * 1e-3) / 1e9
+        names = launched_kernels(variant, n, r, cfg.radar_mode)
+        traffic = profiled_traffic(names) if names else None
+        e2e_value = agents_total * args.e2e_steps / e2e_s
         line = {
             "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K_,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / K_, "higher_is_better": True, "scaling": "weak",
@@ -477,29 +623,36 @@ def main():
                        "reset": "device-side OD sampling from the map's origin/destination table" if args.reset_source == "od" else "scenario bank of %d" % args.scenarios,
                        "l2": "state+actions+outputs per step = %.0f MB > 126 MB L2, 8 rotating action buffers; no flush needed" % (envs * n * bytes_per / 1e6),
                        "tile_envs": args.tile_envs, "sharding": "envs by instance, no data-path collective"},
-            "e2e": {"value": agents_total * args.e2e_steps / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
-            "gpu_launches": int(launches),
-            "kernels": {"env_kernel(step+autoreset)_ms": step_kernel_ms, "host_issue_ms_per_step": host_issue_ms},
+            "repeat": {"blocks": n_blocks, "steps_per_block": K_, "ms_per_step_median": elapsed_ms / K_, "ms_per_step_min": float(block_ms.min()) / K_,
+                       "ms_per_step_max": float(block_ms.max()) / K_, "spread": float((block_ms.max() - block_ms.min()) / np.median(block_ms)),
+                       "note": "every block = exactly --steps steps between barrier + synchronize, CUDA events, max over ranks; value / ms_per_step are the median block"},
+            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+                    "roofline": {"bound": "host link (PCIe D2H into pinned memory)", "peak": agents_total / copy_s, "unit": "agent-steps/s", "frac": e2e_value * copy_s / agents_total,
+                                 "peak_GBs": (h2d + d2h) * world / copy_s / 1e9, "achieved_GBs": (h2d + d2h) * world * args.e2e_steps / e2e_s / 1e9,
+                                 "how": "the same pinned buffers and byte counts copied with no kernel in between, all ranks at once, timed the same way"}},
+            "gpu_launches": int(launches) * n_blocks,
+            "kernels": {"env_kernel(step+autoreset)_ms": step_kernel_ms, "host_issue_ms_per_step": host_issue_ms, "launches_per_step": launches / K_},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": profiled_traffic(("env_kernel<1,", " 10, 36,")) if args.workload == "c3" else None,
-                         "traffic_note": "bytes per step = step launch + reset launch, profiles/r1_env_kernel_v2*_ncu_full_summary.csv (one ncu --set full capture of each)",
+                         "traffic": traffic,
+                         "traffic_note": ("bytes per step = step launch + reset launch, profiles/%s + %s: one ncu --set full capture of each, of this very source (hash %s)" % (PROFILED + (source_hash(),)))
+                                         if traffic else "no ncu capture of this build (source hash %s) and these kernels under profiles/: null" % source_hash(),
                          "peak_kind": peak_kind, "bytes_per_agent_step": bytes_per,
-                         "kernel": "env_kernel<%s>: the step launch and the reset launch of one step, timed together" % variant.upper()},
+                         "kernel": ("%s + %s" % tuple(names)) if names else "env_kernel<%s>" % variant.upper()},
             "clocks": clocks,
-            "roofline_issue": None,
+            "issue_slots": None,
             "episode_stats": {k: float(v) for k, v in zip(K.STAT_NAMES, stats)},
         }
-        # what actually bounds the kernel (it is not HBM): warp-instruction issue.  Instructions per step (both launches) come from the
-        # committed ncu capture, the launch time and SM clock are this run's; peak = 4 schedulers x SMs x clock.
-        inst = profiled_metric("smsp__inst_executed.sum", ("env_kernel<1,", " 10, 36")) if args.workload == "c3" else None
+        # What bounds the kernel in practice (it is not HBM): warp-instruction issue.  This is a UTILISATION of the issue slots
+        # by the kernel's own instruction count - not a roofline fraction: it would rise if the kernel executed more instructions.
+        inst = profiled_metric("smsp__inst_executed.sum", names) if names else None
         if inst and clocks and clocks.get("sm_mhz"):
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             peak_issue = 4.0 * sms * clocks["sm_mhz"] * 1e6
-            line["roofline_issue"] = {"bound": "issue", "achieved": inst / (step_kernel_ms * 1e-3), "peak": peak_issue, "unit": "warp-inst/s",
-                                      "frac": inst / (step_kernel_ms * 1e-3) / peak_issue, "warp_inst_per_agent_step": inst / (envs * n),
-                                      "note": "instructions per step (step launch + reset launch) from profiles/r1_env_kernel_v2*_ncu_full_summary.csv; ncu itself reports smsp__issue_active and the pipe shares (profiles/README.md)"}
+            line["issue_slots"] = {"warp_inst_per_agent_step": inst / (envs * n), "utilisation": inst / (step_kernel_ms * 1e-3) / peak_issue,
+                                   "note": "instructions per step (step launch + reset launch) from the same committed captures; 4 schedulers x SMs x sampled clock"}
         if world == 1 and not args.no_aux and preset_name == "tdcpa_v2":
+            line["low_reset_regime"] = low_reset_regime(env, dev, acts)
             line["policy_rollout"] = policy_rollout(env, dev)
         if world == 1 and not args.no_aux and preset_name == "att":
             line["policy_rollout"] = policy_rollout_att(env, dev)

@@ -17,6 +17,8 @@
  *   - calls enqueue work on the given CUDA stream and return without synchronising;
  *   - return value 0 = ok, negative = AAC_ERR_*; aac_last_error() gives the message (thread local);
  *   - one AacEnv per device shard; a handle is not thread-safe, different handles are independent;
+ *   - all calls on ONE handle must be stream-ordered: issue them on one stream (or order the streams yourself): the
+ *     persistent kernels of a handle share its group counters, two of its launches must never run concurrently;
  *   - positions in AacState are LOCAL coordinates: global metres minus the map's bound centre
  *     (AacMapDesc.origin_*), float32.  Observations are emitted in the reference's global frame.
  */

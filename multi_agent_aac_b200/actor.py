@@ -12,7 +12,11 @@ actions come back in the `[E, N, 2]` layout `BatchedDroneEnv.step` takes, so a r
     actor = BatchedActor.for_env(env); actor.load_state_dict(reference_actor.state_dict())
     obs = env.reset()
     for _ in range(T):
-        obs, reward, done, info = env.step(actor(obs, noise_scale=var), autoreset=True)
+        obs, reward, done, info = env.step(actor(obs, noise_scale=var), autoreset=True)   # fresh noise at every call
+
+Exploration noise is `act + var * randn(2)` drawn anew for every drone at every call (V2/maddpg_agent:1290-1294).  The
+draws are counter based, keyed by (noise_seed, row); with no `noise_seed` the actor advances its own call counter, so
+successive calls never repeat a draw; pass `noise_seed` to make a call reproducible.
 
 Compute: bf16 tensor-core GEMM chain with fp32 accumulation inside one fused sm_100a kernel
 (csrc/aac_actor.cu); there is no fallback path.
@@ -78,8 +82,17 @@ class BatchedActor:
             raise ValueError("own / nbr / grid disagree on the number of rows")
         return n
 
-    def forward(self, own, nbr, grid, noise_scale=0.0, noise_seed=0, out=None):
-        """actions [..., 2] = clamp(actor(own, nbr, grid) + noise_scale * N(0, 1), -1, 1); leading dims follow `own`."""
+    def _seed(self, noise_seed):
+        """None -> this actor's own call counter (a new draw at every call), else the caller's seed."""
+        if noise_seed is not None:
+            return int(noise_seed)
+        self._calls = getattr(self, "_calls", 0) + 1
+        return 0x5EED0000 + self._calls
+
+    def forward(self, own, nbr, grid, noise_scale=0.0, noise_seed=None, out=None):
+        """actions [..., 2] = clamp(actor(own, nbr, grid) + noise_scale * N(0, 1), -1, 1); leading dims follow `own`.
+        noise_seed=None: fresh noise at every call; an int makes the call reproducible."""
+        noise_seed = self._seed(noise_seed)
         n = self._rows(own, nbr, grid)
         if out is None:
             out = torch.empty(tuple(own.shape[:-1]) + (K.NACT,), dtype=torch.float32, device=self.device)
@@ -90,7 +103,7 @@ class BatchedActor:
                                           out.data_ptr(), stream), "aac_actor_forward")
         return out
 
-    def __call__(self, obs, noise_scale=0.0, noise_seed=0, out=None):
+    def __call__(self, obs, noise_scale=0.0, noise_seed=None, out=None):
         """`obs`: the dict `BatchedDroneEnv.reset/step` returns ([obs, obs_full_nei, obs_grid] of V2/maddpg_agent:1243-1245)."""
         return self.forward(obs["norm_own"], obs["norm_nbr"], obs["radar"], noise_scale, noise_seed, out)
 
@@ -160,8 +173,12 @@ class BatchedAttActor:
         with torch.cuda.device(self.device):
             self._check(K.lib().aac_actor_att_load(self._h, C.byref(params)), "aac_actor_att_load")
 
-    def forward(self, own, grid, nei, noise_scale=0.0, noise_seed=0, out=None):
-        """actions [..., 2]; own [..., d_own], grid [..., d_grid], nei [..., n_nei, d_nei] (leading dims follow `own`)."""
+    def forward(self, own, grid, nei, noise_scale=0.0, noise_seed=None, out=None):
+        """actions [..., 2]; own [..., d_own], grid [..., d_grid], nei [..., n_nei, d_nei] (leading dims follow `own`).
+        noise_seed=None: fresh exploration noise at every call (the actor's own call counter keys the draws)."""
+        if noise_seed is None:
+            self._calls = getattr(self, "_calls", 0) + 1
+            noise_seed = 0x5EED0000 + self._calls
         for t, tail, name in ((own, (self.d_own,), "own"), (grid, (self.d_grid,), "grid"), (nei, (self.n_nei, self.d_nei), "nei")):
             if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device or tuple(t.shape[-len(tail):]) != tail:
                 raise ValueError("%s must be a contiguous float32 tensor [..., %s] on %s" % (name, ", ".join(map(str, tail)), self.device))
@@ -175,7 +192,7 @@ class BatchedAttActor:
                                                   int(noise_seed), out.data_ptr(), stream), "aac_actor_att_forward")
         return out
 
-    def __call__(self, obs, noise_scale=0.0, noise_seed=0, out=None):
+    def __call__(self, obs, noise_scale=0.0, noise_seed=None, out=None):
         """`obs`: the dict an att-preset `BatchedDroneEnv` returns ([obs, obs_grid, obs_nei] of ATT/maddpg_agent:457-459)."""
         return self.forward(obs["norm_own"], obs["radar"], obs["norm_nbr6"], noise_scale, noise_seed, out)
 

@@ -21,6 +21,7 @@ struct AacEnv {
     CtaLayout cl{};
     MapDev *d_maps = nullptr;
     int n_maps = 0;
+    std::vector<int> h_gx, h_gy;   // grid sizes of the installed maps (table validation)
     float4 *d_ray = nullptr;
     std::vector<float4> h_ray;   // host copy: the walk constants are derived from it once the cell size is known (aac_set_maps)
     DdaRay *d_dda = nullptr;
@@ -209,6 +210,8 @@ extern "C" int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *
     CU(cudaMemcpy(env->d_maps, host.data(), sizeof(MapDev) * n_maps, cudaMemcpyHostToDevice));
     env->n_maps = n_maps;
     env->cell = maps[0].cell;
+    env->h_gx.resize(n_maps); env->h_gy.resize(n_maps);
+    for (int m = 0; m < n_maps; ++m) { env->h_gx[m] = maps[m].gx; env->h_gy[m] = maps[m].gy; }
     // the rays as constants of the cell walk (aac_radar.cuh): they depend on the cell size
     std::vector<DdaRay> dda(env->h_ray.size());
     for (size_t k = 0; k < dda.size(); ++k) dda[k] = make_dda_ray(env->h_ray[k].x, env->h_ray[k].y, env->cell);
@@ -219,8 +222,9 @@ extern "C" int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *
 extern "C" int aac_set_bank(AacEnv *env, const AacBank *bank) {
     if (!env || !bank || bank->n_scenarios < 1 || !bank->cells || !bank->w) return fail(AAC_ERR_ARG, "aac_set_bank: bad argument");
     const size_t S = bank->n_scenarios, N = env->cfg.n_agents, W = env->cfg.w_max;
+    const size_t w_cap = env->cfg.variant == AAC_VARIANT_MM ? 31 : W;   // multipleMap keeps the remaining waypoints in a 32-bit mask ((1 << w) - 2)
     for (size_t k = 0; k < S * N; ++k)
-        if (bank->w[k] < 2 || bank->w[k] > W) return fail(AAC_ERR_ARG, "aac_set_bank: reference line needs 2..w_max vertices");
+        if (bank->w[k] < 2 || bank->w[k] > w_cap) return fail(AAC_ERR_ARG, "aac_set_bank: reference line needs 2..w_max (multipleMap: 31) vertices");
     if (bank->map_id)
         for (size_t k = 0; k < S; ++k)
             if (bank->map_id[k] < 0 || bank->map_id[k] >= (env->n_maps ? env->n_maps : 1)) return fail(AAC_ERR_ARG, "aac_set_bank: map_id out of range");
@@ -251,16 +255,32 @@ extern "C" int aac_set_od_tables(AacEnv *env, const AacOdTable *tables, int32_t 
         *dst = d;
         return cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
     };
+    // every check runs before the first upload of a table, and an error frees what earlier tables uploaded
+    auto reject = [&](const char *msg) {
+        for (void *b : bufs) cudaFree(b);
+        return fail(AAC_ERR_ARG, msg);
+    };
+    const int w_cap = env->cfg.variant == AAC_VARIANT_MM ? 31 : env->cfg.w_max;   // multipleMap keeps the remaining waypoints in a 32-bit mask
     for (int m = 0; m < n_maps; ++m) {
         const AacOdTable &t = tables[m];
-        if (t.n_cells < 2 || !t.cell_code || !t.path_off || !t.path_len || !t.path_cells) return fail(AAC_ERR_ARG, "aac_set_od_tables: incomplete table");
+        if (t.n_cells < 2 || !t.cell_code || !t.path_off || !t.path_len || !t.path_cells) return reject("aac_set_od_tables: incomplete table");
         for (int q = 0; q < 4; ++q)
-            if (t.pool_off[q + 1] <= t.pool_off[q]) return fail(AAC_ERR_ARG, "aac_set_od_tables: every quadrant pool needs at least one cell");
-        if (t.pool_off[0] != 0 || t.pool_off[4] != t.n_cells) return fail(AAC_ERR_ARG, "aac_set_od_tables: pool offsets do not cover the cells");
+            if (t.pool_off[q + 1] <= t.pool_off[q]) return reject("aac_set_od_tables: every quadrant pool needs at least one cell");
+        if (t.pool_off[0] != 0 || t.pool_off[4] != t.n_cells) return reject("aac_set_od_tables: pool offsets do not cover the cells");
+        if (t.n_path_cells < 0 || (t.n_path_cells & 7)) return reject("aac_set_od_tables: path_cells must be padded to a multiple of 8");
         const size_t P = t.n_cells;
-        for (size_t k = 0; k < P * P; ++k)
-            if (t.path_len[k] > env->cfg.w_max || (t.path_len[k] && (t.path_off[k] & 7u))) return fail(AAC_ERR_ARG, "aac_set_od_tables: a path has more than w_max vertices or is not 8-cell aligned");
-        if (t.n_path_cells & 7) return fail(AAC_ERR_ARG, "aac_set_od_tables: path_cells must be padded to a multiple of 8");
+        const int gx = env->d_maps ? env->h_gx[m] : 255, gy = env->d_maps ? env->h_gy[m] : 255;
+        for (size_t k = 0; k < P; ++k)
+            if ((t.cell_code[k] >> 8) >= gx || (t.cell_code[k] & 255) >= gy) return reject("aac_set_od_tables: a pool cell lies outside the map's grid");
+        for (size_t k = 0; k < P * P; ++k) {
+            if (!t.path_len[k]) continue;
+            if (t.path_len[k] < 2 || t.path_len[k] > w_cap || (t.path_off[k] & 7u)) return reject("aac_set_od_tables: a path has fewer than 2 or more than w_max (multipleMap: 31) vertices or is not 8-cell aligned");
+            if ((int64_t)t.path_off[k] + ((t.path_len[k] + 7) & ~7) > t.n_path_cells) return reject("aac_set_od_tables: a path runs past the end of path_cells");
+            for (int v = 0; v < t.path_len[k]; ++v) {
+                const uint16_t c = t.path_cells[t.path_off[k] + v];
+                if ((c >> 8) >= gx || (c & 255) >= gy) return reject("aac_set_od_tables: a path vertex lies outside the map's grid");
+            }
+        }
         OdDev &o = host[m];
         o.n_cells = t.n_cells;
         for (int q = 0; q < 5; ++q) o.pool_off[q] = t.pool_off[q];

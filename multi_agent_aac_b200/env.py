@@ -176,6 +176,11 @@ class BatchedDroneEnv:
             self.out[k] = t
         self._out_c = self._out_struct(self.out)
 
+    def _on_stream(self):
+        """Context in which torch ops are ordered with this env's launches (its own stream when one was given)."""
+        import contextlib
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+
     def _stream_ptr(self):
         s = self.stream if self.stream is not None else torch.cuda.current_stream(self.device)
         return C.c_void_p(s.cuda_stream)
@@ -241,6 +246,13 @@ class BatchedDroneEnv:
             py[k] = ey0 + (iy.astype(np.float32) + np.float32(0.5)) * cell
             code[k] = (ix << 8) | iy
         st, dev = probe.state, self.device
+        with self._on_stream():
+            self._fill_probe(probe, st, dev, px, py, code, n_maps, per_map, N, R, S)
+        ptr = lambda key: C.c_void_p(self._rtab[key].data_ptr()) if key in self._rtab else None
+        with torch.cuda.device(self.device):
+            K.check(self.L.aac_set_radar_table(self.h, ptr("radar"), ptr("radar_min"), ptr("radar_hit"), ptr("min_bits")), "aac_set_radar_table")
+
+    def _fill_probe(self, probe, st, dev, px, py, code, n_maps, per_map, N, R, S):
         st["px"].copy_(torch.from_numpy(px.reshape(-1, N)).to(dev))
         st["py"].copy_(torch.from_numpy(py.reshape(-1, N)).to(dev))
         cells = torch.from_numpy(code.reshape(-1, N).astype(np.int16)).to(dev)
@@ -258,16 +270,16 @@ class BatchedDroneEnv:
             self._rtab["radar_min"], self._rtab["radar_hit"] = grab("radar_min"), grab("radar_hit")
         torch.cuda.synchronize(dev)
         probe.close()
-        ptr = lambda key: C.c_void_p(self._rtab[key].data_ptr()) if key in self._rtab else None
-        with torch.cuda.device(self.device):
-            K.check(self.L.aac_set_radar_table(self.h, ptr("radar"), ptr("radar_min"), ptr("radar_hit"), ptr("min_bits")), "aac_set_radar_table")
 
     # ------------------------------------------------------------------ the env surface
     def reset(self, mask=None):
         """reset_world for the masked envs (all when mask is None) from the scenario bank."""
         m = None
         if mask is not None:
-            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            with self._on_stream():
+                m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            if self.stream is not None:
+                m.record_stream(self.stream)   # the reset kernel reads it after this call returns
         with torch.cuda.device(self.device):
             K.check(self.L.aac_reset(self.h, C.c_void_p(m.data_ptr()) if m is not None else None, C.byref(self._out_c),
                                      self._stream_ptr()), "aac_reset")
@@ -337,8 +349,9 @@ class BatchedDroneEnv:
         return {k: v.detach().cpu().clone() for k, v in self.state.items()}
 
     def load_state_dict(self, sd):
-        for k, v in sd.items():
-            self.state[k].copy_(v.to(self.device))
+        with self._on_stream():
+            for k, v in sd.items():
+                self.state[k].copy_(v.to(self.device))
         return self.observe()
 
     def close(self):
@@ -356,6 +369,10 @@ class BatchedDroneEnv:
     def set_episode(self, e, starts, lines, headings, map_id=0):
         """Install reset data for env `e` exactly as reset_world leaves it (ATT:301-372): start positions
         (global metres), reference lines (lists of cell-centre vertices) and headings."""
+        with self._on_stream():
+            self._set_episode(e, starts, lines, headings, map_id)
+
+    def _set_episode(self, e, starts, lines, headings, map_id):
         st, g = self.state, self.maps[map_id]
         ox, oy = g.origin
         N, W = self.N, self.cfg.w_max
@@ -414,6 +431,10 @@ class BatchedDroneEnv:
     def load_agent_state(self, pos, vel, heading=None, reach=None, wp_cur=None, prev_nn=None):
         """Overwrite the kinematic state (global metres) -- used by parity tests to keep the float32
         env on the float64 trajectory."""
+        with self._on_stream():
+            self._load_agent_state(pos, vel, heading, reach, wp_cur, prev_nn)
+
+    def _load_agent_state(self, pos, vel, heading, reach, wp_cur, prev_nn):
         st, dev = self.state, self.device
         org = self._env_origins()
         pos = np.asarray(pos, dtype=np.float64)

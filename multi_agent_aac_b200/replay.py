@@ -11,8 +11,13 @@ random (step, env) pairs with the next observation taken from the following slot
 copied on the way in.
 
 Slot s holds obs_s (what the actor saw), act_s, and the outcome of act_s: reward_s, done_s, terminated_s.  The
-observation produced by act_s lands in slot s + 1; for an env whose episode ended at s (terminated_s) that row is
-already the next episode's first observation (fused auto-reset), which is what the learner's (1 - done) mask expects.
+observation produced by act_s lands in slot s + 1; for an env whose episode ended at s (terminated_s != 0) that row is
+already the NEXT episode's first observation (auto-reset), so it must never be bootstrapped from.  `done` alone does
+not say that: the reference ends an episode with done = False at the step cap and when every drone has arrived, and
+pushes the true next state in those cases (ATT/ma_main:448-462, V2/ma_main:578-589).  `sample` therefore returns
+`bootstrap` = (terminated == 0): multiply the target critic's value by it instead of by (1 - done).  Crash endings are
+treated exactly as the reference treats them; the two done = False endings are treated as terminal (time-limit
+truncation handled as termination) rather than bootstrapped from an unrelated episode.
 """
 from __future__ import annotations
 
@@ -64,7 +69,9 @@ class DeviceReplay:
 
     def sample(self, batch, generator=None):
         """`batch` joint transitions (all N drones of one env at one step), uniformly over the stored ones:
-        dict of obs / act / reward / done / terminated / next_obs tensors with leading dimension `batch`."""
+        dict of obs / act / reward / done / terminated / bootstrap / next_obs tensors with leading dimension `batch`.
+        `bootstrap` [batch] is 1.0 where next_obs continues the same episode and 0.0 where the episode ended at this step
+        (next_obs is then the first observation of the following episode: mask the bootstrap term with it)."""
         if self.filled == 0:
             raise ValueError("the ring holds no completed transition yet")
         dev = self.env.device
@@ -77,4 +84,5 @@ class DeviceReplay:
             out["next_" + k] = self.obs[k][(s + 1) % self.T, e]
         for k, t in self.res.items():
             out[k] = t[s, e]
+        out["bootstrap"] = (out["terminated"] == 0).to(torch.float32)
         return out

@@ -170,6 +170,49 @@ def test_device_replay_ring_is_written_in_place():
         assert all(torch.equal(b["next_" + k][sel], nobs[k][e]) for k in OBS_KEYS)
 
 
+def test_replay_bootstrap_mask_covers_step_cap_endings():
+    """An episode that ends at the step cap carries done = 0 (ATT/ma_main:448-462): the ring's `bootstrap` mask - not
+    (1 - done) - must switch the bootstrap term off, because next_obs already belongs to the next episode."""
+    import torch
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import synthetic_map
+    from multi_agent_aac_b200.replay import DeviceReplay
+    from multi_agent_aac_b200.reset import OdTable
+    gmap = synthetic_map(seed=0)
+    env = BatchedDroneEnv(preset("tdcpa_v2", n_envs=64, n_agents=3, n_rays=18, w_max=32, seed=2, episode_length=2), gmap)
+    env.set_od_tables([OdTable(gmap, w_max=32)])
+    env.reset()
+    ring = DeviceReplay(env, 8)
+    ring.begin()
+    saw_cap = False
+    for t in range(5):
+        ring.action_slot().zero_()          # hovering drones neither crash nor arrive: the only ending is the step cap
+        _, _, done, info = ring.step()
+        cap = (info["terminated"] & 1).bool() & ~done.any(dim=1).bool()
+        saw_cap |= bool(cap.any())
+    assert saw_cap
+    b = ring.sample(2048, generator=torch.Generator(device="cuda").manual_seed(1))
+    ended = b["terminated"] != 0
+    assert bool(ended.any()) and bool((b["bootstrap"][ended] == 0).all()) and bool((b["bootstrap"][~ended] == 1).all())
+    capped = ended & ~b["done"].any(dim=1).bool()
+    assert bool(capped.any())               # (1 - done) would have bootstrapped these from an unrelated episode
+
+
+def test_actor_noise_is_fresh_at_every_call_unless_seeded():
+    import torch
+    from multi_agent_aac_b200.actor import BatchedActor
+    actor = BatchedActor(7, 45, 36, 256)
+    actor.load_state_dict(actor_oracle.reference_like_params(7, 45, 36, 3))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    own, nbr, grid = (torch.rand((256, d), device="cuda", generator=g) for d in (7, 45, 36))
+    clean = actor.forward(own, nbr, grid)
+    a, b = actor.forward(own, nbr, grid, noise_scale=0.1), actor.forward(own, nbr, grid, noise_scale=0.1)
+    assert not torch.equal(a, b)                                  # choose_action draws np.random.randn(2) per call (V2/maddpg_agent:1290-1294)
+    assert 0.03 < float((a - clean).std()) < 0.3 and abs(float(((a - clean) * (b - clean)).mean())) < 2e-3   # independent draws
+    c, d = actor.forward(own, nbr, grid, noise_scale=0.1, noise_seed=5), actor.forward(own, nbr, grid, noise_scale=0.1, noise_seed=5)
+    assert torch.equal(c, d)
+
+
 @pytest.mark.parametrize("name", ["actor_att", "actor_att_n5_r18"])
 def test_att_actor_matches_reference_fixture(name):
     """ActorNetwork_ATT_TwoPortion in fp32 against the float64 outputs of the unmodified reference class: 2e-5 absolute
