@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AAC_ABI_VERSION 2
+#define AAC_ABI_VERSION 3
 
 /* variants */
 #define AAC_VARIANT_ATT 0 /* one_model_att: radar senses other drones' 64-gons, summed reward      */
@@ -50,6 +50,15 @@ extern "C" {
 #define AAC_OUT_TCPA_PAIR 0x04 /* tcpa_pair, nbr_order                                               */
 #define AAC_OUT_RADAR_AUX 0x08 /* radar_min, radar_hit                                               */
 #define AAC_OUT_PARTS 0x10     /* reward parts, branch                                               */
+
+/* Radar target classes of the later fork (CS = MADDPG_ownENV_randomOD_radar_N_model_use_tdCPA_forV2_changeskin/
+ * env_simulator_..._changeskin.py:1379-1506).  AacConfig.radar_targets = 0 keeps the variant's own
+ * radar; any other value (tdCPA_forV2 only) switches to the fork's TRUE-MINIMUM radar over the classes named: */
+#define AAC_TARGET_CELLS 0x1    /* occupied grid cells (the older variants' buildings)                               */
+#define AAC_TARGET_BOUNDS 0x2   /* the four boundary SEGMENTS of the bound rectangle            (CS:676-680, :1418-1428) */
+#define AAC_TARGET_CLOUDS 0x4   /* moving clouds: outline of Point(pos).buffer(radius)          (CS:1430-1456)        */
+#define AAC_TARGET_AIRCRAFT 0x8 /* the other drones' protective outlines (include_other_AC)     (CS:1458-1490)        */
+#define AAC_MAX_CLOUDS 8
 
 #define AAC_ERR_ARG -1
 #define AAC_ERR_CUDA -2
@@ -87,6 +96,14 @@ typedef struct {
                                where they are, crashes do not end the episode (V2:3729-3734, :3128-3156, :3551-3587) */
     int32_t autoreset_launches; /* aac_step_autoreset / aac_step_host: 1 = one fused launch, 2 = step launch + reset launch,
                                0 = choose by batch size (two launches pay off on large tdCPA_forV2 batches) */
+    /* the later fork's sensor classes (tdCPA_forV2 only; all zero = off) */
+    int32_t radar_targets;  /* AAC_TARGET_* */
+    int32_t n_nbr_obs;      /* > 0: only the nearest n neighbours enter norm_nbr / raw_nbr, rows of 5 * n floats
+                               (use_nearestN_neigh_wRadar / N_neigh, CS:1799-1802) */
+    int32_t n_clouds;       /* <= AAC_MAX_CLOUDS */
+    float clouds[AAC_MAX_CLOUDS][6]; /* start x, y, goal x, y (global metres), radius, speed: a cloud starts every episode at its start
+                               and moves speed * dt towards its goal per step until closer than 1 m (cloud.py; CS:598-664, :4667-4681;
+                               calculate_next_position) */
 } AacConfig;
 
 /* one 10 m occupancy grid (ATT/grid_env_generation:140-185) */
@@ -136,10 +153,11 @@ typedef struct {
     float *tcpa_pair;     /* [E,N,N-1,4] tcpa,d,pre_tcpa,pre_d in neighbour order  AAC_OUT_TCPA_PAIR */
     int8_t *nbr_order;    /* [E,N,N-1]                                             AAC_OUT_TCPA_PAIR */
     float *radar_min;     /* [E,N,R]                                               AAC_OUT_RADAR_AUX */
-    int16_t *radar_hit;   /* [E,N,R] cell ix*gy+iy | gx*gy+{0..3} bound | gx*gy+4+j drone | -1 */
+    int16_t *radar_hit;   /* [E,N,R] cell ix*gy+iy | gx*gy+{0..3} bound | gx*gy+4+j drone | gx*gy+4+N+c cloud | -1 */
     float *parts;         /* [E,N,8] dist_to_goal, near_drone, near_bldg, small_step, cross_err,
                              after_dist_hg, min_radar, nearest_dist                AAC_OUT_PARTS */
     int8_t *branch;       /* [E,N] 0 bound 1 building 2 drone 3 goal 4 normal      AAC_OUT_PARTS */
+    uint8_t *cloud_contact; /* [E,N] the drone's protective circle overlaps a cloud (CS:4099-4110); may be NULL */
 } AacOut;
 
 /* pre-planned episodes the device resets from (host arrays; see reset.py ScenarioBank) */

@@ -11,12 +11,14 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AAC_LIB") or os.path.join(_HERE, "libaac_env.so")   # AAC_LIB: A/B builds while tuning kernels
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("aac_kernels.cu", "aac_capi.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", "aac_kernels.cuh"), os.path.join(os.path.dirname(_HERE), "include", "aac_env.h")]
+HEADERS = [os.path.join(_HERE, "csrc", "aac_kernels.cuh"), os.path.join(_HERE, "csrc", "aac_radar.cuh"), os.path.join(os.path.dirname(_HERE), "include", "aac_env.h")]
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 VARIANT_ATT, VARIANT_V2, VARIANT_MM = 0, 1, 2
 RADAR_MIN, RADAR_LAST_HIT = 0, 1
 OUT_RAW, OUT_NBR6, OUT_TCPA_PAIR, OUT_RADAR_AUX, OUT_PARTS = 0x01, 0x02, 0x04, 0x08, 0x10
+TARGET_CELLS, TARGET_BOUNDS, TARGET_CLOUDS, TARGET_AIRCRAFT = 0x1, 0x2, 0x4, 0x8   # the later fork's radar target classes
+MAX_CLOUDS = 8
 MAP_STRIDE = 1024
 N_STATS = 16
 STAT_NAMES = ["episodes", "steps", "return_sum", "bound_crash", "building_crash", "drone_crash", "drone_crash_nearest",
@@ -33,7 +35,8 @@ class AacConfig(C.Structure):
                 ("episode_length", C.c_int32), ("out_flags", C.c_int32), ("tile_envs", C.c_int32),
                 ("block_threads", C.c_int32), ("env_id_base", C.c_int64), ("seed", C.c_uint64),
                 ("dt", C.c_float), ("vmax", C.c_float), ("acc_max", C.c_float), ("prot", C.c_float),
-                ("ray_len", C.c_float), ("goal_r", C.c_float), ("eval_by_step", C.c_int32), ("autoreset_launches", C.c_int32)]
+                ("ray_len", C.c_float), ("goal_r", C.c_float), ("eval_by_step", C.c_int32), ("autoreset_launches", C.c_int32),
+                ("radar_targets", C.c_int32), ("n_nbr_obs", C.c_int32), ("n_clouds", C.c_int32), ("clouds", (C.c_float * 6) * MAX_CLOUDS)]
 
 
 class AacMapDesc(C.Structure):
@@ -45,7 +48,7 @@ STATE_FIELDS = ["px", "py", "vx", "vy", "heading", "meta", "ref_cells", "ref_w",
                 "ep_return", "map_id", "wp_mask"]
 OUT_FIELDS = ["norm_own", "norm_nbr", "radar", "norm_nbr6", "raw_own", "raw_nbr", "raw_nbr6", "reward", "done",
               "check_goal", "bbc", "terminated", "tcpa_min", "tcpa_pair", "nbr_order", "radar_min", "radar_hit", "parts",
-              "branch"]
+              "branch", "cloud_contact"]
 
 
 class AacState(C.Structure):

@@ -22,6 +22,7 @@ struct AacEnv {
     MapDev *d_maps = nullptr;
     int n_maps = 0;
     std::vector<int> h_gx, h_gy;   // grid sizes of the installed maps (table validation)
+    double h_ox = 0.0, h_oy = 0.0; // local-frame origin of map 0 (clouds are configured in global metres)
     float4 *d_ray = nullptr;
     std::vector<float4> h_ray;   // host copy: the walk constants are derived from it once the cell size is known (aac_set_maps)
     DdaRay *d_dda = nullptr;
@@ -80,6 +81,16 @@ extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
         return fail(AAC_ERR_ARG, "aac_create: the multipleMap variant has no neighbour outputs");
     if (cfg->eval_by_step && cfg->variant != AAC_VARIANT_V2) return fail(AAC_ERR_ARG, "aac_create: eval_by_step is a mode of the tdCPA_forV2 variant");
     if (cfg->autoreset_launches < 0 || cfg->autoreset_launches > 2) return fail(AAC_ERR_ARG, "aac_create: autoreset_launches must be 0, 1 or 2");
+    if (cfg->radar_targets || cfg->n_nbr_obs || cfg->n_clouds) {   // the later fork's sensor classes
+        if (cfg->variant != AAC_VARIANT_V2 || cfg->eval_by_step) return fail(AAC_ERR_ARG, "aac_create: the sensor classes extend the tdCPA_forV2 variant (training mode)");
+        if (cfg->radar_targets & ~0xF) return fail(AAC_ERR_ARG, "aac_create: unknown radar target class");
+        if (cfg->n_clouds < 0 || cfg->n_clouds > AAC_MAX_CLOUDS) return fail(AAC_ERR_ARG, "aac_create: at most AAC_MAX_CLOUDS clouds");
+        if ((cfg->radar_targets & AAC_TARGET_CLOUDS) && cfg->n_clouds < 1) return fail(AAC_ERR_ARG, "aac_create: AAC_TARGET_CLOUDS without clouds");
+        if (cfg->n_nbr_obs < 0 || cfg->n_nbr_obs > cfg->n_agents - 1) return fail(AAC_ERR_ARG, "aac_create: n_nbr_obs must lie in 0 .. n_agents - 1");
+        if (cfg->n_nbr_obs && (cfg->out_flags & (AAC_OUT_NBR6 | AAC_OUT_TCPA_PAIR))) return fail(AAC_ERR_ARG, "aac_create: the per-pair optional outputs cover every neighbour: not with n_nbr_obs");
+        for (int c = 0; c < cfg->n_clouds; ++c)
+            if (!(cfg->clouds[c][4] > 0) || !(cfg->clouds[c][5] >= 0)) return fail(AAC_ERR_ARG, "aac_create: a cloud needs a positive radius and a non-negative speed");
+    }
     if (cfg->n_envs < 1) return fail(AAC_ERR_ARG, "aac_create: n_envs < 1");
     if (cfg->n_agents < 1 || cfg->n_agents > AAC_MAX_AGENTS) return fail(AAC_ERR_ARG, "aac_create: n_agents out of range");
     if (cfg->n_rays < 1 || cfg->n_rays > AAC_MAX_RAYS || 360 % cfg->n_rays) return fail(AAC_ERR_ARG, "aac_create: n_rays must divide 360");
@@ -210,6 +221,7 @@ extern "C" int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *
     CU(cudaMemcpy(env->d_maps, host.data(), sizeof(MapDev) * n_maps, cudaMemcpyHostToDevice));
     env->n_maps = n_maps;
     env->cell = maps[0].cell;
+    env->h_ox = maps[0].origin_x; env->h_oy = maps[0].origin_y;
     env->h_gx.resize(n_maps); env->h_gy.resize(n_maps);
     for (int m = 0; m < n_maps; ++m) { env->h_gx[m] = maps[m].gx; env->h_gy[m] = maps[m].gy; }
     // the rays as constants of the cell walk (aac_radar.cuh): they depend on the cell size
@@ -531,13 +543,13 @@ static int check_out(const AacEnv *env, const AacOut *o, int mode) {
 }
 
 // advance every per-env / per-drone pointer of the state and output blocks to env `e_lo`
-static void offset_rows(AacState &s, AacOut &o, size_t e_lo, size_t N, size_t R, size_t W, size_t D) {
-    const size_t a = e_lo * N, M = N - 1;
+static void offset_rows(AacState &s, AacOut &o, size_t e_lo, size_t N, size_t R, size_t W, size_t D, size_t Mo) {
+    const size_t a = e_lo * N, M = N - 1;   // Mo: neighbours per drone in norm_nbr / raw_nbr (nearest-N selection)
 #define ADV(ptr, n) if (ptr) ptr += (n)
     ADV(s.px, a); ADV(s.py, a); ADV(s.vx, a); ADV(s.vy, a); ADV(s.heading, a); ADV(s.meta, a); ADV(s.ref_cells, a * W); ADV(s.ref_w, a);
     ADV(s.wall_count, a); ADV(s.ep_step, e_lo); ADV(s.ep_index, e_lo); ADV(s.ep_return, e_lo); ADV(s.map_id, e_lo); ADV(s.wp_mask, a);
-    ADV(o.norm_own, a * D); ADV(o.norm_nbr, a * 5 * M); ADV(o.radar, a * R); ADV(o.norm_nbr6, a * 6 * M);
-    ADV(o.raw_own, a * D); ADV(o.raw_nbr, a * 5 * M); ADV(o.raw_nbr6, a * 6 * M);
+    ADV(o.norm_own, a * D); ADV(o.norm_nbr, a * 5 * Mo); ADV(o.radar, a * R); ADV(o.norm_nbr6, a * 6 * M);
+    ADV(o.raw_own, a * D); ADV(o.raw_nbr, a * 5 * Mo); ADV(o.raw_nbr6, a * 6 * M); ADV(o.cloud_contact, a);
     ADV(o.reward, a); ADV(o.done, a); ADV(o.check_goal, a); ADV(o.bbc, e_lo * 4); ADV(o.terminated, e_lo); ADV(o.tcpa_min, a * 4);
     ADV(o.tcpa_pair, a * 4 * M); ADV(o.nbr_order, a * M); ADV(o.radar_min, a * R); ADV(o.radar_hit, a * R); ADV(o.parts, a * 8); ADV(o.branch, a);
 #undef ADV
@@ -559,6 +571,25 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     const AacConfig &c = env->cfg;
     p.E = c.n_envs; p.N = c.n_agents; p.R = c.n_rays; p.W = c.w_max; p.G = env->group;
     p.radar_mode = c.radar_mode; p.sum_reward = c.sum_reward; p.ep_len = c.episode_length; p.out_flags = c.out_flags; p.eval_by_step = c.eval_by_step;
+    p.radar_targets = c.radar_targets; p.n_nbr_obs = c.n_nbr_obs; p.n_clouds = c.n_clouds;
+    for (int ci = 0; ci < c.n_clouds; ++ci) {
+        // local frame; the stop step is found by walking the cloud as the fork does (calculate_next_position, float64)
+        const double ox = env->h_ox, oy = env->h_oy, travel = (double)c.clouds[ci][5] * c.dt;
+        double x = c.clouds[ci][0], y = c.clouds[ci][1];
+        const double gx = c.clouds[ci][2], gy = c.clouds[ci][3];
+        const double d0 = sqrt((gx - x) * (gx - x) + (gy - y) * (gy - y));
+        int n_stop = 0;
+        while (n_stop < (1 << 20) && travel > 0) {
+            const double d = sqrt((gx - x) * (gx - x) + (gy - y) * (gy - y));
+            if (d < 1.0) break;
+            x += (gx - x) / d * travel; y += (gy - y) / d * travel;
+            ++n_stop;
+        }
+        CloudDev &cd = p.clouds[ci];
+        cd.sx = (float)(c.clouds[ci][0] - ox); cd.sy = (float)(c.clouds[ci][1] - oy);
+        cd.dx = d0 >= 1.0 ? (float)((gx - c.clouds[ci][0]) / d0) : 0.0f; cd.dy = d0 >= 1.0 ? (float)((gy - c.clouds[ci][1]) / d0) : 0.0f;
+        cd.travel = (float)travel; cd.radius = c.clouds[ci][4]; cd.n_stop = n_stop; cd.pad_ = 0;
+    }
     p.cell = env->cell; p.dt = c.dt; p.vmax = c.vmax; p.acc_max = c.acc_max; p.prot = c.prot; p.ray_len = c.ray_len; p.goal_r = c.goal_r;
     p.env_id_base = c.env_id_base; p.seed = c.seed;
     p.maps = env->d_maps; p.n_maps = env->n_maps; p.ray_tab = env->d_ray; p.dda_tab = env->d_dda; p.walk_tab = env->d_walk; p.autoreset = autoreset;
@@ -572,7 +603,7 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
         p.env_id_base += e_lo;
         if (p.mask) p.mask += e_lo;
         if (p.actions) p.actions += (size_t)e_lo * c.n_agents * 2;
-        offset_rows(p.st, p.out, e_lo, c.n_agents, c.n_rays, c.w_max, own_dim(c.variant, c.n_agents));
+        offset_rows(p.st, p.out, e_lo, c.n_agents, c.n_rays, c.w_max, own_dim(c.variant, c.n_agents), c.n_nbr_obs > 0 ? c.n_nbr_obs : c.n_agents - 1);
     }
     cudaError_t e = launch_env_kernel(c.variant, p, mode, env->threads, env->sms, &env->grid, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "env_kernel launch");
@@ -650,6 +681,7 @@ extern "C" int aac_step_host(AacEnv *env, const float *actions_host, const AacOu
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t E = env->cfg.n_envs, N = env->cfg.n_agents, M = N - 1, R = env->cfg.n_rays;
     const size_t D = own_dim(env->cfg.variant, (int)N);
+    const size_t Mo = env->cfg.n_nbr_obs > 0 ? (size_t)env->cfg.n_nbr_obs : M;
     if (!env->d_actions) CU(cudaMalloc(&env->d_actions, E * N * 2 * sizeof(float)));
     if (!env->pipe[0]) {
         for (auto &s : env->pipe) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -678,8 +710,8 @@ extern "C" int aac_step_host(AacEnv *env, const float *actions_host, const AacOu
                                                                      : launch(env, MODE_STEP, nullptr, env->d_actions, od, s, autoreset ? 1 : 0, (int)e_lo, (int)cnt, 1 + (int)ch);
         if (rc) return rc;
         // the wide observation blocks leave with their chunk ...
-        ROWS(norm_own, N * D * 4, e_lo, cnt, s); ROWS(norm_nbr, N * 5 * M * 4, e_lo, cnt, s); ROWS(radar, N * R * 4, e_lo, cnt, s);
-        ROWS(norm_nbr6, N * M * 24, e_lo, cnt, s); ROWS(raw_own, N * D * 4, e_lo, cnt, s); ROWS(raw_nbr, N * 5 * M * 4, e_lo, cnt, s);
+        ROWS(norm_own, N * D * 4, e_lo, cnt, s); ROWS(norm_nbr, N * 5 * Mo * 4, e_lo, cnt, s); ROWS(radar, N * R * 4, e_lo, cnt, s);
+        ROWS(norm_nbr6, N * M * 24, e_lo, cnt, s); ROWS(raw_own, N * D * 4, e_lo, cnt, s); ROWS(raw_nbr, N * 5 * Mo * 4, e_lo, cnt, s);
         ROWS(raw_nbr6, N * M * 24, e_lo, cnt, s); ROWS(tcpa_pair, N * M * 16, e_lo, cnt, s); ROWS(radar_min, N * R * 4, e_lo, cnt, s);
         ROWS(radar_hit, N * R * 2, e_lo, cnt, s);
     }
@@ -693,7 +725,7 @@ extern "C" int aac_step_host(AacEnv *env, const float *actions_host, const AacOu
     }
     ROWS(reward, N * 4, 0, E, last); ROWS(done, N, 0, E, last); ROWS(check_goal, N, 0, E, last); ROWS(bbc, 4, 0, E, last);
     ROWS(terminated, 1, 0, E, last); ROWS(tcpa_min, N * 16, 0, E, last); ROWS(nbr_order, N * M, 0, E, last);
-    ROWS(parts, N * 32, 0, E, last); ROWS(branch, N, 0, E, last);
+    ROWS(parts, N * 32, 0, E, last); ROWS(branch, N, 0, E, last); ROWS(cloud_contact, N, 0, E, last);
 #undef ROWS
     CU(cudaEventRecord(env->pipe_ev[0], last));
     CU(cudaStreamWaitEvent(stream, env->pipe_ev[0], 0));

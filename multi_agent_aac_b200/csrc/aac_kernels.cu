@@ -299,6 +299,37 @@ __device__ __forceinline__ void radar_drones_ray(const float *s_px, const float 
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
+// ---- the later fork's sensor classes (CS:1379-1506; aac_env.h AAC_TARGET_*) ----------------------------------------
+__device__ __forceinline__ float2 cloud_pos(const CloudDev &c, int k) {
+    const float s = (float)min(k, c.n_stop) * c.travel;
+    return make_float2(fmaf(c.dx, s, c.sx), fmaf(c.dy, s, c.sy));
+}
+// ray q + t d (t in [0, 1]) against the OUTLINE of the regular 64-gon of radius r centred at the origin: parameter of the
+// nearest intersection point (entry when the ray starts outside, exit when it starts inside), +inf when there is none
+// (CS:1436-1448: min over the points of line n polygon.boundary)
+__device__ __noinline__ float ray_gon_outline(float qx, float qy, float dx, float dy, float r) {
+    // the polygon lies inside its circle: a ray that stays farther than r from the centre cannot touch it
+    float tt = -(qx * dx + qy * dy) / (dx * dx + dy * dy);
+    tt = fminf(fmaxf(tt, 0.0f), 1.0f);
+    const float cx = fmaf(tt, dx, qx), cy = fmaf(tt, dy, qy);
+    if (cx * cx + cy * cy > r * r * 1.00001f) return CUDART_INF_F;
+    const float apo = r * c_apo;
+    float lo = 0.0f, hi = 1.0f;
+    bool inside = true;
+#pragma unroll 1
+    for (int e = 0; e < 64; ++e) {   // clip to every half-plane n_e . x <= apothem
+        const float f0 = apo - fmaf(c_n64[e].x, qx, c_n64[e].y * qy);
+        const float f1 = -fmaf(c_n64[e].x, dx, c_n64[e].y * dy);
+        inside = inside && f0 >= 0.0f;
+        if (f1 == 0.0f) { if (f0 < 0.0f) return CUDART_INF_F; continue; }
+        const float t = -f0 / f1;
+        if (f1 > 0.0f) lo = fmaxf(lo, t); else hi = fminf(hi, t);
+        if (lo > hi) return CUDART_INF_F;
+    }
+    if (!inside) return lo;
+    return hi < 1.0f ? hi : CUDART_INF_F;
+}
+
 // per-warp shared-memory slice (32 drone slots) and the handles a warp needs
 struct Warp {
     const MapDev *map;
@@ -336,8 +367,10 @@ __device__ __forceinline__ void flush_items(float *dst, int n_valid, const float
 
 // observation pipeline for the drones [a_lo, a_lo + n_ag) of the warp's group (whole envs):
 // neighbour order + window -> { pairs | rays | own block }.  `cells` = the lane's reference-line row.
-template <int VAR, bool AUX, bool LEAN, int NT, int RT, int RM>
-__device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, const int a_lo, const int n_ag, const uint16_t *cells, const bool tab) {
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, int RM, bool CS>
+__device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, const int a_lo, const int n_ag, const uint16_t *cells, const bool tab,
+                                              const bool step_mode) {
+    // step_mode: the observation closes a step (sensor configurations: the clouds have moved once more than ep_step says)
     const int radar_mode = RM < 0 ? p.radar_mode : RM;   // RM >= 0: the radar mode is a compile-time constant of the instantiation
     // tab: the drones of the range have just been reset, i.e. stand on cell centres, and the handle has a radar table:
     // their ranges are looked up (they are what this very code computes for that cell, see aac_set_radar_table)
@@ -418,10 +451,12 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
 
     // ---- ordered pairs -> tdCPA (cur, pre) and the neighbour blocks of the observation
     if (M > 0 && VAR != AAC_VARIANT_MM) {
-        const int n_items = n_ag * M;
-        const size_t pg0 = (size_t)(w.a0 + a_lo) * M;  // global index of the range's first pair
-        for (Walk it(lane, 32, M); it.hi * M + it.lo - lane < n_items; it.next()) {
-            const int idx = it.hi * M + it.lo, base = idx - lane;   // base = first item of this warp iteration
+        // Mo = neighbours per drone that enter the blocks: all of them, or (sensor configurations) the nearest n_nbr_obs
+        const int Mo = (CS && p.n_nbr_obs > 0) ? min(p.n_nbr_obs, M) : M;
+        const int n_items = n_ag * Mo;
+        const size_t pg0 = (size_t)(w.a0 + a_lo) * Mo;  // global index of the range's first pair
+        for (Walk it(lane, 32, Mo); it.hi * Mo + it.lo - lane < n_items; it.next()) {
+            const int idx = it.hi * Mo + it.lo, base = idx - lane;   // base = first item of this warp iteration
             const int n_valid = min(32, n_items - base);
             const bool ok = idx < n_items;
             const int aa = a_lo + (ok ? it.hi : 0), k = ok ? it.lo : 0, pi = aa * M + k;
@@ -511,6 +546,60 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
                     return out;
                 }
                 const uint2 wn = w.win[aa];
+                if (CS) {
+                    // the later fork's radar: true minimum over the configured target classes, in ray-parameter space
+                    const MapDev &mr = map_of(aa);
+                    const float4 ray = w.ray[k];
+                    const float px = w.px[aa], py = w.py[aa];
+                    const int nb = mr.gx * mr.gy, ebb = (aa / N) * N;
+                    float best = CUDART_INF_F;
+                    id = -1;
+                    if (p.radar_targets & AAC_TARGET_CELLS) {
+                        bool ok_walk = false;
+                        float o1 = len, m1 = len;
+                        int id1 = -1;
+                        if (!(wn.x & WIN5_SLOW)) {   // the walk with no boundary line in reach (the lines are a class of their own here)
+                            const float4 rel = w.wrel[aa];
+                            ok_walk = cast_grid_fast<AUX ? 3 : 1, AUX>(dr, WalkRef{0u, nullptr}, p.cell, make_float4(rel.x, rel.y, CUDART_INF_F, CUDART_INF_F),
+                                                                     wn.x & ~WIN5_NEAR_BOUND, (int)(short)(wn.y & 0xFFFF), (int)(short)(wn.y >> 16), mr.gx, mr.gy, len, false, o1, m1, id1);
+                        }
+                        if (!ok_walk) {
+                            const SlowCast sc = cast_grid_slow<AUX>(mr, ray, px, py, wn.x & ~WIN5_NEAR_BOUND, len, 0);
+                            m1 = sc.out_min; id1 = sc.id;
+                        }
+                        if (m1 < len) { best = m1 / len; id = id1; }
+                    }
+                    if (p.radar_targets & AAC_TARGET_BOUNDS) {   // left, right, top, bottom segments (CS:676-680)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const bool vert = b < 2;
+                            const float line = b == 0 ? -mr.hx : b == 1 ? mr.hx : b == 2 ? mr.hy : -mr.hy;
+                            const float dd = vert ? ray.x : ray.y, pp = vert ? px : py, inv = vert ? ray.z : ray.w;
+                            if (dd != 0.0f) {
+                                const float t = (line - pp) * inv;
+                                const float other = vert ? fmaf(t, ray.y, py) : fmaf(t, ray.x, px);
+                                if (t >= 0.0f && t <= 1.0f && fabsf(other) <= (vert ? mr.hy : mr.hx) && t < best) { best = t; id = nb + b; }
+                            }
+                        }
+                    }
+                    if (p.radar_targets & AAC_TARGET_CLOUDS) {
+                        const int kc = p.st.ep_step[w.e_lo + aa / N] + (step_mode ? 1 : 0);   // the clouds move at the top of step (CS:4667-4681)
+                        for (int ci = 0; ci < p.n_clouds; ++ci) {
+                            const float2 c = cloud_pos(p.clouds[ci], kc);
+                            const float t = ray_gon_outline(px - c.x, py - c.y, ray.x, ray.y, p.clouds[ci].radius);
+                            if (t < best) { best = t; id = nb + 4 + N + ci; }
+                        }
+                    }
+                    if (p.radar_targets & AAC_TARGET_AIRCRAFT)
+                        for (int j = 0; j < N; ++j) {
+                            if (ebb + j == aa) continue;
+                            const float t = ray_gon_outline(px - w.px[ebb + j], py - w.py[ebb + j], ray.x, ray.y, p.prot);
+                            if (t < best) { best = t; id = nb + 4 + j; }
+                        }
+                    out = best == CUDART_INF_F ? len : best * len;
+                    out_min = out;
+                    return out;
+                }
                 bool done = false;
                 if (!(wn.x & WIN5_SLOW)) {
                     int gx = 0, gy = 0;
@@ -612,6 +701,15 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
             if (VAR == AAC_VARIANT_V2) q[6] = w.hd[a];
         }
         w.atgoal[a] = gons_touch(gx - px, gy - py, p.prot + p.goal_r) ? 1 : 0;
+        if (CS && p.out.cloud_contact) {   // the protective 64-gon overlaps a cloud's (polygons_single_cloud_conflict, CS:4099-4110)
+            const int kc = p.st.ep_step[w.e_lo + a / N] + (step_mode ? 1 : 0);
+            bool touch = false;
+            for (int ci = 0; ci < p.n_clouds && (p.radar_targets & AAC_TARGET_CLOUDS); ++ci) {
+                const float2 c = cloud_pos(p.clouds[ci], kc);
+                touch = touch || gons_touch(c.x - px, c.y - py, p.prot + p.clouds[ci].radius);
+            }
+            p.out.cloud_contact[w.a0 + a] = touch ? 1 : 0;
+        }
     }
     __syncwarp();
     {   // own rows of the range are contiguous: coalesced copy
@@ -814,7 +912,7 @@ constexpr int MT_STEP_ONLY = 3;
 #ifndef AAC_MIN_BLOCKS
 #define AAC_MIN_BLOCKS 4   // resident CTAs of 256 threads per SM the register allocation aims at (64 registers)
 #endif
-template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1, int RM = -1>
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1, int RM = -1, bool CS = false>
 __global__ void __launch_bounds__(MAX_THREADS, AAC_MIN_BLOCKS) env_kernel(const __grid_constant__ KParams p, const int mode_arg) {
     constexpr bool STEP_ONLY = MT == MT_STEP_ONLY;
     const int mode = MT < 0 ? mode_arg : (STEP_ONLY ? (int)MODE_STEP : MT);
@@ -937,7 +1035,7 @@ __global__ void __launch_bounds__(MAX_THREADS, AAC_MIN_BLOCKS) env_kernel(const 
                 a_lo = g * N; n_ag = N;
                 cl = lane < N ? row : p.st.ref_cells;
             }
-            observe_range<VAR, AUX, LEAN, NT, RT, RM>(p, w, a_lo, n_ag, cl, job > 0 && p.rtab != nullptr);
+            observe_range<VAR, AUX, LEAN, NT, RT, RM, CS>(p, w, a_lo, n_ag, cl, job > 0 && p.rtab != nullptr, job == 0 && mode == MODE_STEP);
             if (job > 0 || mode != MODE_STEP) continue;
 
             // ---- reward / collision / goal per drone
@@ -1256,11 +1354,11 @@ __global__ void __launch_bounds__(MAX_THREADS, AAC_MIN_BLOCKS) env_kernel(const 
     }
 }
 
-template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1, int RM = -1>
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1, int RM = -1, bool CS = false>
 static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     const int wpc = threads / 32;
     const int groups = (p.E + p.G - 1) / p.G;
-    auto fn = env_kernel<VAR, AUX, LEAN, NT, RT, EVS, MT, RM>;
+    auto fn = env_kernel<VAR, AUX, LEAN, NT, RT, EVS, MT, RM, CS>;
     static int opted_in[64] = {0};   // dynamic shared memory this instantiation has opted in to, per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1315,6 +1413,9 @@ cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threa
             if (p.N == 3 && p.R == 18) return launch_aux<AAC_VARIANT_MM, 3, 18>(p, mode, threads, sms, grid_cache, stream);
             return launch_aux<AAC_VARIANT_MM, 0, 0>(p, mode, threads, sms, grid_cache, stream);
         case AAC_VARIANT_V2:
+            if (p.radar_targets || p.n_nbr_obs)   // the later fork's sensor classes: one generic instantiation per output set
+                return (p.out_flags & AAC_OUT_RADAR_AUX) ? launch_one<AAC_VARIANT_V2, true, false, 0, 0, false, -1, -1, true>(p, mode, threads, sms, grid_cache, stream)
+                                                         : launch_one<AAC_VARIANT_V2, false, false, 0, 0, false, -1, -1, true>(p, mode, threads, sms, grid_cache, stream);
             if (p.eval_by_step)  // evaluation mode: one generic instantiation per output set
                 return (p.out_flags & AAC_OUT_RADAR_AUX) ? launch_one<AAC_VARIANT_V2, true, false, 0, 0, true>(p, mode, threads, sms, grid_cache, stream)
                                                          : launch_one<AAC_VARIANT_V2, false, false, 0, 0, true>(p, mode, threads, sms, grid_cache, stream);

@@ -21,6 +21,13 @@ struct OdDev {
     const uint16_t *path_cells;
 };
 
+// one cloud on the device (local frame): position after k steps = start + dir * (min(k, n_stop) * travel)
+struct CloudDev {
+    float sx, sy, dx, dy;   // start, unit direction towards the goal (0 when the start already lies within 1 m of it)
+    float travel, radius;   // speed * dt, radius of the 64-gon
+    int n_stop, pad_;       // steps after which the cloud has come closer than 1 m to its goal and stays
+};
+
 enum Mode : int { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_RESET = 2 };
 
 // shared-memory carve-up (byte offsets), computed once on the host: CTA-wide data, then one slice per warp
@@ -46,6 +53,8 @@ struct WarpLayout {
 struct KParams {
     int E, N, R, W, G;      // G = envs per warp (G * N <= 32)
     int radar_mode, sum_reward, ep_len, out_flags, eval_by_step;
+    int radar_targets, n_nbr_obs, n_clouds;   // the later fork's sensor classes (aac_env.h); all zero = off
+    CloudDev clouds[AAC_MAX_CLOUDS];
     // radar of a drone standing on a cell centre, per (map, cell, ray): what every freshly reset drone observes (aac_set_radar_table)
     const float *rtab, *rtab_min;
     const int16_t *rtab_hit;

@@ -48,15 +48,25 @@ class EnvConfig:
     block_threads: int = 0
     eval_by_step: bool = False    # V2 only: evaluation "by sorties" (args.mode == 'eval', evaluation_by_episode == False)
     autoreset_launches: int = 0   # step(autoreset=True): 1 = fused launch, 2 = step launch + reset launch, 0 = by batch size
+    # the later fork's sensor classes (v2 only; CS = ...forV2_changeskin/env_simulator_...:1379-1506)
+    radar_targets: int = 0        # K.TARGET_*: 0 = the variant's own radar, else the fork's true-minimum radar over these classes
+    n_nbr_obs: int = 0            # > 0: only the nearest n neighbours enter norm_nbr (use_nearestN_neigh_wRadar / N_neigh, CS:1799-1802)
+    clouds: tuple = ()            # rows (start x, y, goal x, y, radius, speed), global metres (cloud.py; CS:598-664, :4667-4681)
 
 
 def preset(name, **kw) -> EnvConfig:
     """`att`: one_model_att defaults; `tdcpa_v2`: tdCPA_forV2 defaults (last-hit radar as in the source);
-    `multimap`: radar_multipleMap defaults."""
+    `multimap`: radar_multipleMap defaults; `changeskin_sensors`: tdCPA_forV2 with the later fork's sensor classes."""
     if name == "att":
         base = EnvConfig(variant="att", sum_reward=True, episode_length=50, out_flags=K.OUT_NBR6)
     elif name in ("tdcpa_v2", "v2"):
         base = EnvConfig(variant="v2", sum_reward=False, episode_length=100, radar_mode=K.RADAR_LAST_HIT)
+    elif name in ("changeskin_sensors", "cs"):
+        # tdCPA_forV2 with the later fork's sensors: boundary segments + clouds + other aircraft, true minimum, the two nearest
+        # neighbours, protectiveBound 5 (CS agent file), the fork's two training clouds (CS:600-602; cloud.py: radius 12, 2 m/s)
+        base = EnvConfig(variant="v2", sum_reward=False, episode_length=100, radar_mode=K.RADAR_MIN, prot=5.0,
+                         radar_targets=K.TARGET_BOUNDS | K.TARGET_CLOUDS | K.TARGET_AIRCRAFT, n_nbr_obs=2,
+                         clouds=((30.0, 185.0, 180.0, 80.0, 12.0, 2.0), (30.0, 100.0, 180.0, 30.0, 12.0, 2.0)))
     elif name in ("multimap", "mm"):
         # radar_multipleMap: per-episode maps, true-min radar, coe_a = 20 hard-coded in step (MM:2025),
         # 150-step episodes (MM/ma_main:970)
@@ -91,7 +101,11 @@ class BatchedDroneEnv:
         with torch.cuda.device(self.device):
             c = K.AacConfig(K.ABI_VERSION, VARIANTS[cfg.variant], E, N, R, W, cfg.radar_mode, int(cfg.sum_reward),
                             cfg.episode_length, cfg.out_flags, cfg.tile_envs, cfg.block_threads, cfg.env_id_base, cfg.seed,
-                            cfg.dt, cfg.vmax, cfg.acc_max, cfg.prot, cfg.ray_len, cfg.goal_r, int(cfg.eval_by_step), int(cfg.autoreset_launches))
+                            cfg.dt, cfg.vmax, cfg.acc_max, cfg.prot, cfg.ray_len, cfg.goal_r, int(cfg.eval_by_step), int(cfg.autoreset_launches),
+                            int(cfg.radar_targets), int(cfg.n_nbr_obs), len(cfg.clouds))
+            for ci, row in enumerate(cfg.clouds):
+                for q in range(6):
+                    c.clouds[ci][q] = float(row[q])
             h = C.c_void_p()
             K.check(self.L.aac_create(C.byref(c), C.byref(h)), "aac_create")
             self.h = h
@@ -140,15 +154,18 @@ class BatchedDroneEnv:
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, **kw)
         o = {"norm_own": z((E, N, D), f32), "radar": z((E, N, R), f32), "reward": z((E, N), f32), "done": z((E, N), u8),
              "check_goal": z((E, N), u8), "bbc": z((E, 4), u8), "terminated": z((E,), u8), "tcpa_min": z((E, N, 4), f32)}
+        Mo = cfg.n_nbr_obs if cfg.n_nbr_obs > 0 else M      # neighbours per drone in the neighbour block (nearest-N selection)
         if cfg.variant == "v2":
-            o["norm_nbr"] = z((E, N, 5 * M), f32)
+            o["norm_nbr"] = z((E, N, 5 * Mo), f32)
+        if cfg.clouds:
+            o["cloud_contact"] = z((E, N), u8)
         fl = cfg.out_flags
         if fl & K.OUT_NBR6:
             o["norm_nbr6"] = z((E, N, M, 6), f32)
         if fl & K.OUT_RAW:
             o["raw_own"] = z((E, N, D), f32)
             if cfg.variant == "v2":
-                o["raw_nbr"] = z((E, N, 5 * M), f32)
+                o["raw_nbr"] = z((E, N, 5 * Mo), f32)
             if fl & K.OUT_NBR6:
                 o["raw_nbr6"] = z((E, N, M, 6), f32)
         if fl & K.OUT_TCPA_PAIR:
@@ -302,7 +319,7 @@ class BatchedDroneEnv:
             K.check(fn(self.h, C.c_void_p(actions.data_ptr()), C.byref(self._out_c), self._stream_ptr()), "aac_step")
         o = self.out
         info = {k: o[k] for k in ("check_goal", "bbc", "terminated", "tcpa_min", "tcpa_pair", "nbr_order", "radar_min",
-                                  "radar_hit", "parts", "branch") if k in o}
+                                  "radar_hit", "parts", "branch", "cloud_contact") if k in o}
         return self.obs(), o["reward"], o["done"], info
 
     def autoreset(self):

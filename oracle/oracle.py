@@ -25,13 +25,14 @@ class OracleCfg(C.Structure):
                 ("radar_mode", C.c_int32), ("sum_reward", C.c_int32), ("gx", C.c_int32), ("gy", C.c_int32),
                 ("dt", C.c_double), ("vmax", C.c_double), ("acc_max", C.c_double), ("prot", C.c_double),
                 ("ray_len", C.c_double), ("goal_r", C.c_double), ("bound", C.c_double * 4),
-                ("x0c", C.c_double), ("y0c", C.c_double), ("cell", C.c_double), ("eval_by_step", C.c_int32), ("pad_", C.c_int32)]
+                ("x0c", C.c_double), ("y0c", C.c_double), ("cell", C.c_double), ("eval_by_step", C.c_int32), ("radar_targets", C.c_int32),
+                ("n_nbr_obs", C.c_int32), ("n_clouds", C.c_int32), ("clouds", (C.c_double * 6) * 8)]
 
 
-_STATE_FIELDS = ["pos", "vel", "heading", "reach", "wp_cur", "wall_cnt", "prev_nn", "vflags", "ref_line", "ref_w", "wp_mask"]
+_STATE_FIELDS = ["pos", "vel", "heading", "reach", "wp_cur", "wall_cnt", "prev_nn", "vflags", "ref_line", "ref_w", "wp_mask", "ep_step"]
 _OUT_FIELDS = ["raw_own", "norm_own", "raw_nbr", "norm_nbr", "radar", "radar_min", "radar_hit", "raw_nbr6",
                "norm_nbr6", "nbr_order", "tcpa", "conflict", "reward", "done", "check_goal", "bbc", "parts",
-               "margin", "branch", "tcpa_min"]
+               "margin", "branch", "tcpa_min", "cloud_contact"]
 
 
 class _State(C.Structure):
@@ -67,7 +68,9 @@ class OracleEnv:
     multipleMap variant, a list of them (env e lives on maps[env_map[e]])."""
 
     def __init__(self, variant, gmap, n_envs, n_agents, n_rays=18, w_max=32, radar_mode=None, sum_reward=None,
-                 vmax=5.0, acc_max=None, eval_by_step=False):
+                 vmax=5.0, acc_max=None, eval_by_step=False, radar_targets=0, n_nbr_obs=0, clouds=(), prot=2.5):
+        """radar_targets / n_nbr_obs / clouds: the later fork's sensor classes (bit0 cells, bit1 boundary segments, bit2 clouds,
+        bit3 other aircraft; nearest-N neighbour block; clouds = rows of start x, y, goal x, y, radius, speed)."""
         maps = list(gmap) if isinstance(gmap, (list, tuple)) else [gmap]
         self.variant, self.maps, self.gmap = variant, maps, maps[0]
         self.E, self.N, self.R, self.w_max = n_envs, n_agents, n_rays, w_max
@@ -84,11 +87,15 @@ class OracleEnv:
             cfg = self.cfgs[k]
             cfg.variant, cfg.n_agents, cfg.n_rays, cfg.w_max = VARIANT_IDS[variant], n_agents, n_rays, w_max
             cfg.radar_mode, cfg.sum_reward, cfg.gx, cfg.gy = radar_mode, sum_reward, m.gx, m.gy
-            cfg.dt, cfg.vmax, cfg.acc_max, cfg.prot, cfg.ray_len, cfg.goal_r = 0.5, vmax, acc_max, 2.5, 15.0, 1.0
+            cfg.dt, cfg.vmax, cfg.acc_max, cfg.prot, cfg.ray_len, cfg.goal_r = 0.5, vmax, acc_max, prot, 15.0, 1.0
             for q in range(4):
                 cfg.bound[q] = float(m.bound[q])
             cfg.x0c, cfg.y0c, cfg.cell = m.x0c, m.y0c, float(m.grid_length)
             cfg.eval_by_step = int(bool(eval_by_step))
+            cfg.radar_targets, cfg.n_nbr_obs, cfg.n_clouds = int(radar_targets), int(n_nbr_obs), len(clouds)
+            for ci, row in enumerate(clouds):
+                for q in range(6):
+                    cfg.clouds[ci][q] = float(row[q])
             self.occ[k, :m.gx * m.gy] = np.ascontiguousarray(m.occ, dtype=np.uint8).reshape(-1)
         self.cfg = self.cfgs[0]
         self.env_map = np.zeros(n_envs, dtype=np.int32)
@@ -99,17 +106,19 @@ class OracleEnv:
             "reach": np.zeros((E, N), i), "wp_cur": np.zeros((E, N), i), "wall_cnt": np.zeros((E, N), i),
             "prev_nn": np.full((E, N, 2), -1, i), "vflags": np.zeros((E, N), i),
             "ref_line": np.zeros((E, N, w_max, 2), f), "ref_w": np.full((E, N), 2, i), "wp_mask": np.full((E, N), 2, i),
+            "ep_step": np.zeros((E,), i),
         }
         d = own_dim(variant, N)
+        Mo = min(n_nbr_obs, M) if n_nbr_obs > 0 else M
         self.out = {
             "raw_own": np.zeros((E, N, d), f), "norm_own": np.zeros((E, N, d), f),
-            "raw_nbr": np.zeros((E, N, 5 * M), f), "norm_nbr": np.zeros((E, N, 5 * M), f),
+            "raw_nbr": np.zeros((E, N, 5 * Mo), f), "norm_nbr": np.zeros((E, N, 5 * Mo), f),
             "radar": np.zeros((E, N, R), f), "radar_min": np.zeros((E, N, R), f), "radar_hit": np.zeros((E, N, R), i),
             "raw_nbr6": np.zeros((E, N, M, 6), f), "norm_nbr6": np.zeros((E, N, M, 6), f),
             "nbr_order": np.zeros((E, N, M), i), "tcpa": np.zeros((E, N, M, 4), f), "conflict": np.zeros((E, N, 2), i),
             "reward": np.zeros((E, N), f), "done": np.zeros((E, N), i), "check_goal": np.zeros((E, N), i),
             "bbc": np.zeros((E, 4), i), "parts": np.zeros((E, N, 8), f), "margin": np.zeros((E, N), f),
-            "branch": np.zeros((E, N), i), "tcpa_min": np.zeros((E, N, 4), f),
+            "branch": np.zeros((E, N), i), "tcpa_min": np.zeros((E, N, 4), f), "cloud_contact": np.zeros((E, N), i),
         }
         self._s = _State(*[self.state[n].ctypes.data for n in _STATE_FIELDS])
         self._o = _Out(*[self.out[n].ctypes.data for n in _OUT_FIELDS])
@@ -133,6 +142,7 @@ class OracleEnv:
         s["wall_cnt"][e] = 0
         s["vflags"][e] = 0
         s["prev_nn"][e] = -1
+        s["ep_step"][e] = 0
 
     def observe(self):
         lib().oracle_observe_maps(self.cfgs, self.occ.ctypes.data_as(C.c_void_p), C.c_int(self.occ_stride),
@@ -155,10 +165,17 @@ class OracleEnv:
                                           C.c_double(float(xy[1])), C.c_int(int(k)), C.c_int(int(cand_id)), C.byref(d))
         return d.value if ok else None
 
-    def radar_probe(self, pos, i, map_id=0):
-        """Radar of drone `i` for the position set pos[N,2] -> (stored value[R], true min[R], hit id[R])."""
+    def radar_probe(self, pos, i, map_id=0, k_cloud=0):
+        """Radar of drone `i` for the position set pos[N,2] -> (stored value[R], true min[R], hit id[R]); k_cloud = steps the
+        clouds have moved (sensor configurations)."""
         pos = np.ascontiguousarray(pos, dtype=np.float64)
         out, omin, hit = np.zeros(self.R), np.zeros(self.R), np.zeros(self.R, dtype=np.int32)
         lib().oracle_radar(C.byref(self.cfgs[map_id]), self.occ[map_id].ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p), C.c_int(i),
-                           out.ctypes.data_as(C.c_void_p), omin.ctypes.data_as(C.c_void_p), hit.ctypes.data_as(C.c_void_p))
+                           C.c_int(int(k_cloud)), out.ctypes.data_as(C.c_void_p), omin.ctypes.data_as(C.c_void_p), hit.ctypes.data_as(C.c_void_p))
         return out, omin, hit
+
+    def cloud_positions(self, k):
+        """[n_clouds, 2] after k steps."""
+        out = np.zeros((self.cfg.n_clouds, 2))
+        lib().oracle_clouds(C.byref(self.cfg), C.c_int(int(k)), out.ctypes.data_as(C.c_void_p))
+        return out

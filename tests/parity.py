@@ -127,6 +127,7 @@ def sync_oracle(orc, env, envs=None, full=False):
     pn = s["prev_nn"].copy()
     pn[pn == 255] = -1
     st["prev_nn"][sel] = pn[sel]
+    st["ep_step"][sel] = env.state["ep_step"].cpu().numpy()[sel]     # sensor configurations: the clouds' clock
     if "wp_mask" in s:
         st["wp_mask"][sel] = s["wp_mask"][sel].astype(np.int32)
         orc.env_map[sel] = s["map_id"][sel]
@@ -219,7 +220,7 @@ def compare_obs(T, variant, g, o, where, env_ok, s_gpu, orc, rows=None):
                            (-RADAR_EPS, -RADAR_EPS), (RADAR_EPS, -RADAR_EPS), (-RADAR_EPS, RADAR_EPS)):
                 pos = orc.state["pos"][e].copy()
                 pos[i] += (dx, dy)
-                out, omin, _ = orc.radar_probe(pos, i, map_id=int(orc.env_map[e]))
+                out, omin, _ = orc.radar_probe(pos, i, map_id=int(orc.env_map[e]), k_cloud=int(orc.state["ep_step"][e]))
                 ref = out if k == "radar" else omin
                 any_nan |= np.isnan(ref)
                 lo, hi = np.fmin(lo, ref), np.fmax(hi, ref)
@@ -248,7 +249,7 @@ def compare_obs(T, variant, g, o, where, env_ok, s_gpu, orc, rows=None):
         pos = orc.state["pos"][e]
         want = float(o["radar"][e, i, r])
         tie = False
-        if variant != "att":
+        if variant != "att" and not orc.cfg.radar_targets:
             d_g = float(orc.cfg.ray_len) if gh < 0 else orc.radar_candidate(pos[i], r, gh, mid)
             d_o = float(orc.cfg.ray_len) if oh < 0 else orc.radar_candidate(pos[i], r, oh, mid)
             if d_g is not None and d_o is not None and abs(d_g - d_o) <= RTOL * abs(d_o) + ATOL["radar"] and abs(d_g - want) <= RTOL * abs(want) + ATOL["radar"]:
@@ -258,7 +259,7 @@ def compare_obs(T, variant, g, o, where, env_ok, s_gpu, orc, rows=None):
                            (-RADAR_EPS, -RADAR_EPS), (RADAR_EPS, -RADAR_EPS), (-RADAR_EPS, RADAR_EPS)):
                 pp = pos.copy()
                 pp[i] += (dx, dy)
-                if int(orc.radar_probe(pp, i, map_id=mid)[2][r]) == gh:
+                if int(orc.radar_probe(pp, i, map_id=mid, k_cloud=int(orc.state["ep_step"][e]))[2][r]) == gh:
                     tie = True
                     break
         if tie:
@@ -269,9 +270,10 @@ def compare_obs(T, variant, g, o, where, env_ok, s_gpu, orc, rows=None):
 
 
 def lockstep(variant, n_envs, n_agents, n_rays, steps, seed=0, radar_mode=None, n_scen=128, cluster=None, map_seed=0,
-             device="cuda:0", autoreset=True, tile_envs=0, block_threads=0, action_scale=1.0, eval_by_step=False):
+             device="cuda:0", autoreset=True, tile_envs=0, block_threads=0, action_scale=1.0, eval_by_step=False, sensors=None):
     """Returns a Tally.  `cluster` = radius (m): after every reset drones 1.. are moved next to drone 0 so
-    that drone-radar / near-drone / collision branches fire."""
+    that drone-radar / near-drone / collision branches fire.  `sensors` = dict(radar_targets, n_nbr_obs, clouds, prot, bound):
+    the later fork's sensor classes on the tdCPA_forV2 variant."""
     E, N, R, M = n_envs, n_agents, n_rays, n_agents - 1
     if radar_mode is None:
         radar_mode = RADAR_LAST_HIT if variant == "v2" else RADAR_MIN
@@ -282,13 +284,17 @@ def lockstep(variant, n_envs, n_agents, n_rays, steps, seed=0, radar_mode=None, 
         bank = MultiMapBank(gmap, N, n_scen, w_max=32, seed=seed)
         M = 0   # no neighbour terms on the multipleMap path
     else:
-        gmap = synthetic_map(seed=map_seed)
-        cfg = preset("att" if variant == "att" else "tdcpa_v2", n_envs=E, n_agents=N, n_rays=R, w_max=32, out_flags=ALL_OUT,
-                     radar_mode=radar_mode, seed=seed, tile_envs=tile_envs, block_threads=block_threads, eval_by_step=eval_by_step)
+        sk = dict(sensors or {})
+        gmap = synthetic_map(bound=sk.pop("bound", None), seed=map_seed)
+        out_flags = ALL_OUT if not sk.get("n_nbr_obs") else (K.OUT_RAW | K.OUT_RADAR_AUX | K.OUT_PARTS)   # per-pair outputs cover every neighbour
+        cfg = preset("att" if variant == "att" else "tdcpa_v2", n_envs=E, n_agents=N, n_rays=R, w_max=32, out_flags=out_flags,
+                     radar_mode=radar_mode, seed=seed, tile_envs=tile_envs, block_threads=block_threads, eval_by_step=eval_by_step, **sk)
         bank = ScenarioBank(gmap, N, n_scen, w_max=32, seed=seed)
     env = BatchedDroneEnv(cfg, gmap, device=device)
     env.set_bank(bank)
-    orc = OracleEnv(variant, gmap, E, N, R, w_max=32, radar_mode=radar_mode, eval_by_step=eval_by_step)
+    okw = {} if not sensors else dict(radar_targets=cfg.radar_targets, n_nbr_obs=cfg.n_nbr_obs, clouds=cfg.clouds, prot=cfg.prot)
+    orc = OracleEnv(variant, gmap, E, N, R, w_max=32, radar_mode=radar_mode, eval_by_step=eval_by_step, **okw)
+    pairs_out = "nbr_order" in env.out    # per-pair optional outputs are off with a nearest-N neighbour block
     rng = np.random.default_rng(seed + 1)
     T = Tally()
 
@@ -315,7 +321,9 @@ def lockstep(variant, n_envs, n_agents, n_rays, steps, seed=0, radar_mode=None, 
         rows[envs] = True
         env_ok = sort_ok(orc, o)
         compare_obs(T, variant, g, o, where, env_ok, None, orc, rows=rows)
-        if M > 0:
+        if "cloud_contact" in g:
+            T.equal("cloud_contact", g["cloud_contact"], o["cloud_contact"], where, mask=_bcast(rows, g["cloud_contact"].shape))
+        if M > 0 and pairs_out:
             T.equal("nbr_order", g["nbr_order"], o["nbr_order"], where, mask=_bcast(env_ok & rows, g["nbr_order"].shape))
 
     def sort_ok(orc_, o):
@@ -350,11 +358,16 @@ def lockstep(variant, n_envs, n_agents, n_rays, steps, seed=0, radar_mode=None, 
             moving = np.linalg.norm(so["vel"], axis=-1) > 1e-3
             T.close("heading", np.where(moving, dh, 0.0), np.zeros_like(dh), where, 2e-5)
         radar_tie_env = compare_obs(T, variant, g, o, where, env_ok, s_gpu, orc)
-        if M > 0:
+        if "cloud_contact" in g:   # overlap of two 64-gons: compared away from the touching distance
+            cl = np.array([orc.cloud_positions(int(k)) for k in orc.state["ep_step"]])                      # [E, C, 2]
+            gap = np.abs(np.linalg.norm(so["pos"][:, :, None, :] - cl[:, None, :, :], axis=-1) - (cfg.prot + np.array([c[4] for c in cfg.clouds])))
+            T.equal("cloud_contact", g["cloud_contact"], o["cloud_contact"], where, mask=(gap > 0.02).all(axis=2))
+        if M > 0 and pairs_out:
             T.equal("nbr_order", g["nbr_order"], o["nbr_order"], where, mask=_bcast(env_ok, g["nbr_order"].shape))
             # tdCPA: t = (r.w)/|w|^2 and d = |-r + w t| are ill-conditioned for nearly equal velocities.  The
             # float32 state carries dv = 2e-6 m/s of rounding per velocity and dr = 2e-5 m per position, so the
             # first-order floor is |dt| <= (|r| dv + |w| dr) / |w|^2 + 2 |t| dv / |w|, |dd| <= |w| |dt| + |t| dv + dr
+        if M > 0 and pairs_out:
             tp_g, tp_o = g["tcpa_pair"].astype(np.float64), o["tcpa"]
             order = o["nbr_order"].astype(np.int64)
             vel, pos = so["vel"], so["pos"]

@@ -9,7 +9,7 @@ from tests.replay import GOLDEN_DIR, load_case, load_case_mm, oracle_margins_mm,
 
 pytestmark = pytest.mark.gpu
 
-ALL_GOLDEN = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(f).startswith("actor"))
+ALL_GOLDEN = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(f).startswith(("actor", "cs_")))
 GOLDEN = [n for n in ALL_GOLDEN if not n.startswith("mm_")]
 GOLDEN_MM = [n for n in ALL_GOLDEN if n.startswith("mm_")]
 
@@ -101,6 +101,58 @@ def test_lockstep_ragged_tile_and_single_drone():
 
 def test_lockstep_r72_n20():
     _run(variant="v2", n_envs=32, n_agents=20, n_rays=72, steps=20, seed=9)
+
+
+SENSORS = dict(radar_targets=2 | 4 | 8, n_nbr_obs=2, prot=5.0, bound=[0, 200, 0, 200],
+               clouds=((30.0, 185.0, 180.0, 80.0, 12.0, 2.0), (30.0, 100.0, 180.0, 30.0, 12.0, 2.0)))   # the later fork's training set-up (CS:600-602)
+
+
+def test_sensor_classes_reference_vectors():
+    """The later fork's sensor classes against vectors of its UNMODIFIED class (tests/golden/cs_sensors.npz):
+    true-minimum radar over boundary segments, moving clouds' outlines and other aircraft's outlines, and the nearest-N
+    neighbour block, observed by the CUDA env at the fixture's 320 states (all of them in one batch)."""
+    import numpy as np
+    import torch
+    from multi_agent_aac_b200 import _capi as K
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from oracle.oracle import OracleEnv, RADAR_MIN
+    from tests.test_oracle_golden import load_sensor_fixture
+    d, n, r, n_neigh, gmap = load_sensor_fixture()
+    E = len(d["pos"])
+    clouds = tuple(tuple(float(v) for v in row) for row in d["cloud_cfg"])
+    for targets, key in ((2 | 4 | 8, "radar"), (2 | 4, "radar_noac")):
+        cfg = preset("changeskin_sensors", n_envs=E, n_agents=n, n_rays=r, w_max=32, radar_targets=targets, n_nbr_obs=n_neigh, clouds=clouds,
+                     out_flags=K.OUT_RAW | K.OUT_RADAR_AUX)
+        env = BatchedDroneEnv(cfg, gmap)
+        env.load_agent_state(d["pos"], d["vel"], heading=d["heading"])
+        env.state["ep_step"].copy_(torch.tensor(d["cloud_k"].astype(np.int32), device=env.device))
+        env.observe()
+        got = {k: v.cpu().numpy().astype(np.float64) for k, v in env.out.items()}
+        assert got["norm_nbr"].shape == (E, n, 5 * n_neigh)
+        assert np.allclose(got["raw_nbr"], d["raw_nbr"], rtol=1e-4, atol=1e-4) and np.allclose(got["norm_nbr"], d["norm_nbr"], rtol=1e-4, atol=2e-6)
+        bad = np.abs(got["radar"] - d[key]) > 1e-4 * np.abs(d[key]) + 2e-4
+        # every mismatch must be bracketed by the checker's own answers at positions displaced by the float32 resolution (grazing rays)
+        orc = OracleEnv("v2", gmap, 1, n, r, w_max=32, radar_mode=RADAR_MIN, radar_targets=targets, n_nbr_obs=n_neigh, clouds=clouds, prot=cfg.prot)
+        for q, i, k in zip(*np.nonzero(bad)):
+            lo = hi = d[key][q, i, k]
+            for dx, dy in ((5e-5, 0), (-5e-5, 0), (0, 5e-5), (0, -5e-5), (5e-5, 5e-5), (-5e-5, -5e-5), (5e-5, -5e-5), (-5e-5, 5e-5)):
+                pp = d["pos"][q].copy()
+                pp[i] += (dx, dy)
+                v = orc.radar_probe(pp, i, k_cloud=int(d["cloud_k"][q]))[0][k]
+                lo, hi = min(lo, v), max(hi, v)
+            assert lo - 1e-3 <= got["radar"][q, i, k] <= hi + 1e-3, (key, q, i, k, got["radar"][q, i, k], d[key][q, i, k])
+        assert bad.sum() <= 0.002 * bad.size
+        assert (d[key] < 15 - 1e-9).mean() > 0.2      # the fixture's rays do hit things
+        env.close()
+
+
+def test_lockstep_sensor_classes():
+    """Sensor configuration in lock step with the checker (itself pinned to the fork's class by tests/test_oracle_golden.py):
+    clouds move with the episode clock, resets restart them, clustered starts make the aircraft outlines fire."""
+    T = _run(variant="v2", n_envs=192, n_agents=4, n_rays=18, steps=70, seed=12, radar_mode=parity.RADAR_MIN, cluster=14.0, sensors=SENSORS)
+    assert T.n.get("cloud_contact", 0) > 0
+    _run(variant="v2", n_envs=96, n_agents=6, n_rays=36, steps=40, seed=13, radar_mode=parity.RADAR_MIN,
+         sensors=dict(SENSORS, radar_targets=1 | 2 | 4 | 8, n_nbr_obs=3))      # + the grid cells of the older variants
 
 
 def test_fused_autoreset_equals_step_then_autoreset():

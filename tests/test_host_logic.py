@@ -93,8 +93,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_sizes_match_header_layout():
-    assert ctypes.sizeof(_capi.AacConfig) == 12 * 4 + 16 + 6 * 4 + 2 * 4
-    assert ctypes.sizeof(_capi.AacState) == 14 * 8 and ctypes.sizeof(_capi.AacOut) == 19 * 8
+    # ABI 3: + radar_targets, n_nbr_obs, n_clouds, clouds[8][6]; 300 bytes padded to the int64 members' alignment
+    assert ctypes.sizeof(_capi.AacConfig) == (12 * 4 + 16 + 6 * 4 + 2 * 4 + 3 * 4 + 8 * 6 * 4 + 7) // 8 * 8
+    assert ctypes.sizeof(_capi.AacState) == 14 * 8 and ctypes.sizeof(_capi.AacOut) == 20 * 8
     assert ctypes.sizeof(_capi.AacMapDesc) == 2 * 4 + 4 * 4 + 5 * 4
 
 

@@ -10,7 +10,7 @@ from multi_agent_aac_b200.maps import synthetic_map
 from oracle.oracle import OracleEnv, RADAR_MIN
 from tests.replay import GOLDEN_DIR, load_case, load_case_mm, replay, replay_mm
 
-ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(f).startswith("actor"))
+ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(f).startswith(("actor", "cs_")))
 GOLDEN = [n for n in ALL if not n.startswith("mm_")]
 GOLDEN_MM = [n for n in ALL if n.startswith("mm_")]
 
@@ -107,3 +107,40 @@ def test_radar_properties_and_crash_flags():
             assert (out["bbc"][done_env, :3].any(axis=1)).all(), "done implies a bound/building/drone flag"
             assert (~out["bbc"][~done_env, :3].any(axis=1)).all()
             assert np.all(np.linalg.norm(env.state["vel"], axis=-1) <= 5.0 + 1e-9)
+
+
+def load_sensor_fixture():
+    """tests/golden/cs_sensors.npz: vectors of the later fork's unmodified class (tests/golden/gen_golden_sensors.py)."""
+    import numpy as np
+    from multi_agent_aac_b200.maps import GridMap
+    d = np.load(os.path.join(GOLDEN_DIR, "cs_sensors.npz"))
+    n, r, n_neigh = (int(v) for v in d["meta"][:3])
+    gmap = GridMap(bound=[float(v) for v in d["bound"]], grid_length=10, occ=d["occ"].astype(np.uint8))
+    return d, n, r, n_neigh, gmap
+
+
+def test_sensor_classes_match_the_later_forks_class():
+    """Clouds' kinematics, the true-minimum radar over boundary segments / cloud outlines / other aircraft's outlines and the
+    nearest-N neighbour block against vectors recorded from the fork's own `step` and `cur_state_norm_state_v3`."""
+    import numpy as np
+    from oracle.oracle import OracleEnv, RADAR_MIN
+    d, n, r, n_neigh, gmap = load_sensor_fixture()
+    clouds = [tuple(row) for row in d["cloud_cfg"]]
+    prot = float(d["meta"][3]) if d["meta"][3] else 5.0       # the fork's protectiveBound (CS agent file: 5)
+    orc = OracleEnv("v2", gmap, 1, n, r, w_max=32, radar_mode=RADAR_MIN, radar_targets=2 | 4 | 8, n_nbr_obs=n_neigh, clouds=clouds, prot=prot)
+    noac = OracleEnv("v2", gmap, 1, n, r, w_max=32, radar_mode=RADAR_MIN, radar_targets=2 | 4, n_nbr_obs=n_neigh, clouds=clouds, prot=prot)
+    for k in range(len(d["cloud_traj"])):                       # calculate_next_position, step after step
+        assert np.allclose(orc.cloud_positions(k), d["cloud_traj"][k], rtol=0, atol=1e-9), k
+    hits = 0
+    for q in range(len(d["pos"])):
+        for env, key in ((orc, "radar"), (noac, "radar_noac")):
+            st = env.state
+            st["pos"][0], st["vel"][0], st["heading"][0], st["ep_step"][0] = d["pos"][q], d["vel"][q], d["heading"][q], int(d["cloud_k"][q])
+            st["ref_line"][0, :, 0], st["ref_line"][0, :, 1], st["ref_w"][0] = d["pos"][q], d["pos"][q] + 10.0, 2
+            o = env.observe()
+            assert np.allclose(o["radar"][0], d[key][q], rtol=1e-9, atol=1e-9), (q, key, np.abs(o["radar"][0] - d[key][q]).max())
+        hits += int((d["radar"][q] < 15 - 1e-9).sum())
+        assert np.allclose(o["raw_nbr"][0], d["raw_nbr"][q], rtol=1e-9, atol=1e-9), q
+        assert np.allclose(o["norm_nbr"][0], d["norm_nbr"][q], rtol=1e-9, atol=1e-9), q
+        assert o["norm_nbr"].shape[-1] == 5 * n_neigh
+    assert hits > 0.5 * d["radar"].size
