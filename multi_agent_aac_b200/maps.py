@@ -187,16 +187,33 @@ def _polygon_touches_squares(poly, cx, cy, h):
     return hit
 
 
-def gridmap_from_polygons(polygons, bound, grid_length=10, extent=(1800, 1300)):
+def gridmap_from_polygons(polygons, bound, grid_length=10, extent=(1800, 1300), heights=None):
     """Building footprints (vertex lists in metres) -> GridMap, the way the reference builds `world_map_2D`
     (ATT/grid_env_generation:140-171): grid points at multiples of `grid_length` over `extent`, a cell (the square of
     half side grid_length / 2 around its grid point) is occupied when it is not disjoint from some footprint, holes
     enclosed by occupied cells are filled (`ndimage.binary_fill_holes`), and the bounded map is the cells whose
-    grid point lies inside the closed bound."""
+    grid point lies inside the closed bound.  `heights` (one per footprint): the reference fills the cell's column up to
+    ceil(mean height of the footprints it meets / grid_length) layers and reads layer 0 (:150-153), so a cell counts
+    only when that mean height is positive; None = every footprint counts."""
     from scipy import ndimage
     g, h = grid_length, grid_length / 2.0
     nx, ny = int(math.ceil(extent[0] / g)), int(math.ceil(extent[1] / g))   # initialize_3d_array_environment's x / y extents
-    env = np.zeros((nx, ny), dtype=bool)
+    if heights is not None:
+        hsum, hcnt = np.zeros((nx, ny)), np.zeros((nx, ny), dtype=np.int64)
+        for poly, hgt in zip(polygons, heights):
+            p = np.asarray(poly, dtype=np.float64)
+            ix0, ix1 = max(int(math.floor((p[:, 0].min() - h) / g)), 0), min(int(math.ceil((p[:, 0].max() + h) / g)), nx - 1)
+            iy0, iy1 = max(int(math.floor((p[:, 1].min() - h) / g)), 0), min(int(math.ceil((p[:, 1].max() + h) / g)), ny - 1)
+            if ix1 < ix0 or iy1 < iy0:
+                continue
+            ix, iy = np.meshgrid(np.arange(ix0, ix1 + 1), np.arange(iy0, iy1 + 1), indexing="ij")
+            hit = _polygon_touches_squares(p, ix.ravel() * g, iy.ravel() * g, h)
+            np.add.at(hsum, (ix.ravel()[hit], iy.ravel()[hit]), float(hgt))
+            np.add.at(hcnt, (ix.ravel()[hit], iy.ravel()[hit]), 1)
+        env = (hcnt > 0) & (np.ceil(np.divide(hsum, np.maximum(hcnt, 1)) / g) >= 1)
+        polygons = []
+    else:
+        env = np.zeros((nx, ny), dtype=bool)
     for poly in polygons:
         p = np.asarray(poly, dtype=np.float64)
         ix0, ix1 = max(int(math.floor((p[:, 0].min() - h) / g)), 0), min(int(math.ceil((p[:, 0].max() + h) / g)), nx - 1)
@@ -216,3 +233,89 @@ def gridmap_from_polygons(polygons, bound, grid_length=10, extent=(1800, 1300)):
     sub = env[xl:xl + gx, yl:yl + gy]
     occ[:sub.shape[0], :sub.shape[1]] = sub
     return GridMap(list(bound), g, occ)
+
+
+# ---- shapefile ingestion (ATT/grid_env_generation:108-134; the reference reads it with geopandas) ---------------------
+
+SVY21_X = (14550.0, 16262.89690000005, 1800.0)   # min, max, span of the reference's area in SVY21 easting  (ATT/grid_env_generation:127)
+SVY21_Y = (36200.0, 37448.60029999912, 1300.0)   # ... northing                                            (:128)
+
+
+def svy21_to_metres(x, y):
+    """The reference's `coordinate_to_meter` (ATT/grid_env_generation:27-31) with its hard-coded area: note that it
+    multiplies by (max - min) / span, as the source does."""
+    return ((np.asarray(x, dtype=np.float64) - SVY21_X[0]) * ((SVY21_X[1] - SVY21_X[0]) / SVY21_X[2]),
+            (np.asarray(y, dtype=np.float64) - SVY21_Y[0]) * ((SVY21_Y[1] - SVY21_Y[0]) / SVY21_Y[2]))
+
+
+def read_shapefile(path):
+    """Minimal ESRI shapefile reader for building footprints: polygon records (shape types 5 / 15 / 25) of `path`.shp and
+    the attribute rows of the .dbf next to it.  Returns (rings, rows, field_names): rings[k] = exterior ring of record k
+    as an [n, 2] array (the first part, which is what the reference uses: `row[6].exterior`), rows[k] = its attribute
+    values (numbers parsed, text stripped)."""
+    import struct
+    base = path[:-4] if path.lower().endswith(".shp") else path
+    raw = open(base + ".shp", "rb").read()
+    if struct.unpack(">i", raw[:4])[0] != 9994:
+        raise ValueError("%s.shp is not a shapefile" % base)
+    rings, pos = [], 100
+    while pos + 8 <= len(raw):
+        _, words = struct.unpack(">ii", raw[pos:pos + 8])
+        rec = raw[pos + 8:pos + 8 + 2 * words]
+        pos += 8 + 2 * words
+        stype = struct.unpack("<i", rec[:4])[0]
+        if stype == 0:
+            rings.append(np.zeros((0, 2)))
+            continue
+        if stype not in (5, 15, 25):
+            raise ValueError("shape type %d: only polygon shapefiles are supported" % stype)
+        n_parts, n_points = struct.unpack("<ii", rec[36:44])
+        parts = list(struct.unpack("<%di" % n_parts, rec[44:44 + 4 * n_parts])) + [n_points]
+        pts = np.frombuffer(rec, dtype="<f8", count=2 * n_points, offset=44 + 4 * n_parts).reshape(n_points, 2)
+        rings.append(np.array(pts[parts[0]:parts[1]], dtype=np.float64))
+    rows, names = [], []
+    try:
+        dbf = open(base + ".dbf", "rb").read()
+    except FileNotFoundError:
+        return rings, [[] for _ in rings], names
+    n_rec, hdr_len, rec_len = struct.unpack("<IHH", dbf[4:12])
+    fields, off = [], 32
+    while dbf[off] != 0x0D:
+        name = dbf[off:off + 11].split(b"\x00")[0].decode("latin1")
+        fields.append((name, chr(dbf[off + 11]), dbf[off + 16]))
+        off += 32
+    names = [f[0] for f in fields]
+    for k in range(n_rec):
+        rec = dbf[hdr_len + k * rec_len:hdr_len + (k + 1) * rec_len]
+        vals, o = [], 1
+        for _, ftype, flen in fields:
+            txt = rec[o:o + flen].decode("latin1").strip()
+            o += flen
+            if ftype in "NF":
+                try:
+                    vals.append(float(txt) if txt else 0.0)
+                except ValueError:
+                    vals.append(0.0)
+            else:
+                vals.append(txt)
+        rows.append(vals)
+    return rings, rows, names
+
+
+def gridmap_from_shapefile(path, bound, height_field=2, grid_length=10, extent=(1800, 1300), transform=svy21_to_metres):
+    """`env_generation(shapeFilePath, bound)` (ATT/grid_env_generation:108-185) without geopandas: read the footprints,
+    drop duplicate geometries (:110-115), convert SVY21 to the reference's metre frame (:124-130), take the height from
+    attribute column `height_field` (the reference's `row[2]`), rasterise and fill holes (`gridmap_from_polygons`)."""
+    rings, rows, _ = read_shapefile(path)
+    seen, polys, heights = set(), [], []
+    for ring, row in zip(rings, rows):
+        if len(ring) < 3:
+            continue
+        key = ring.tobytes()
+        if key in seen:
+            continue
+        seen.add(key)
+        x, y = transform(ring[:, 0], ring[:, 1]) if transform else (ring[:, 0], ring[:, 1])
+        polys.append(np.stack([x, y], -1))
+        heights.append(float(row[height_field]) if len(row) > height_field else 1.0)
+    return gridmap_from_polygons(polys, bound, grid_length, extent, heights=heights)

@@ -370,6 +370,14 @@ class Polygon(BaseGeometry):
         self._ring = ring
 
     @property
+    def wkb(self):
+        """A hashable byte image of the shell (the reference only hashes it to drop duplicate footprints, ATT/grid_env_generation:112-114)."""
+        return b"GLP1" + np.asarray(self._ring, dtype=np.float64).tobytes()
+
+    def disjoint(self, other):
+        return not self.intersects(other)
+
+    @property
     def exterior(self):
         return LinearRing(self._ring)
 
@@ -634,7 +642,12 @@ def install_as_shapely():
     affinity = types.ModuleType("shapely.affinity")
     affinity.scale = lambda g, *a, **k: g
     wkb = types.ModuleType("shapely.wkb")
+    wkb.loads = lambda b: Polygon(np.frombuffer(b[4:], dtype=np.float64).reshape(-1, 2).tolist())
+    point_mod = types.ModuleType("shapely.geometry.point")   # `from shapely.geometry.point import Point` (ATT/grid_env_generation:20)
+    point_mod.Point = Point
+    geometry.__path__ = []
+    geometry.point = point_mod
     root.geometry, root.strtree, root.ops, root.affinity, root.wkb = geometry, strtree, ops, affinity, wkb
-    sys.modules.update({"shapely": root, "shapely.geometry": geometry, "shapely.strtree": strtree,
+    sys.modules.update({"shapely": root, "shapely.geometry": geometry, "shapely.geometry.point": point_mod, "shapely.strtree": strtree,
                         "shapely.ops": ops, "shapely.affinity": affinity, "shapely.wkb": wkb})
     return root
