@@ -10,7 +10,7 @@ from multi_agent_aac_b200.maps import synthetic_map
 from oracle.oracle import OracleEnv, RADAR_MIN
 from tests.replay import GOLDEN_DIR, load_case, load_case_mm, replay, replay_mm
 
-ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(f).startswith(("actor", "cs_")))
+ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(f).startswith(("actor", "cs_", "mapgen")))
 GOLDEN = [n for n in ALL if not n.startswith("mm_")]
 GOLDEN_MM = [n for n in ALL if n.startswith("mm_")]
 
