@@ -20,7 +20,7 @@ struct AacEnv {
     WarpLayout wl{};
     CtaLayout cl{};
     MapDev *d_maps = nullptr;
-    int n_maps = 0;
+    int n_maps = 0, n_staged = 1;   // maps in the table / staged per CTA in shared memory
     std::vector<int> h_gx, h_gy;   // grid sizes of the installed maps (table validation)
     double h_ox = 0.0, h_oy = 0.0; // local-frame origin of map 0 (clouds are configured in global metres)
     float4 *d_ray = nullptr;
@@ -221,6 +221,15 @@ extern "C" int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *
     CU(cudaMemcpy(env->d_maps, host.data(), sizeof(MapDev) * n_maps, cudaMemcpyHostToDevice));
     env->n_maps = n_maps;
     env->cell = maps[0].cell;
+    // multipleMap: the whole table goes to shared memory with the prologue's bulk copy when it is small (the reference's 14 maps: 4.5 KB)
+    env->n_staged = (env->cfg.variant == AAC_VARIANT_MM && n_maps <= MAX_STAGED_MAPS) ? n_maps : 1;
+    {
+        const int optin = max_smem_optin();
+        CtaLayout cl = make_cta_layout(env->wl, env->cfg.n_rays, env->threads / 32, env->n_staged);
+        if (optin > 0 && (int)cl.total > optin) { env->n_staged = 1; cl = make_cta_layout(env->wl, env->cfg.n_rays, env->threads / 32, 1); }
+        env->cl = cl;
+        env->grid = 0;   // the residency is queried again with the new shared-memory size
+    }
     env->h_ox = maps[0].origin_x; env->h_oy = maps[0].origin_y;
     env->h_gx.resize(n_maps); env->h_gy.resize(n_maps);
     for (int m = 0; m < n_maps; ++m) { env->h_gx[m] = maps[m].gx; env->h_gy[m] = maps[m].gy; }
@@ -592,7 +601,7 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     }
     p.cell = env->cell; p.dt = c.dt; p.vmax = c.vmax; p.acc_max = c.acc_max; p.prot = c.prot; p.ray_len = c.ray_len; p.goal_r = c.goal_r;
     p.env_id_base = c.env_id_base; p.seed = c.seed;
-    p.maps = env->d_maps; p.n_maps = env->n_maps; p.ray_tab = env->d_ray; p.dda_tab = env->d_dda; p.walk_tab = env->d_walk; p.autoreset = autoreset;
+    p.maps = env->d_maps; p.n_maps = env->n_maps; p.n_staged = env->n_staged; p.ray_tab = env->d_ray; p.dda_tab = env->d_dda; p.walk_tab = env->d_walk; p.autoreset = autoreset;
     p.bank_cells = env->d_bank_cells; p.bank_w = env->d_bank_w; p.bank_map = env->d_bank_map; p.n_scen = env->n_scen; p.od = env->d_od;
     p.mask = mask; p.actions = actions; p.stats = env->d_stats;
     p.rtab = env->rtab; p.rtab_min = env->rtab_min; p.rtab_hit = env->rtab_hit; p.rtab_minr = env->rtab_minr;

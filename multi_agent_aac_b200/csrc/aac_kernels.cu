@@ -379,8 +379,9 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
     const int N = NT ? NT : p.N, M = N - 1, R = RT ? RT : p.R, Mp = M | 1;
     const int D = own_dim(VAR, N);
     const int flags = LEAN ? 0 : p.out_flags;   // LEAN: no optional output was requested, their code is compiled out
-    // one map staged in shared memory, or (multipleMap) the env's own map read through L1
-    auto map_of = [&](const int aa) -> const MapDev & { return VAR == AAC_VARIANT_MM ? p.maps[w.amap[aa]] : *w.map; };
+    // one map staged in shared memory, or (multipleMap) the env's own map out of the staged table (w.map = the table in
+    // shared memory when it fits, else the table in global memory)
+    auto map_of = [&](const int aa) -> const MapDev & { return VAR == AAC_VARIANT_MM ? w.map[w.amap[aa]] : *w.map; };
     const float inv_vmax = 1.0f / p.vmax;
     const bool mine = lane < n_ag;
     const int a = a_lo + lane;           // the lane's drone in the drone-per-lane phases
@@ -758,7 +759,7 @@ __device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp
     int map_row = 0;
     const unsigned key = use_od ? episode_key(p.seed, gid, ep) : 0u;
     if (VAR == AAC_VARIANT_MM) map_row = use_od ? (int)(draw(key, 0) % (unsigned)p.n_maps) : (p.bank_map ? p.bank_map[scen] : 0);
-    const MapDev &mp = VAR == AAC_VARIANT_MM ? p.maps[map_row] : *w.map;
+    const MapDev &mp = VAR == AAC_VARIANT_MM ? w.map[map_row] : *w.map;
     __syncwarp();
     if (lane == 0) {
         p.st.ep_index[ge] = ep + 1;
@@ -933,8 +934,9 @@ __global__ void __launch_bounds__(MAX_THREADS, AAC_MIN_BLOCKS) env_kernel(const 
     if (tid == 0) {
         mbar_init(s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(s_bar, sizeof(MapDev));
-        bulk_g2s(s_map, p.maps, sizeof(MapDev), s_bar);
+        // the map - for multipleMap the whole table of maps when it fits the budget (14 maps = 4.5 KB) - by ONE bulk copy
+        mbar_expect_tx(s_bar, p.n_staged * (unsigned)sizeof(MapDev));
+        bulk_g2s(s_map, p.maps, p.n_staged * (unsigned)sizeof(MapDev), s_bar);
         if (blockIdx.x == 0) p.work[p.parity ^ 1] = 0;   // the next launch's group counter
     }
     for (int k = tid; k < p.R; k += blockDim.x) s_ray[k] = p.ray_tab[k];
@@ -947,7 +949,7 @@ __global__ void __launch_bounds__(MAX_THREADS, AAC_MIN_BLOCKS) env_kernel(const 
 
     unsigned char *ws = smem + CL.warps + (size_t)warp * WL.total;
     Warp w;
-    w.map = s_map; w.ray = s_ray; w.dda = s_dda; w.walk.s = smem_u32(s_walk); w.walk.p = nullptr; w.lane = lane;
+    w.map = (VAR == AAC_VARIANT_MM && p.n_staged < p.n_maps) ? p.maps : s_map; w.ray = s_ray; w.dda = s_dda; w.walk.s = smem_u32(s_walk); w.walk.p = nullptr; w.lane = lane;
     w.px = reinterpret_cast<float *>(ws + WS_CUR); w.py = w.px + 32; w.vx = w.py + 32; w.vy = w.vx + 32; w.hd = w.vy + 32;
     w.ppx = reinterpret_cast<float *>(ws + WS_PRE); w.ppy = w.ppx + 32; w.pvx = w.ppy + 32; w.pvy = w.pvx + 32;
     w.meta = reinterpret_cast<unsigned *>(ws + WS_META); w.meta2 = w.meta + 32; w.minr = w.meta2 + 32; w.agf = w.minr + 32; w.wpm = w.agf + 32;
@@ -1040,7 +1042,7 @@ __global__ void __launch_bounds__(MAX_THREADS, AAC_MIN_BLOCKS) env_kernel(const 
 
             // ---- reward / collision / goal per drone
             if (mine) {
-                const MapDev &mp = VAR == AAC_VARIANT_MM ? p.maps[w.amap[a]] : *s_map;
+                const MapDev &mp = VAR == AAC_VARIANT_MM ? w.map[w.amap[a]] : *s_map;
                 const int eb = my_env * N, i = a - eb;
                 const float px = w.px[a], py = w.py[a];
                 const int nw = w.refw[a];
@@ -1386,14 +1388,15 @@ static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, 
 template <int VAR, int NT, int RT>
 static cudaError_t launch_aux(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     if (p.out_flags == 0) {
-        if (VAR == AAC_VARIANT_V2 && NT > 0 && RT > 0) {   // the two launches of a large batch's step: one kernel per mode and radar mode
-            const bool lh = p.radar_mode == AAC_RADAR_LAST_HIT;
+        if (NT > 0 && RT > 0) {   // the two launches of a step (and the plain step / reset calls): one kernel per mode and radar mode
+            constexpr bool V2 = VAR == AAC_VARIANT_V2;
+            const bool lh = V2 && p.radar_mode == AAC_RADAR_LAST_HIT;
             if (mode == MODE_STEP && !p.autoreset)
-                return lh ? launch_one<VAR, false, true, NT, RT, false, MT_STEP_ONLY, AAC_RADAR_LAST_HIT>(p, mode, threads, sms, grid_cache, stream)
-                          : launch_one<VAR, false, true, NT, RT, false, MT_STEP_ONLY, AAC_RADAR_MIN>(p, mode, threads, sms, grid_cache, stream);
+                return lh ? launch_one<VAR, false, true, NT, RT, false, MT_STEP_ONLY, V2 ? AAC_RADAR_LAST_HIT : -1>(p, mode, threads, sms, grid_cache, stream)
+                          : launch_one<VAR, false, true, NT, RT, false, MT_STEP_ONLY, V2 ? AAC_RADAR_MIN : -1>(p, mode, threads, sms, grid_cache, stream);
             if (mode == MODE_RESET)
-                return lh ? launch_one<VAR, false, true, NT, RT, false, MODE_RESET, AAC_RADAR_LAST_HIT>(p, mode, threads, sms, grid_cache, stream)
-                          : launch_one<VAR, false, true, NT, RT, false, MODE_RESET, AAC_RADAR_MIN>(p, mode, threads, sms, grid_cache, stream);
+                return lh ? launch_one<VAR, false, true, NT, RT, false, MODE_RESET, V2 ? AAC_RADAR_LAST_HIT : -1>(p, mode, threads, sms, grid_cache, stream)
+                          : launch_one<VAR, false, true, NT, RT, false, MODE_RESET, V2 ? AAC_RADAR_MIN : -1>(p, mode, threads, sms, grid_cache, stream);
         }
         return launch_one<VAR, false, true, NT, RT>(p, mode, threads, sms, grid_cache, stream);
     }

@@ -65,6 +65,7 @@ struct KParams {
     unsigned long long seed;
     const MapDev *maps;
     int n_maps;
+    int n_staged;           // maps staged per CTA in shared memory by the prologue's bulk copy (1, or all of them: multipleMap)
     const float4 *ray_tab;  // [R] (dx, dy, 1/dx, 1/dy) of the ray at k*360/R degrees; exact zeros on the axes, 1/0 = +inf
     const DdaRay *dda_tab;  // [R] the same rays as the constants of the cell walk (aac_radar.cuh)
     const uint4 *walk_tab;  // [WALK_BYTES / 16] the walk table
@@ -104,11 +105,13 @@ __host__ __device__ inline WarpLayout make_warp_layout(int variant, int N, int f
     return L;
 }
 
-inline CtaLayout make_cta_layout(const WarpLayout &WL, int R, int warps) {
+constexpr int MAX_STAGED_MAPS = 16;   // multipleMap: the whole table travels to shared memory when it has at most this many maps (5 KB)
+
+inline CtaLayout make_cta_layout(const WarpLayout &WL, int R, int warps, int n_staged = 1) {
     CtaLayout L;
     unsigned o = 0;
     auto take = [&](unsigned bytes) { unsigned r = o; o = align16(o + bytes); return r; };
-    L.map = take(sizeof(MapDev));
+    L.map = take(n_staged * sizeof(MapDev));
     L.ray = take(R * 16);
     L.dda = take(R * sizeof(DdaRay));
     L.walk = take(WALK_BYTES);
