@@ -431,6 +431,24 @@ def emit(line):
     out.flush()
 
 
+def bind_to_gpu_cpus(local_rank):
+    """Pin this rank to the CPUs NVML reports as local to its GPU (its NUMA node) BEFORE any pinned host memory is allocated,
+    so that the pinned buffers of the end-to-end path live next to the GPU's PCIe root.  Returns a description for the line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus local to gpu %d (nvml)" % (len(cpus), local_rank)
+    except Exception as e:
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
 def self_launch(args):
     """`python bench.py --gpus N` outside torchrun: start the N ranks the way the driver does."""
     import socket
@@ -503,6 +521,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    affinity = bind_to_gpu_cpus(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -630,7 +649,8 @@ def main():
                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                     "roofline": {"bound": "host link (PCIe D2H into pinned memory)", "peak": agents_total / copy_s, "unit": "agent-steps/s", "frac": e2e_value * copy_s / agents_total,
                                  "peak_GBs": (h2d + d2h) * world / copy_s / 1e9, "achieved_GBs": (h2d + d2h) * world * args.e2e_steps / e2e_s / 1e9,
-                                 "how": "the same pinned buffers and byte counts copied with no kernel in between, all ranks at once, timed the same way"}},
+                                 "how": "the same pinned buffers and byte counts copied with no kernel in between, all ranks at once, timed the same way",
+                                 "cpu_affinity": affinity}},
             "gpu_launches": int(launches) * n_blocks,
             "kernels": {"env_kernel(step+autoreset)_ms": step_kernel_ms, "host_issue_ms_per_step": host_issue_ms, "launches_per_step": launches / K_},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
