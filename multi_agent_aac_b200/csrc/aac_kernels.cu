@@ -914,7 +914,8 @@ constexpr int MT_STEP_ONLY = 3;
 #define AAC_MIN_BLOCKS 4   // resident CTAs of 256 threads per SM the register allocation aims at (64 registers)
 #endif
 template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1, int RM = -1, bool CS = false>
-__global__ void __launch_bounds__(MAX_THREADS, AAC_MIN_BLOCKS) env_kernel(const __grid_constant__ KParams p, const int mode_arg) {
+__global__ void __launch_bounds__(MAX_THREADS, NT >= 16 ? 3 : AAC_MIN_BLOCKS) env_kernel(   // 20-drone envs: 85 registers, no spills, measured 5 % faster on C5
+const __grid_constant__ KParams p, const int mode_arg) {
     constexpr bool STEP_ONLY = MT == MT_STEP_ONLY;
     const int mode = MT < 0 ? mode_arg : (STEP_ONLY ? (int)MODE_STEP : MT);
     extern __shared__ __align__(16) unsigned char smem[];
