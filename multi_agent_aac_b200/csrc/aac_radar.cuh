@@ -76,9 +76,10 @@ constexpr float DDA_NEVER = 1e30f;   // stands in for 1 / 0: an axis-parallel ra
                                      // product with it is a NaN or an infinity
 struct __align__(16) DdaRay {
     float idx, idy;      // 1 / dx, 1 / dy of the ray vector (length = ray_len); DDA_NEVER for an axis-parallel component
-    float cx, cy;        // first crossing: t1 = a * id + c with c = (cell if d > 0 else 0) * id; the second one lies cell * |id| further
+    float cx, cy;        // first crossing: t1 = a * id + c with c = (cell if d > 0 else 0) * id
+    float stepx, stepy;  // cell * |1 / dx|, cell * |1 / dy|: the second crossing lies that much further
     unsigned quad;       // byte offset of the ray's direction quadrant in the walk table
-    unsigned pad_[3];
+    unsigned pad_;
 };
 
 // The walk table: which window bit each of the four crossings enters.  The crossings tx1 < tx2, ty1 < ty2 merge in one of
@@ -114,8 +115,10 @@ inline DdaRay make_dda_ray(float dx, float dy, float cell) {
     r.idy = dy != 0.0f ? 1.0f / dy : DDA_NEVER;
     r.cx = dx >= 0.0f ? cell * r.idx : 0.0f;
     r.cy = dy >= 0.0f ? cell * r.idy : 0.0f;
+    r.stepx = cell * fabsf(r.idx);
+    r.stepy = cell * fabsf(r.idy);
     r.quad = ((dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u)) * WALK_QUAD_BYTES;
-    r.pad_[0] = r.pad_[1] = r.pad_[2] = 0;
+    r.pad_ = 0;
     return r;
 }
 
@@ -180,6 +183,17 @@ inline unsigned dda_bit(int pos) { return (pos >= 32 || pos < 0) ? 0u : 1u << po
 inline int dda_top(unsigned x) { return x ? 31 - __builtin_clz(x) : -1; }
 #define AAC_FMA(a, b, c) fmaf((a), (b), (c))
 #endif
+// x / y pairs in the packed single-precision pipe of sm_100 (FFMA2 / FADD2 / FMUL2: one instruction for both axes); component-wise
+// with the same roundings anywhere else (the host build of the CPU-side checks)
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+#define AAC_FMA2(a, b, c) __ffma2_rn((a), (b), (c))
+#define AAC_FADD2(a, b) __fadd2_rn((a), (b))
+#define AAC_FMUL2(a, b) __fmul2_rn((a), (b))
+#else
+#define AAC_FMA2(a, b, c) make_float2(fmaf((a).x, (b).x, (c).x), fmaf((a).y, (b).y, (c).y))
+#define AAC_FADD2(a, b) make_float2((a).x + (b).x, (a).y + (b).y)
+#define AAC_FMUL2(a, b) make_float2((a).x * (b).x, (a).y * (b).y)
+#endif
 
 // the walk table as the kernels see it: a shared-memory address (one ld.shared.v4 per ray, no generic-pointer arithmetic);
 // a plain pointer on the host
@@ -200,8 +214,10 @@ struct WalkRef {
 template <int WANT, bool AUX>
 AAC_HD bool radar_dda(const DdaRay &r, const WalkRef walk, const float cell, const float ax, const float ay, const unsigned win, float &t_min,
                       float &t_last, int &b_min, int &b_last) {
-    const float tx1 = AAC_FMA(ax, r.idx, r.cx), ty1 = AAC_FMA(ay, r.idy, r.cy);
-    const float tx2 = AAC_FMA(cell, fabsf(r.idx), tx1), ty2 = AAC_FMA(cell, fabsf(r.idy), ty1);
+    (void)cell;
+    const float2 c1 = AAC_FMA2(make_float2(ax, ay), make_float2(r.idx, r.idy), make_float2(r.cx, r.cy));   // first crossings, both axes at once
+    const float2 c2 = AAC_FADD2(c1, make_float2(r.stepx, r.stepy));
+    const float tx1 = c1.x, ty1 = c1.y, tx2 = c2.x, ty2 = c2.y;
     const bool clean = (tx1 != ty1) & (tx1 != ty2) & (tx2 != ty1) & (tx2 != ty2);
     // the merge order of the crossings and how many of them lie on the ray select the row of the walk table
     unsigned off = r.quad;
@@ -349,7 +365,8 @@ AAC_HD bool cast_grid_fast(const DdaRay &r, const WalkRef walk, const float cell
         id_last = b_last < 0 ? -1 : (ixc - 2 + b_last / 5) * gy + iyc - 2 + b_last % 5;
     }
     // boundary lines: t = (line - p) / d; an axis-parallel ray (1 / d = DDA_NEVER) or a line out of reach (+inf) is never valid
-    const float tbx = AAC_FMUL(rec.z, r.idx), tby = AAC_FMUL(rec.w, r.idy);
+    const float2 tb = AAC_FMUL2(make_float2(rec.z, rec.w), make_float2(r.idx, r.idy));
+    const float tbx = tb.x, tby = tb.y;
     const bool vx = tbx >= 0.0f && tbx <= 1.0f, vy = tby >= 0.0f && tby <= 1.0f;
     if (WANT & 2) {
         t_last = vx ? tbx : t_last;
