@@ -787,7 +787,11 @@ __device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp
         };
         int s_idx = 0, tq = 0, code = 0;
         if (lane < N) code = candidate(lane, 0, s_idx, tq);
-        for (int i = 1; i < N; ++i) {                         // drone 0 keeps its first draw
+        // Starts sit on cell centres: while the separation is below one cell (2 * protectiveBound < grid length, the
+        // reference's 5 m on a 10 m grid) only two drones on the SAME cell are too close, and when no two first draws
+        // coincide - most episodes - every drone keeps its draw and the drone-by-drone loop below has nothing to do
+        const bool distinct = sep2 < 1.0f && __all_sync(FULL, lane >= N || __match_any_sync(__activemask(), lane < N ? code : -1 - lane) == (1u << lane));
+        for (int i = 1; i < N && !distinct; ++i) {            // drone 0 keeps its first draw
             for (int attempt = 1; attempt < 48; ++attempt) {
                 const int ci = __shfl_sync(FULL, code, i);
                 const float dx = (float)((ci >> 8) - (code >> 8)), dy = (float)((ci & 255) - (code & 255));
@@ -992,8 +996,9 @@ const __grid_constant__ KParams p, const int mode_arg) {
         const int my_env = mine ? a / N : 0;
         const uint16_t *cells = p.st.ref_cells + (size_t)(mine ? ga : a0) * W;
 
-        // ---- load the per-drone records; integrate the action (ATT:2655-2713)
-        if (mine) {
+        // ---- load the per-drone records; integrate the action (ATT:2655-2713).  A reset launch re-initialises every env it
+        //      touches (init_env fills all of a drone's slots) and stores only those: it never reads the old records
+        if (mine && mode != MODE_RESET) {
             float px = p.st.px[ga], py = p.st.py[ga], vx = p.st.vx[ga], vy = p.st.vy[ga], hd = p.st.heading[ga];
             const unsigned meta = p.st.meta[ga];
             w.ppx[a] = px; w.ppy[a] = py; w.pvx[a] = vx; w.pvy[a] = vy;
