@@ -93,10 +93,11 @@ def profiled_metric(name, kernel_names):
 
 def launched_kernels(variant, n, r, radar_mode):
     """The two instantiations one aac_step_autoreset call launches for the specialised tdCPA_forV2 shapes (aac_kernels.cu
-    launch_aux): env_kernel<VAR, AUX, LEAN, N, R, EVS, MT, RM>, MT = 3 step-only / 2 reset-only."""
+    launch_aux): env_kernel<VAR, AUX, LEAN, N, R, EVS, MT, RM, CS>, MT = 3 step-only / 2 reset-only, RM = radar mode, CS = 0
+    (no later-fork sensors)."""
     if variant != "v2" or (n, r) not in ((10, 36), (20, 72)):
         return None
-    return ["env_kernel<1,0,1,%d,%d,0,3,%d>" % (n, r, radar_mode), "env_kernel<1,0,1,%d,%d,0,2,%d>" % (n, r, radar_mode)]
+    return ["env_kernel<1,0,1,%d,%d,0,3,%d,0>" % (n, r, radar_mode), "env_kernel<1,0,1,%d,%d,0,2,%d,0>" % (n, r, radar_mode)]
 
 
 def measured_peak():
