@@ -27,7 +27,7 @@ gen.manual_seed(0)
 
 
 def rollout(name, n, r, flags, source, steps=6, envs=96, **kw):
-    maps = multimap_set(seed=0) if name == "multimap" else synthetic_map(seed=0)
+    maps = multimap_set(seed=0) if name == "multimap" else synthetic_map(bound=[0, 200, 0, 200] if name == "changeskin_sensors" else None, seed=0)
     if name == "multimap":
         flags &= ~(K.OUT_NBR6 | K.OUT_TCPA_PAIR)
     cfg = preset(name, n_envs=envs, n_agents=n, n_rays=r, w_max=32, seed=3, out_flags=flags, **kw)
@@ -60,6 +60,8 @@ if "env" in what:
     rollout("tdcpa_v2", 20, 72, 0, "od", envs=40)
     rollout("tdcpa_v2", 5, 36, ALL_OUT, "od", eval_by_step=True)
     rollout("tdcpa_v2", 1, 18, 0, "bank", envs=9)
+    rollout("changeskin_sensors", 4, 18, K.OUT_RAW | K.OUT_RADAR_AUX | K.OUT_PARTS, "od", steps=12)    # the later fork's sensor classes
+    rollout("changeskin_sensors", 6, 36, 0, "bank", radar_targets=15, n_nbr_obs=3)
 
 if "actor" in what:
     for rows, dims in ((300, (7, 45, 36)), (128 * 150 + 17, (7, 45, 36)), (200, (7, 95, 72))):
