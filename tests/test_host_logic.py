@@ -192,6 +192,27 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert "workload" in line["config"] and line["cpu_baseline"]["cores"] >= 1
 
 
+def test_bench_c1_and_profile_gating():
+    """BASELINE config 1 (one env, one core) prints the contract line on the CPU; the ncu-derived fields of the GPU line are
+    tied to the kernel sources: a capture of another build or another instantiation yields None."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "c1", "--steps", "60"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["cpu_baseline"]["cores"] == 1 and line["steps"] == 60 and line["value"] > 0 and "1 env" in line["cpu_baseline"]["sample"]
+    sys.path.insert(0, ROOT)
+    import bench
+    names = bench.launched_kernels("v2", 10, 36, 1)
+    assert names == ["env_kernel<1,0,1,10,36,0,3,1,0>", "env_kernel<1,0,1,10,36,0,2,1,0>"] and bench.launched_kernels("att", 3, 36, 0) is None
+    rows = bench._profiled_rows(names)
+    if rows is not None:      # the committed summaries belong to this very source: both launches, named exactly
+        assert all(r["Source Hash"][1] == bench.source_hash() for r in rows) and bench.profiled_traffic(names) > 3e8
+    assert bench.profiled_traffic(["env_kernel<1,0,1,10,36,0,3,0,0>", names[1]]) is None      # another radar mode: not these kernels
+    assert bench.profiled_traffic(bench.launched_kernels("v2", 20, 72, 1)) is None
+
+
 def test_actor_library_exports_every_declared_symbol():
     from multi_agent_aac_b200 import _actor_capi
     _actor_capi.build()
