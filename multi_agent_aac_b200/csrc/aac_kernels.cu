@@ -137,7 +137,7 @@ __device__ __forceinline__ float support64_q1(float ax, float ay) {
 __device__ __forceinline__ bool gons_touch(float qx, float qy, float rsum) {
     const float d2 = qx * qx + qy * qy;
     if (d2 > rsum * rsum) return false;
-    const float apo = rsum * c_apo;
+    const float apo = __fmul_rn(rsum, c_apo);   // never fused with the subtraction below: all instantiations decide alike
     if (d2 <= apo * apo) return true;
     return support64_q1(fabsf(qx), fabsf(qy)) - apo <= 0.0f;
 }
@@ -147,7 +147,7 @@ __device__ __forceinline__ bool gon_square_touch(float dxc, float dyc, float h, 
     const float ex = fabsf(dxc) - h, ey = fabsf(dyc) - h;
     if (ex > r || ey > r) return false;
     if (ex <= 0.0f || ey <= 0.0f) return true;
-    return support64_q1(ex, ey) - r * c_apo <= 0.0f;
+    return support64_q1(ex, ey) - __fmul_rn(r, c_apo) <= 0.0f;
 }
 
 // max over i = 0..32 of cos(t0 - i * pi/32): x-extent of one end cap of the GEOS round buffer
@@ -238,7 +238,9 @@ __device__ __forceinline__ void radar_drones_ray(const float *s_px, const float 
     const int lane = threadIdx.x & 31;
     const float dx = ray.x, dy = ray.y;
     const float px = s_px[env_base + i], py = s_py[env_base + i];
-    const float apo = r * c_apo, inv_l2 = 1.0f / (len * len);
+    // (__fmul_rn: the product must not be re-formed next to the subtraction below and fused with it in one instantiation and
+    //  not in another - every instantiation returns the same bits)
+    const float apo = __fmul_rn(r, c_apo), inv_l2 = 1.0f / (len * len);
     float best = len, shortest = CUDART_INF_F;
     int best_id = -1;
     for (int j = 0; j < N; ++j) {
@@ -313,7 +315,7 @@ __device__ __noinline__ float ray_gon_outline(float qx, float qy, float dx, floa
     tt = fminf(fmaxf(tt, 0.0f), 1.0f);
     const float cx = fmaf(tt, dx, qx), cy = fmaf(tt, dy, qy);
     if (cx * cx + cy * cy > r * r * 1.00001f) return CUDART_INF_F;
-    const float apo = r * c_apo;
+    const float apo = __fmul_rn(r, c_apo);
     float lo = 0.0f, hi = 1.0f;
     bool inside = true;
 #pragma unroll 1
@@ -367,9 +369,12 @@ __device__ __forceinline__ void flush_items(float *dst, int n_valid, const float
 
 // observation pipeline for the drones [a_lo, a_lo + n_ag) of the warp's group (whole envs):
 // neighbour order + window -> { pairs | rays | own block }.  `cells` = the lane's reference-line row.
+// MASKED (a literal at the call sites of the mode-specialised launches): only the envs whose bit is set in `active` (bit g = env g of the group; a_lo is 0 then) are observed and stored - the
+// re-initialised envs of a reset.  The drone-per-lane phases take all of them at once; the item-per-lane phases, whose stores
+// are contiguous per env, run env by env.
 template <int VAR, bool AUX, bool LEAN, int NT, int RT, int RM, bool CS>
 __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, const int a_lo, const int n_ag, const uint16_t *cells, const bool tab,
-                                              const bool step_mode) {
+                                              const bool step_mode, const bool MASKED, const unsigned active) {
     // step_mode: the observation closes a step (sensor configurations: the clouds have moved once more than ep_step says)
     const int radar_mode = RM < 0 ? p.radar_mode : RM;   // RM >= 0: the radar mode is a compile-time constant of the instantiation
     // tab: the drones of the range have just been reset, i.e. stand on cell centres, and the handle has a radar table:
@@ -383,8 +388,17 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
     // shared memory when it fits, else the table in global memory)
     auto map_of = [&](const int aa) -> const MapDev & { return VAR == AAC_VARIANT_MM ? w.map[w.amap[aa]] : *w.map; };
     const float inv_vmax = 1.0f / p.vmax;
-    const bool mine = lane < n_ag;
     const int a = a_lo + lane;           // the lane's drone in the drone-per-lane phases
+    const bool mine = lane < n_ag && (!MASKED || ((active >> (a / N)) & 1u));
+    // the contiguous sub-ranges the item-per-lane phases run over: the whole range, or one env at a time
+    auto for_ranges = [&](auto body) {
+        const int n_r = MASKED ? n_ag / N : 1;
+#pragma unroll 1
+        for (int g = 0; g < n_r; ++g) {
+            if (MASKED && !((active >> g) & 1u)) continue;
+            body(MASKED ? g * N : a_lo, MASKED ? N : n_ag);
+        }
+    };
     const int eb = mine ? (a / N) * N : 0;  // first drone of its env
     const MapDev &mp = map_of(mine ? a : a_lo);
 
@@ -451,7 +465,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
     __syncwarp();
 
     // ---- ordered pairs -> tdCPA (cur, pre) and the neighbour blocks of the observation
-    if (M > 0 && VAR != AAC_VARIANT_MM) {
+    if (M > 0 && VAR != AAC_VARIANT_MM) for_ranges([&](const int a_lo, const int n_ag) {
         // Mo = neighbours per drone that enter the blocks: all of them, or (sensor configurations) the nearest n_nbr_obs
         const int Mo = (CS && p.n_nbr_obs > 0) ? min(p.n_nbr_obs, M) : M;
         const int n_items = n_ag * Mo;
@@ -498,13 +512,14 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
                 }
             }
         }
-    }
+    });
 
     // ---- radar.  A warp iteration covers 32 rays of ONE drone (window mask, bounds flag and position are
     //      then warp-uniform: no divergence in the cell loop); the R % 32 leftover rays of several drones
     //      are packed into shared iterations.  Ranges are >= 0, so their bit patterns order like unsigned
     //      integers and nan (0x7FC00000) sorts above every number: the per-drone minimum the reward needs
     //      (min_radar) is one redux.sync per drone and iteration.
+    for_ranges([&](const int a_lo, const int n_ag) {
     if (VAR != AAC_VARIANT_ATT && tab) {
         const size_t rg0 = (size_t)(w.a0 + a_lo) * R;
         // four table reads in flight per lane (they come from L2)
@@ -674,6 +689,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
         else if (VAR == AAC_VARIANT_V2 && radar_mode == AAC_RADAR_LAST_HIT) radar_pass(std::integral_constant<int, 2>{});
         else radar_pass(std::integral_constant<int, 1>{});
     }
+    });
     __syncwarp();
 
     // ---- own block of the observation, goal contact
@@ -713,7 +729,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
         }
     }
     __syncwarp();
-    {   // own rows of the range are contiguous: coalesced copy
+    for_ranges([&](const int a_lo, const int n_ag) {   // own rows of a range are contiguous: coalesced copy
         float *dst = p.out.norm_own + (size_t)(w.a0 + a_lo) * D;
         const float *src = w.own + a_lo * D;
         for (int f = lane; f < n_ag * D; f += 32) dst[f] = src[f];
@@ -722,7 +738,7 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
             const float *sr = w.raw_own + a_lo * D;
             for (int f = lane; f < n_ag * D; f += 32) dr[f] = sr[f];
         }
-    }
+    });
     __syncwarp();
 }
 
@@ -743,14 +759,16 @@ __device__ __forceinline__ unsigned draw(unsigned key, unsigned ctr) {
     return h;
 }
 
-// re-initialise env g of the warp's group: what reset_world leaves behind (ATT:251-372).  Origins, destinations and
-// reference lines come from the map's origin / destination table when one is installed (the device draws them with
-// reset_world's rule, ATT:254-276), else from a pre-planned scenario of the bank.  Returns the lane's reference-line
-// row for the drones of that env.
-template <int VAR>
-__device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp &w, const int g) {
-    const int lane = w.lane, N = p.N, W = p.W;
-    const int ge = w.e_lo + g;
+// re-initialise the envs of the warp's group whose bit is set in `mask`, all at once (lane a = drone a of the group): what
+// reset_world leaves behind (ATT:251-372).  Origins, destinations and reference lines come from the map's origin /
+// destination table when one is installed (the device draws them with reset_world's rule, ATT:254-276), else from a
+// pre-planned scenario of the bank.  Returns the lane's reference-line row (nullptr for a lane outside the masked envs).
+template <int VAR, int NT>
+__device__ __forceinline__ const uint16_t *init_envs(const KParams &p, const Warp &w, const unsigned mask) {
+    const int lane = w.lane, N = NT ? NT : p.N, W = p.W;
+    const int g = lane / N, i = lane - g * N;             // the lane's env of the group and its drone in it
+    const bool act = lane < w.nA && ((mask >> g) & 1u);
+    const int ge = w.e_lo + (act ? g : 0);
     const long long gid = p.env_id_base + ge;
     const int ep = p.st.ep_index[ge];
     const bool use_od = p.od != nullptr;
@@ -760,8 +778,8 @@ __device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp
     const unsigned key = use_od ? episode_key(p.seed, gid, ep) : 0u;
     if (VAR == AAC_VARIANT_MM) map_row = use_od ? (int)(draw(key, 0) % (unsigned)p.n_maps) : (p.bank_map ? p.bank_map[scen] : 0);
     const MapDev &mp = VAR == AAC_VARIANT_MM ? w.map[map_row] : *w.map;
-    __syncwarp();
-    if (lane == 0) {
+    __syncwarp();                                          // every lane has read its env's episode index
+    if (act && i == 0) {
         p.st.ep_index[ge] = ep + 1;
         p.st.ep_step[ge] = 0;
         p.st.ep_return[ge] = 0.0f;
@@ -771,13 +789,13 @@ __device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp
     int nw = 0;
     if (use_od) {
         const OdDev &od = p.od[map_row];
-        // Lane i draws for drone i.  reset_world draws drone by drone and redraws a start until it is more than
-        // 2 * protectiveBound from every EARLIER drone's start (ATT:254-270): the candidates are drawn in parallel
-        // (each drone has its own counter stream), the accept / redraw decisions run drone by drone with the
-        // earlier drones' lanes voting.
+        // Lane (g, i) draws for drone i of env g.  reset_world draws drone by drone and redraws a start until it is more
+        // than 2 * protectiveBound from every EARLIER drone's start (ATT:254-270): the candidates are drawn in parallel
+        // (each drone has its own counter stream), the accept / redraw decisions run drone by drone - for all the masked
+        // envs in lockstep - with the earlier drones' lanes of the same env voting.
         const float sep2 = 4.0f * p.prot * p.prot * mp.inv_cell * mp.inv_cell;   // (2 * protectiveBound)^2 in cells^2
-        auto candidate = [&](const int i, const int attempt, int &s_idx, int &tq) -> int {
-            const unsigned base = 1u + 256u * (unsigned)i + 4u * (unsigned)attempt;
+        auto candidate = [&](const int di, const int attempt, int &s_idx, int &tq) -> int {
+            const unsigned base = 1u + 256u * (unsigned)di + 4u * (unsigned)attempt;
             const int sq = draw(key, base) >> 30;
             tq = (int)(draw(key, base + 1) % 3u);
             if (tq >= sq) ++tq;                               // a different quadrant for the goal (ATT:256-258)
@@ -786,48 +804,53 @@ __device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp
             return od.cell_code[s_idx];
         };
         int s_idx = 0, tq = 0, code = 0;
-        if (lane < N) code = candidate(lane, 0, s_idx, tq);
+        if (act) code = candidate(i, 0, s_idx, tq);
         // Starts sit on cell centres: while the separation is below one cell (2 * protectiveBound < grid length, the
-        // reference's 5 m on a 10 m grid) only two drones on the SAME cell are too close, and when no two first draws
-        // coincide - most episodes - every drone keeps its draw and the drone-by-drone loop below has nothing to do
-        const bool distinct = sep2 < 1.0f && __all_sync(FULL, lane >= N || __match_any_sync(__activemask(), lane < N ? code : -1 - lane) == (1u << lane));
-        for (int i = 1; i < N && !distinct; ++i) {            // drone 0 keeps its first draw
+        // reference's 5 m on a 10 m grid) only two drones on the SAME cell are too close, and when no two first draws of
+        // an env coincide - most episodes - every drone keeps its draw and the drone-by-drone loop below has nothing to do
+        const unsigned same = __match_any_sync(FULL, act ? ((g << 16) | code) : (0x40000000 | lane));
+        const bool distinct = __all_sync(FULL, !act || (sep2 < 1.0f && same == (1u << lane)));
+        const unsigned emask = (N >= 32 ? FULL : ((1u << N) - 1u)) << (g * N & 31);   // the lanes of the lane's env
+        for (int ii = 1; ii < N && !distinct; ++ii) {         // drone 0 keeps its first draw
             for (int attempt = 1; attempt < 48; ++attempt) {
-                const int ci = __shfl_sync(FULL, code, i);
+                const int ci = __shfl_sync(FULL, code, (g * N + ii) & 31);
                 const float dx = (float)((ci >> 8) - (code >> 8)), dy = (float)((ci & 255) - (code & 255));
-                if (!__ballot_sync(FULL, lane < i && dx * dx + dy * dy <= sep2)) break;
-                if (lane == i) code = candidate(i, attempt, s_idx, tq);
+                const unsigned conf = __ballot_sync(FULL, act && i < ii && dx * dx + dy * dy <= sep2);
+                const bool redo = act && (conf & emask);      // the env's drone ii is too close to an earlier one
+                if (!__any_sync(FULL, redo)) break;
+                if (redo && i == ii) code = candidate(ii, attempt, s_idx, tq);
             }
         }
-        int pr = 0;
-        if (lane < N) {
+        if (act) {
             const int n_t = od.pool_off[tq + 1] - od.pool_off[tq];
-            const int t_idx = od.pool_off[tq] + (int)(draw(key, 1u + 256u * (unsigned)lane + 3u) % (unsigned)n_t);
-            pr = s_idx * od.n_cells + t_idx;
-        }
-        if (lane < N) {
+            const int t_idx = od.pool_off[tq] + (int)(draw(key, 1u + 256u * (unsigned)i + 3u) % (unsigned)n_t);
+            const int pr = s_idx * od.n_cells + t_idx;
             nw = od.path_len[pr];
             const uint16_t *src = od.path_cells + od.path_off[pr];   // 16-byte aligned: paths are padded to 8 cells
             const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-            uint4 *d4 = reinterpret_cast<uint4 *>(p.st.ref_cells + ((size_t)ge * N + lane) * W);
+            uint4 *d4 = reinterpret_cast<uint4 *>(p.st.ref_cells + ((size_t)ge * N + i) * W);
             for (int k = 0; k < (nw + 7) >> 3; ++k) d4[k] = s4[k];
             row = src;
         }
         __syncwarp();
     } else {
-        // reference lines: 16-byte chunks bank -> global state (W is a multiple of 8)
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.bank_cells + (size_t)scen * N * W);
-        uint4 *dst = reinterpret_cast<uint4 *>(p.st.ref_cells + (size_t)ge * N * W);
-        for (int c = lane; c < N * W / 8; c += 32) dst[c] = src[c];
-        if (lane < N) {
-            row = p.bank_cells + ((size_t)scen * N + lane) * W;
-            nw = p.bank_w[(size_t)scen * N + lane];
+        // reference lines: 16-byte chunks bank -> global state (W is a multiple of 8), env by env with the whole warp
+        for (unsigned left = mask; left; left &= left - 1u) {
+            const int gg = __ffs(left) - 1;
+            const unsigned sc = __shfl_sync(FULL, scen, gg * N);
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.bank_cells + (size_t)sc * N * W);
+            uint4 *dst = reinterpret_cast<uint4 *>(p.st.ref_cells + (size_t)(w.e_lo + gg) * N * W);
+            for (int c = lane; c < N * W / 8; c += 32) dst[c] = src[c];
+        }
+        if (act) {
+            row = p.bank_cells + ((size_t)scen * N + i) * W;
+            nw = p.bank_w[(size_t)scen * N + i];
         }
     }
-    if (lane < N) {
-        const int a = g * N + lane;
+    if (act) {
+        const int a = lane;
         w.refw[a] = (uint8_t)nw;
-        p.st.ref_w[(size_t)ge * N + lane] = (uint8_t)nw;
+        p.st.ref_w[(size_t)ge * N + i] = (uint8_t)nw;
         const uint4 head = *reinterpret_cast<const uint4 *>(row);   // table paths and bank rows start on 16-byte boundaries
         reinterpret_cast<uint4 *>(w.c8)[a] = head;
         const unsigned c0 = head.x & 0xFFFFu, c1 = head.x >> 16;
@@ -837,7 +860,7 @@ __device__ __forceinline__ const uint16_t *init_env(const KParams &p, const Warp
         w.ppx[a] = px; w.ppy[a] = py; w.pvx[a] = 0.0f; w.pvy[a] = 0.0f;
         w.meta[a] = 0xFFFF0000u;
         if (VAR == AAC_VARIANT_MM) { w.amap[a] = (uint8_t)map_row; w.wpm[a] = (1u << nw) - 2u; }   // every vertex after the start (MM:345)
-        if (p.st.wall_count) p.st.wall_count[(size_t)ge * N + lane] = 0;
+        if (p.st.wall_count) p.st.wall_count[(size_t)ge * N + i] = 0;
     }
     __syncwarp();
     return row;
@@ -997,7 +1020,7 @@ const __grid_constant__ KParams p, const int mode_arg) {
         const uint16_t *cells = p.st.ref_cells + (size_t)(mine ? ga : a0) * W;
 
         // ---- load the per-drone records; integrate the action (ATT:2655-2713).  A reset launch re-initialises every env it
-        //      touches (init_env fills all of a drone's slots) and stores only those: it never reads the old records
+        //      touches (init_envs fills all of a drone's slots) and stores only those: it never reads the old records
         if (mine && mode != MODE_RESET) {
             float px = p.st.px[ga], py = p.st.py[ga], vx = p.st.vx[ga], vy = p.st.vy[ga], hd = p.st.heading[ga];
             const unsigned meta = p.st.meta[ga];
@@ -1024,26 +1047,23 @@ const __grid_constant__ KParams p, const int mode_arg) {
         }
         __syncwarp();
 
-        // Jobs of a group: job 0 = the whole group (step / observe), job g+1 = env g alone after it has been
-        // re-initialised (reset mode: the masked envs; step mode: the envs that just terminated).  One copy
-        // of the pipeline serves them all.
         unsigned reset_mask = 0, store_mask = (w.ng >= 32) ? FULL : ((1u << w.ng) - 1u);
         if (mode == MODE_RESET) {
             bool m = lane < w.ng && (!p.mask || p.mask[w.e_lo + lane]);
             reset_mask = __ballot_sync(FULL, m);
             store_mask = reset_mask;
         }
-        for (int job = (mode == MODE_RESET ? 1 : 0); job <= (STEP_ONLY ? 0 : w.ng); ++job) {
-            int a_lo = 0, n_ag = nA;
+        // Jobs of a group: job 0 = the whole group (step / observe), job 1 = the envs to re-initialise, all at once (reset
+        // mode: the masked envs; step mode: the envs that just terminated).  One copy of the pipeline serves both.
+        for (int job = (mode == MODE_RESET ? 1 : 0); job <= (STEP_ONLY ? 0 : 1); ++job) {
             const uint16_t *cl = cells;
             if (job > 0) {
-                const int g = job - 1;
-                if (!((reset_mask >> g) & 1u)) continue;
-                const uint16_t *row = init_env<VAR>(p, w, g);
-                a_lo = g * N; n_ag = N;
-                cl = lane < N ? row : p.st.ref_cells;
+                if (!reset_mask) break;
+                const uint16_t *row = init_envs<VAR, NT>(p, w, reset_mask);
+                cl = row ? row : p.st.ref_cells;
             }
-            observe_range<VAR, AUX, LEAN, NT, RT, RM, CS>(p, w, a_lo, n_ag, cl, job > 0 && p.rtab != nullptr, job == 0 && mode == MODE_STEP);
+            observe_range<VAR, AUX, LEAN, NT, RT, RM, CS>(p, w, 0, nA, cl, job > 0 && p.rtab != nullptr, job == 0 && mode == MODE_STEP,
+                                                          STEP_ONLY ? false : (MT == MODE_RESET ? true : job > 0), job > 0 ? reset_mask : FULL);
             if (job > 0 || mode != MODE_STEP) continue;
 
             // ---- reward / collision / goal per drone
