@@ -1003,6 +1003,8 @@ const __grid_constant__ KParams p, const int mode_arg) {
     // ---- persistent warp: fetch a group of G whole envs, run the pipeline, fetch the next
     const int n_groups = (p.E + G - 1) / G;
     for (;;) {
+        // (claiming the next group ahead of time hides the atomic's round trip but was measured 4 % SLOWER: with four to five
+        //  groups per warp a group claimed early by a busy warp is a group an idle warp cannot take at the tail)
         int gi = 0;
         if (lane == 0) gi = atomicAdd(&p.work[p.parity], 1);
         gi = __shfl_sync(FULL, gi, 0);
@@ -1253,7 +1255,7 @@ const __grid_constant__ KParams p, const int mode_arg) {
                         branch = 4;
                     }
                 }
-                if (collide_building && p.st.wall_count) p.st.wall_count[ga] += 1;
+                if (collide_building && p.st.wall_count) atomicAdd(p.st.wall_count + ga, 1);   // result unused: a reduction, nothing to wait for
                 w.agf[a] = res | (branch << F_BRANCH_SHIFT);
                 w.agr[a] = rew;
                 if (flags & AAC_OUT_PARTS) {
@@ -1273,6 +1275,7 @@ const __grid_constant__ KParams p, const int mode_arg) {
             unsigned bbc = 0, any_done = 0, all_reach = 1, n_reach = 0, any_goal = 0, term = 0;
             int step = 0;
             float ret = 0.0f;
+            if (lane < w.ng) { step = p.st.ep_step[w.e_lo + lane]; ret = p.st.ep_return[w.e_lo + lane]; }   // in flight across the ballots below
             if (!EVS) {
                 // every drone's outcome flags meet in a handful of ballots; an env lane reads its env's bits out of them
                 const unsigned f = mine ? w.agf[a] : (4u << F_BRANCH_SHIFT), br = (f >> F_BRANCH_SHIFT) & 7u;
@@ -1324,8 +1327,8 @@ const __grid_constant__ KParams p, const int mode_arg) {
                     for (int i = 0; i < N; ++i) w.agr[eb + i] = sum;
                     sum *= (float)N;
                 }
-                step = p.st.ep_step[ge] + 1;
-                ret = p.st.ep_return[ge] + sum;
+                step += 1;
+                ret += sum;
                 term = (step > p.ep_len ? 1u : 0u) | (any_done ? 2u : 0u) | (all_reach ? 4u : 0u);
                 reinterpret_cast<uchar4 *>(p.out.bbc)[ge] = make_uchar4(bbc & 1, (bbc >> 1) & 1, (bbc >> 2) & 1, (bbc >> 3) & 1);
                 p.out.terminated[ge] = (uint8_t)term;
