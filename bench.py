@@ -40,7 +40,10 @@ def algorithmic_bytes(variant, n, r):
     return 4 * (26 + 2 * W_REF + obs)
 
 
-PROFILED = ("r2_env_kernel_v2_step_ncu_full_summary.csv", "r2_env_kernel_v2_reset_ncu_full_summary.csv")   # step launch, reset launch
+# committed `ncu --set full` summaries of the launches of one C3 step: the phased launch (step loop + reset loop in one
+# kernel, what aac_step_autoreset runs for C3) or the step launch and the reset launch (--launches 2)
+PROFILED = {1: ("r2_env_kernel_v2_phased_ncu_full_summary.csv",),
+            2: ("r2_env_kernel_v2_step_ncu_full_summary.csv", "r2_env_kernel_v2_reset_ncu_full_summary.csv")}
 
 
 def source_hash():
@@ -59,7 +62,9 @@ def _profiled_rows(kernel_names):
     exactly the kernel instantiation this run launches AND was taken from this very source."""
     import csv
     out = []
-    for name, want in zip(PROFILED, kernel_names):
+    for name, want in zip(PROFILED[len(kernel_names)], kernel_names):
+        if not os.path.exists(os.path.join(ROOT, "profiles", name)):
+            return None
         rows = {r[0]: (r[1], r[2]) for r in csv.reader(open(os.path.join(ROOT, "profiles", name))) if len(r) == 3}
         got = rows.get("Kernel Name", ("", ""))[1].replace("aac::", "").replace("(int)", "").replace("(bool)", "").replace(" ", "")
         if want.replace(" ", "") not in got or rows.get("Source Hash", ("", ""))[1] != source_hash():
@@ -91,13 +96,17 @@ def profiled_metric(name, kernel_names):
         return None
 
 
-def launched_kernels(variant, n, r, radar_mode):
-    """The two instantiations one aac_step_autoreset call launches for the specialised tdCPA_forV2 shapes (aac_kernels.cu
-    launch_aux): env_kernel<VAR, AUX, LEAN, N, R, EVS, MT, RM, CS>, MT = 3 step-only / 2 reset-only, RM = radar mode, CS = 0
-    (no later-fork sensors)."""
+def launched_kernels(variant, n, r, radar_mode, launches_per_step):
+    """The instantiations one aac_step_autoreset call launches for the specialised tdCPA_forV2 shapes (aac_kernels.cu
+    launch_aux): env_kernel<VAR, AUX, LEAN, N, R, EVS, MT, RM, CS>, MT = 4 phased (one launch: step loop, then reset loop) or
+    3 step-only + 2 reset-only (two launches), RM = radar mode, CS = 0 (no later-fork sensors)."""
     if variant != "v2" or (n, r) not in ((10, 36), (20, 72)):
         return None
-    return ["env_kernel<1,0,1,%d,%d,0,3,%d,0>" % (n, r, radar_mode), "env_kernel<1,0,1,%d,%d,0,2,%d,0>" % (n, r, radar_mode)]
+    if launches_per_step == 1:
+        return ["env_kernel<1,0,1,%d,%d,0,4,%d,0>" % (n, r, radar_mode)]
+    if launches_per_step == 2:
+        return ["env_kernel<1,0,1,%d,%d,0,3,%d,0>" % (n, r, radar_mode), "env_kernel<1,0,1,%d,%d,0,2,%d,0>" % (n, r, radar_mode)]
+    return None
 
 
 def measured_peak():
@@ -631,7 +640,7 @@ def main():
         value = agents_total * K_ / (elapsed_ms * 1e-3)
         peak, peak_kind = measured_peak()
         achieved = envs * n * bytes_per / (step_kernel_ms * 1e-3) / 1e9
-        names = launched_kernels(variant, n, r, cfg.radar_mode)
+        names = launched_kernels(variant, n, r, cfg.radar_mode, int(round(launches / K_)))
         traffic = profiled_traffic(names) if names else None
         e2e_value = agents_total * args.e2e_steps / e2e_s
         line = {
@@ -656,10 +665,10 @@ def main():
             "kernels": {"env_kernel(step+autoreset)_ms": step_kernel_ms, "host_issue_ms_per_step": host_issue_ms, "launches_per_step": launches / K_},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
-                         "traffic_note": ("bytes per step = step launch + reset launch, profiles/%s + %s: one ncu --set full capture of each, of this very source (hash %s)" % (PROFILED + (source_hash(),)))
+                         "traffic_note": ("bytes per step, summed over the step's launch(es), profiles/%s: one ncu --set full capture of each, of this very source (hash %s)" % (" + ".join(PROFILED[len(names)]), source_hash()))
                                          if traffic else "no ncu capture of this build (source hash %s) and these kernels under profiles/: null" % source_hash(),
                          "peak_kind": peak_kind, "bytes_per_agent_step": bytes_per,
-                         "kernel": ("%s + %s" % tuple(names)) if names else "env_kernel<%s>" % variant.upper()},
+                         "kernel": " + ".join(names) if names else "env_kernel<%s>" % variant.upper()},
             "clocks": clocks,
             "issue_slots": None,
             "episode_stats": {k: float(v) for k, v in zip(K.STAT_NAMES, stats)},
@@ -671,7 +680,7 @@ def main():
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             peak_issue = 4.0 * sms * clocks["sm_mhz"] * 1e6
             line["issue_slots"] = {"warp_inst_per_agent_step": inst / (envs * n), "utilisation": inst / (step_kernel_ms * 1e-3) / peak_issue,
-                                   "note": "instructions per step (step launch + reset launch) from the same committed captures; 4 schedulers x SMs x sampled clock"}
+                                   "note": "instructions per step (all launches of the step) from the same committed captures; 4 schedulers x SMs x sampled clock"}
         if world == 1 and not args.no_aux and preset_name == "tdcpa_v2":
             line["low_reset_regime"] = low_reset_regime(env, dev, acts)
             line["policy_rollout"] = policy_rollout(env, dev)

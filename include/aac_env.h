@@ -94,8 +94,10 @@ typedef struct {
     float goal_r;           /* 1     (ATT:2266) */
     int32_t eval_by_step;   /* V2 only: args.mode == 'eval' with evaluation_by_episode == False: crashed / arrived drones stay
                                where they are, crashes do not end the episode (V2:3729-3734, :3128-3156, :3551-3587) */
-    int32_t autoreset_launches; /* aac_step_autoreset / aac_step_host: 1 = one fused launch, 2 = step launch + reset launch,
-                               0 = choose by batch size (two launches pay off on large tdCPA_forV2 batches) */
+    int32_t autoreset_launches; /* aac_step_autoreset / aac_step_host: 1 = one fused launch (each group is stepped and its finished
+                               envs re-initialised at once), 2 = step launch + reset launch, 3 = one phased launch (every group
+                               is stepped, then the finished envs are re-initialised by whichever warp is free: the benchmark
+                               shapes with out_flags == 0 only, else as 2), 0 = choose by batch size */
     /* the later fork's sensor classes (tdCPA_forV2 only; all zero = off) */
     int32_t radar_targets;  /* AAC_TARGET_* */
     int32_t n_nbr_obs;      /* > 0: only the nearest n neighbours enter norm_nbr / raw_nbr, rows of 5 * n floats

@@ -39,6 +39,8 @@ struct AacEnv {
     float *d_actions = nullptr;  // staging for aac_step_host
     double *d_stats = nullptr;
     int *d_work = nullptr;       // ping-pong group counters of the persistent kernel
+    unsigned long long *d_flags = nullptr;   // [groups] phased launch: (epoch << 32) | terminated envs of the group
+    int epoch = 0;               // phased launches so far
     int sms = 0;
     int grid = 0;                // resident CTAs per SM of the kernel, queried at the first launch
     float cell = 0.0f;           // cell size of the maps (all maps of a handle share it)
@@ -80,7 +82,7 @@ extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
     if (cfg->variant == AAC_VARIANT_MM && (cfg->out_flags & (AAC_OUT_NBR6 | AAC_OUT_TCPA_PAIR)))
         return fail(AAC_ERR_ARG, "aac_create: the multipleMap variant has no neighbour outputs");
     if (cfg->eval_by_step && cfg->variant != AAC_VARIANT_V2) return fail(AAC_ERR_ARG, "aac_create: eval_by_step is a mode of the tdCPA_forV2 variant");
-    if (cfg->autoreset_launches < 0 || cfg->autoreset_launches > 2) return fail(AAC_ERR_ARG, "aac_create: autoreset_launches must be 0, 1 or 2");
+    if (cfg->autoreset_launches < 0 || cfg->autoreset_launches > 3) return fail(AAC_ERR_ARG, "aac_create: autoreset_launches must be 0, 1, 2 or 3");
     if (cfg->radar_targets || cfg->n_nbr_obs || cfg->n_clouds) {   // the later fork's sensor classes
         if (cfg->variant != AAC_VARIANT_V2 || cfg->eval_by_step) return fail(AAC_ERR_ARG, "aac_create: the sensor classes extend the tdCPA_forV2 variant (training mode)");
         if (cfg->radar_targets & ~0xF) return fail(AAC_ERR_ARG, "aac_create: unknown radar target class");
@@ -159,8 +161,8 @@ extern "C" int aac_create(const AacConfig *cfg, AacEnv **out) {
     make_walk_table(walk.data());
     CU(cudaMalloc(&env->d_walk, WALK_BYTES));
     CU(cudaMemcpy(env->d_walk, walk.data(), WALK_BYTES, cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&env->d_work, 2 * 17 * sizeof(int)));   // one ping-pong pair for whole-range launches, 16 for pipeline chunks
-    CU(cudaMemset(env->d_work, 0, 2 * 17 * sizeof(int)));
+    CU(cudaMalloc(&env->d_work, 4 * 17 * sizeof(int)));   // ping-pong pairs of (step, reset) counters: one for whole-range launches, 16 for pipeline chunks
+    CU(cudaMemset(env->d_work, 0, 4 * 17 * sizeof(int)));
     CU(cudaMalloc(&env->d_stats, sizeof(double) * AAC_N_STATS));
     CU(cudaMemset(env->d_stats, 0, sizeof(double) * AAC_N_STATS));
     *out = env;
@@ -179,6 +181,7 @@ extern "C" void aac_destroy(AacEnv *env) {
     cudaFree(env->d_actions);
     cudaFree(env->d_stats);
     cudaFree(env->d_work);
+    cudaFree(env->d_flags);
     cudaFree(env->d_od);
     for (void *b : env->od_bufs) cudaFree(b);
     for (auto &s : env->pipe) if (s) cudaStreamDestroy(s);
@@ -605,8 +608,23 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     p.bank_cells = env->d_bank_cells; p.bank_w = env->d_bank_w; p.bank_map = env->d_bank_map; p.n_scen = env->n_scen; p.od = env->d_od;
     p.mask = mask; p.actions = actions; p.stats = env->d_stats;
     p.rtab = env->rtab; p.rtab_min = env->rtab_min; p.rtab_hit = env->rtab_hit; p.rtab_minr = env->rtab_minr;
-    p.work = env->d_work + 2 * pair; p.parity = (int)(env->pair_launches[pair] & 1);
+    p.work = env->d_work + 4 * pair; p.parity = (int)(env->pair_launches[pair] & 1);
     p.st = env->st; p.out = *out; p.CL = env->cl; p.WL = env->wl;
+    if (autoreset == 2) {   // phased launch: per-group completion flags, tagged with the launch's epoch
+        if (e_lo % env->group) return fail(AAC_ERR_ARG, "phased launch: the env range must start on a group boundary");
+        if (!env->d_flags) {
+            const size_t n_groups = ((size_t)c.n_envs + env->group - 1) / env->group;
+            CU(cudaMalloc(&env->d_flags, n_groups * sizeof(unsigned long long)));
+            CU(cudaMemset(env->d_flags, 0, n_groups * sizeof(unsigned long long)));
+        }
+        if (env->epoch == 0x7FFFFFFF) {   // the epoch wraps: start over with clean flags
+            CU(cudaDeviceSynchronize());
+            CU(cudaMemset(env->d_flags, 0, (((size_t)c.n_envs + env->group - 1) / env->group) * sizeof(unsigned long long)));
+            env->epoch = 0;
+        }
+        p.flags = env->d_flags + e_lo / env->group;
+        p.epoch = ++env->epoch;
+    }
     if (e_cnt > 0) {
         p.E = e_cnt;
         p.env_id_base += e_lo;
@@ -642,12 +660,32 @@ extern "C" int aac_observe(AacEnv *env, const AacOut *out, void *stream) { retur
 extern "C" int aac_step(AacEnv *env, const float *actions_dev, const AacOut *out, void *stream) {
     return launch(env, MODE_STEP, nullptr, actions_dev, out, stream);
 }
-// Two launches on the stream - the step, then the re-initialisation of the envs it terminated - leave exactly the
-// state and outputs of the single fused launch (tests/test_gpu_parity.py::test_fused_autoreset_equals_step_then_autoreset)
-// and are faster: each launch's executed code is a smaller part of the kernel, which is bound by instruction issue and
-// instruction-cache misses (C3: 0.330 ms against 0.362 ms fused).
+// The step of every env, then the re-initialisation of the envs it terminated - as two launches on the stream, or as the two
+// loops of one phased launch - leave exactly the state and outputs of the single fused launch (tests/test_gpu_parity.py::
+// test_fused_autoreset_equals_step_then_autoreset, ::test_mode_specialised_launches_equal_fused_launch) and are faster: the
+// code a warp executes at any one time is a smaller part of the kernel, which is bound by instruction issue and
+// instruction-cache misses (C3: 0.330 ms against 0.362 ms fused, round 1).
+// Step loop and reset loop in ONE launch (env_kernel MT_PHASED) instead of two launches?  The reset work then fills the tail
+// of the step loop - the last group of every warp, run at falling occupancy - and one launch ramp goes away.  Measured on
+// B200, same box: C3 (21 846 groups, 4.6 per resident warp) 0.2531 -> 0.2453 ms; C5's shard (131 072 groups, 37 per warp:
+// the tail is 1 / 37 of the loop) 1.715 -> 1.748 ms.  So: where the instantiation exists and a resident warp gets at most
+// 8 groups, unless the configuration says which.
+static bool phased_autoreset(const AacEnv *env, int e_cnt = 0) {
+    const AacConfig &c = env->cfg;
+    if (c.autoreset_launches != 3 && c.autoreset_launches != 0) return false;
+    if (c.autoreset_launches == 0) {
+        const long long groups = ((long long)(e_cnt > 0 ? e_cnt : c.n_envs) + env->group - 1) / env->group;
+        if (groups > 8LL * env->sms * 32) return false;
+    }
+    KParams q;
+    memset(&q, 0, sizeof(q));
+    q.N = c.n_agents; q.R = c.n_rays; q.out_flags = c.out_flags; q.radar_targets = c.radar_targets; q.n_nbr_obs = c.n_nbr_obs; q.eval_by_step = c.eval_by_step;
+    return phased_launch_available(c.variant, q);
+}
 static int step_then_reset(AacEnv *env, const float *actions_dev, const AacOut *out, void *stream, int e_lo = 0, int e_cnt = 0, int pair = 0) {
     if (out && !out->terminated) return fail(AAC_ERR_ARG, "reward / done / check_goal / bbc / terminated / tcpa_min must be provided");
+    // both loops in one launch where the shape has the instantiation: the reset work fills the step loop's tail
+    if (phased_autoreset(env, e_cnt)) return launch(env, MODE_STEP, nullptr, actions_dev, out, stream, 2, e_lo, e_cnt, pair);
     const int rc = launch(env, MODE_STEP, nullptr, actions_dev, out, stream, 0, e_lo, e_cnt, pair);
     if (rc) return rc;
     return launch(env, MODE_RESET, out->terminated, nullptr, out, stream, 0, e_lo, e_cnt, pair);
@@ -661,6 +699,7 @@ static bool split_autoreset(const AacEnv *env, int e_cnt = 0) {
     const AacConfig &c = env->cfg;
     if (c.autoreset_launches == 1) return false;
     if (c.autoreset_launches == 2) return true;
+    if (c.autoreset_launches == 3) return phased_autoreset(env, e_cnt);
     const double items = (double)(e_cnt > 0 ? e_cnt : c.n_envs) * c.n_agents * (c.n_agents - 1 + c.n_rays);
     return c.variant == AAC_VARIANT_V2 && items >= 8e6;
 }

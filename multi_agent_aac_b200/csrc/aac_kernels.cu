@@ -300,6 +300,14 @@ __device__ __forceinline__ void radar_drones_ray(const float *s_px, const float 
 // ------------------------------------------------------------------------------------ kernel
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long *ptr) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned long long *ptr, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(ptr), "l"(v) : "memory");
+}
 
 // ---- the later fork's sensor classes (CS:1379-1506; aac_env.h AAC_TARGET_*) ----------------------------------------
 __device__ __forceinline__ float2 cloud_pos(const CloudDev &c, int k) {
@@ -937,82 +945,51 @@ __device__ __noinline__ void evs_collisions(const KParams &p, const Warp &w, int
 // MT_STEP_ONLY = MODE_STEP without the fused auto-reset; MODE_RESET): the step launch then carries no reset code and the
 // reset launch no reward code - less code per launch is what the instruction cache rewards.
 constexpr int MT_STEP_ONLY = 3;
+constexpr int MT_PHASED = 4;   // one launch: MT_STEP_ONLY's loop over all groups, then MODE_RESET's over the groups with terminated envs
 #ifndef AAC_MIN_BLOCKS
 #define AAC_MIN_BLOCKS 4   // resident CTAs of 256 threads per SM the register allocation aims at (64 registers)
 #endif
-template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1, int RM = -1, bool CS = false>
-__global__ void __launch_bounds__(MAX_THREADS, NT >= 16 ? 3 : AAC_MIN_BLOCKS) env_kernel(   // 20-drone envs: 85 registers, no spills, measured 5 % faster on C5
-const __grid_constant__ KParams p, const int mode_arg) {
+// The persistent warp's loop over groups for one mode (MT as in env_kernel).  PHASE: 0 = the launch runs this loop alone;
+// 1 / 2 = first / second loop of a phased launch (MT_PHASED: every group is stepped, then - by whichever warp gets to it -
+// the envs it terminated are re-initialised): loop 1 publishes a group's completion in p.flags (release), loop 2 takes
+// the groups from a second counter and waits for the group's flag (acquire).  A flag is (epoch << 32) | the group's
+// terminated-env bits: loop 2 learns from the one word both that the group is through and which envs to re-initialise.
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS, int MT, int RM, bool CS, int PHASE>
+__device__ __forceinline__ void group_loop(const KParams &p, Warp &w, const int mode_arg, const MapDev *s_map, int &st_i, float &st_f) {
     constexpr bool STEP_ONLY = MT == MT_STEP_ONLY;
     const int mode = MT < 0 ? mode_arg : (STEP_ONLY ? (int)MODE_STEP : MT);
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = w.lane;
     const int N = NT ? NT : p.N, M = N - 1, W = p.W, G = p.G;
     const int Mp = M | 1;
     const int flags = LEAN ? 0 : p.out_flags;   // LEAN: no optional output was requested, their code is compiled out
-    const CtaLayout &CL = p.CL;
-    const WarpLayout &WL = p.WL;
-
-    MapDev *s_map = reinterpret_cast<MapDev *>(smem + CL.map);
-    float4 *s_ray = reinterpret_cast<float4 *>(smem + CL.ray);
-    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem + CL.bar);
-
-    // ---- CTA prologue: the map arrives by one TMA bulk copy, the ray table by plain loads.  This is the
-    //      only CTA-wide synchronisation of the kernel.
-    if (tid == 0) {
-        mbar_init(s_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // the map - for multipleMap the whole table of maps when it fits the budget (14 maps = 4.5 KB) - by ONE bulk copy
-        mbar_expect_tx(s_bar, p.n_staged * (unsigned)sizeof(MapDev));
-        bulk_g2s(s_map, p.maps, p.n_staged * (unsigned)sizeof(MapDev), s_bar);
-        if (blockIdx.x == 0) p.work[p.parity ^ 1] = 0;   // the next launch's group counter
-    }
-    for (int k = tid; k < p.R; k += blockDim.x) s_ray[k] = p.ray_tab[k];
-    DdaRay *s_dda = reinterpret_cast<DdaRay *>(smem + CL.dda);
-    for (int k = tid; k < p.R; k += blockDim.x) s_dda[k] = p.dda_tab[k];
-    uint4 *s_walk = reinterpret_cast<uint4 *>(smem + CL.walk);
-    for (int k = tid; k < (int)(WALK_BYTES / 16); k += blockDim.x) s_walk[k] = p.walk_tab[k];
-    __syncthreads();
-    mbar_wait(s_bar, 0);
-
-    unsigned char *ws = smem + CL.warps + (size_t)warp * WL.total;
-    Warp w;
-    w.map = (VAR == AAC_VARIANT_MM && p.n_staged < p.n_maps) ? p.maps : s_map; w.ray = s_ray; w.dda = s_dda; w.walk.s = smem_u32(s_walk); w.walk.p = nullptr; w.lane = lane;
-    w.px = reinterpret_cast<float *>(ws + WS_CUR); w.py = w.px + 32; w.vx = w.py + 32; w.vy = w.vx + 32; w.hd = w.vy + 32;
-    w.ppx = reinterpret_cast<float *>(ws + WS_PRE); w.ppy = w.ppx + 32; w.pvx = w.ppy + 32; w.pvy = w.pvx + 32;
-    w.meta = reinterpret_cast<unsigned *>(ws + WS_META); w.meta2 = w.meta + 32; w.minr = w.meta2 + 32; w.agf = w.minr + 32; w.wpm = w.agf + 32;
-    w.agr = reinterpret_cast<float *>(ws + WS_AGR);
-    w.atgoal = ws + WS_BYTES; w.refw = w.atgoal + 32; w.rs = w.refw + 32; w.amap = w.rs + 32;
-    w.win = reinterpret_cast<uint2 *>(ws + WS_WIN);
-    w.wrel = reinterpret_cast<float4 *>(ws + WS_WREL);
-    w.stg = reinterpret_cast<float *>(ws + WS_STG);
-    w.c8 = reinterpret_cast<uint16_t *>(ws + WS_C8);
-    // the variable part: compile-time offsets too when the drone count is a template parameter
-    const WarpLayout VL = NT ? make_warp_layout(VAR, NT, 0) : WL;
-    w.d2 = reinterpret_cast<float *>(ws + VL.d2);
-    w.order = ws + VL.order;
-    w.own = reinterpret_cast<float *>(ws + VL.own);
-    w.raw_own = reinterpret_cast<float *>(ws + (NT ? WL.raw_own : VL.raw_own));
-
-    // episode counters of this lane's envs (ATT/ma_main:581-637), flushed once per warp
-    // lane j of the warp carries statistic j (aac_read_stats order; lane 2 = the sum of returns, a float): two registers
-    // per lane instead of ten
-    int st_i = 0;
-    float st_f = 0.0f;
+    int *const counter = p.work + 2 * p.parity + (PHASE == 2 ? 1 : 0);
 
     // ---- persistent warp: fetch a group of G whole envs, run the pipeline, fetch the next
     const int n_groups = (p.E + G - 1) / G;
+    int done_gi = -1;   // PHASE 1: the group whose completion flag is still to be published, and its terminated envs
+    unsigned done_mask = 0;
+    auto publish = [&]() { st_release(p.flags + done_gi, ((unsigned long long)(unsigned)p.epoch << 32) | done_mask); };
     for (;;) {
         // (claiming the next group ahead of time hides the atomic's round trip but was measured 4 % SLOWER: with four to five
         //  groups per warp a group claimed early by a busy warp is a group an idle warp cannot take at the tail)
         int gi = 0;
-        if (lane == 0) gi = atomicAdd(&p.work[p.parity], 1);
+        if (lane == 0) gi = atomicAdd(counter, 1);
         gi = __shfl_sync(FULL, gi, 0);
         if (gi >= n_groups) break;
         w.e_lo = gi * G;
         w.ng = max(0, min(G, p.E - w.e_lo));
         // reset launch: a group none of whose envs is masked has nothing to do (with a trained policy most groups)
-        if (mode == MODE_RESET && p.mask && !__ballot_sync(FULL, lane < w.ng && p.mask[w.e_lo + lane])) continue;
+        unsigned group_mask = 0;
+        if (PHASE == 2) {   // the group's step has left its results (whichever warp ran it)
+            if (lane == 0) {
+                unsigned long long f;
+                while ((unsigned)((f = ld_acquire(p.flags + gi)) >> 32) != (unsigned)p.epoch) __nanosleep(64);
+                group_mask = (unsigned)f;
+            }
+            group_mask = __shfl_sync(FULL, group_mask, 0);
+            if (!group_mask) continue;
+        }
+        if (PHASE != 2 && mode == MODE_RESET && p.mask && !__ballot_sync(FULL, lane < w.ng && p.mask[w.e_lo + lane])) continue;
         w.a0 = w.e_lo * N;
         w.nA = w.ng * N;
         const int nA = w.nA, a0 = w.a0;
@@ -1048,11 +1025,14 @@ const __grid_constant__ KParams p, const int mode_arg) {
             if (VAR == AAC_VARIANT_MM) { w.amap[a] = (uint8_t)p.st.map_id[w.e_lo + my_env]; w.wpm[a] = p.st.wp_mask[ga]; }
         }
         __syncwarp();
+        // PHASE 1: the previous group's flag leaves here - its stores (ordered before this point for every lane by the
+        // __syncwarp()s since) have drained while this group's records were on their way, so the release waits for nothing
+        if (PHASE == 1 && done_gi >= 0 && lane == 0) publish();
 
-        unsigned reset_mask = 0, store_mask = (w.ng >= 32) ? FULL : ((1u << w.ng) - 1u);
+        unsigned reset_mask = 0, store_mask = (w.ng >= 32) ? FULL : ((1u << w.ng) - 1u), term_mask = 0;
         if (mode == MODE_RESET) {
             bool m = lane < w.ng && (!p.mask || p.mask[w.e_lo + lane]);
-            reset_mask = __ballot_sync(FULL, m);
+            reset_mask = PHASE == 2 ? group_mask : __ballot_sync(FULL, m);
             store_mask = reset_mask;
         }
         // Jobs of a group: job 0 = the whole group (step / observe), job 1 = the envs to re-initialise, all at once (reset
@@ -1338,6 +1318,7 @@ const __grid_constant__ KParams p, const int mode_arg) {
             }
             // episode counters (ATT/ma_main:581-637) of the envs that finished, summed over the group
             const unsigned tb = __ballot_sync(FULL, term != 0);
+            term_mask = tb;
             if (tb && p.stats) {
                 const int steps_sum = __reduce_add_sync(FULL, term ? step : 0), reach_sum = __reduce_add_sync(FULL, term ? (int)n_reach : 0);
                 float r = term ? ret : 0.0f;
@@ -1376,6 +1357,73 @@ const __grid_constant__ KParams p, const int mode_arg) {
             if (VAR == AAC_VARIANT_MM) p.st.wp_mask[ga] = w.wpm[a];
         }
         __syncwarp();
+        done_gi = gi; done_mask = term_mask;
+    }
+    if (PHASE == 1 && done_gi >= 0 && lane == 0) publish();
+}
+
+
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1, int RM = -1, bool CS = false>
+__global__ void __launch_bounds__(MAX_THREADS, NT >= 16 ? 3 : AAC_MIN_BLOCKS) env_kernel(   // 20-drone envs: 85 registers, no spills, measured 5 % faster on C5
+const __grid_constant__ KParams p, const int mode_arg) {
+    const int mode = MT < 0 ? mode_arg : ((MT == MT_STEP_ONLY || MT == MT_PHASED) ? (int)MODE_STEP : MT);
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const CtaLayout &CL = p.CL;
+    const WarpLayout &WL = p.WL;
+
+    MapDev *s_map = reinterpret_cast<MapDev *>(smem + CL.map);
+    float4 *s_ray = reinterpret_cast<float4 *>(smem + CL.ray);
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem + CL.bar);
+
+    // ---- CTA prologue: the map arrives by one TMA bulk copy, the ray table by plain loads.  This is the
+    //      only CTA-wide synchronisation of the kernel.
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the map - for multipleMap the whole table of maps when it fits the budget (14 maps = 4.5 KB) - by ONE bulk copy
+        mbar_expect_tx(s_bar, p.n_staged * (unsigned)sizeof(MapDev));
+        bulk_g2s(s_map, p.maps, p.n_staged * (unsigned)sizeof(MapDev), s_bar);
+        if (blockIdx.x == 0) { p.work[2 * (p.parity ^ 1)] = 0; p.work[2 * (p.parity ^ 1) + 1] = 0; }   // the next launch's group counters
+    }
+    for (int k = tid; k < p.R; k += blockDim.x) s_ray[k] = p.ray_tab[k];
+    DdaRay *s_dda = reinterpret_cast<DdaRay *>(smem + CL.dda);
+    for (int k = tid; k < p.R; k += blockDim.x) s_dda[k] = p.dda_tab[k];
+    uint4 *s_walk = reinterpret_cast<uint4 *>(smem + CL.walk);
+    for (int k = tid; k < (int)(WALK_BYTES / 16); k += blockDim.x) s_walk[k] = p.walk_tab[k];
+    __syncthreads();
+    mbar_wait(s_bar, 0);
+
+    unsigned char *ws = smem + CL.warps + (size_t)warp * WL.total;
+    Warp w;
+    w.map = (VAR == AAC_VARIANT_MM && p.n_staged < p.n_maps) ? p.maps : s_map; w.ray = s_ray; w.dda = s_dda; w.walk.s = smem_u32(s_walk); w.walk.p = nullptr; w.lane = lane;
+    w.px = reinterpret_cast<float *>(ws + WS_CUR); w.py = w.px + 32; w.vx = w.py + 32; w.vy = w.vx + 32; w.hd = w.vy + 32;
+    w.ppx = reinterpret_cast<float *>(ws + WS_PRE); w.ppy = w.ppx + 32; w.pvx = w.ppy + 32; w.pvy = w.pvx + 32;
+    w.meta = reinterpret_cast<unsigned *>(ws + WS_META); w.meta2 = w.meta + 32; w.minr = w.meta2 + 32; w.agf = w.minr + 32; w.wpm = w.agf + 32;
+    w.agr = reinterpret_cast<float *>(ws + WS_AGR);
+    w.atgoal = ws + WS_BYTES; w.refw = w.atgoal + 32; w.rs = w.refw + 32; w.amap = w.rs + 32;
+    w.win = reinterpret_cast<uint2 *>(ws + WS_WIN);
+    w.wrel = reinterpret_cast<float4 *>(ws + WS_WREL);
+    w.stg = reinterpret_cast<float *>(ws + WS_STG);
+    w.c8 = reinterpret_cast<uint16_t *>(ws + WS_C8);
+    // the variable part: compile-time offsets too when the drone count is a template parameter
+    const WarpLayout VL = NT ? make_warp_layout(VAR, NT, 0) : WL;
+    w.d2 = reinterpret_cast<float *>(ws + VL.d2);
+    w.order = ws + VL.order;
+    w.own = reinterpret_cast<float *>(ws + VL.own);
+    w.raw_own = reinterpret_cast<float *>(ws + (NT ? WL.raw_own : VL.raw_own));
+
+    // episode counters of this lane's envs (ATT/ma_main:581-637), flushed once per warp
+    // lane j of the warp carries statistic j (aac_read_stats order; lane 2 = the sum of returns, a float): two registers
+    // per lane instead of ten
+    int st_i = 0;
+    float st_f = 0.0f;
+
+    if (MT == MT_PHASED) {
+        group_loop<VAR, AUX, LEAN, NT, RT, EVS, MT_STEP_ONLY, RM, CS, 1>(p, w, mode_arg, s_map, st_i, st_f);
+        group_loop<VAR, AUX, LEAN, NT, RT, EVS, MODE_RESET, RM, CS, 2>(p, w, mode_arg, s_map, st_i, st_f);
+    } else {
+        group_loop<VAR, AUX, LEAN, NT, RT, EVS, MT, RM, CS, 0>(p, w, mode_arg, s_map, st_i, st_f);
     }
 
     // ---- warp epilogue: the counters leave, one atomic per statistic and warp
@@ -1420,6 +1468,9 @@ static cudaError_t launch_aux(const KParams &p, int mode, int threads, int sms, 
         if (NT > 0 && RT > 0) {   // the two launches of a step (and the plain step / reset calls): one kernel per mode and radar mode
             constexpr bool V2 = VAR == AAC_VARIANT_V2;
             const bool lh = V2 && p.radar_mode == AAC_RADAR_LAST_HIT;
+            if (mode == MODE_STEP && p.autoreset == 2)
+                return lh ? launch_one<VAR, false, true, NT, RT, false, MT_PHASED, V2 ? AAC_RADAR_LAST_HIT : -1>(p, mode, threads, sms, grid_cache, stream)
+                          : launch_one<VAR, false, true, NT, RT, false, MT_PHASED, V2 ? AAC_RADAR_MIN : -1>(p, mode, threads, sms, grid_cache, stream);
             if (mode == MODE_STEP && !p.autoreset)
                 return lh ? launch_one<VAR, false, true, NT, RT, false, MT_STEP_ONLY, V2 ? AAC_RADAR_LAST_HIT : -1>(p, mode, threads, sms, grid_cache, stream)
                           : launch_one<VAR, false, true, NT, RT, false, MT_STEP_ONLY, V2 ? AAC_RADAR_MIN : -1>(p, mode, threads, sms, grid_cache, stream);
@@ -1433,8 +1484,19 @@ static cudaError_t launch_aux(const KParams &p, int mode, int threads, int sms, 
                                              : launch_one<VAR, false, false, NT, RT>(p, mode, threads, sms, grid_cache, stream);
 }
 
+bool phased_launch_available(int variant, const KParams &p) {
+    if (p.out_flags != 0) return false;
+    switch (variant) {   // the shapes launch_env_kernel specialises on both counts
+        case AAC_VARIANT_ATT: return p.N == 3 && (p.R == 36 || p.R == 18);
+        case AAC_VARIANT_MM: return p.N == 3 && p.R == 18;
+        case AAC_VARIANT_V2: return !p.radar_targets && !p.n_nbr_obs && !p.eval_by_step && ((p.N == 10 && p.R == 36) || (p.N == 20 && p.R == 72));
+        default: return false;
+    }
+}
+
 cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     if (p.E <= 0) return cudaSuccess;
+    if (p.autoreset == 2 && (mode != MODE_STEP || !phased_launch_available(variant, p) || !p.flags)) return cudaErrorNotSupported;
     switch (variant) {
         // the reference's own shapes (3 drones; 18 rays, or the 36 of the batched configuration) are specialised too
         case AAC_VARIANT_ATT:

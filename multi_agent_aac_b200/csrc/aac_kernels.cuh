@@ -79,7 +79,9 @@ struct KParams {
     const float *actions;
     double *stats;        // [AAC_N_STATS]
     int *work;            // [2] group counters of the persistent warps, ping-pong between launches
-    int parity;           // which counter this launch consumes (it zeroes the other one)
+    int parity;           // which counter pair this launch consumes: work[2 * parity + {0, 1}] (it zeroes the other pair)
+    unsigned long long *flags;   // [groups] phased launch: (epoch of the step loop that last completed the group) << 32 | its terminated envs
+    int epoch;            // this launch's epoch (phased launch)
     AacState st;
     AacOut out;
     CtaLayout CL;
@@ -123,6 +125,8 @@ inline CtaLayout make_cta_layout(const WarpLayout &WL, int R, int warps, int n_s
 
 // fills the __constant__ polygon tables of the current device (call once per device)
 cudaError_t upload_constants();
+// a phased launch (autoreset == 2: step loop, then reset loop, one launch) exists for this variant / shape / output set
+bool phased_launch_available(int variant, const KParams &p);
 cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream);
 int max_smem_optin();
 

@@ -47,7 +47,7 @@ class EnvConfig:
     tile_envs: int = 0
     block_threads: int = 0
     eval_by_step: bool = False    # V2 only: evaluation "by sorties" (args.mode == 'eval', evaluation_by_episode == False)
-    autoreset_launches: int = 0   # step(autoreset=True): 1 = fused launch, 2 = step launch + reset launch, 0 = by batch size
+    autoreset_launches: int = 0   # step(autoreset=True): 1 = fused launch, 2 = step launch + reset launch, 3 = one phased launch, 0 = by batch size
     # the later fork's sensor classes (v2 only; CS = ...forV2_changeskin/env_simulator_...:1379-1506)
     radar_targets: int = 0        # K.TARGET_*: 0 = the variant's own radar, else the fork's true-minimum radar over these classes
     n_nbr_obs: int = 0            # > 0: only the nearest n neighbours enter norm_nbr (use_nearestN_neigh_wRadar / N_neigh, CS:1799-1802)
