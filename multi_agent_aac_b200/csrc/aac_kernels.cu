@@ -300,7 +300,10 @@ __device__ __forceinline__ void radar_drones_ray(const float *s_px, const float 
 // ------------------------------------------------------------------------------------ kernel
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
-__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long *ptr) {
+// The reset loop's read of a group's flag: an acquire.  (ld.acquire.gpu compiles to the load plus CCTL.IVALL, which empties the
+// SM's L1 once per group; a relaxed load - defensible here, the reset loop loads nothing the step loop stored - was measured
+// and is not faster: C3 0.2302 against 0.2301 ms.)
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *ptr) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ptr) : "memory");
     return v;
@@ -530,18 +533,19 @@ __device__ __forceinline__ void observe_range(const KParams &p, const Warp &w, c
     for_ranges([&](const int a_lo, const int n_ag) {
     if (VAR != AAC_VARIANT_ATT && tab) {
         const size_t rg0 = (size_t)(w.a0 + a_lo) * R;
-        // four table reads in flight per lane (they come from L2)
-        for (int f0 = lane; f0 < n_ag * R; f0 += 128) {
-            float v[4];
-            size_t src[4];
+        // twelve table reads in flight per lane (they come from L2): one round trip for the 360 ranges of a 10-drone env
+        constexpr int TB = 12;
+        for (int f0 = lane; f0 < n_ag * R; f0 += 32 * TB) {
+            float v[TB];
+            unsigned src[TB];   // (a table has fewer than 2^31 entries: 14 maps x 1024 cells x R)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < TB; ++u) {
                 const int f = f0 + 32 * u, q = f / R, k = f - q * R;
-                src[u] = f < n_ag * R ? (size_t)w.win[a_lo + q].y * R + k : 0;
+                src[u] = f < n_ag * R ? w.win[a_lo + q].y * (unsigned)R + (unsigned)k : 0u;
                 v[u] = __ldg(p.rtab + src[u]);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < TB; ++u) {
                 const int f = f0 + 32 * u;
                 if (f < n_ag * R) {
                     p.out.radar[rg0 + f] = v[u];
@@ -795,6 +799,7 @@ __device__ __forceinline__ const uint16_t *init_envs(const KParams &p, const War
     }
     const uint16_t *row = nullptr;
     int nw = 0;
+    uint4 head = make_uint4(0u, 0u, 0u, 0u);   // the first 8 vertices of the lane's reference line
     if (use_od) {
         const OdDev &od = p.od[map_row];
         // Lane (g, i) draws for drone i of env g.  reset_world draws drone by drone and redraws a start until it is more
@@ -837,7 +842,17 @@ __device__ __forceinline__ const uint16_t *init_envs(const KParams &p, const War
             const uint16_t *src = od.path_cells + od.path_off[pr];   // 16-byte aligned: paths are padded to 8 cells
             const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
             uint4 *d4 = reinterpret_cast<uint4 *>(p.st.ref_cells + ((size_t)ge * N + i) * W);
-            for (int k = 0; k < (nw + 7) >> 3; ++k) d4[k] = s4[k];
+            const int nc = (nw + 7) >> 3;
+            for (int k0 = 0; k0 < nc; k0 += 4) {   // four 16-byte chunks (a whole 32-vertex line) in flight
+                uint4 t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k0 + u < nc) t[u] = s4[k0 + u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k0 + u < nc) d4[k0 + u] = t[u];
+                if (k0 == 0) head = t[0];
+            }
             row = src;
         }
         __syncwarp();
@@ -853,13 +868,13 @@ __device__ __forceinline__ const uint16_t *init_envs(const KParams &p, const War
         if (act) {
             row = p.bank_cells + ((size_t)scen * N + i) * W;
             nw = p.bank_w[(size_t)scen * N + i];
+            head = *reinterpret_cast<const uint4 *>(row);   // bank rows start on 16-byte boundaries
         }
     }
     if (act) {
         const int a = lane;
         w.refw[a] = (uint8_t)nw;
         p.st.ref_w[(size_t)ge * N + i] = (uint8_t)nw;
-        const uint4 head = *reinterpret_cast<const uint4 *>(row);   // table paths and bank rows start on 16-byte boundaries
         reinterpret_cast<uint4 *>(w.c8)[a] = head;
         const unsigned c0 = head.x & 0xFFFFu, c1 = head.x >> 16;
         const float px = cell_cx(mp, c0 >> 8), py = cell_cy(mp, c0 & 255);
@@ -952,7 +967,7 @@ constexpr int MT_PHASED = 4;   // one launch: MT_STEP_ONLY's loop over all group
 // The persistent warp's loop over groups for one mode (MT as in env_kernel).  PHASE: 0 = the launch runs this loop alone;
 // 1 / 2 = first / second loop of a phased launch (MT_PHASED: every group is stepped, then - by whichever warp gets to it -
 // the envs it terminated are re-initialised): loop 1 publishes a group's completion in p.flags (release), loop 2 takes
-// the groups from a second counter and waits for the group's flag (acquire).  A flag is (epoch << 32) | the group's
+// the groups from a second counter and waits for the group's flag (see ld_flag).  A flag is (epoch << 32) | the group's
 // terminated-env bits: loop 2 learns from the one word both that the group is through and which envs to re-initialise.
 template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS, int MT, int RM, bool CS, int PHASE>
 __device__ __forceinline__ void group_loop(const KParams &p, Warp &w, const int mode_arg, const MapDev *s_map, int &st_i, float &st_f) {
@@ -983,7 +998,7 @@ __device__ __forceinline__ void group_loop(const KParams &p, Warp &w, const int 
         if (PHASE == 2) {   // the group's step has left its results (whichever warp ran it)
             if (lane == 0) {
                 unsigned long long f;
-                while ((unsigned)((f = ld_acquire(p.flags + gi)) >> 32) != (unsigned)p.epoch) __nanosleep(64);
+                while ((unsigned)((f = ld_flag(p.flags + gi)) >> 32) != (unsigned)p.epoch) __nanosleep(64);
                 group_mask = (unsigned)f;
             }
             group_mask = __shfl_sync(FULL, group_mask, 0);
