@@ -642,6 +642,45 @@ def test_every_instantiation_runs():
     assert out.stdout.strip().endswith("done")
 
 
+def test_phased_launches_on_concurrent_streams():
+    """Two handles stepping at the same time on their own streams (phased launches: every warp of either kernel may wait on a
+    per-group flag that a warp of the SAME kernel publishes; the kernels share the SMs) must each leave what a handle stepping
+    alone leaves, bit for bit."""
+    import torch
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import synthetic_map
+    from multi_agent_aac_b200.reset import OdTable
+    gmap = synthetic_map(seed=0)
+    tab = OdTable(gmap, w_max=32, planner="device")
+    E, n, r, steps = 30000, 10, 36, 12
+    streams = [None, torch.cuda.Stream(), torch.cuda.Stream()]
+    envs = []
+    for st in streams:
+        env = BatchedDroneEnv(preset("tdcpa_v2", n_envs=E, n_agents=n, n_rays=r, w_max=32, seed=13, autoreset_launches=3), gmap, stream=st)
+        env.set_od_tables([tab])
+        env.reset()
+        envs.append(env)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    acts = [(torch.rand((E, n, 2), device="cuda", generator=gen) * 2 - 1).contiguous() for _ in range(steps)]
+    torch.cuda.synchronize()
+    for t in range(steps):          # the reference run, alone on the device
+        envs[0].step(acts[t], autoreset=True)
+    torch.cuda.synchronize()
+    l0 = [e.launch_count for e in envs]
+    for t in range(steps):          # the two others interleaved, nothing between them but the launches
+        envs[1].step(acts[t], autoreset=True)
+        envs[2].step(acts[t], autoreset=True)
+    torch.cuda.synchronize()
+    assert envs[1].launch_count - l0[1] == steps       # one phased launch per step
+    for other in envs[1:]:
+        for k in envs[0].out:
+            assert torch.equal(envs[0].out[k].view(torch.uint8), other.out[k].view(torch.uint8)), k
+        for k in envs[0].state:
+            assert torch.equal(envs[0].state[k].view(torch.uint8), other.state[k].view(torch.uint8)), k
+    assert envs[0].read_stats()[0] == envs[1].read_stats()[0] == envs[2].read_stats()[0] > 0
+
+
 @pytest.mark.parametrize("n,r,E", [(10, 36, 3001), (20, 72, 700), (10, 36, 40000)])
 def test_mode_specialised_launches_equal_fused_launch(n, r, E):
     """The benchmark shapes without optional outputs run their two-launch auto-reset through kernels specialised on the
