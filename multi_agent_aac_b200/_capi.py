@@ -80,12 +80,31 @@ def nvcc_command(out=LIB_PATH):
             "-Xcompiler", "-fPIC", "-shared", "-o", out] + SOURCES
 
 
+def sources_digest():
+    """sha256 over the sources, the headers and the compile command: what a built library is good for."""
+    import hashlib
+    h = hashlib.sha256(" ".join(nvcc_command("-")[1:]).encode())
+    for p in SOURCES + HEADERS:
+        h.update(open(p, "rb").read())
+    return h.hexdigest()
+
+
+def _built_digest():
+    try:
+        return open(LIB_PATH + ".srchash").read().strip()
+    except OSError:
+        return None
+
+
 def build(force=False):
-    """Compile libaac_env.so for sm_100a (cross-compiles without a GPU)."""
-    newest = max(os.path.getmtime(p) for p in SOURCES + HEADERS)
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+    """Compile libaac_env.so for sm_100a (cross-compiles without a GPU).  Gated on the CONTENT of the sources (a digest
+    written next to the library), not on modification times: a library left over from other sources is rebuilt."""
+    want = sources_digest()
+    if not force and os.path.exists(LIB_PATH) and _built_digest() == want:
         return LIB_PATH
     subprocess.check_call(nvcc_command())
+    with open(LIB_PATH + ".srchash", "w") as f:
+        f.write(want + "\n")
     return LIB_PATH
 
 
@@ -99,6 +118,9 @@ def lib():
     if not os.path.exists(LIB_PATH):
         raise AacError("libaac_env.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(there is no CPU fallback)")
+    if not os.environ.get("AAC_LIB") and _built_digest() not in (None, sources_digest()):
+        raise AacError(os.path.basename(LIB_PATH) + " was built from other sources than the ones in this tree: run "
+                       "`python -c 'import __graft_entry__ as g; g.build()'`")
     L = C.CDLL(LIB_PATH)
     P = C.c_void_p
     L.aac_create.argtypes = [C.POINTER(AacConfig), C.POINTER(P)]

@@ -321,3 +321,21 @@ def test_shapefile_ingestion_matches_reference_env_generation():
         import gen_golden_mapgen as gen
         emb, ones2, zeros2, g, extent = gen.run_reference(base + ".shp")
         assert {tuple(c) for c in ones2} == ones and {tuple(c) for c in zeros2} == zeros and g == 10 and tuple(extent) == (1800, 1300)
+
+
+def test_build_is_gated_on_source_content_not_mtime():
+    """A library next to a digest of other sources is rebuilt by build() and refused by lib() (no silent stale binary)."""
+    from multi_agent_aac_b200 import _capi
+    _capi.build()
+    side = _capi.LIB_PATH + ".srchash"
+    good = open(side).read()
+    assert good.strip() == _capi.sources_digest()
+    try:
+        open(side, "w").write("0" * 64 + "\n")
+        _capi._lib = None
+        with pytest.raises(_capi.AacError, match="other sources"):
+            _capi.lib()
+    finally:
+        open(side, "w").write(good)
+        _capi._lib = None
+    assert _capi.lib() is not None
