@@ -52,8 +52,10 @@ def nvcc_command(out=LIB_PATH):
 def sources_digest():
     """sha256 over the sources, the headers and the compile command: what a built library is good for."""
     import hashlib
-    h = hashlib.sha256(" ".join(nvcc_command("-")[1:]).encode())
+    flags = [a for a in nvcc_command("-")[1:] if not os.path.isabs(a)]   # the tree may live anywhere: no paths in the digest
+    h = hashlib.sha256(" ".join(flags).encode())
     for p in SOURCES + HEADERS:
+        h.update(os.path.basename(p).encode())
         h.update(open(p, "rb").read())
     return h.hexdigest()
 

@@ -309,8 +309,9 @@ class BatchedDroneEnv:
 
     def step(self, actions: torch.Tensor, autoreset=False, fused=False):
         """actions [E, N, 2] float32 on the device, in [-1, 1] -> (obs, reward, done, info).  autoreset: the envs that
-        terminate are re-initialised and their observation rows carry the reset observation (aac_step_autoreset: step
-        launch + reset launch; fused=True: the single-launch variant aac_step_fused, bit-identical results)."""
+        terminate are re-initialised and their observation rows carry the reset observation (aac_step_autoreset: one fused
+        launch, a step launch + a reset launch, or one phased launch - the library's rule or `autoreset_launches`;
+        fused=True: the single-launch variant aac_step_fused; bit-identical results either way)."""
         if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous() \
                 or tuple(actions.shape) != (self.E, self.N, 2):
             raise ValueError("actions must be a contiguous float32 [E, N, 2] tensor on %s" % self.device)

@@ -250,3 +250,17 @@ def test_att_actor_rollout_through_env():
         assert act.shape == (1111, 3, 2) and np.abs(act.reshape(3333, 2).cpu().numpy() - ref).max() <= 2e-5
         obs, reward, done, info = env.step(actor(obs, noise_scale=0.3, noise_seed=t), autoreset=True)
     assert torch.isfinite(reward).all()
+
+
+@pytest.mark.gpu
+def test_example_driver_runs():
+    """examples/rollout_v2.py: the reference's loop skeleton (choose_action -> step -> replay -> sample) on the batched path."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "rollout_v2.py"), "--envs", "2048", "--steps", "40"],
+                         cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-800:] + out.stderr[-1500:]
+    assert "agent-steps/s" in out.stdout and "episodes" in out.stdout
+
