@@ -681,8 +681,9 @@ def test_phased_launches_on_concurrent_streams():
     assert envs[0].read_stats()[0] == envs[1].read_stats()[0] == envs[2].read_stats()[0] > 0
 
 
-@pytest.mark.parametrize("n,r,E", [(10, 36, 3001), (20, 72, 700), (10, 36, 40000)])
-def test_mode_specialised_launches_equal_fused_launch(n, r, E):
+@pytest.mark.parametrize("variant,n,r,E", [("tdcpa_v2", 10, 36, 3001), ("tdcpa_v2", 20, 72, 700), ("tdcpa_v2", 10, 36, 40000),
+                                           ("att", 3, 36, 9001), ("att", 3, 18, 2000), ("multimap", 3, 18, 9001)])
+def test_mode_specialised_launches_equal_fused_launch(variant, n, r, E):
     """The benchmark shapes without optional outputs run their two-launch auto-reset through kernels specialised on the
     mode (step without reset code, reset without reward code): state, outputs and counters must equal the fused launch's
     and the generic-mode path's (step, then autoreset through the runtime-mode kernel of a non-lean handle is covered by
@@ -690,14 +691,15 @@ def test_mode_specialised_launches_equal_fused_launch(n, r, E):
     import numpy as np
     import torch
     from multi_agent_aac_b200.env import BatchedDroneEnv, preset
-    from multi_agent_aac_b200.maps import synthetic_map
+    from multi_agent_aac_b200.maps import multimap_set, synthetic_map
     from multi_agent_aac_b200.reset import OdTable
-    gmap = synthetic_map(seed=0)
-    tab = OdTable(gmap, w_max=32, planner="device")
+    maps = multimap_set(seed=0)[:4] if variant == "multimap" else [synthetic_map(seed=0)]
+    tabs = [OdTable(m, w_max=32, planner="device") for m in maps]
     envs = []
     for launches in (1, 2, 3):   # 3: the phased launch (step loop, then reset loop behind per-group completion flags)
-        env = BatchedDroneEnv(preset("tdcpa_v2", n_envs=E, n_agents=n, n_rays=r, w_max=32, seed=9, autoreset_launches=launches), gmap)
-        env.set_od_tables([tab])
+        env = BatchedDroneEnv(preset(variant, n_envs=E, n_agents=n, n_rays=r, w_max=32, seed=9, autoreset_launches=launches),
+                              maps if variant == "multimap" else maps[0])
+        env.set_od_tables(tabs)
         env.reset()          # MODE_RESET through the specialised kernel on both handles
         envs.append(env)
     gen = torch.Generator(device="cuda")
