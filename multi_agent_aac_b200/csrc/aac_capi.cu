@@ -674,6 +674,7 @@ static bool phased_autoreset(const AacEnv *env, int e_cnt = 0) {
     const AacConfig &c = env->cfg;
     if (c.autoreset_launches != 3 && c.autoreset_launches != 0) return false;
     if (c.autoreset_launches == 0) {
+        if (c.variant != AAC_VARIANT_V2) return false;   // multipleMap at C4: two launches 0.0713, phased 0.0734, fused 0.0747 ms
         const long long groups = ((long long)(e_cnt > 0 ? e_cnt : c.n_envs) + env->group - 1) / env->group;
         if (groups > 8LL * env->sms * 32) return false;
     }
@@ -693,15 +694,17 @@ static int step_then_reset(AacEnv *env, const float *actions_dev, const AacOut *
 // One fused launch or two?  Measured on B200 (tests/tools/unfused_time.py): the second launch costs about 0.011 ms,
 // the smaller executed code per launch saves 9-12 % of a tdCPA_forV2 step: C3 (65 536 x 10 x 36) 0.362 -> 0.330 ms,
 // C5 (131 072 x 20 x 72) 2.88 -> 2.52 ms, but C2 (one_model_att 4096 x 3) 0.031 -> 0.041 and C4 (multipleMap 65 536 x 3)
-// 0.088 -> 0.100.  Two launches for tdCPA_forV2 batches of at least 8M (ray + pair) items, one otherwise, unless the
-// configuration says which.
+// 0.088 -> 0.100 (round 1).  Round 2, with every finished env of a warp's group re-initialised in one pass, C4 turned: fused
+// 0.0747, two launches 0.0713 ms (C2 stays: 0.0347 against 0.0447).  Two launches (or the phased launch, phased_autoreset)
+// for tdCPA_forV2 batches of at least 8M (ray + pair) items and multipleMap batches of at least 3M, one fused launch
+// otherwise, unless the configuration says which.
 static bool split_autoreset(const AacEnv *env, int e_cnt = 0) {
     const AacConfig &c = env->cfg;
     if (c.autoreset_launches == 1) return false;
     if (c.autoreset_launches == 2) return true;
     if (c.autoreset_launches == 3) return phased_autoreset(env, e_cnt);
     const double items = (double)(e_cnt > 0 ? e_cnt : c.n_envs) * c.n_agents * (c.n_agents - 1 + c.n_rays);
-    return c.variant == AAC_VARIANT_V2 && items >= 8e6;
+    return (c.variant == AAC_VARIANT_V2 && items >= 8e6) || (c.variant == AAC_VARIANT_MM && items >= 3e6);
 }
 extern "C" int aac_step_autoreset(AacEnv *env, const float *actions_dev, const AacOut *out, void *stream) {
     if (!env) return fail(AAC_ERR_ARG, "null handle");

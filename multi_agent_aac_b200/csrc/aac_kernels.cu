@@ -995,9 +995,8 @@ __device__ __forceinline__ void group_loop(const KParams &p, Warp &w, const int 
         if (gi >= n_groups) break;
         w.e_lo = gi * G;
         w.ng = max(0, min(G, p.E - w.e_lo));
-        // reset launch: a group none of whose envs is masked has nothing to do (with a trained policy most groups)
-        unsigned group_mask = 0;
-        if (PHASE == 2) {   // the group's step has left its results (whichever warp ran it)
+        unsigned group_mask = 0;   // PHASE 2: the envs of the group its step terminated
+        if (PHASE == 2) {   // wait until the group's step has left its results (whichever warp ran it)
             if (lane == 0) {
                 unsigned long long f;
                 while ((unsigned)((f = ld_flag(p.flags + gi)) >> 32) != (unsigned)p.epoch) __nanosleep(64);
@@ -1006,6 +1005,7 @@ __device__ __forceinline__ void group_loop(const KParams &p, Warp &w, const int 
             group_mask = __shfl_sync(FULL, group_mask, 0);
             if (!group_mask) continue;
         }
+        // reset launch: a group none of whose envs is masked has nothing to do (with a trained policy most groups)
         if (PHASE != 2 && mode == MODE_RESET && p.mask && !__ballot_sync(FULL, lane < w.ng && p.mask[w.e_lo + lane])) continue;
         w.a0 = w.e_lo * N;
         w.nA = w.ng * N;
