@@ -201,7 +201,13 @@ int aac_set_maps(AacEnv *env, const AacMapDesc *maps, const uint8_t *occ /* [M,A
  * kernel itself computes.  The arrays stay caller-owned; all NULL removes the table; aac_set_maps removes it too. */
 int aac_set_radar_table(AacEnv *env, const float *radar, const float *radar_min, const int16_t *radar_hit, const uint32_t *min_bits);
 int aac_set_bank(AacEnv *env, const AacBank *bank);
-/* one table per map (host pointers, copied); resets draw from the tables instead of the scenario bank */
+/* one table per map (host pointers, copied); resets draw from the tables instead of the scenario bank.
+ * A table with path_off = path_len = path_cells = NULL carries the pools only: the reference line of every episode is then
+ * searched when the episode starts, on the device, by the warp that re-initialises the env - reset_world's per-episode
+ * jps_find_path + pruning (ATT:317-331), the same planner as aac_plan_path, so the episodes are those of a table with paths,
+ * bit for bit, without its P^2 paths.  An unreachable goal or a line of more than w_max vertices cannot be reported from
+ * there: the line falls back to start -> goal and statistic [10] counts it.  Not with the sensor / evaluation
+ * configurations (radar_targets, n_nbr_obs, eval_by_step), which keep tables with paths. */
 int aac_set_od_tables(AacEnv *env, const AacOdTable *tables, int32_t n_maps);
 /* Host-only helper: the reference's grid search (ATT/jps_straight.py:17-70: best-first on f = g + Manhattan, first
  * minimum in discovery order, neighbours visited in the order (0,-1), (0,1), (-1,0), (1,0), cells never re-opened)
@@ -244,7 +250,8 @@ int aac_step_host(AacEnv *env, const float *actions_host, const AacOut *out_dev,
 /* episode statistics accumulated on the device since the last call with reset != 0 (mirrors the
  * per-100-episode counters of ATT/ma_main:581-637): [0] episodes, [1] steps, [2] sum of returns,
  * [3] bound crash episodes, [4] building, [5] drone, [6] drone-crash-with-nearest, [7] episodes in
- * which every drone reached its goal, [8] drones that reached, [9] step-cap endings, [10..15] 0.
+ * which every drone reached its goal, [8] drones that reached, [9] step-cap endings, [10] reference lines that fell
+ * back to start -> goal in the per-episode search (pools-only tables), [11..15] 0.
  * Synchronises the stream. */
 #define AAC_N_STATS 16
 int aac_read_stats(AacEnv *env, double *stats_host /* [AAC_N_STATS] */, int32_t reset, void *cuda_stream);

@@ -22,7 +22,7 @@ MAX_CLOUDS = 8
 MAP_STRIDE = 1024
 N_STATS = 16
 STAT_NAMES = ["episodes", "steps", "return_sum", "bound_crash", "building_crash", "drone_crash", "drone_crash_nearest",
-              "all_reached", "drones_reached", "step_cap"]
+              "all_reached", "drones_reached", "step_cap", "plan_fallback"]
 
 EXPORTS = ["aac_create", "aac_destroy", "aac_set_maps", "aac_set_radar_table", "aac_set_bank", "aac_set_od_tables", "aac_plan_path", "aac_plan_paths_device", "aac_bind_state", "aac_reset", "aac_observe",
            "aac_step", "aac_step_autoreset", "aac_step_fused", "aac_autoreset", "aac_step_host", "aac_read_stats", "aac_launch_count", "aac_own_dim",

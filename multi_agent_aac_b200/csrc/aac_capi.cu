@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -39,6 +40,8 @@ struct AacEnv {
     float *d_actions = nullptr;  // staging for aac_step_host
     double *d_stats = nullptr;
     int *d_work = nullptr;       // ping-pong group counters of the persistent kernel
+    bool od_plan = false;        // an origin / destination table has pools only: paths are searched per episode on the device
+    uint8_t *d_plan_scratch = nullptr;   // per-warp scratch of that search
     unsigned long long *d_flags = nullptr;   // [groups] phased launch: (epoch << 32) | terminated envs of the group
     int epoch = 0;               // phased launches so far
     int sms = 0;
@@ -182,6 +185,7 @@ extern "C" void aac_destroy(AacEnv *env) {
     cudaFree(env->d_stats);
     cudaFree(env->d_work);
     cudaFree(env->d_flags);
+    cudaFree(env->d_plan_scratch);
     cudaFree(env->d_od);
     for (void *b : env->od_bufs) cudaFree(b);
     for (auto &s : env->pipe) if (s) cudaStreamDestroy(s);
@@ -285,18 +289,24 @@ extern "C" int aac_set_od_tables(AacEnv *env, const AacOdTable *tables, int32_t 
         return fail(AAC_ERR_ARG, msg);
     };
     const int w_cap = env->cfg.variant == AAC_VARIANT_MM ? 31 : env->cfg.w_max;   // multipleMap keeps the remaining waypoints in a 32-bit mask
+    bool any_plan = false;
     for (int m = 0; m < n_maps; ++m) {
         const AacOdTable &t = tables[m];
-        if (t.n_cells < 2 || !t.cell_code || !t.path_off || !t.path_len || !t.path_cells) return reject("aac_set_od_tables: incomplete table");
+        // pools without paths: the reference line of every episode is searched on the device when the episode starts
+        // (reset_world's per-episode jps_find_path, ATT:317), by the warp that re-initialises the env
+        const bool pools_only = !t.path_off && !t.path_len && !t.path_cells;
+        if (pools_only && (env->cfg.radar_targets || env->cfg.n_nbr_obs || env->cfg.eval_by_step))
+            return reject("aac_set_od_tables: the sensor / evaluation configurations need tables with paths");
+        if (t.n_cells < 2 || !t.cell_code || (!pools_only && (!t.path_off || !t.path_len || !t.path_cells))) return reject("aac_set_od_tables: incomplete table");
         for (int q = 0; q < 4; ++q)
             if (t.pool_off[q + 1] <= t.pool_off[q]) return reject("aac_set_od_tables: every quadrant pool needs at least one cell");
         if (t.pool_off[0] != 0 || t.pool_off[4] != t.n_cells) return reject("aac_set_od_tables: pool offsets do not cover the cells");
-        if (t.n_path_cells < 0 || (t.n_path_cells & 7)) return reject("aac_set_od_tables: path_cells must be padded to a multiple of 8");
+        if (!pools_only && (t.n_path_cells < 0 || (t.n_path_cells & 7))) return reject("aac_set_od_tables: path_cells must be padded to a multiple of 8");
         const size_t P = t.n_cells;
         const int gx = env->d_maps ? env->h_gx[m] : 255, gy = env->d_maps ? env->h_gy[m] : 255;
         for (size_t k = 0; k < P; ++k)
             if ((t.cell_code[k] >> 8) >= gx || (t.cell_code[k] & 255) >= gy) return reject("aac_set_od_tables: a pool cell lies outside the map's grid");
-        for (size_t k = 0; k < P * P; ++k) {
+        for (size_t k = 0; k < P * P && !pools_only; ++k) {
             if (!t.path_len[k]) continue;
             if (t.path_len[k] < 2 || t.path_len[k] > w_cap || (t.path_off[k] & 7u)) return reject("aac_set_od_tables: a path has fewer than 2 or more than w_max (multipleMap: 31) vertices or is not 8-cell aligned");
             if ((int64_t)t.path_off[k] + ((t.path_len[k] + 7) & ~7) > t.n_path_cells) return reject("aac_set_od_tables: a path runs past the end of path_cells");
@@ -309,9 +319,12 @@ extern "C" int aac_set_od_tables(AacEnv *env, const AacOdTable *tables, int32_t 
         o.n_cells = t.n_cells;
         for (int q = 0; q < 5; ++q) o.pool_off[q] = t.pool_off[q];
         cudaError_t e;
-        if ((e = upload(t.cell_code, P * 2, (const void **)&o.cell_code)) != cudaSuccess || (e = upload(t.path_off, P * P * 4, (const void **)&o.path_off)) != cudaSuccess ||
-            (e = upload(t.path_len, P * P, (const void **)&o.path_len)) != cudaSuccess ||
-            (e = upload(t.path_cells, (size_t)t.n_path_cells * 2, (const void **)&o.path_cells)) != cudaSuccess) {
+        o.path_off = nullptr; o.path_len = nullptr; o.path_cells = nullptr;
+        any_plan = any_plan || pools_only;
+        if ((e = upload(t.cell_code, P * 2, (const void **)&o.cell_code)) != cudaSuccess ||
+            (!pools_only && ((e = upload(t.path_off, P * P * 4, (const void **)&o.path_off)) != cudaSuccess ||
+                             (e = upload(t.path_len, P * P, (const void **)&o.path_len)) != cudaSuccess ||
+                             (e = upload(t.path_cells, (size_t)t.n_path_cells * 2, (const void **)&o.path_cells)) != cudaSuccess))) {
             for (void *b : bufs) cudaFree(b);
             return cuda_fail(e, "aac_set_od_tables upload");
         }
@@ -319,6 +332,7 @@ extern "C" int aac_set_od_tables(AacEnv *env, const AacOdTable *tables, int32_t 
     cudaFree(env->d_od);
     for (void *b : env->od_bufs) cudaFree(b);
     env->od_bufs = bufs;
+    env->od_plan = any_plan;
     env->d_od = nullptr;
     CU(cudaMalloc(&env->d_od, sizeof(OdDev) * n_maps));
     CU(cudaMemcpy(env->d_od, host.data(), sizeof(OdDev) * n_maps, cudaMemcpyHostToDevice));
@@ -379,116 +393,18 @@ extern "C" int aac_plan_path(const uint8_t *occ, int32_t gx, int32_t gy, int32_t
     return (int)keep.size();
 }
 
-// ---- the same search on the device: one warp per origin / destination pair ----------------------------------------
-// The frontier keeps discovery order; a popped entry is tombstoned in place (f = 0xFFFF) instead of erased, so "the
-// first minimum in discovery order" is the minimum of (f << 16 | position) over the live entries: the lanes scan the
-// list in strides and meet in one redux.  A cell is queued at most once, so every array is bounded by the cell count.
-// Scratch per warp (global memory, L1 / L2 resident for the reference's 23 x 13 .. 31 x 21 grids): status u8[n],
-// g u16[n], parent u16[n], frontier cell u16[n], frontier f u16[n].
-constexpr int PLAN_SCRATCH_PER_CELL = 9;
-constexpr unsigned PLAN_DEAD = 0xFFFFu;
-
+// ---- the same search on the device: one warp per origin / destination pair (aac_plan.cuh) ------------------------------
 __global__ void __launch_bounds__(256) plan_paths_kernel(const uint8_t *__restrict__ occ, const int gx, const int gy, const uint16_t *__restrict__ pairs,
                                                          const long long n_pairs, uint16_t *__restrict__ out_cells, int *__restrict__ out_len,
                                                          const int max_cells, uint8_t *__restrict__ scratch) {
-    const unsigned FULLM = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int n = gx * gy;
-    const size_t n_al = ((size_t)n + 7) & ~(size_t)7;
-    uint8_t *status = scratch + (size_t)warp * n_al * PLAN_SCRATCH_PER_CELL;
-    uint16_t *gcost = reinterpret_cast<uint16_t *>(status + n_al), *parent = gcost + n_al, *fcell = parent + n_al, *ff = fcell + n_al;
+    uint8_t *mine = scratch + (size_t)warp * plan_scratch_bytes((size_t)gx * gy);
     for (long long pi = warp; pi < n_pairs; pi += n_warps) {
         const int sc = pairs[2 * pi], tc = pairs[2 * pi + 1];
-        const int tx = tc >> 8, ty = tc & 255;
-        const int s = (sc >> 8) * gy + (sc & 255), t = tx * gy + ty;
-        for (int c = lane; c < n; c += 32) status[c] = 0;
-        __syncwarp();
-        if (lane == 0) { status[s] = 1; gcost[s] = 0; parent[s] = PLAN_DEAD; fcell[0] = (uint16_t)s; ff[0] = 0; }
-        __syncwarp();
-        int head = 0, tail = 1, live = 1;   // live entries lie in [head, tail)
-        bool found = false;
-        for (;;) {
-            unsigned key = 0xFFFFFFFFu;
-            for (int k = head + lane; k < tail; k += 32) {
-                const unsigned f = ff[k];
-                if (f != PLAN_DEAD) key = min(key, (f << 16) | (unsigned)k);
-            }
-            key = __reduce_min_sync(FULLM, key);
-            if (key == 0xFFFFFFFFu) break;   // frontier empty: the goal is unreachable
-            const int kb = (int)(key & 0xFFFFu), cur = fcell[kb];
-            if (cur == t) { found = true; break; }
-            const int cx = cur / gy, cy = cur - cx * gy, g1 = gcost[cur] + 1;
-            __syncwarp();
-            if (lane == 0) ff[kb] = (uint16_t)PLAN_DEAD;
-            while (head < tail && (head == kb || ff[head] == PLAN_DEAD)) ++head;   // warp-uniform: every lane reads the same entries
-            // neighbours in the reference's order (0,-1), (0,1), (-1,0), (1,0): lane d takes the d-th
-            const int nx = cx + (lane == 2 ? -1 : lane == 3 ? 1 : 0), ny = cy + (lane == 0 ? -1 : lane == 1 ? 1 : 0);
-            bool push = lane < 4 && nx >= 0 && ny >= 0 && nx < gx && ny < gy;
-            const int c = nx * gy + ny;
-            if (push) push = !occ[c] && !status[c];
-            const unsigned m = __ballot_sync(FULLM, push);
-            if (push) {
-                const int k = tail + __popc(m & ((1u << lane) - 1u));
-                status[c] = 1;
-                gcost[c] = (uint16_t)g1;
-                parent[c] = (uint16_t)cur;
-                fcell[k] = (uint16_t)c;
-                ff[k] = (uint16_t)(g1 + abs(nx - tx) + abs(ny - ty));
-            }
-            tail += __popc(m);
-            live += __popc(m) - 1;
-            __syncwarp();
-            // a long search leaves tombstones between the live entries: squeeze them out, order kept, once they outnumber
-            // the live ones (write position <= read position, a chunk is read before it is written)
-            if (tail - head > 64 && 2 * live < tail - head) {
-                int wpos = 0;
-                for (int k0 = head; k0 < tail; k0 += 32) {
-                    const int k = k0 + lane;
-                    const unsigned f = k < tail ? ff[k] : PLAN_DEAD;
-                    const unsigned cc = k < tail ? fcell[k] : 0u;
-                    const unsigned keep = __ballot_sync(FULLM, f != PLAN_DEAD);
-                    __syncwarp();
-                    if (f != PLAN_DEAD) {
-                        const int dst = wpos + __popc(keep & ((1u << lane) - 1u));
-                        ff[dst] = (uint16_t)f;
-                        fcell[dst] = (uint16_t)cc;
-                    }
-                    wpos += __popc(keep);
-                    __syncwarp();
-                }
-                head = 0;
-                tail = wpos;
-            }
-        }
-        // walk back from the goal; the cells where the direction changes are the same in either direction (ATT:321-331)
-        if (lane == 0) {
-            int cnt = 0;
-            if (found) {
-                for (int pass = 0; pass < 2; ++pass) {   // count, then write from the back
-                    int k = 0, c = t, pc = parent[c];
-                    auto emit = [&](int cell) {
-                        if (pass == 1 && cnt <= max_cells) out_cells[pi * max_cells + (cnt - 1 - k)] = (uint16_t)(((cell / gy) << 8) | (cell % gy));
-                        ++k;
-                    };
-                    emit(c);
-                    if (pc != (int)PLAN_DEAD) {
-                        int d = pc - c;   // steps are +-1 or +-gy: the index difference names the direction
-                        for (;;) {
-                            const int nc = parent[pc];
-                            if (nc == (int)PLAN_DEAD) break;
-                            const int e = nc - pc;
-                            if (e != d) { emit(pc); d = e; }
-                            pc = nc;
-                        }
-                        emit(pc);
-                    }
-                    if (pass == 0) cnt = k;
-                }
-            }
-            out_len[pi] = !found ? 0 : (cnt > max_cells ? -1 : cnt);
-        }
-        __syncwarp();
+        const int s = (sc >> 8) * gy + (sc & 255), t = (tc >> 8) * gy + (tc & 255);
+        const int cnt = plan_path_warp([&](const int c) { return occ[c] != 0; }, gx, gy, s, t, mine, out_cells + pi * max_cells, max_cells);
+        if (lane == 0) out_len[pi] = cnt;
     }
 }
 
@@ -506,14 +422,14 @@ extern "C" int aac_plan_paths_device(const uint8_t *occ, int32_t gx, int32_t gy,
     const int threads = 256, wpc = threads / 32;
     int64_t grid = (n_pairs + wpc - 1) / wpc;
     if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;   // 8 resident CTAs of 256 threads per SM: persistent warps
-    const size_t n = (size_t)gx * gy, n_al = (n + 7) & ~(size_t)7, n_warps = (size_t)grid * wpc;
+    const size_t n = (size_t)gx * gy, n_warps = (size_t)grid * wpc;
     uint8_t *d_occ = nullptr, *d_scratch = nullptr;
     uint16_t *d_pairs = nullptr, *d_cells = nullptr;
     int *d_len = nullptr;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
     if (ok(cudaMalloc(&d_occ, n)) && ok(cudaMalloc(&d_pairs, (size_t)n_pairs * 4)) && ok(cudaMalloc(&d_cells, (size_t)n_pairs * max_cells * 2)) &&
-        ok(cudaMalloc(&d_len, (size_t)n_pairs * 4)) && ok(cudaMalloc(&d_scratch, n_warps * n_al * PLAN_SCRATCH_PER_CELL)) &&
+        ok(cudaMalloc(&d_len, (size_t)n_pairs * 4)) && ok(cudaMalloc(&d_scratch, n_warps * plan_scratch_bytes(n))) &&
         ok(cudaMemcpyAsync(d_occ, occ, n, cudaMemcpyHostToDevice, stream)) &&
         ok(cudaMemcpyAsync(d_pairs, pairs, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, stream)) &&
         ok(cudaMemsetAsync(d_cells, 0, (size_t)n_pairs * max_cells * 2, stream))) {
@@ -610,6 +526,13 @@ static int launch(AacEnv *env, int mode, const uint8_t *mask, const float *actio
     p.rtab = env->rtab; p.rtab_min = env->rtab_min; p.rtab_hit = env->rtab_hit; p.rtab_minr = env->rtab_minr;
     p.work = env->d_work + 4 * pair; p.parity = (int)(env->pair_launches[pair] & 1);
     p.st = env->st; p.out = *out; p.CL = env->cl; p.WL = env->wl;
+    if (env->od_plan && (mode == MODE_RESET || autoreset)) {   // per-episode path search: scratch for every warp that can be resident
+        size_t cells = 0;
+        for (int m = 0; m < (env->n_maps ? env->n_maps : 1); ++m) cells = std::max(cells, (size_t)env->h_gx[m] * env->h_gy[m]);
+        p.plan_stride = (unsigned)plan_scratch_bytes(cells);
+        if (!env->d_plan_scratch) CU(cudaMalloc(&env->d_plan_scratch, (size_t)env->sms * 64 * p.plan_stride   /* 64 resident warps per SM at most */));
+        p.plan_scratch = env->d_plan_scratch;
+    }
     if (autoreset == 2) {   // phased launch: per-group completion flags, tagged with the launch's epoch
         if (e_lo % env->group) return fail(AAC_ERR_ARG, "phased launch: the env range must start on a group boundary");
         if (!env->d_flags) {
@@ -673,6 +596,7 @@ extern "C" int aac_step(AacEnv *env, const float *actions_dev, const AacOut *out
 static bool phased_autoreset(const AacEnv *env, int e_cnt = 0) {
     const AacConfig &c = env->cfg;
     if (c.autoreset_launches != 3 && c.autoreset_launches != 0) return false;
+    if (env->od_plan) return false;   // per-episode path search lives in the run-time-mode kernels
     if (c.autoreset_launches == 0) {
         if (c.variant != AAC_VARIANT_V2) return false;   // multipleMap at C4: two launches 0.0713, phased 0.0734, fused 0.0747 ms
         const long long groups = ((long long)(e_cnt > 0 ? e_cnt : c.n_envs) + env->group - 1) / env->group;

@@ -775,7 +775,8 @@ __device__ __forceinline__ unsigned draw(unsigned key, unsigned ctr) {
 // reset_world leaves behind (ATT:251-372).  Origins, destinations and reference lines come from the map's origin /
 // destination table when one is installed (the device draws them with reset_world's rule, ATT:254-276), else from a
 // pre-planned scenario of the bank.  Returns the lane's reference-line row (nullptr for a lane outside the masked envs).
-template <int VAR, int NT>
+// PL: the instantiation carries the per-episode path search for maps whose table has pools but no paths (aac_plan.cuh).
+template <int VAR, int NT, bool PL>
 __device__ __forceinline__ const uint16_t *init_envs(const KParams &p, const Warp &w, const unsigned mask) {
     const int lane = w.lane, N = NT ? NT : p.N, W = p.W;
     const int g = lane / N, i = lane - g * N;             // the lane's env of the group and its drone in it
@@ -834,9 +835,38 @@ __device__ __forceinline__ const uint16_t *init_envs(const KParams &p, const War
                 if (redo && i == ii) code = candidate(ii, attempt, s_idx, tq);
             }
         }
+        int t_idx = 0;
         if (act) {
             const int n_t = od.pool_off[tq + 1] - od.pool_off[tq];
-            const int t_idx = od.pool_off[tq] + (int)(draw(key, 1u + 256u * (unsigned)i + 3u) % (unsigned)n_t);
+            t_idx = od.pool_off[tq] + (int)(draw(key, 1u + 256u * (unsigned)i + 3u) % (unsigned)n_t);
+        }
+        if (PL && __any_sync(FULL, act && od.path_cells == nullptr)) {
+            // no table of paths for this map: reset_world's per-episode search (jps_find_path + pruning, ATT:317-331), one drone
+            // after the other with the whole warp on each, straight into the drone's reference-line row of the state
+            uint8_t *scratch = p.plan_scratch + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * p.plan_stride;
+            const int t_code = act ? (int)od.cell_code[t_idx] : 0;
+            const int wcap = VAR == AAC_VARIANT_MM ? min(W, 31) : W;
+            for (unsigned left = __ballot_sync(FULL, act && od.path_cells == nullptr); left; left &= left - 1u) {
+                const int src = __ffs(left) - 1;
+                const int sc = __shfl_sync(FULL, code, src), tc = __shfl_sync(FULL, t_code, src);
+                const int mrow = __shfl_sync(FULL, map_row, src), gee = __shfl_sync(FULL, ge, src), ii = __shfl_sync(FULL, i, src);
+                const MapDev &mq = VAR == AAC_VARIANT_MM ? w.map[mrow] : *w.map;
+                const int gyq = mq.gy;
+                uint16_t *dst = p.st.ref_cells + ((size_t)gee * N + ii) * W;
+                int cnt = plan_path_warp([&](const int c) { return occupied(mq, c / gyq, c - (c / gyq) * gyq); }, mq.gx, gyq, (sc >> 8) * gyq + (sc & 255),
+                                         (tc >> 8) * gyq + (tc & 255), scratch, dst, wcap);
+                if (cnt < 2) {   // unreachable goal, or more vertices than the row holds: a straight line, and the counter says so
+                    if (lane == 0) { dst[0] = (uint16_t)sc; dst[1] = (uint16_t)tc; if (p.stats) atomicAdd(p.stats + 10, 1.0); }
+                    cnt = 2;
+                }
+                if (lane == 0)
+                    for (int k = cnt; k < ((cnt + 7) & ~7); ++k) dst[k] = 0;   // whole 16-byte chunks, zero padded as the table's paths are
+                __syncwarp();
+                if (lane == src) { nw = cnt; row = dst; }
+            }
+            if (act && od.path_cells == nullptr) head = *reinterpret_cast<const uint4 *>(row);
+        }
+        if (act && !(PL && od.path_cells == nullptr)) {
             const int pr = s_idx * od.n_cells + t_idx;
             nw = od.path_len[pr];
             const uint16_t *src = od.path_cells + od.path_off[pr];   // 16-byte aligned: paths are padded to 8 cells
@@ -970,7 +1000,7 @@ constexpr int MT_PHASED = 4;   // one launch: MT_STEP_ONLY's loop over all group
 // the envs it terminated are re-initialised): loop 1 publishes a group's completion in p.flags (release), loop 2 takes
 // the groups from a second counter and waits for the group's flag (see ld_flag).  A flag is (epoch << 32) | the group's
 // terminated-env bits: loop 2 learns from the one word both that the group is through and which envs to re-initialise.
-template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS, int MT, int RM, bool CS, int PHASE>
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS, int MT, int RM, bool CS, int PHASE, bool PL>
 __device__ __forceinline__ void group_loop(const KParams &p, Warp &w, const int mode_arg, const MapDev *s_map, int &st_i, float &st_f) {
     constexpr bool STEP_ONLY = MT == MT_STEP_ONLY;
     const int mode = MT < 0 ? mode_arg : (STEP_ONLY ? (int)MODE_STEP : MT);
@@ -1058,7 +1088,7 @@ __device__ __forceinline__ void group_loop(const KParams &p, Warp &w, const int 
             const uint16_t *cl = cells;
             if (job > 0) {
                 if (!reset_mask) break;
-                const uint16_t *row = init_envs<VAR, NT>(p, w, reset_mask);
+                const uint16_t *row = init_envs<VAR, NT, PL>(p, w, reset_mask);
                 cl = row ? row : p.st.ref_cells;
             }
             observe_range<VAR, AUX, LEAN, NT, RT, RM, CS>(p, w, 0, nA, cl, job > 0 && p.rtab != nullptr, job == 0 && mode == MODE_STEP,
@@ -1380,7 +1410,7 @@ __device__ __forceinline__ void group_loop(const KParams &p, Warp &w, const int 
 }
 
 
-template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1, int RM = -1, bool CS = false>
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1, int RM = -1, bool CS = false, bool PL = false>
 __global__ void __launch_bounds__(MAX_THREADS, NT >= 16 ? 3 : AAC_MIN_BLOCKS) env_kernel(   // 20-drone envs: 85 registers, no spills, measured 5 % faster on C5
 const __grid_constant__ KParams p, const int mode_arg) {
     const int mode = MT < 0 ? mode_arg : ((MT == MT_STEP_ONLY || MT == MT_PHASED) ? (int)MODE_STEP : MT);
@@ -1437,10 +1467,10 @@ const __grid_constant__ KParams p, const int mode_arg) {
     float st_f = 0.0f;
 
     if (MT == MT_PHASED) {
-        group_loop<VAR, AUX, LEAN, NT, RT, EVS, MT_STEP_ONLY, RM, CS, 1>(p, w, mode_arg, s_map, st_i, st_f);
-        group_loop<VAR, AUX, LEAN, NT, RT, EVS, MODE_RESET, RM, CS, 2>(p, w, mode_arg, s_map, st_i, st_f);
+        group_loop<VAR, AUX, LEAN, NT, RT, EVS, MT_STEP_ONLY, RM, CS, 1, PL>(p, w, mode_arg, s_map, st_i, st_f);
+        group_loop<VAR, AUX, LEAN, NT, RT, EVS, MODE_RESET, RM, CS, 2, PL>(p, w, mode_arg, s_map, st_i, st_f);
     } else {
-        group_loop<VAR, AUX, LEAN, NT, RT, EVS, MT, RM, CS, 0>(p, w, mode_arg, s_map, st_i, st_f);
+        group_loop<VAR, AUX, LEAN, NT, RT, EVS, MT, RM, CS, 0, PL>(p, w, mode_arg, s_map, st_i, st_f);
     }
 
     // ---- warp epilogue: the counters leave, one atomic per statistic and warp
@@ -1450,11 +1480,11 @@ const __grid_constant__ KParams p, const int mode_arg) {
     }
 }
 
-template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1, int RM = -1, bool CS = false>
+template <int VAR, bool AUX, bool LEAN, int NT, int RT, bool EVS = false, int MT = -1, int RM = -1, bool CS = false, bool PL = false>
 static cudaError_t launch_one(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     const int wpc = threads / 32;
     const int groups = (p.E + p.G - 1) / p.G;
-    auto fn = env_kernel<VAR, AUX, LEAN, NT, RT, EVS, MT, RM, CS>;
+    auto fn = env_kernel<VAR, AUX, LEAN, NT, RT, EVS, MT, RM, CS, PL>;
     static int opted_in[64] = {0};   // dynamic shared memory this instantiation has opted in to, per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1511,9 +1541,26 @@ bool phased_launch_available(int variant, const KParams &p) {
     }
 }
 
+// the run-time-mode kernels with the per-episode path search compiled in (a map's origin / destination table has pools only)
+template <int VAR>
+static cudaError_t launch_plan(const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
+    if (p.out_flags == 0) return launch_one<VAR, false, true, 0, 0, false, -1, -1, false, true>(p, mode, threads, sms, grid_cache, stream);
+    return (p.out_flags & AAC_OUT_RADAR_AUX) ? launch_one<VAR, true, false, 0, 0, false, -1, -1, false, true>(p, mode, threads, sms, grid_cache, stream)
+                                             : launch_one<VAR, false, false, 0, 0, false, -1, -1, false, true>(p, mode, threads, sms, grid_cache, stream);
+}
+
 cudaError_t launch_env_kernel(int variant, const KParams &p, int mode, int threads, int sms, int *grid_cache, cudaStream_t stream) {
     if (p.E <= 0) return cudaSuccess;
-    if (p.autoreset == 2 && (mode != MODE_STEP || !phased_launch_available(variant, p) || !p.flags)) return cudaErrorNotSupported;
+    if (p.autoreset == 2 && (mode != MODE_STEP || !phased_launch_available(variant, p) || !p.flags || p.plan_scratch)) return cudaErrorNotSupported;
+    if (p.plan_scratch) {
+        if (p.radar_targets || p.n_nbr_obs || p.eval_by_step) return cudaErrorNotSupported;   // (sensor / evaluation configurations: tables with paths)
+        switch (variant) {
+            case AAC_VARIANT_ATT: return launch_plan<AAC_VARIANT_ATT>(p, mode, threads, sms, grid_cache, stream);
+            case AAC_VARIANT_MM: return launch_plan<AAC_VARIANT_MM>(p, mode, threads, sms, grid_cache, stream);
+            case AAC_VARIANT_V2: return launch_plan<AAC_VARIANT_V2>(p, mode, threads, sms, grid_cache, stream);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (variant) {
         // the reference's own shapes (3 drones; 18 rays, or the 36 of the batched configuration) are specialised too
         case AAC_VARIANT_ATT:

@@ -5,6 +5,7 @@
 
 #include "../../include/aac_env.h"
 #include "aac_radar.cuh"
+#include "aac_plan.cuh"
 
 namespace aac {
 
@@ -80,6 +81,8 @@ struct KParams {
     double *stats;        // [AAC_N_STATS]
     int *work;            // [2] group counters of the persistent warps, ping-pong between launches
     int parity;           // which counter pair this launch consumes: work[2 * parity + {0, 1}] (it zeroes the other pair)
+    uint8_t *plan_scratch;       // per-warp scratch of the per-episode path search (pools-only origin / destination tables), else NULL
+    unsigned plan_stride;        // bytes per warp
     unsigned long long *flags;   // [groups] phased launch: (epoch of the step loop that last completed the group) << 32 | its terminated envs
     int epoch;            // this launch's epoch (phased launch)
     AacState st;

@@ -226,9 +226,10 @@ class BatchedDroneEnv:
             arr[k].n_cells = t.n_cells
             for q in range(5):
                 arr[k].pool_off[q] = int(t.pool_off[q])
-            arr[k].cell_code, arr[k].path_off = t.cell_code.ctypes.data, t.path_off.ctypes.data
-            arr[k].path_len, arr[k].path_cells = t.path_len.ctypes.data, t.path_cells.ctypes.data
-            arr[k].n_path_cells = int(t.path_cells.size)
+            arr[k].cell_code = t.cell_code.ctypes.data
+            if t.path_cells is not None:       # else pools only: paths are searched per episode on the device
+                arr[k].path_off, arr[k].path_len, arr[k].path_cells = t.path_off.ctypes.data, t.path_len.ctypes.data, t.path_cells.ctypes.data
+                arr[k].n_path_cells = int(t.path_cells.size)
         with torch.cuda.device(self.device):
             K.check(self.L.aac_set_od_tables(self.h, arr, len(tables)), "aac_set_od_tables")
         self._od = tables

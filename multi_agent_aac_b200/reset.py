@@ -225,13 +225,17 @@ class OdTable:
     (ATT:154-197) and the pruned grid path between every start / goal pair in different quadrants, planned by the
     library's planner (the reference's search and tie-breaking, ATT/jps_straight.py:17-70): `planner="host"` calls
     `aac_plan_path` pair by pair, `planner="device"` plans every pair in one launch (`aac_plan_paths_device`, identical
-    results).  With a table installed the device draws origins and destinations itself at every reset (ATT:254-276)."""
+    results).  With a table installed the device draws origins and destinations itself at every reset (ATT:254-276).
+    `paths=False` builds the pools only: the reference line of every episode is then searched on the device when the episode
+    starts, by the warp that re-initialises the env (`reset_world`'s per-episode `jps_find_path`, ATT:317) - same planner,
+    same episodes bit for bit, no P^2 table (an unreachable goal or a path of more than w_max vertices cannot raise there: the
+    line falls back to start -> goal and `read_stats()[10]` counts it)."""
 
-    def __init__(self, gmap: GridMap, w_max=32, planner="host"):
+    def __init__(self, gmap: GridMap, w_max=32, planner="host", paths=True):
         from . import _capi as K
         lib = K.lib()
         assert planner in ("host", "device")
-        self.gmap, self.w_max, self.planner = gmap, w_max, planner
+        self.gmap, self.w_max, self.planner, self.has_paths = gmap, w_max, planner, bool(paths)
         pools = gmap.target_pools()
         cells, pool_off, quad = [], [0], []
         for q in range(4):
@@ -242,6 +246,9 @@ class OdTable:
         P = len(cells)
         self.n_cells, self.pool_off = P, np.array(pool_off, dtype=np.int32)
         self.cell_code = np.array([ix * 256 + iy for ix, iy in cells], dtype=np.uint16)
+        if not paths:
+            self.path_off = self.path_len = self.path_cells = None
+            return
         self.path_off = np.zeros(P * P, dtype=np.uint32)
         self.path_len = np.zeros(P * P, dtype=np.uint8)
         quad = np.array(quad)

@@ -85,3 +85,45 @@ def test_device_planner_rejects_bad_arguments():
     assert lib.aac_plan_paths_device(None, 4, 4, None, 1, None, None, 8, None) == -1
     c, n = plan_paths_device(grid(occ), np.zeros((0, 4), dtype=np.int64), 8)
     assert c.shape == (0, 8) and n.shape == (0,)
+
+
+@pytest.mark.gpu
+# (shapes that run the same run-time-shape kernels with and without the search: the instantiations specialised on the drone
+#  count keep their neighbour distances with the 5 low mantissa bits replaced by the sort index)
+@pytest.mark.parametrize("variant,n,r,E", [("tdcpa_v2", 7, 24, 3000), ("tdcpa_v2", 5, 24, 1500), ("att", 4, 18, 2000), ("multimap", 2, 18, 3000)])
+def test_per_episode_planning_equals_the_table(variant, n, r, E):
+    """Pools-only origin / destination tables: every episode's reference lines are searched on the device by the warp that
+    re-initialises the env (reset_world's per-episode jps_find_path, ATT:317-331).  State, observations, rewards and counters
+    must equal those of a handle that looks the same paths up in the all-pairs table, bit for bit, through resets and
+    auto-resets; no line may have fallen back."""
+    import numpy as np
+    import torch
+    from multi_agent_aac_b200.env import BatchedDroneEnv, preset
+    from multi_agent_aac_b200.maps import multimap_set, synthetic_map
+    from multi_agent_aac_b200.reset import OdTable
+    maps = multimap_set(seed=0)[:4] if variant == "multimap" else [synthetic_map(seed=0)]
+    envs = []
+    for paths in (True, False):
+        env = BatchedDroneEnv(preset(variant, n_envs=E, n_agents=n, n_rays=r, w_max=32, seed=31), maps if variant == "multimap" else maps[0])
+        env.set_od_tables([OdTable(m, w_max=32, planner="device", paths=paths) for m in maps])
+        env.reset()
+        envs.append(env)
+    def same(tag):
+        for k in envs[0].out:
+            assert torch.equal(envs[0].out[k].view(torch.uint8), envs[1].out[k].view(torch.uint8)), (tag, k)
+        for k in envs[0].state:
+            assert torch.equal(envs[0].state[k].view(torch.uint8), envs[1].state[k].view(torch.uint8)), (tag, k)
+    same("reset")
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(2)
+    for t in range(15):
+        act = (torch.rand((E, n, 2), device="cuda", generator=gen) * 2 - 1).contiguous()
+        for env in envs:
+            env.step(act, autoreset=True)
+        same(t)
+    mask = (torch.arange(E, device="cuda") % 3 == 0).to(torch.uint8)
+    for env in envs:
+        env.reset(mask)
+    same("masked reset")
+    s0, s1 = envs[0].read_stats(), envs[1].read_stats()
+    assert s0[0] == s1[0] > 0 and s1[10] == 0 and np.array_equal(s0[[1, 3, 4, 5, 6, 7, 8, 9]], s1[[1, 3, 4, 5, 6, 7, 8, 9]])
