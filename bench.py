@@ -51,7 +51,7 @@ def source_hash():
     carries the same hash (tests/tools/ncu_summary.py writes it into the summary's `Source Hash` row)."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("aac_kernels.cu", "aac_kernels.cuh", "aac_radar.cuh", "aac_capi.cu"):
+    for f in ("aac_kernels.cu", "aac_kernels.cuh", "aac_radar.cuh", "aac_plan.cuh", "aac_capi.cu"):
         h.update(open(os.path.join(ROOT, "multi_agent_aac_b200", "csrc", f), "rb").read())
     h.update(open(os.path.join(ROOT, "include", "aac_env.h"), "rb").read())
     return h.hexdigest()[:16]
@@ -98,14 +98,14 @@ def profiled_metric(name, kernel_names):
 
 def launched_kernels(variant, n, r, radar_mode, launches_per_step):
     """The instantiations one aac_step_autoreset call launches for the specialised tdCPA_forV2 shapes (aac_kernels.cu
-    launch_aux): env_kernel<VAR, AUX, LEAN, N, R, EVS, MT, RM, CS>, MT = 4 phased (one launch: step loop, then reset loop) or
-    3 step-only + 2 reset-only (two launches), RM = radar mode, CS = 0 (no later-fork sensors)."""
+    launch_aux): env_kernel<VAR, AUX, LEAN, N, R, EVS, MT, RM, CS, PL>, MT = 4 phased (one launch: step loop, then reset loop) or
+    3 step-only + 2 reset-only (two launches), RM = radar mode, CS = 0 (no later-fork sensors), PL = 0 (no per-episode search)."""
     if variant != "v2" or (n, r) not in ((10, 36), (20, 72)):
         return None
     if launches_per_step == 1:
-        return ["env_kernel<1,0,1,%d,%d,0,4,%d,0>" % (n, r, radar_mode)]
+        return ["env_kernel<1,0,1,%d,%d,0,4,%d,0,0>" % (n, r, radar_mode)]
     if launches_per_step == 2:
-        return ["env_kernel<1,0,1,%d,%d,0,3,%d,0>" % (n, r, radar_mode), "env_kernel<1,0,1,%d,%d,0,2,%d,0>" % (n, r, radar_mode)]
+        return ["env_kernel<1,0,1,%d,%d,0,3,%d,0,0>" % (n, r, radar_mode), "env_kernel<1,0,1,%d,%d,0,2,%d,0,0>" % (n, r, radar_mode)]
     return None
 
 

@@ -11,7 +11,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AAC_LIB") or os.path.join(_HERE, "libaac_env.so")   # AAC_LIB: A/B builds while tuning kernels
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("aac_kernels.cu", "aac_capi.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", "aac_kernels.cuh"), os.path.join(_HERE, "csrc", "aac_radar.cuh"), os.path.join(os.path.dirname(_HERE), "include", "aac_env.h")]
+HEADERS = [os.path.join(_HERE, "csrc", "aac_kernels.cuh"), os.path.join(_HERE, "csrc", "aac_radar.cuh"), os.path.join(_HERE, "csrc", "aac_plan.cuh"),
+           os.path.join(os.path.dirname(_HERE), "include", "aac_env.h")]
 
 ABI_VERSION = 3
 VARIANT_ATT, VARIANT_V2, VARIANT_MM = 0, 1, 2

@@ -205,15 +205,15 @@ def test_bench_c1_and_profile_gating():
     sys.path.insert(0, ROOT)
     import bench
     names = bench.launched_kernels("v2", 10, 36, 1, 2)
-    assert names == ["env_kernel<1,0,1,10,36,0,3,1,0>", "env_kernel<1,0,1,10,36,0,2,1,0>"] and bench.launched_kernels("att", 3, 36, 0, 2) is None
+    assert names == ["env_kernel<1,0,1,10,36,0,3,1,0,0>", "env_kernel<1,0,1,10,36,0,2,1,0,0>"] and bench.launched_kernels("att", 3, 36, 0, 2) is None
     phased = bench.launched_kernels("v2", 10, 36, 1, 1)
-    assert phased == ["env_kernel<1,0,1,10,36,0,4,1,0>"]
+    assert phased == ["env_kernel<1,0,1,10,36,0,4,1,0,0>"]
     for ks in (names, phased):
         rows = bench._profiled_rows(ks)
         if rows is not None:      # the committed summaries belong to this very source: every launch of the step, named exactly
             assert all(r["Source Hash"][1] == bench.source_hash() for r in rows) and bench.profiled_traffic(ks) > 3e8
-    assert bench.profiled_traffic(["env_kernel<1,0,1,10,36,0,3,0,0>", names[1]]) is None      # another radar mode: not these kernels
-    assert bench.profiled_traffic(["env_kernel<1,0,1,10,36,0,4,0,0>"]) is None
+    assert bench.profiled_traffic(["env_kernel<1,0,1,10,36,0,3,0,0,0>", names[1]]) is None      # another radar mode: not these kernels
+    assert bench.profiled_traffic(["env_kernel<1,0,1,10,36,0,4,0,0,0>"]) is None
     assert bench.profiled_traffic(bench.launched_kernels("v2", 20, 72, 1, 2)) is None
 
 
