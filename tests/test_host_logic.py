@@ -339,3 +339,14 @@ def test_build_is_gated_on_source_content_not_mtime():
         open(side, "w").write(good)
         _capi._lib = None
     assert _capi.lib() is not None
+
+
+def test_pools_only_od_table_has_the_same_pools_and_no_paths():
+    """OdTable(paths=False): the quadrant pools of the full table, no P^2 paths (the device searches per episode)."""
+    from multi_agent_aac_b200.maps import synthetic_map
+    from multi_agent_aac_b200.reset import OdTable
+    gmap = synthetic_map(seed=0)
+    full, pools = OdTable(gmap, w_max=32), OdTable(gmap, w_max=32, paths=False)
+    assert pools.n_cells == full.n_cells and np.array_equal(pools.pool_off, full.pool_off) and np.array_equal(pools.cell_code, full.cell_code)
+    assert pools.path_cells is None and pools.path_off is None and pools.path_len is None and not pools.has_paths and full.has_paths
+    assert full.path_cells.size % 8 == 0 and int(full.path_len.max()) <= 32
