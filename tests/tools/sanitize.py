@@ -35,7 +35,7 @@ def rollout(name, n, r, flags, source, steps=6, envs=96, **kw):
     if source == "bank":
         env.set_bank(MultiMapBank(maps, n, 64, w_max=32, seed=1) if name == "multimap" else ScenarioBank(maps, n, 64, w_max=32, seed=1))
     else:
-        env.set_od_tables([OdTable(m, w_max=32, planner="device") for m in (maps if isinstance(maps, list) else [maps])])
+        env.set_od_tables([OdTable(m, w_max=32, planner="device", paths=(source != "pools")) for m in (maps if isinstance(maps, list) else [maps])])
     env.reset()
     env.observe()
     for t in range(steps):
@@ -60,6 +60,9 @@ if "env" in what:
     rollout("tdcpa_v2", 20, 72, 0, "od", envs=40)
     rollout("tdcpa_v2", 5, 36, ALL_OUT, "od", eval_by_step=True)
     rollout("tdcpa_v2", 1, 18, 0, "bank", envs=9)
+    rollout("tdcpa_v2", 10, 36, ALL_OUT, "pools", envs=130)      # pools-only tables: the per-episode search inside the reset
+    rollout("multimap", 3, 18, 0, "pools", envs=200)
+    rollout("att", 3, 18, 0, "pools", envs=70, tile_envs=4, block_threads=64)
     rollout("changeskin_sensors", 4, 18, K.OUT_RAW | K.OUT_RADAR_AUX | K.OUT_PARTS, "od", steps=12)    # the later fork's sensor classes
     rollout("changeskin_sensors", 6, 36, 0, "bank", radar_targets=15, n_nbr_obs=3)
 
