@@ -436,8 +436,8 @@ def test_full_size_c4_lockstep():
 @pytest.mark.parametrize("E,N,R,n_check,n_steps", [(65536, 10, 36, 4096, 6), (131072, 20, 72, 2048, 4)])
 def test_full_size_c3_properties_and_oracle_check(E, N, R, n_check, n_steps):
     """BASELINE config C3 at full size (65 536 envs x 10 drones x 36 rays) and one GPU's shard of C5 (1M envs x 20 drones x
-    72 rays over 8 GPUs), on the path bench.py times: no optional outputs (lean kernels), step launch + reset launch
-    through the mode-specialised instantiations.  Every step: size-independent properties on every env, determinism
+    72 rays over 8 GPUs), on the path bench.py times: no optional outputs (lean kernels), the mode-specialised
+    instantiations - C3: the phased launch (step loop + reset loop in one kernel), C5: step launch + reset launch.  Every step: size-independent properties on every env, determinism
     across two handles, and `n_check` randomly chosen envs (4096 for C3) against the oracle - the transition (reward,
     done, goal, bound_building_check, terminated and the stepped observation) from a snapshot taken before the step,
     and the reset observation of the envs that finished from the state the reset left."""
