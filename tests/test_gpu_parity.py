@@ -9,7 +9,7 @@ from tests.replay import GOLDEN_DIR, load_case, load_case_mm, oracle_margins_mm,
 
 pytestmark = pytest.mark.gpu
 
-ALL_GOLDEN = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(f).startswith(("actor", "cs_", "mapgen")))
+ALL_GOLDEN = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(f).startswith(("actor", "cs_", "mapgen", "jps_")))
 GOLDEN = [n for n in ALL_GOLDEN if not n.startswith("mm_")]
 GOLDEN_MM = [n for n in ALL_GOLDEN if n.startswith("mm_")]
 

@@ -38,6 +38,25 @@ def test_device_od_table_equals_host_od_table():
         assert int(a.path_len.astype(np.int64).sum()) > 0
 
 
+def test_device_planner_equals_the_reference_jps():
+    """The device search against paths of the UNMODIFIED reference jps_find_path (tests/golden/jps_paths.npz, made by
+    tests/golden/gen_golden_jps.py): 1200 pairs on three grids, 112 of them unreachable; the pruned line expanded back to cells
+    is the reference's path cell for cell."""
+    import os
+    from tests.test_oracle_golden import _expand
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jps_paths.npz"))
+    for name in ("single", "multi5", "walled"):
+        occ, pairs, flat, off = z[name + "_occ"], z[name + "_pairs"], z[name + "_cells"], z[name + "_off"]
+        cells, length = plan_paths_device(grid(occ), pairs, 64)
+        for k in range(len(pairs)):
+            want = [divmod(int(c), 256) for c in flat[off[k]:off[k + 1]]]
+            if not want:
+                assert length[k] == 0, (name, k)
+                continue
+            got = [divmod(int(c), 256) for c in cells[k, :length[k]]]
+            assert _expand(got) == want, (name, k)
+
+
 def test_device_planner_edge_cases():
     # a walled pocket (unreachable goal), start == goal, adjacent cells, a start on an occupied cell, and a path
     # with more vertices than max_cells

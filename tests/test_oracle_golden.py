@@ -10,7 +10,7 @@ from multi_agent_aac_b200.maps import synthetic_map
 from oracle.oracle import OracleEnv, RADAR_MIN
 from tests.replay import GOLDEN_DIR, load_case, load_case_mm, replay, replay_mm
 
-ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(f).startswith(("actor", "cs_", "mapgen")))
+ALL = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(f).startswith(("actor", "cs_", "mapgen", "jps_")))
 GOLDEN = [n for n in ALL if not n.startswith("mm_")]
 GOLDEN_MM = [n for n in ALL if n.startswith("mm_")]
 
@@ -144,3 +144,45 @@ def test_sensor_classes_match_the_later_forks_class():
         assert np.allclose(o["norm_nbr"][0], d["norm_nbr"][q], rtol=1e-9, atol=1e-9), q
         assert o["norm_nbr"].shape[-1] == 5 * n_neigh
     assert hits > 0.5 * d["radar"].size
+
+
+def _expand(cells):
+    """Pruned line (vertices where the direction changes) -> every cell along it."""
+    out = [cells[0]]
+    for a, b in zip(cells[:-1], cells[1:]):
+        dx, dy = np.sign(b[0] - a[0]), np.sign(b[1] - a[1])
+        assert (dx == 0) != (dy == 0), (a, b)              # axis-parallel legs only
+        x, y = a
+        while (x, y) != tuple(b):
+            x, y = x + dx, y + dy
+            out.append((int(x), int(y)))
+    return out
+
+
+def test_planner_equals_the_reference_jps():
+    """aac_plan_path (host; the search the origin / destination tables and the per-episode device search share) against paths
+    of the UNMODIFIED reference jps_find_path (tests/golden/gen_golden_jps.py): the pruned line, expanded back to cells, is
+    the reference's path cell for cell - same tie-breaking - and unreachable goals are reported as such."""
+    import ctypes
+    from multi_agent_aac_b200 import _capi
+    _capi.build()
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    z = np.load(os.path.join(GOLDEN_DIR, "jps_paths.npz"))
+    n_none = 0
+    for name in ("single", "multi5", "walled"):
+        occ, pairs, flat, off = z[name + "_occ"], z[name + "_pairs"], z[name + "_cells"], z[name + "_off"]
+        gx, gy = occ.shape
+        buf = np.zeros(64, dtype=np.uint16)
+        for k, (sx, sy, tx, ty) in enumerate(pairs):
+            want = [divmod(int(c), 256) for c in flat[off[k]:off[k + 1]]]
+            n = lib.aac_plan_path(occ.ctypes.data_as(ctypes.c_void_p), int(gx), int(gy), int(sx), int(sy), int(tx), int(ty),
+                                  buf.ctypes.data_as(ctypes.c_void_p), 64)
+            if not want:
+                assert n == 0, (name, k)
+                n_none += 1
+                continue
+            assert n >= 2, (name, k, n)
+            got = [divmod(int(c), 256) for c in buf[:n]]
+            assert got[0] == (sx, sy) and got[-1] == (tx, ty)
+            assert _expand(got) == want, (name, k)
+    assert n_none > 20
