@@ -173,3 +173,24 @@ def test_gon_against_cell_and_goal_contact_match_opencv_and_sympy():
         if area_g > 1e-3:
             assert gap < 0
     assert n_touch >= 30 and n_apart >= 20 and n_exact == 8
+
+
+def test_swept_capsule_against_a_boundary_line_matches_sympy():
+    """ATT:2172-2173, :2507: `boundary_line.intersects(LineString([pre, pos]).buffer(2.5, cap_style='round'))` - the stadium
+    geos_lite builds (convex) against the long boundary segment, decided exactly by sympy on the same vertices."""
+    rng = np.random.default_rng(14)
+    n_hit = n_miss = 0
+    for n in range(40):
+        xb = float(rng.choice([0.0, 60.0]))
+        sign = 1.0 if xb == 0.0 else -1.0
+        pos = np.array([xb + sign * (2.5 + rng.uniform(-0.03, 0.03)), rng.uniform(5, 55)])     # around first contact of the cap
+        step = rng.uniform(0, 2.5) * np.array([math.cos(a := rng.uniform(0, 2 * math.pi)), math.sin(a)])
+        pre = pos + sign * np.array([abs(step[0]), step[1]]) if n % 4 else pos.copy()         # moving towards the line, or standing still
+        cap = G.LineString([tuple(pre), tuple(pos)]).buffer(2.5, cap_style="round")
+        bound = G.LineString([(xb, -9999.0), (xb, 9999.0)])
+        poly, seg = spoly(cap), sseg((xb, -9999.0), (xb, 9999.0))
+        want = bool(boundary_hits(poly, seg)) or inside_closed(poly, seg.p1)
+        assert bound.intersects(cap) == want, (n, pre, pos, xb)
+        n_hit += want
+        n_miss += not want
+    assert n_hit >= 8 and n_miss >= 8
