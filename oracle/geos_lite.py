@@ -7,6 +7,9 @@ reference's hot path calls.  shapely itself is not installable in the build cont
 control flow, observation layout and reward branches execute verbatim, and only the geometry
 primitives below are restated.  Parity status: the geometry layer is "parity unpinned"
 (no GEOS binary here to compare against); everything above it is pinned by the real reference.
+What is checked without GEOS: the constructions against the answers GEOS / shapely publish, and
+the predicates against sympy's exact geometry and OpenCV on the polygons built here
+(tests/test_geos_conformance.py, tests/test_geometry_independent.py).
 
 Call sites this module has to serve (ATT = MADDPG_ownENV_randomOD_radar_one_model_att/
 env_simulator_randomOD_radar_sur_drones_oneModel_att.py):
