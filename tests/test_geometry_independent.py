@@ -194,3 +194,36 @@ def test_swept_capsule_against_a_boundary_line_matches_sympy():
         n_hit += want
         n_miss += not want
     assert n_hit >= 8 and n_miss >= 8
+
+
+def test_reference_line_projection_matches_sympy():
+    """ATT:3203-3214, UV2:413-441: `line.project(p)` (arc length of the nearest point of the reference polyline),
+    `line.interpolate(d)` and `p.distance(line)` on axis-parallel polylines like the reference lines (cell centres joined
+    where the direction changes) - against sympy's exact point / segment distances and projections, leg by leg."""
+    rng = np.random.default_rng(15)
+    for n in range(60):
+        k = int(rng.integers(2, 7))
+        pts = [np.array([5.0 + 10.0 * int(rng.integers(0, 8)), 5.0 + 10.0 * int(rng.integers(0, 8))])]
+        horiz = bool(rng.integers(0, 2))
+        while len(pts) < k:
+            step = 10.0 * int(rng.integers(1, 5)) * rng.choice([-1, 1])
+            pts.append(pts[-1] + (np.array([step, 0.0]) if horiz else np.array([0.0, step])))
+            horiz = not horiz
+        p = pts[int(rng.integers(0, k))] + rng.uniform(-12, 12, 2) + 1e-3 * rng.uniform(0.1, 1.0, 2)   # (off the bisectors: no exact ties)
+        line, P = G.LineString([tuple(q) for q in pts]), Point2D(Rational(p[0]), Rational(p[1]))
+        best, arc, run = None, None, Rational(0)
+        for a, b in zip(pts[:-1], pts[1:]):
+            seg = sseg(a, b)
+            q = seg.projection(P)                       # foot on the carrier line, clamped to the leg below
+            if not seg.contains(q):
+                q = min((seg.p1, seg.p2), key=lambda e: (e.x - P.x) ** 2 + (e.y - P.y) ** 2)
+            dd = (q.x - P.x) ** 2 + (q.y - P.y) ** 2
+            if best is None or dd < best:               # first leg attaining the minimum wins
+                best, arc = dd, run + abs(q.x - seg.p1.x) + abs(q.y - seg.p1.y)     # legs are axis-parallel: L1 = length
+            run += abs(seg.p2.x - seg.p1.x) + abs(seg.p2.y - seg.p1.y)
+        got_arc = line.project(G.Point(*p))
+        assert abs(got_arc - float(arc)) <= 1e-9, (n, pts, p)
+        assert abs(G.Point(*p).distance(line) - math.sqrt(float(best))) <= 1e-9, (n, pts, p)
+        back = line.interpolate(got_arc)
+        assert abs(G.Point(*p).distance(back) - math.sqrt(float(best))) <= 1e-9, (n, pts, p)
+        assert abs(line.length - float(run)) <= 1e-9
